@@ -1,0 +1,168 @@
+/* stk.h — C ABI of libstk.so, the sm_100a kernel library behind stonkgs_b200.
+ *
+ * The reference (stonkgs/stonkgs) is pure Python on top of HuggingFace BERT and has no FFI layer;
+ * its hot path is `STonKGsForPreTraining.forward` (src/stonkgs/models/stonkgs_model.py:149-258) and
+ * the extraction loop of `get_stonkgs_embeddings` (src/stonkgs/models/stonkgs_for_embeddings.py:176-184).
+ * Each entry point below replaces one piece of that path; the reference lines it replaces are cited.
+ * "HF" = transformers/models/bert/modeling_bert.py (the third-party arithmetic the reference calls).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (PyTorch tensors); the library never
+ *    allocates or frees caller-visible memory, workspaces are passed in;
+ *  - every call takes (device ordinal, cudaStream_t as void*) and is asynchronous on that stream;
+ *  - return value: 0 = ok, negative = STK_ERR_*; stk_last_error() gives the text (thread-local);
+ *  - bf16 tensors are passed as void* (raw uint16 storage), row-major, leading dimension in ELEMENTS;
+ *  - no exceptions cross the boundary; functions are re-entrant (backward runs on the autograd thread).
+ */
+#ifndef STK_H_
+#define STK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STK_OK 0
+#define STK_ERR_BAD_ARG (-1)
+#define STK_ERR_CUDA (-2)
+#define STK_ERR_UNSUPPORTED (-3)
+
+#define STK_VERSION 100
+
+/* library version (STK_VERSION) */
+int stk_version(void);
+/* copies the calling thread's last error text into buf (NUL terminated); returns its length */
+int stk_last_error(char* buf, size_t n);
+/* number of kernel launches issued by this library in the calling process so far */
+long long stk_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Embedding stages
+ * ---------------------------------------------------------------------------------------------- */
+
+/* A1 — input stage of the frozen LM backbone: out = LN(word[id] + type[0] + pos[p]).
+ * Replaces `self.lm_backbone(input_ids[:, :256])` embeddings (stonkgs_model.py:178 -> HF:72-112,
+ * called with ids only, so token type is 0 and there is no mask).
+ * ids: int64 [B, S] with row pitch ids_pitch (elements), so the text half of a [B,512] batch can be
+ * passed in place.  word/pos/type tables and LayerNorm gain/bias are fp32.  out: bf16 [B*S, 768].
+ * err_flag (device int, may be NULL) is set to 1 if an id is outside [0, vocab). */
+int stk_embed_text_ln_fwd(int device, void* stream, const int64_t* ids, int64_t ids_pitch, int B, int S,
+                          const float* word, int vocab, const float* pos, const float* type_emb,
+                          const float* gamma, const float* beta, void* out_bf16, int* err_flag);
+
+/* A3+A4 — joint embedding stage: for t < 256 the row is the LM-backbone hidden state, for t >= 256
+ * it is the KG table row T[input_ids[b, t]] (dense table restating stonkgs_model.py:123-141,182-189);
+ * out = LN((row + type[token_type]) + pos[t])   (stonkgs_model.py:193-210 -> HF:102-112).
+ * input_ids/token_type_ids: int64 [B, 512] (token_type_ids may be NULL = 0 for t<256, 1 otherwise).
+ * lm_hidden: bf16 [B, 256, 768]; kg_table: fp32 [table_rows, 768].
+ * out: bf16 [B*512, 768]; mean/rstd: fp32 [B*512] saved for backward (may be NULL);
+ * inputs_embeds_out: optional fp32 [B*512, 768] copy of the un-normalised gathered rows (bit-exact
+ * gather check / API parity).  err_flag set to 1 on an id outside [0, table_rows) (reference: KeyError). */
+int stk_embed_joint_ln_fwd(int device, void* stream, const int64_t* input_ids, const int64_t* token_type_ids,
+                           int B, const void* lm_hidden_bf16, const float* kg_table, int64_t table_rows,
+                           const float* pos, const float* type_emb, const float* gamma, const float* beta,
+                           void* out_bf16, float* mean, float* rstd, float* inputs_embeds_out, int* err_flag);
+
+/* Backward of the joint embedding stage (the gathered rows are frozen: no gradient flows to them).
+ * dy: bf16 [B*512, 768].  Accumulates (+=) into fp32 dpos [512,768], dtype [2,768], dgamma, dbeta [768]. */
+int stk_embed_joint_ln_bwd(int device, void* stream, const int64_t* input_ids, const int64_t* token_type_ids,
+                           int B, const void* lm_hidden_bf16, const float* kg_table, int64_t table_rows,
+                           const float* pos, const float* type_emb, const float* gamma, const float* mean,
+                           const float* rstd, const void* dy_bf16, float* dpos, float* dtype, float* dgamma,
+                           float* dbeta);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm over rows of 768 (HF:294-298, 352-356, 481-485; eps = 1e-12)
+ * ---------------------------------------------------------------------------------------------- */
+int stk_layernorm_fwd(int device, void* stream, const void* x_bf16, int M, const float* gamma, const float* beta,
+                      void* y_bf16, float* mean, float* rstd);
+/* dx: bf16 [M,768]; dgamma/dbeta: fp32 [768], accumulated (+=).  x is the forward INPUT. */
+int stk_layernorm_bwd(int device, void* stream, const void* dy_bf16, const void* x_bf16, int M, const float* gamma,
+                      const float* mean, const float* rstd, void* dx_bf16, float* dgamma, float* dbeta);
+
+/* ------------------------------------------------------------------------------------------------
+ * tcgen05 GEMM:  C[M,N] = epilogue( A[M,K] * B[N,K]^T )      (bf16 in, fp32 accumulate in TMEM)
+ * Replaces every nn.Linear on the path (HF:158-160,179-181,287-298,330-356,456-468,471-485;
+ * stonkgs_model.py:62-73) and their autograd backward.
+ *
+ * a_major / b_major: 0 = K-major (A stored [M][K], B stored [N][K], i.e. nn.Linear weight layout),
+ *                    1 = MN-major (A stored [K][M], B stored [K][N]).
+ *   forward  y = x W^T      : A = x (K-major), B = W  (K-major)
+ *   dgrad    dx = dy W      : A = dy (K-major), B = W (MN-major: W is [N_out=K][N_in=N])
+ *   wgrad    dW = dy^T x    : A = dy (MN-major: dy is [tokens=K][M]), B = x (MN-major)
+ * lda/ldb/ldc: row pitch in elements of the stored matrices.
+ * ---------------------------------------------------------------------------------------------- */
+enum {
+  STK_EPI_BIAS = 0,          /* C(bf16) = acc + bias[n]                    (bias may be NULL)         */
+  STK_EPI_BIAS_GELU = 1,     /* C(bf16) = gelu_erf(acc + bias)                                        */
+  STK_EPI_BIAS_GELU_SAVE = 2,/* C(bf16) = gelu_erf(u), C2(bf16) = u = acc + bias  (training forward)  */
+  STK_EPI_BIAS_RESID = 3,    /* C(bf16) = acc + bias + R[m,n]              (R bf16, pitch ldr)        */
+  STK_EPI_BIAS_TANH_F32 = 4, /* C(fp32) = tanh(acc + bias)                 (pooler, HF:456-468)       */
+  STK_EPI_DGELU = 5,         /* C(bf16) = acc * gelu_erf'(R[m,n])          (R = saved pre-activation) */
+  STK_EPI_F32_ADD = 6,       /* C(fp32) += acc   (TMA reduce-add; split-K and grad accumulation)      */
+  STK_EPI_F32 = 7,           /* C(fp32) = acc                                                          */
+  STK_EPI_CE_STATS = 8,      /* no C: per-row (max, sum exp) partials + target logit (A9+A10 fwd)     */
+  STK_EPI_CE_DLOGIT = 9      /* C(bf16) = (exp(acc - lse[m]) - [n+n_offset == label[m]]) * *scale_dev   */
+};
+
+typedef struct StkGemmEpilogue {
+  const float* bias;      /* [N] fp32 or NULL */
+  const void* resid;      /* bf16 [M, ldr]: residual (BIAS_RESID) or saved pre-activation (DGELU) */
+  int64_t ldr;
+  void* c2;               /* second output (BIAS_GELU_SAVE): bf16 [M, ldc2] */
+  int64_t ldc2;
+  const int32_t* labels;  /* CE: [M] target column in the FULL vocabulary, or -1 */
+  const float* lse;       /* CE_DLOGIT: [M] log-sum-exp of the full row */
+  const float* scale_dev; /* CE_DLOGIT: device scalar, gradient scale (upstream grad / labelled-row count) */
+  float* ce_partial;      /* CE_STATS: fp32 [M, ce_pitch, 2] (max, sumexp) per 128-column slab */
+  int64_t ce_pitch;       /* number of slabs in the full vocabulary = 2 * ceil(N_full / 256) */
+  float* tgt_logit;       /* CE_STATS: [M] logit of the target column (written by the owning slab) */
+  int32_t n_offset;       /* CE: first vocabulary column of this call's B block (multiple of 256) */
+} StkGemmEpilogue;
+
+int stk_gemm(int device, void* stream, int a_major, int b_major, const void* A_bf16, int64_t lda,
+             const void* B_bf16, int64_t ldb, int M, int N, int K, int epilogue, void* C, int64_t ldc,
+             const StkGemmEpilogue* epi, int split_k);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused masked-softmax attention (HF:115-140 eager / 192-205 sdpa; additive key mask HF:666-672)
+ * qkv: bf16 [B*S, 2304] = [Q | K | V], head h at columns h*64 of each third.  S in {128, 256, 384, 512}.
+ * key_bias: fp32 [B, S] additive bias per key (0 or finfo.min), NULL = no mask (LM backbone).
+ * out: bf16 [B*S, 768].  lse: optional fp32 [B, 12, S] (row log-sum-exp of the scaled, biased scores).
+ * ---------------------------------------------------------------------------------------------- */
+int stk_attn_fwd(int device, void* stream, const void* qkv_bf16, const float* key_bias, int B, int S,
+                 void* out_bf16, float* lse);
+/* dqkv: bf16 [B*S, 2304].  dout/out: bf16 [B*S, 768].  workspace: fp32 [B*12*S] (row dot(dO,O)). */
+int stk_attn_bwd(int device, void* stream, const void* qkv_bf16, const float* key_bias, int B, int S,
+                 const void* out_bf16, const void* dout_bf16, const float* lse, float* workspace,
+                 void* dqkv_bf16);
+
+/* ------------------------------------------------------------------------------------------------
+ * Small fused helpers
+ * ---------------------------------------------------------------------------------------------- */
+/* int64 attention_mask [B,S] (1 = attend) -> fp32 additive key bias (0 / finfo.min), HF:666-672 */
+int stk_mask_to_bias(int device, void* stream, const int64_t* mask, int64_t n, float* bias);
+/* fp32 -> bf16 cast of n elements (weights after load / optimizer step) */
+int stk_cast_f32_to_bf16(int device, void* stream, const float* src, void* dst_bf16, int64_t n);
+/* gather rows: dst[i,:] = src[idx[i],:] for bf16 rows of 768 (labelled-row compaction for the heads) */
+int stk_gather_rows(int device, void* stream, const void* src_bf16, const int32_t* idx, int n_rows, void* dst_bf16);
+/* scatter-add rows: dst[idx[i],:] += src[i,:]  (bf16 += bf16; idx unique) — head gradient back to the sequence */
+int stk_scatter_add_rows(int device, void* stream, const void* src_bf16, const int32_t* idx, int n_rows,
+                         void* dst_bf16);
+/* column sums: out[n] (+)= sum_m x[m,n], x bf16 [M, ld]; bias gradients */
+int stk_colsum(int device, void* stream, const void* x_bf16, int64_t ld, int M, int N, float* out, int accumulate);
+/* CE finalisation (stonkgs_model.py:229-245): reduce the slab partials to lse[m] and
+ * loss_sum += sum_m (lse[m] - tgt[m]); count is the number of rows. */
+int stk_ce_finalize(int device, void* stream, const float* ce_partial, int64_t ce_pitch, const float* tgt_logit,
+                    int M, float* lse, float* row_loss);
+/* A8+A11: pooled -> Linear(768->2) -> CE (HF:528-533); pooled fp32 [B,768]; logits fp32 [B,2];
+ * row_loss fp32 [B] (may be NULL when labels is NULL) */
+int stk_nsp_head_fwd(int device, void* stream, const float* pooled, int B, const float* w, const float* b,
+                     const int64_t* labels, float* logits, float* row_loss);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STK_H_ */

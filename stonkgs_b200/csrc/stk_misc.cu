@@ -1,0 +1,240 @@
+// stk_misc.cu — small HBM-bound helpers around the GEMM / attention kernels: mask -> additive key
+// bias, fp32 -> bf16 weight casts, labelled-row gather / scatter-add for the heads, column sums
+// (bias gradients), cross-entropy finalisation and the NSP head.
+//
+// Reference lines: HF modeling_bert.py:666-672 (extended attention mask), stonkgs_model.py:229-245
+// (three mean cross-entropies), HF:528-533 (seq_relationship head).
+#include <atomic>
+#include <float.h>
+
+#include "stk_common.cuh"
+#include "stk_host.h"
+
+namespace stk {
+
+extern std::atomic<long long> g_launches;
+
+__global__ void mask_to_bias_kernel(const int64_t* __restrict__ mask, int64_t n, float* __restrict__ bias) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // (1 - mask) * finfo(float32).min, exactly as HF builds the additive mask
+  if (i < n) bias[i] = (1.0f - static_cast<float>(mask[i])) * (-FLT_MAX);
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 8;
+  for (int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src + i));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(src + i) + 1);
+      *reinterpret_cast<uint4*>(dst + i) = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w),
+                                                      pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+    } else {
+      for (int64_t j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+    }
+  }
+}
+
+// one warp per row of 768 bf16 (1536 B = 3 x 16 B per lane)
+__global__ void __launch_bounds__(256) gather_rows_kernel(const __nv_bfloat16* __restrict__ src,
+                                                          const int32_t* __restrict__ idx, int n_rows,
+                                                          __nv_bfloat16* __restrict__ dst) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const uint4* s = reinterpret_cast<const uint4*>(src + static_cast<int64_t>(__ldg(idx + row)) * kHidden);
+  uint4* d = reinterpret_cast<uint4*>(dst + static_cast<int64_t>(row) * kHidden);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) d[lane + 32 * i] = __ldg(s + lane + 32 * i);
+}
+
+__global__ void __launch_bounds__(256) scatter_add_rows_kernel(const __nv_bfloat16* __restrict__ src,
+                                                               const int32_t* __restrict__ idx, int n_rows,
+                                                               __nv_bfloat16* __restrict__ dst) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const uint4* s = reinterpret_cast<const uint4*>(src + static_cast<int64_t>(row) * kHidden);
+  uint4* d = reinterpret_cast<uint4*>(dst + static_cast<int64_t>(__ldg(idx + row)) * kHidden);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const uint4 a = __ldg(s + lane + 32 * i);
+    uint4 b = d[lane + 32 * i];
+    b.x = pack_bf16x2(bf16_lo(a.x) + bf16_lo(b.x), bf16_hi(a.x) + bf16_hi(b.x));
+    b.y = pack_bf16x2(bf16_lo(a.y) + bf16_lo(b.y), bf16_hi(a.y) + bf16_hi(b.y));
+    b.z = pack_bf16x2(bf16_lo(a.z) + bf16_lo(b.z), bf16_hi(a.z) + bf16_hi(b.z));
+    b.w = pack_bf16x2(bf16_lo(a.w) + bf16_lo(b.w), bf16_hi(a.w) + bf16_hi(b.w));
+    d[lane + 32 * i] = b;
+  }
+}
+
+// column sums of a bf16 matrix: block = 8 warps over a 64-column strip and a slab of rows;
+// lane owns 2 adjacent columns (128 B per warp per row), warps stride over rows.
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int M, int N,
+                                                     int rows_per_block, float* __restrict__ out) {
+  __shared__ float red[8][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 64 + lane * 2;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, M);
+  float a0 = 0.f, a1 = 0.f;
+  if (n < N) {
+    const __nv_bfloat16* p = x + n;
+    int r = r0 + warp;
+    for (; r + 24 < r1; r += 32) {  // 4 independent loads in flight per lane
+      uint32_t v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint32_t*>(p + static_cast<int64_t>(r + 8 * u) * ld));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a0 += bf16_lo(v[u]); a1 += bf16_hi(v[u]); }
+    }
+    for (; r < r1; r += 8) {
+      const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(p + static_cast<int64_t>(r) * ld));
+      a0 += bf16_lo(v); a1 += bf16_hi(v);
+    }
+  }
+  red[warp][lane * 2] = a0;
+  red[warp][lane * 2 + 1] = a1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    if (c < N) atomicAdd(out + c, s);
+  }
+}
+
+// one warp per row: combine the (max, sumexp) slab partials into lse and the row loss
+__global__ void __launch_bounds__(256) ce_finalize_kernel(const float2* __restrict__ part, int64_t pitch,
+                                                          const float* __restrict__ tgt, int M,
+                                                          float* __restrict__ lse_out, float* __restrict__ row_loss) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float2* p = part + static_cast<int64_t>(row) * pitch;
+  float mx = -INFINITY;
+  for (int64_t i = lane; i < pitch; i += 32) mx = fmaxf(mx, __ldg(&p[i].x));
+  mx = warp_max(mx);
+  float s = 0.f;
+  for (int64_t i = lane; i < pitch; i += 32) {
+    const float2 v = __ldg(p + i);
+    if (v.x > -INFINITY) s += v.y * exp2f((v.x - mx) * 1.4426950408889634f);
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    const float lse = mx + logf(s);
+    lse_out[row] = lse;
+    if (row_loss) row_loss[row] = lse - __ldg(tgt + row);
+  }
+}
+
+// one warp per sample: logits = pooled . w^T + b ; row loss = logsumexp - logit[label]
+__global__ void __launch_bounds__(256) nsp_head_fwd_kernel(const float* __restrict__ pooled, int B,
+                                                           const float* __restrict__ w, const float* __restrict__ bias,
+                                                           const int64_t* __restrict__ labels,
+                                                           float* __restrict__ logits, float* __restrict__ row_loss) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  float s0 = 0.f, s1 = 0.f;
+  for (int c = lane; c < kHidden; c += 32) {
+    const float x = __ldg(pooled + static_cast<int64_t>(b) * kHidden + c);
+    s0 = fmaf(x, __ldg(w + c), s0);
+    s1 = fmaf(x, __ldg(w + kHidden + c), s1);
+  }
+  s0 = warp_sum(s0) + __ldg(bias);
+  s1 = warp_sum(s1) + __ldg(bias + 1);
+  if (lane == 0) {
+    logits[2 * b] = s0;
+    logits[2 * b + 1] = s1;
+    if (labels && row_loss) {
+      const float m = fmaxf(s0, s1);
+      const float lse = m + logf(expf(s0 - m) + expf(s1 - m));
+      const int64_t l = __ldg(labels + b);
+      row_loss[b] = lse - (l == 0 ? s0 : s1);
+    }
+  }
+}
+
+}  // namespace stk
+
+using namespace stk;
+
+#define STK_LAUNCHED()                                  \
+  do {                                                  \
+    STK_CHECK_CUDA(cudaGetLastError());                 \
+    g_launches.fetch_add(1, std::memory_order_relaxed); \
+    return STK_OK;                                      \
+  } while (0)
+
+extern "C" int stk_mask_to_bias(int device, void* stream, const int64_t* mask, int64_t n, float* bias) {
+  STK_REQUIRE(mask && bias && n > 0, "stk_mask_to_bias: bad arguments");
+  STK_CHECK_CUDA(cudaSetDevice(device));
+  mask_to_bias_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, n, bias);
+  STK_LAUNCHED();
+}
+
+extern "C" int stk_cast_f32_to_bf16(int device, void* stream, const float* src, void* dst, int64_t n) {
+  STK_REQUIRE(src && dst && n > 0, "stk_cast_f32_to_bf16: bad arguments");
+  STK_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+              "stk_cast_f32_to_bf16: pointers must be 16-byte aligned");
+  STK_CHECK_CUDA(cudaSetDevice(device));
+  int64_t blocks = (n / 8 + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(num_sms(device)) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  cast_f32_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), n);
+  STK_LAUNCHED();
+}
+
+extern "C" int stk_gather_rows(int device, void* stream, const void* src, const int32_t* idx, int n_rows, void* dst) {
+  STK_REQUIRE(src && idx && dst && n_rows > 0, "stk_gather_rows: bad arguments");
+  STK_CHECK_CUDA(cudaSetDevice(device));
+  gather_rows_kernel<<<(n_rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), idx, n_rows, static_cast<__nv_bfloat16*>(dst));
+  STK_LAUNCHED();
+}
+
+extern "C" int stk_scatter_add_rows(int device, void* stream, const void* src, const int32_t* idx, int n_rows,
+                                    void* dst) {
+  STK_REQUIRE(src && idx && dst && n_rows > 0, "stk_scatter_add_rows: bad arguments");
+  STK_CHECK_CUDA(cudaSetDevice(device));
+  scatter_add_rows_kernel<<<(n_rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), idx, n_rows, static_cast<__nv_bfloat16*>(dst));
+  STK_LAUNCHED();
+}
+
+extern "C" int stk_colsum(int device, void* stream, const void* x, int64_t ld, int M, int N, float* out,
+                          int accumulate) {
+  STK_REQUIRE(x && out && M > 0 && N > 0 && ld % 2 == 0 && N % 2 == 0, "stk_colsum: bad arguments");
+  STK_CHECK_CUDA(cudaSetDevice(device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!accumulate) STK_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, s));
+  const int strips = (N + 63) / 64;
+  int slabs = (num_sms(device) * 4 + strips - 1) / strips;
+  int rows_per_block = (M + slabs - 1) / slabs;
+  if (rows_per_block < 64) rows_per_block = 64;
+  slabs = (M + rows_per_block - 1) / rows_per_block;
+  colsum_kernel<<<dim3(strips, slabs), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ld, M, N, rows_per_block, out);
+  STK_LAUNCHED();
+}
+
+extern "C" int stk_ce_finalize(int device, void* stream, const float* ce_partial, int64_t ce_pitch,
+                               const float* tgt_logit, int M, float* lse, float* row_loss) {
+  STK_REQUIRE(ce_partial && lse && M > 0 && ce_pitch > 0, "stk_ce_finalize: bad arguments");
+  STK_REQUIRE(row_loss == nullptr || tgt_logit != nullptr, "stk_ce_finalize: row_loss needs tgt_logit");
+  STK_CHECK_CUDA(cudaSetDevice(device));
+  ce_finalize_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float2*>(ce_partial), ce_pitch, tgt_logit, M, lse, row_loss);
+  STK_LAUNCHED();
+}
+
+extern "C" int stk_nsp_head_fwd(int device, void* stream, const float* pooled, int B, const float* w, const float* b,
+                                const int64_t* labels, float* logits, float* row_loss) {
+  STK_REQUIRE(pooled && w && b && logits && B > 0, "stk_nsp_head_fwd: bad arguments");
+  STK_CHECK_CUDA(cudaSetDevice(device));
+  nsp_head_fwd_kernel<<<(B + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(pooled, B, w, b, labels, logits,
+                                                                                   row_loss);
+  STK_LAUNCHED();
+}

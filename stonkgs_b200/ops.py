@@ -1,0 +1,254 @@
+"""torch-tensor front ends of the C ABI (include/stk.h).
+
+PyTorch is used for device memory and streams only; every function here launches hand-written
+sm_100a kernels from libstk.so on the current CUDA stream and fails loudly otherwise.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GELU_SAVE, EPI_BIAS_RESID, EPI_BIAS_TANH_F32, EPI_CE_DLOGIT,
+                   EPI_CE_STATS, EPI_DGELU, EPI_F32, EPI_F32_ADD, GemmEpilogue, check)
+
+H = 768
+HEADS = 12
+
+_F32_EPIS = (EPI_F32, EPI_F32_ADD, EPI_BIAS_TANH_F32)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _ctx(t: torch.Tensor):
+    if not t.is_cuda:
+        raise _lib.StkError("stonkgs_b200 kernels need CUDA tensors (there is no CPU path)")
+    dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    return dev, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _req(t: torch.Tensor, dtype, name: str):
+    if t.dtype != dtype or not t.is_cuda:
+        raise _lib.StkError(f"{name}: expected CUDA {dtype}, got {t.dtype} on {t.device}")
+    return t
+
+
+def launch_count() -> int:
+    return int(_lib.load().stk_launch_count())
+
+
+# --------------------------------------------------------------------------------------------------
+# embedding stages / LayerNorm
+# --------------------------------------------------------------------------------------------------
+def embed_text_ln(ids: torch.Tensor, word, pos, type_emb, gamma, beta, err_flag=None) -> torch.Tensor:
+    """ids: int64 [B, S] (may be a column slice of a wider tensor). Returns bf16 [B*S, 768]."""
+    _req(ids, torch.int64, "ids")
+    B, S = ids.shape
+    assert ids.stride(1) == 1
+    dev, stream = _ctx(ids)
+    out = torch.empty((B * S, H), dtype=torch.bfloat16, device=ids.device)
+    check(_lib.load().stk_embed_text_ln_fwd(dev, stream, _ptr(ids), ids.stride(0), B, S, _ptr(word), word.shape[0],
+                                            _ptr(pos), _ptr(type_emb), _ptr(gamma), _ptr(beta), _ptr(out),
+                                            _ptr(err_flag)), "stk_embed_text_ln_fwd")
+    return out
+
+
+def embed_joint_ln(input_ids, token_type_ids, lm_hidden, kg_table, pos, type_emb, gamma, beta, *, save_stats=False,
+                   want_inputs_embeds=False, err_flag=None):
+    """Returns (out bf16 [B*512,768], mean, rstd, inputs_embeds fp32 or None)."""
+    _req(input_ids, torch.int64, "input_ids")
+    B = input_ids.shape[0]
+    assert input_ids.shape[1] == 512 and input_ids.is_contiguous()
+    if token_type_ids is not None:
+        _req(token_type_ids, torch.int64, "token_type_ids")
+        assert token_type_ids.is_contiguous() and token_type_ids.shape == input_ids.shape
+    _req(lm_hidden, torch.bfloat16, "lm_hidden")
+    _req(kg_table, torch.float32, "kg_table")
+    dev, stream = _ctx(input_ids)
+    out = torch.empty((B * 512, H), dtype=torch.bfloat16, device=input_ids.device)
+    mean = rstd = emb = None
+    if save_stats:
+        mean = torch.empty(B * 512, dtype=torch.float32, device=input_ids.device)
+        rstd = torch.empty_like(mean)
+    if want_inputs_embeds:
+        emb = torch.empty((B * 512, H), dtype=torch.float32, device=input_ids.device)
+    check(_lib.load().stk_embed_joint_ln_fwd(dev, stream, _ptr(input_ids), _ptr(token_type_ids), B, _ptr(lm_hidden),
+                                             _ptr(kg_table), kg_table.shape[0], _ptr(pos), _ptr(type_emb),
+                                             _ptr(gamma), _ptr(beta), _ptr(out), _ptr(mean), _ptr(rstd), _ptr(emb),
+                                             _ptr(err_flag)), "stk_embed_joint_ln_fwd")
+    return out, mean, rstd, emb
+
+
+def embed_joint_ln_bwd(input_ids, token_type_ids, lm_hidden, kg_table, pos, type_emb, gamma, mean, rstd, dy, dpos,
+                       dtype, dgamma, dbeta):
+    B = input_ids.shape[0]
+    dev, stream = _ctx(input_ids)
+    check(_lib.load().stk_embed_joint_ln_bwd(dev, stream, _ptr(input_ids), _ptr(token_type_ids), B, _ptr(lm_hidden),
+                                             _ptr(kg_table), kg_table.shape[0], _ptr(pos), _ptr(type_emb),
+                                             _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dy), _ptr(dpos), _ptr(dtype),
+                                             _ptr(dgamma), _ptr(dbeta)), "stk_embed_joint_ln_bwd")
+
+
+def layernorm(x: torch.Tensor, gamma, beta, save_stats=False, out=None):
+    _req(x, torch.bfloat16, "x")
+    M = x.shape[0]
+    assert x.shape[1] == H and x.is_contiguous()
+    dev, stream = _ctx(x)
+    y = torch.empty_like(x) if out is None else out
+    mean = rstd = None
+    if save_stats:
+        mean = torch.empty(M, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+    check(_lib.load().stk_layernorm_fwd(dev, stream, _ptr(x), M, _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean),
+                                        _ptr(rstd)), "stk_layernorm_fwd")
+    return (y, mean, rstd) if save_stats else y
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, out=None):
+    """dgamma/dbeta are accumulated into. Returns dx (bf16)."""
+    M = x.shape[0]
+    dev, stream = _ctx(x)
+    dx = torch.empty_like(x) if out is None else out
+    check(_lib.load().stk_layernorm_bwd(dev, stream, _ptr(dy), _ptr(x), M, _ptr(gamma), _ptr(mean), _ptr(rstd),
+                                        _ptr(dx), _ptr(dgamma), _ptr(dbeta)), "stk_layernorm_bwd")
+    return dx
+
+
+# --------------------------------------------------------------------------------------------------
+# GEMM
+# --------------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, b: torch.Tensor, *, M: int, N: int, K: int, a_major: int = 0, b_major: int = 0,
+         epilogue: int = EPI_BIAS, out: Optional[torch.Tensor] = None, bias=None, resid=None, c2=None, labels=None,
+         lse=None, scale_dev=None, ce_partial=None, tgt_logit=None, n_offset: int = 0, split_k: int = 1):
+    """C[M,N] = epilogue(A[M,K] B[N,K]^T); a/b are 2-D bf16 tensors in the stored layout
+    (K-major: [M,K] / [N,K]; MN-major: [K,M] / [K,N]); row stride = leading dimension."""
+    _req(a, torch.bfloat16, "A")
+    _req(b, torch.bfloat16, "B")
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    dev, stream = _ctx(a)
+    epi = GemmEpilogue()
+    epi.bias = bias.data_ptr() if bias is not None else None
+    if resid is not None:
+        assert resid.stride(1) == 1
+        epi.resid = resid.data_ptr()
+        epi.ldr = resid.stride(0)
+    if c2 is not None:
+        epi.c2 = c2.data_ptr()
+        epi.ldc2 = c2.stride(0)
+    if labels is not None:
+        _req(labels, torch.int32, "labels")
+        epi.labels = labels.data_ptr()
+    epi.lse = lse.data_ptr() if lse is not None else None
+    epi.scale_dev = scale_dev.data_ptr() if scale_dev is not None else None
+    if ce_partial is not None:
+        epi.ce_partial = ce_partial.data_ptr()
+        epi.ce_pitch = ce_partial.shape[1]
+    epi.tgt_logit = tgt_logit.data_ptr() if tgt_logit is not None else None
+    epi.n_offset = n_offset
+    if epilogue != EPI_CE_STATS:
+        if out is None:
+            dt = torch.float32 if epilogue in _F32_EPIS else torch.bfloat16
+            out = torch.empty((M, N), dtype=dt, device=a.device)
+        assert out.stride(1) == 1
+        ldc = out.stride(0)
+    else:
+        ldc = 0
+    check(_lib.load().stk_gemm(dev, stream, a_major, b_major, _ptr(a), a.stride(0), _ptr(b), b.stride(0), M, N, K,
+                               epilogue, _ptr(out), ldc, ctypes.byref(epi), split_k), "stk_gemm")
+    return out
+
+
+def linear(x, w, bias=None, epilogue=EPI_BIAS, **kw):
+    """y = epilogue(x @ w.T + bias) for x [M,K], w [N,K] (nn.Linear layout)."""
+    return gemm(x, w, M=x.shape[0], N=w.shape[0], K=x.shape[1], bias=bias, epilogue=epilogue, **kw)
+
+
+# --------------------------------------------------------------------------------------------------
+# attention
+# --------------------------------------------------------------------------------------------------
+def attention(qkv: torch.Tensor, key_bias: Optional[torch.Tensor], B: int, S: int, save_lse=False, out=None):
+    _req(qkv, torch.bfloat16, "qkv")
+    assert qkv.shape == (B * S, 3 * H) and qkv.is_contiguous()
+    dev, stream = _ctx(qkv)
+    ctx = torch.empty((B * S, H), dtype=torch.bfloat16, device=qkv.device) if out is None else out
+    lse = torch.empty((B, HEADS, S), dtype=torch.float32, device=qkv.device) if save_lse else None
+    check(_lib.load().stk_attn_fwd(dev, stream, _ptr(qkv), _ptr(key_bias), B, S, _ptr(ctx), _ptr(lse)),
+          "stk_attn_fwd")
+    return (ctx, lse) if save_lse else ctx
+
+
+def attention_bwd(qkv, key_bias, B, S, out, dout, lse):
+    dev, stream = _ctx(qkv)
+    dqkv = torch.empty_like(qkv)
+    ws = torch.empty(B * HEADS * S, dtype=torch.float32, device=qkv.device)
+    check(_lib.load().stk_attn_bwd(dev, stream, _ptr(qkv), _ptr(key_bias), B, S, _ptr(out), _ptr(dout), _ptr(lse),
+                                   _ptr(ws), _ptr(dqkv)), "stk_attn_bwd")
+    return dqkv
+
+
+# --------------------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------------------
+def mask_to_bias(mask: torch.Tensor) -> torch.Tensor:
+    _req(mask, torch.int64, "attention_mask")
+    mask = mask.contiguous()
+    dev, stream = _ctx(mask)
+    bias = torch.empty(mask.shape, dtype=torch.float32, device=mask.device)
+    check(_lib.load().stk_mask_to_bias(dev, stream, _ptr(mask), mask.numel(), _ptr(bias)), "stk_mask_to_bias")
+    return bias
+
+
+def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(src, torch.float32, "src")
+    assert src.is_contiguous()
+    dev, stream = _ctx(src)
+    dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device) if out is None else out
+    check(_lib.load().stk_cast_f32_to_bf16(dev, stream, _ptr(src), _ptr(dst), src.numel()), "stk_cast_f32_to_bf16")
+    return dst
+
+
+def gather_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    _req(idx, torch.int32, "idx")
+    dev, stream = _ctx(src)
+    n = idx.numel()
+    dst = torch.empty((n, H), dtype=torch.bfloat16, device=src.device)
+    if n:
+        check(_lib.load().stk_gather_rows(dev, stream, _ptr(src), _ptr(idx), n, _ptr(dst)), "stk_gather_rows")
+    return dst
+
+
+def scatter_add_rows(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor) -> None:
+    dev, stream = _ctx(src)
+    if idx.numel():
+        check(_lib.load().stk_scatter_add_rows(dev, stream, _ptr(src), _ptr(idx), idx.numel(), _ptr(dst)),
+              "stk_scatter_add_rows")
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor, accumulate: bool = False) -> torch.Tensor:
+    dev, stream = _ctx(x)
+    M, N = x.shape
+    check(_lib.load().stk_colsum(dev, stream, _ptr(x), x.stride(0), M, N, _ptr(out), int(accumulate)), "stk_colsum")
+    return out
+
+
+def ce_finalize(ce_partial, tgt_logit, M):
+    dev, stream = _ctx(ce_partial)
+    lse = torch.empty(M, dtype=torch.float32, device=ce_partial.device)
+    row_loss = torch.empty(M, dtype=torch.float32, device=ce_partial.device)
+    check(_lib.load().stk_ce_finalize(dev, stream, _ptr(ce_partial), ce_partial.shape[1], _ptr(tgt_logit), M,
+                                      _ptr(lse), _ptr(row_loss)), "stk_ce_finalize")
+    return lse, row_loss
+
+
+def nsp_head(pooled, w, b, labels=None):
+    dev, stream = _ctx(pooled)
+    B = pooled.shape[0]
+    logits = torch.empty((B, 2), dtype=torch.float32, device=pooled.device)
+    row_loss = torch.empty(B, dtype=torch.float32, device=pooled.device) if labels is not None else None
+    check(_lib.load().stk_nsp_head_fwd(dev, stream, _ptr(pooled), B, _ptr(w), _ptr(b), _ptr(labels), _ptr(logits),
+                                       _ptr(row_loss)), "stk_nsp_head_fwd")
+    return logits, row_loss

@@ -1,0 +1,412 @@
+"""Bring-up probe for the CUDA kernels: each case runs in its own subprocess (a trapped kernel
+poisons the CUDA context) under a timeout and reports one JSON object; the parent writes
+gpurun_out/probe.json.  Run on the GPU box:
+
+    python tools/gpu_probe.py [case ...]
+
+This is a development aid (diagnostics are more verbose than the pytest parity tests).
+"""
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _err_report(got, ref, name, tol):
+    import torch
+    got = got.float()
+    ref = ref.float()
+    d = (got - ref).abs()
+    out = {"case": name, "max_abs": float(d.max()), "mean_abs": float(d.mean()), "ref_absmax": float(ref.abs().max()),
+           "nan": int(torch.isnan(got).sum()), "ok": bool(d.max() <= tol and not torch.isnan(got).any())}
+    if not out["ok"]:
+        bad = d > tol
+        out["bad_frac"] = float(bad.float().mean())
+        if got.dim() == 2:
+            M, N = got.shape
+            rb = bad.float().reshape(-1, N).mean(1)
+            cb = bad.float().mean(0)
+            out["bad_rows_first64"] = [round(float(x), 2) for x in rb[:64]]
+            out["bad_cols_first128"] = [round(float(x), 2) for x in cb[:128]]
+            out["got_00"] = [[round(float(v), 4) for v in got[i, :8]] for i in range(min(4, M))]
+            out["ref_00"] = [[round(float(v), 4) for v in ref[i, :8]] for i in range(min(4, M))]
+    return out
+
+
+def case_elementwise():
+    import torch
+    from stonkgs_b200 import ops
+    torch.manual_seed(0)
+    dev = "cuda"
+    res = []
+    M = 1000
+    x = torch.randn(M, 768, device=dev).bfloat16()
+    g = (1 + 0.1 * torch.randn(768, device=dev)).float()
+    b = (0.1 * torch.randn(768, device=dev)).float()
+    y, mean, rstd = ops.layernorm(x, g, b, save_stats=True)
+    ref = torch.nn.functional.layer_norm(x.float(), (768,), g, b, 1e-12)
+    res.append(_err_report(y, ref, "layernorm_fwd", 2e-2))
+    # LN bwd
+    dy = torch.randn(M, 768, device=dev).bfloat16()
+    dg = torch.zeros(768, device=dev)
+    db = torch.zeros(768, device=dev)
+    dx = ops.layernorm_bwd(dy, x, g, mean, rstd, dg, db)
+    xr = x.float().requires_grad_(True)
+    gr = g.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    torch.nn.functional.layer_norm(xr, (768,), gr, br, 1e-12).backward(dy.float())
+    res.append(_err_report(dx, xr.grad, "layernorm_bwd_dx", 3e-2))
+    res.append(_err_report(dg, gr.grad, "layernorm_bwd_dgamma", 2e-2 * gr.grad.abs().max().item()))
+    res.append(_err_report(db, br.grad, "layernorm_bwd_dbeta", 1e-3 * br.grad.abs().max().item() + 1e-3))
+    # embed text
+    B, S, V = 3, 256, 5000
+    word = torch.randn(V, 768, device=dev)
+    pos = torch.randn(512, 768, device=dev)
+    typ = torch.randn(2, 768, device=dev)
+    ids_full = torch.randint(0, V, (B, 512), device=dev)
+    out = ops.embed_text_ln(ids_full[:, :256], word, pos, typ, g, b)
+    ref = torch.nn.functional.layer_norm((word[ids_full[:, :256]] + typ[0]) + pos[:256], (768,), g, b, 1e-12)
+    res.append(_err_report(out.view(B, S, 768), ref, "embed_text_ln", 3e-2))
+    # embed joint
+    N = 3000
+    table = torch.randn(N + 3, 768, device=dev)
+    lm = torch.randn(B, 256, 768, device=dev).bfloat16()
+    ids = torch.randint(0, N + 3, (B, 512), device=dev)
+    tt = torch.cat([torch.zeros(B, 256, dtype=torch.long), torch.ones(B, 256, dtype=torch.long)], 1).to(dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    out, mean, rstd, emb = ops.embed_joint_ln(ids, tt, lm, table, pos, typ, g, b, save_stats=True,
+                                              want_inputs_embeds=True, err_flag=flag)
+    src = torch.cat([lm.float(), table[ids[:, 256:]]], 1)
+    res.append({"case": "embed_joint_gather_bitexact", "ok": bool(torch.equal(emb.view(B, 512, 768), src)),
+                "flag": int(flag.item())})
+    ref = torch.nn.functional.layer_norm((src + typ[tt]) + pos, (768,), g, b, 1e-12)
+    res.append(_err_report(out.view(B, 512, 768), ref, "embed_joint_ln", 3e-2))
+    out2, _, _, _ = ops.embed_joint_ln(ids, None, lm, table, pos, typ, g, b)
+    res.append({"case": "embed_joint_default_types", "ok": bool(torch.equal(out, out2))})
+    bad = ids.clone()
+    bad[0, 300] = N + 3
+    ops.embed_joint_ln(bad, tt, lm, table, pos, typ, g, b, err_flag=flag)
+    res.append({"case": "embed_joint_oob_flag", "ok": int(flag.item()) == 1})
+    # embed joint bwd
+    dy = torch.randn(B * 512, 768, device=dev).bfloat16()
+    dpos = torch.zeros(512, 768, device=dev)
+    dtyp = torch.zeros(2, 768, device=dev)
+    dg = torch.zeros(768, device=dev)
+    db = torch.zeros(768, device=dev)
+    ops.embed_joint_ln_bwd(ids, tt, lm, table, pos, typ, g, mean, rstd, dy, dpos, dtyp, dg, db)
+    pr = pos.clone().requires_grad_(True)
+    tr = typ.clone().requires_grad_(True)
+    gr = g.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    torch.nn.functional.layer_norm((src + tr[tt]) + pr, (768,), gr, br, 1e-12).backward(dy.float().view(B, 512, 768))
+    res.append(_err_report(dpos, pr.grad, "embed_joint_bwd_dpos", 1e-3 * pr.grad.abs().max().item() + 1e-4))
+    res.append(_err_report(dtyp, tr.grad, "embed_joint_bwd_dtype", 1e-3 * tr.grad.abs().max().item() + 1e-3))
+    res.append(_err_report(dg, gr.grad, "embed_joint_bwd_dgamma", 1e-3 * gr.grad.abs().max().item() + 1e-3))
+    res.append(_err_report(db, br.grad, "embed_joint_bwd_dbeta", 1e-3 * br.grad.abs().max().item() + 1e-3))
+    # misc
+    w = torch.randn(1000, 77, device=dev)
+    res.append({"case": "cast_bf16", "ok": bool(torch.equal(ops.cast_bf16(w), w.bfloat16()))})
+    m = torch.randint(0, 2, (4, 512), device=dev)
+    ref = (1.0 - m.float()) * torch.finfo(torch.float32).min
+    res.append({"case": "mask_to_bias", "ok": bool(torch.equal(ops.mask_to_bias(m), ref))})
+    idx = torch.randperm(M, device=dev)[:300].int()
+    res.append({"case": "gather_rows", "ok": bool(torch.equal(ops.gather_rows(x, idx), x[idx.long()]))})
+    dst = torch.randn(M, 768, device=dev).bfloat16()
+    want = dst.clone()
+    want[idx.long()] = (want[idx.long()].float() + x[:300].float()).bfloat16()
+    ops.scatter_add_rows(x[:300].contiguous(), idx, dst)
+    res.append({"case": "scatter_add_rows", "ok": bool(torch.equal(dst, want))})
+    cs = torch.empty(768, device=dev)
+    ops.colsum(x, cs)
+    res.append(_err_report(cs, x.float().sum(0), "colsum", 1e-2))
+    pooled = torch.randn(5, 768, device=dev)
+    wn = torch.randn(2, 768, device=dev) * 0.05
+    bn = torch.randn(2, device=dev)
+    lab = torch.randint(0, 2, (5,), device=dev)
+    lg, rl = ops.nsp_head(pooled, wn, bn, lab)
+    lref = pooled @ wn.T + bn
+    res.append(_err_report(lg, lref, "nsp_logits", 1e-4))
+    res.append(_err_report(rl, torch.nn.functional.cross_entropy(lref, lab, reduction="none"), "nsp_row_loss", 1e-4))
+    return res
+
+
+def _gemm_ref(a, b, a_major, b_major):
+    A = a.float() if a_major == 0 else a.float().T
+    Bm = b.float() if b_major == 0 else b.float().T
+    return A @ Bm.T
+
+
+def _mk(rows, cols, dev, scale=1.0):
+    import torch
+    return (torch.randn(rows, cols, device=dev) * scale).bfloat16()
+
+
+def case_gemm_basic():
+    """Smallest possible: one tile, K = 64 (one k-block), then a few more shapes; fp32 output."""
+    import torch
+    from stonkgs_b200 import ops
+    torch.manual_seed(1)
+    res = []
+    for (M, N, K) in [(128, 256, 64), (128, 256, 256), (256, 512, 768), (384, 768, 3072), (1000, 1000, 520)]:
+        a = _mk(M, K, "cuda")
+        b = _mk(N, K, "cuda")
+        c = ops.gemm(a, b, M=M, N=N, K=K, epilogue=ops.EPI_F32)
+        torch.cuda.synchronize()
+        res.append(_err_report(c, _gemm_ref(a, b, 0, 0), f"gemm_kk_f32_{M}x{N}x{K}", 1e-2 * (K ** 0.5) / 8))
+    return res
+
+
+def case_gemm_epilogues():
+    import torch
+    from stonkgs_b200 import ops
+    torch.manual_seed(2)
+    res = []
+    M, N, K = 520, 768, 768
+    a = _mk(M, K, "cuda", 0.5)
+    w = _mk(N, K, "cuda", 0.05)
+    bias = torch.randn(N, device="cuda") * 0.5
+    acc = _gemm_ref(a, w, 0, 0)
+    tol = 3e-2
+    res.append(_err_report(ops.linear(a, w, bias), acc + bias, "epi_bias", tol))
+    res.append(_err_report(ops.linear(a, w, None), acc, "epi_nobias", tol))
+    res.append(_err_report(ops.linear(a, w, bias, ops.EPI_BIAS_GELU), torch.nn.functional.gelu(acc + bias),
+                           "epi_bias_gelu", tol))
+    pre = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    act = ops.linear(a, w, bias, ops.EPI_BIAS_GELU_SAVE, c2=pre)
+    res.append(_err_report(act, torch.nn.functional.gelu(acc + bias), "epi_gelu_save_act", tol))
+    res.append(_err_report(pre, acc + bias, "epi_gelu_save_pre", tol))
+    r = _mk(M, N, "cuda")
+    res.append(_err_report(ops.linear(a, w, bias, ops.EPI_BIAS_RESID, resid=r), acc + bias + r.float(),
+                           "epi_bias_resid", 4e-2))
+    res.append(_err_report(ops.linear(a, w, bias, ops.EPI_BIAS_TANH_F32), torch.tanh(acc + bias), "epi_tanh_f32", 2e-3))
+    u = _mk(M, N, "cuda")
+    uf = u.float().requires_grad_(True)
+    torch.nn.functional.gelu(uf).sum().backward()
+    res.append(_err_report(ops.linear(a, w, None, ops.EPI_DGELU, resid=u), acc * uf.grad, "epi_dgelu", tol))
+    # strided A (pooler reads row 0 of every sequence): lda = 512*768
+    seq = _mk(4 * 512, 768, "cuda", 0.5)
+    a0 = seq.view(4, 512, 768)[:, 0]
+    res.append(_err_report(ops.gemm(a0, w, M=4, N=N, K=K, epilogue=ops.EPI_BIAS_TANH_F32, bias=bias),
+                           torch.tanh(a0.float() @ w.float().T + bias), "epi_tanh_strided_rows", 2e-3))
+    return res
+
+
+def case_gemm_majors():
+    """dgrad (B MN-major) and wgrad (A and B MN-major, split-K reduce-add)."""
+    import torch
+    from stonkgs_b200 import ops
+    torch.manual_seed(3)
+    res = []
+    # dgrad: dx[M, Kin] = dy[M, Nout] @ W[Nout, Kin]  -> A = dy (K-major, K=Nout), B = W stored [K=Nout][N=Kin]
+    Mt, Nout, Kin = 520, 768, 3072
+    dy = _mk(Mt, Nout, "cuda", 0.5)
+    W = _mk(Nout, Kin, "cuda", 0.05)
+    ref = dy.float() @ W.float()
+    res.append(_err_report(ops.gemm(dy, W, M=Mt, N=Kin, K=Nout, b_major=1, epilogue=ops.EPI_BIAS), ref, "dgrad_bf16", 3e-2))
+    res.append(_err_report(ops.gemm(dy, W, M=Mt, N=Kin, K=Nout, b_major=1, epilogue=ops.EPI_F32), ref, "dgrad_f32", 2e-2))
+    r = _mk(Mt, Kin, "cuda")
+    res.append(_err_report(ops.gemm(dy, W, M=Mt, N=Kin, K=Nout, b_major=1, epilogue=ops.EPI_BIAS_RESID, resid=r),
+                           ref + r.float(), "dgrad_resid", 4e-2))
+    c = torch.randn(Mt, Kin, device="cuda")
+    want = c + ref
+    ops.gemm(dy, W, M=Mt, N=Kin, K=Nout, b_major=1, epilogue=ops.EPI_F32_ADD, out=c)
+    res.append(_err_report(c, want, "dgrad_f32_add", 2e-2))
+    # wgrad: dW[Nout, Kin] = dy^T[Nout, Mt] @ x[Mt, Kin] -> A = dy stored [K=Mt][M=Nout], B = x stored [K=Mt][N=Kin]
+    for (Mt, Nout, Kin, split) in [(512, 768, 768, 1), (2048, 768, 3072, 4), (1000, 2304, 768, 3), (304, 768, 768, 2)]:
+        dy = _mk(Mt, Nout, "cuda", 0.5)
+        x = _mk(Mt, Kin, "cuda", 0.5)
+        ref = dy.float().T @ x.float()
+        res.append(_err_report(ops.gemm(dy, x, M=Nout, N=Kin, K=Mt, a_major=1, b_major=1, epilogue=ops.EPI_F32), ref,
+                               f"wgrad_f32_{Mt}", 1e-2 * Mt ** 0.5 / 4))
+        c = torch.zeros(Nout, Kin, device="cuda")
+        ops.gemm(dy, x, M=Nout, N=Kin, K=Mt, a_major=1, b_major=1, epilogue=ops.EPI_F32_ADD, out=c, split_k=split)
+        res.append(_err_report(c, ref, f"wgrad_splitk{split}_{Mt}", 1e-2 * Mt ** 0.5 / 4))
+    return res
+
+
+def case_gemm_ce():
+    import torch
+    from stonkgs_b200 import ops
+    torch.manual_seed(4)
+    res = []
+    M, V, K = 304, 28996, 768
+    h = _mk(M, K, "cuda", 1.0)
+    W = _mk(V, K, "cuda", 0.05)
+    labels = torch.randint(0, V, (M,), device="cuda").int()
+    labels[0] = V - 1
+    labels[1] = 0
+    pitch = 2 * ((V + 255) // 256)
+    part = torch.zeros(M, pitch, 2, device="cuda")
+    tgt = torch.zeros(M, device="cuda")
+    ops.gemm(h, W, M=M, N=V, K=K, epilogue=ops.EPI_CE_STATS, labels=labels, ce_partial=part, tgt_logit=tgt)
+    lse, row_loss = ops.ce_finalize(part, tgt, M)
+    logits = h.float() @ W.float().T
+    res.append(_err_report(lse, torch.logsumexp(logits, -1), "ce_lse", 2e-3))
+    res.append(_err_report(tgt, logits.gather(1, labels.long()[:, None])[:, 0], "ce_tgt_logit", 2e-3))
+    res.append(_err_report(row_loss, torch.nn.functional.cross_entropy(logits, labels.long(), reduction="none"),
+                           "ce_row_loss", 3e-3))
+    # chunked variant with n_offset (two calls over vocabulary blocks)
+    part2 = torch.zeros(M, pitch, 2, device="cuda")
+    tgt2 = torch.zeros(M, device="cuda")
+    cut = 256 * 50
+    ops.gemm(h, W[:cut], M=M, N=cut, K=K, epilogue=ops.EPI_CE_STATS, labels=labels, ce_partial=part2, tgt_logit=tgt2)
+    ops.gemm(h, W[cut:], M=M, N=V - cut, K=K, epilogue=ops.EPI_CE_STATS, labels=labels, ce_partial=part2,
+             tgt_logit=tgt2, n_offset=cut)
+    lse2, _ = ops.ce_finalize(part2, tgt2, M)
+    res.append(_err_report(lse2, torch.logsumexp(logits, -1), "ce_lse_chunked", 2e-3))
+    res.append(_err_report(tgt2, tgt, "ce_tgt_chunked", 1e-6))
+    # dlogit
+    scale = torch.tensor([1.0 / M], device="cuda")
+    dl = torch.empty(M, V, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(h, W, M=M, N=V, K=K, epilogue=ops.EPI_CE_DLOGIT, labels=labels, lse=lse, scale_dev=scale, out=dl)
+    ref = torch.softmax(logits, -1)
+    ref[torch.arange(M), labels.long()] -= 1
+    ref /= M
+    res.append(_err_report(dl, ref, "ce_dlogit", 3e-5))
+    return res
+
+
+def _attn_ref(qkv, bias, B, S):
+    import torch
+    q, k, v = qkv.float().view(B, S, 3, 12, 64).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) * 0.125
+    if bias is not None:
+        s = s + bias[:, None, None, :]
+    p = torch.softmax(s, -1)
+    o = (p @ v).permute(0, 2, 1, 3).reshape(B * S, 768)
+    return o, torch.logsumexp(s, -1)
+
+
+def case_attn():
+    import torch
+    from stonkgs_b200 import ops
+    torch.manual_seed(5)
+    res = []
+    for (B, S, masked) in [(2, 256, False), (2, 512, True), (1, 128, True), (3, 384, True)]:
+        qkv = _mk(B * S, 2304, "cuda", 1.0)
+        bias = None
+        if masked:
+            m = torch.ones(B, S, dtype=torch.long, device="cuda")
+            for b in range(B):
+                m[b, 40 + 17 * b: S // 2] = 0
+            bias = ops.mask_to_bias(m)
+        out, lse = ops.attention(qkv, bias, B, S, save_lse=True)
+        ref, lref = _attn_ref(qkv, bias, B, S)
+        res.append(_err_report(out, ref, f"attn_fwd_S{S}_mask{int(masked)}", 2e-2))
+        res.append(_err_report(lse, lref, f"attn_lse_S{S}", 2e-3))
+    return res
+
+
+def _time(fn, iters=10, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def case_perf():
+    import torch
+    from stonkgs_b200 import ops
+    res = []
+    M = 65536
+    for (N, K, epi, name) in [(2304, 768, ops.EPI_BIAS, "qkv"), (768, 768, ops.EPI_BIAS_RESID, "wo"),
+                              (3072, 768, ops.EPI_BIAS_GELU, "ffn1"), (768, 3072, ops.EPI_BIAS_RESID, "ffn2")]:
+        a = _mk(M, K, "cuda", 0.5)
+        w = _mk(N, K, "cuda", 0.05)
+        bias = torch.zeros(N, device="cuda")
+        r = _mk(M, N, "cuda") if epi == ops.EPI_BIAS_RESID else None
+        out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+        ms = _time(lambda: ops.gemm(a, w, M=M, N=N, K=K, epilogue=epi, bias=bias, resid=r, out=out))
+        ms_t = _time(lambda: torch.nn.functional.linear(a, w))
+        res.append({"case": f"perf_gemm_{name}", "ms": ms, "tflops": 2.0 * M * N * K / ms / 1e9, "torch_ms": ms_t,
+                    "torch_tflops": 2.0 * M * N * K / ms_t / 1e9, "ok": True})
+    for (B, S) in [(128, 256), (128, 512)]:
+        qkv = _mk(B * S, 2304, "cuda", 1.0)
+        out = torch.empty(B * S, 768, dtype=torch.bfloat16, device="cuda")
+        ms = _time(lambda: ops.attention(qkv, None, B, S, out=out))
+        fl = 4.0 * B * 12 * S * S * 64
+        q, k, v = qkv.view(B, S, 3, 12, 64).permute(2, 0, 3, 1, 4)
+        ms_t = _time(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v))
+        res.append({"case": f"perf_attn_S{S}", "ms": ms, "tflops": fl / ms / 1e9, "torch_sdpa_ms": ms_t,
+                    "torch_tflops": fl / ms_t / 1e9, "ok": True})
+    x = _mk(131072, 768, "cuda")
+    g = torch.ones(768, device="cuda")
+    b = torch.zeros(768, device="cuda")
+    y = torch.empty_like(x)
+    ms = _time(lambda: ops.layernorm(x, g, b, out=y))
+    res.append({"case": "perf_layernorm_131072", "ms": ms, "gbs": 2 * x.numel() * 2 / ms / 1e6, "ok": True})
+    return res
+
+
+CASES = {
+    "elementwise": case_elementwise,
+    "gemm_basic": case_gemm_basic,
+    "gemm_epilogues": case_gemm_epilogues,
+    "gemm_majors": case_gemm_majors,
+    "gemm_ce": case_gemm_ce,
+    "attn": case_attn,
+    "perf": case_perf,
+}
+
+
+def main():
+    if len(sys.argv) >= 3 and sys.argv[1] == "--case":
+        name = sys.argv[2]
+        try:
+            out = CASES[name]()
+        except Exception as e:  # noqa: BLE001
+            import traceback
+            out = [{"case": name, "ok": False, "exception": repr(e), "trace": traceback.format_exc()[-1500:]}]
+        print("PROBE_JSON " + json.dumps(out))
+        return
+    names = sys.argv[1:] or list(CASES)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    results = []
+    for name in names:
+        t0 = time.time()
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", name], capture_output=True,
+                               text=True, timeout=300)
+            got = None
+            for line in r.stdout.splitlines():
+                if line.startswith("PROBE_JSON "):
+                    got = json.loads(line[len("PROBE_JSON "):])
+            if got is None:
+                got = [{"case": name, "ok": False, "rc": r.returncode, "stdout": r.stdout[-1500:], "stderr": r.stderr[-2500:]}]
+        except subprocess.TimeoutExpired as e:
+            got = [{"case": name, "ok": False, "timeout": True, "stdout": (e.stdout or b"")[-1000:].decode(errors="replace")
+                    if isinstance(e.stdout, bytes) else str(e.stdout)[-1000:]}]
+        for g in got:
+            g["group"] = name
+        results += got
+        print(f"[{name}] {time.time() - t0:.1f}s", flush=True)
+        for g in got:
+            brief = {k: v for k, v in g.items() if k in ("case", "ok", "max_abs", "mean_abs", "ms", "tflops",
+                                                         "torch_tflops", "gbs", "exception", "timeout", "rc", "bad_frac")}
+            print("   ", brief, flush=True)
+            if not g.get("ok", False):
+                for k in ("stderr", "trace", "stdout"):
+                    if k in g:
+                        print("     ", k, ":", str(g[k])[-1200:], flush=True)
+        with open(os.path.join(ROOT, "gpurun_out", "probe.json"), "w") as f:
+            json.dump(results, f, indent=1)
+    n_bad = sum(1 for g in results if not g.get("ok", False))
+    print(f"probe: {len(results) - n_bad} ok, {n_bad} failed")
+
+
+if __name__ == "__main__":
+    main()
