@@ -134,7 +134,8 @@ int stk_gemm(int device, void* stream, int a_major, int b_major, const void* A_b
  * ---------------------------------------------------------------------------------------------- */
 int stk_attn_fwd(int device, void* stream, const void* qkv_bf16, const float* key_bias, int B, int S,
                  void* out_bf16, float* lse);
-/* dqkv: bf16 [B*S, 2304].  dout/out: bf16 [B*S, 768].  workspace: fp32 [B*12*S] (row dot(dO,O)). */
+/* dqkv: bf16 [B*S, 2304].  dout/out: bf16 [B*S, 768].
+ * workspace: fp32 [B*S*768 + B*12*S] (dQ accumulator over key blocks, then row dot(dO,O)). */
 int stk_attn_bwd(int device, void* stream, const void* qkv_bf16, const float* key_bias, int B, int S,
                  const void* out_bf16, const void* dout_bf16, const float* lse, float* workspace,
                  void* dqkv_bf16);
@@ -161,6 +162,14 @@ int stk_ce_finalize(int device, void* stream, const float* ce_partial, int64_t c
  * row_loss fp32 [B] (may be NULL when labels is NULL) */
 int stk_nsp_head_fwd(int device, void* stream, const float* pooled, int B, const float* w, const float* b,
                      const int64_t* labels, float* logits, float* row_loss);
+
+/* dx = dy * gelu_erf'(pre), n bf16 elements (n % 8 == 0): backward of the head transform's GELU (HF:481-485) */
+int stk_gelu_bwd(int device, void* stream, const void* dy_bf16, const void* pre_bf16, int64_t n, void* dx_bf16);
+/* Backward of A11+A8: NSP cross-entropy -> seq_relationship Linear -> pooler tanh.
+ * scale_dev: device scalar = upstream grad / B.  dw [2,768], db [2] are accumulated (+=);
+ * dpre: bf16 [B,768] gradient w.r.t. the pooler's pre-activation. */
+int stk_nsp_pool_bwd(int device, void* stream, const float* pooled, const float* logits, const int64_t* labels,
+                     int B, const float* scale_dev, const float* w, float* dw, float* db, void* dpre_bf16);
 
 #ifdef __cplusplus
 }

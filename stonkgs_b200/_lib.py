@@ -61,6 +61,8 @@ _SIGNATURES = {
     "stk_colsum": (c_int, [c_int, _P, _P, c_int64, c_int, c_int, _P, c_int]),
     "stk_ce_finalize": (c_int, [c_int, _P, _P, c_int64, _P, c_int, _P, _P]),
     "stk_nsp_head_fwd": (c_int, [c_int, _P, _P, c_int, _P, _P, _P, _P, _P]),
+    "stk_gelu_bwd": (c_int, [c_int, _P, _P, _P, c_int64, _P]),
+    "stk_nsp_pool_bwd": (c_int, [c_int, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

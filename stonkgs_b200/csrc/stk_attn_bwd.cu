@@ -1,8 +1,326 @@
-// stk_attn_bwd.cu — attention backward (placeholder until the tcgen05 kernel lands).
+// stk_attn_bwd.cu — fused attention backward on tcgen05 (recompute, no S x S tensor in HBM).
+//
+// Autograd backward of HF modeling_bert.py:115-140 (softmax(Q K^T / 8 + mask) V) for the trainable
+// joint encoder (stonkgs_model.py:204-210).  Given Q, K, V (fused QKV activation), O, dO and the
+// saved row log-sum-exp:
+//     P  = exp(Q K^T / 8 + bias - lse)            dV = P^T dO
+//     dP = dO V^T                                 dS = P o (dP - D) / 8,  D = rowsum(dO o O)
+//     dQ = dS K                                   dK = dS^T Q
+//
+// One CTA per (128-key block j, head, batch element) loops over the query blocks i:
+//   warp 8     TMA (K_j, V_j once; Q_i, dO_i double-buffered) + single-thread tcgen05.mma issue
+//   warps 0-7  two threads per query row: read S and dP from TMEM, form P and dS in registers, write
+//              both as bf16 into 128B-swizzled shared tiles that serve BOTH as K-major A operand
+//              (dQ = dS K) and as MN-major A operand (dV = P^T dO, dK = dS^T Q) — no transposes.
+// TMEM columns: S [0,128) | dP [128,256) | dV [256,320) | dK [320,384) | dQ [384,448).
+// dK/dV accumulate in TMEM across the query loop and are written once as bf16 into dQKV;
+// dQ_i partial products go out as fp32 TMA reduce-adds into a workspace (summed over the key
+// blocks in L2) and are converted to bf16 by a small tail kernel.
+#include <atomic>
+
+#include "stk_common.cuh"
 #include "stk_host.h"
 
-extern "C" int stk_attn_bwd(int, void*, const void*, const float*, int, int, const void*, const void*, const float*,
-                            float*, void*) {
-  stk::set_error("stk_attn_bwd: not implemented yet");
-  return STK_ERR_UNSUPPORTED;
+namespace stk {
+
+extern std::atomic<long long> g_launches;
+
+constexpr int ABW_THREADS = 288;
+constexpr float kL2e = 1.4426950408889634f;
+constexpr int ABW_SMEM = 1024 + 16384 * 2 + 32768 * 4 + 512 + 128;
+
+// D[b,h,s] = sum_d dO * O : one warp per token row, 16-lane groups own one head
+__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o,
+                                                            const __nv_bfloat16* __restrict__ dO, int B, int S,
+                                                            float* __restrict__ D) {
+  const int lane = threadIdx.x & 31;
+  const int64_t tok = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (tok >= static_cast<int64_t>(B) * S) return;
+  const int b = static_cast<int>(tok / S), s = static_cast<int>(tok % S);
+  const uint2* po = reinterpret_cast<const uint2*>(o + tok * kHidden);
+  const uint2* pd = reinterpret_cast<const uint2*>(dO + tok * kHidden);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const uint2 a = __ldg(po + lane + 32 * i), g = __ldg(pd + lane + 32 * i);
+    float v = bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) +
+              bf16_hi(a.y) * bf16_hi(g.y);
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((lane & 15) == 0) {
+      const int h = (lane >> 4) + 2 * i;  // chunk (lane + 32 i) covers elements 4c..4c+3 -> head c/16
+      D[(static_cast<int64_t>(b) * kHeads + h) * S + s] = v;
+    }
+  }
+}
+
+// fp32 dQ accumulator [B*S, 768] -> bf16 into the Q third of dQKV [B*S, 2304]
+__global__ void __launch_bounds__(256) attn_bwd_dq_cast_kernel(const float* __restrict__ dq, int64_t rows,
+                                                               __nv_bfloat16* __restrict__ dqkv) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // one thread = 8 elements
+  if (i >= rows * (kHidden / 8)) return;
+  const int64_t r = i / (kHidden / 8);
+  const int c = static_cast<int>(i % (kHidden / 8)) * 8;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(dq + r * kHidden + c));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(dq + r * kHidden + c) + 1);
+  *reinterpret_cast<uint4*>(dqkv + r * (3 * kHidden) + c) =
+      make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+}
+
+__global__ void __launch_bounds__(ABW_THREADS)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
+                const __grid_constant__ CUtensorMap map_dq, const float* __restrict__ key_bias,
+                const float* __restrict__ lse, const float* __restrict__ Dws, int S,
+                __nv_bfloat16* __restrict__ dqkv) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + 16384;
+  uint8_t* sQ = smem + 32768;    // [2][16 KB]
+  uint8_t* sdO = smem + 65536;   // [2][16 KB]
+  uint8_t* sP = smem + 98304;    // [2 key chunks][128 q][128 B]; later the fp32 dQ staging tiles
+  uint8_t* sdS = smem + 131072;
+  float* sBias = reinterpret_cast<float*>(smem + 163840);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 128);
+  uint64_t* bar_kv = bars;
+  uint64_t* bar_q = bars + 1;  // [2]
+  uint64_t* bar_s = bars + 3;
+  uint64_t* bar_p = bars + 4;
+  uint64_t* bar_dq = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int nq = S >> 7;
+  const int row_base = b * S;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      tma_prefetch_desc(&map_qkv);
+      tma_prefetch_desc(&map_do);
+      tma_prefetch_desc(&map_dq);
+      mbar_init(bar_kv, 1);
+      mbar_init(bar_q, 1);
+      mbar_init(bar_q + 1, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 256);
+      mbar_init(bar_dq, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  } else if (threadIdx.x < 128) {
+    sBias[threadIdx.x] = key_bias ? __ldg(key_bias + static_cast<int64_t>(b) * S + j * 128 + threadIdx.x) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t T_S = 0, T_DP = 128, T_DV = 256, T_DK = 320, T_DQ = 384;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_kv, 32768);
+      tma_load_2d(&map_qkv, bar_kv, sK, 768 + h * 64, row_base + j * 128);
+      tma_load_2d(&map_qkv, bar_kv, sV, 1536 + h * 64, row_base + j * 128);
+      mbar_arrive_expect_tx(bar_q, 32768);
+      tma_load_2d(&map_qkv, bar_q, sQ, h * 64, row_base);
+      tma_load_2d(&map_do, bar_q, sdO, h * 64, row_base);
+      mbar_wait(bar_kv, 0);
+
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S, dP
+      constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64, 1, 1);    // dV = P^T dO, dK = dS^T Q
+      constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64, 0, 1);    // dQ = dS K
+      const uint64_t k_desc = umma_smem_desc(smem_u32(sK), 16, 1024);
+      const uint64_t v_desc = umma_smem_desc(smem_u32(sV), 16, 1024);
+      const uint64_t pT_desc = umma_smem_desc(smem_u32(sP), 16384, 1024);
+      const uint64_t dsT_desc = umma_smem_desc(smem_u32(sdS), 16384, 1024);
+
+      for (int i = 0; i < nq; ++i) {
+        const int buf = i & 1;
+        if (i + 1 < nq) {  // prefetch the next query block into the other buffer (free since bar_dq(i-1))
+          mbar_arrive_expect_tx(bar_q + (buf ^ 1), 32768);
+          tma_load_2d(&map_qkv, bar_q + (buf ^ 1), sQ + (buf ^ 1) * 16384, h * 64, row_base + (i + 1) * 128);
+          tma_load_2d(&map_do, bar_q + (buf ^ 1), sdO + (buf ^ 1) * 16384, h * 64, row_base + (i + 1) * 128);
+        }
+        mbar_wait(bar_q + buf, (i >> 1) & 1);
+        tc_fence_after();
+        const uint64_t q_desc = umma_smem_desc(smem_u32(sQ + buf * 16384), 16, 1024);
+        const uint64_t do_desc = umma_smem_desc(smem_u32(sdO + buf * 16384), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + T_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + T_DP, do_desc + 2 * k, v_desc + 2 * k, idesc_s, k > 0);
+        umma_commit(bar_s);
+
+        mbar_wait(bar_p, i & 1);
+        tc_fence_after();
+        // MN-major operands: +2048 B (16 rows of the reduction dimension) per k step
+        const uint64_t doT_desc = umma_smem_desc(smem_u32(sdO + buf * 16384), 8192, 1024);
+        const uint64_t qT_desc = umma_smem_desc(smem_u32(sQ + buf * 16384), 8192, 1024);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem_base + T_DV, pT_desc + k * 128, doT_desc + k * 128, idesc_t, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem_base + T_DK, dsT_desc + k * 128, qT_desc + k * 128, idesc_t, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint64_t ds_desc = umma_smem_desc(smem_u32(sdS + kb * 16384), 16, 1024);
+          const uint64_t kT_desc = umma_smem_desc(smem_u32(sK + kb * 8192), 8192, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + T_DQ, ds_desc + 2 * k, kT_desc + k * 128, idesc_q, (kb | k) > 0);
+        }
+        umma_commit(bar_dq);
+        mbar_wait(bar_dq, i & 1);  // Q/dO[buf], P and dS tiles are free again
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const bool issuer = threadIdx.x == 0;
+    const float scale = 0.125f;
+    const int64_t stat_base = (static_cast<int64_t>(b) * kHeads + h) * S;
+
+    for (int i = 0; i < nq; ++i) {
+      const float row_lse = __ldg(lse + stat_base + i * 128 + row);
+      const float row_D = __ldg(Dws + stat_base + i * 128 + row);
+      if (i > 0) {  // the dQ reduce-add of the previous iteration has finished reading the staging tiles
+        if (issuer) tma_wait_group_read<0>();
+        named_bar_sync(1, 256);
+      }
+      mbar_wait(bar_s, i & 1);
+      tc_fence_after();
+      float p[64];
+      uint8_t* prow = sP + half * 16384 + row * 128;
+      uint8_t* dsrow = sdS + half * 16384 + row * 128;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + T_S + half * 64 + hh * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t w[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int c = hh * 32 + g * 8 + t * 2;
+            const float x0 = fmaf(__uint_as_float(r[g * 8 + t * 2]), scale, sBias[half * 64 + c]);
+            const float x1 = fmaf(__uint_as_float(r[g * 8 + t * 2 + 1]), scale, sBias[half * 64 + c + 1]);
+            p[c] = fast_exp2((x0 - row_lse) * kL2e);
+            p[c + 1] = fast_exp2((x1 - row_lse) * kL2e);
+            w[t] = pack_bf16x2(p[c], p[c + 1]);
+          }
+          *reinterpret_cast<uint4*>(prow + (((hh * 4 + g) ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + T_DP + half * 64 + hh * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t w[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int c = hh * 32 + g * 8 + t * 2;
+            const float d0 = p[c] * (__uint_as_float(r[g * 8 + t * 2]) - row_D) * scale;
+            const float d1 = p[c + 1] * (__uint_as_float(r[g * 8 + t * 2 + 1]) - row_D) * scale;
+            w[t] = pack_bf16x2(d0, d1);
+          }
+          *reinterpret_cast<uint4*>(dsrow + (((hh * 4 + g) ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+
+      mbar_wait(bar_dq, i & 1);
+      tc_fence_after();
+      {  // dQ_i partial: my 32 fp32 columns -> swizzled staging tile (overlays P) -> TMA reduce-add
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + T_DQ + half * 32, r);
+        tmem_ld_wait();
+        uint8_t* srow = sP + half * 16384 + row * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(srow + ((c ^ (row & 7)) << 4)) = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        named_bar_sync(1, 256);
+        if (issuer) {
+          tma_reduce_add_2d(&map_dq, sP, h * 64, row_base + i * 128);
+          tma_reduce_add_2d(&map_dq, sP + 16384, h * 64 + 32, row_base + i * 128);
+          tma_commit_group();
+        }
+      }
+    }
+    if (issuer) tma_wait_group<0>();
+    // dV_j, dK_j: accumulated over all query blocks; lane = key row
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_row + (which == 0 ? T_DV : T_DK) + half * 32, r);
+      tmem_ld_wait();
+      uint4* dst = reinterpret_cast<uint4*>(dqkv + static_cast<int64_t>(row_base + j * 128 + row) * (3 * kHidden) +
+                                            (which == 0 ? 2 * kHidden : kHidden) + h * 64 + half * 32);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t w[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          w[t] = pack_bf16x2(__uint_as_float(r[g * 8 + 2 * t]), __uint_as_float(r[g * 8 + 2 * t + 1]));
+        dst[g] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace stk
+
+using namespace stk;
+
+extern "C" int stk_attn_bwd(int device, void* stream_, const void* qkv, const float* key_bias, int B, int S,
+                            const void* out, const void* dout, const float* lse, float* workspace, void* dqkv) {
+  STK_REQUIRE(qkv && out && dout && lse && workspace && dqkv && B > 0, "stk_attn_bwd: bad arguments");
+  STK_REQUIRE(S == 128 || S == 256 || S == 384 || S == 512, "stk_attn_bwd: S must be 128, 256, 384 or 512 (got %d)", S);
+  STK_CHECK_CUDA(cudaSetDevice(device));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int64_t rows = static_cast<int64_t>(B) * S;
+  float* dq_acc = workspace;                    // [rows, 768]
+  float* Dws = workspace + rows * kHidden;      // [B, 12, S]
+  CUtensorMap map_qkv, map_do, map_dq;
+  int rc = make_tmap_2d(&map_qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, 3 * kHidden, rows, 3 * kHidden * 2, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(&map_do, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dout, kHidden, rows, kHidden * 2, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d(&map_dq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dq_acc, kHidden, rows, kHidden * 4, 32, 128);
+  if (rc) return rc;
+  STK_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, sizeof(float) * rows * kHidden, stream));
+  attn_bwd_prep_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), B, S, Dws);
+  STK_CHECK_CUDA(cudaGetLastError());
+  static bool configured[64] = {};
+  if (!configured[device & 63]) {
+    STK_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ABW_SMEM));
+    configured[device & 63] = true;
+  }
+  attn_bwd_kernel<<<dim3(S / 128, kHeads, B), ABW_THREADS, ABW_SMEM, stream>>>(
+      map_qkv, map_do, map_dq, key_bias, lse, Dws, S, static_cast<__nv_bfloat16*>(dqkv));
+  STK_CHECK_CUDA(cudaGetLastError());
+  attn_bwd_dq_cast_kernel<<<static_cast<unsigned>((rows * (kHidden / 8) + 255) / 256), 256, 0, stream>>>(
+      dq_acc, rows, static_cast<__nv_bfloat16*>(dqkv));
+  STK_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(3, std::memory_order_relaxed);
+  return STK_OK;
 }

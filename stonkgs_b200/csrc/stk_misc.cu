@@ -156,6 +156,59 @@ __global__ void __launch_bounds__(256) nsp_head_fwd_kernel(const float* __restri
   }
 }
 
+
+// dx = dy * gelu_erf'(pre) over n bf16 elements (head transform backward; the encoder's FFN uses the
+// fused DGELU GEMM epilogue instead)
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                       const __nv_bfloat16* __restrict__ pre, int64_t n,
+                                                       __nv_bfloat16* __restrict__ dx) {
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i >= n) return;
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(dy + i));
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(pre + i));
+  uint4 o;
+  o.x = pack_bf16x2(bf16_lo(a.x) * gelu_erf_grad(bf16_lo(u.x)), bf16_hi(a.x) * gelu_erf_grad(bf16_hi(u.x)));
+  o.y = pack_bf16x2(bf16_lo(a.y) * gelu_erf_grad(bf16_lo(u.y)), bf16_hi(a.y) * gelu_erf_grad(bf16_hi(u.y)));
+  o.z = pack_bf16x2(bf16_lo(a.z) * gelu_erf_grad(bf16_lo(u.z)), bf16_hi(a.z) * gelu_erf_grad(bf16_hi(u.z)));
+  o.w = pack_bf16x2(bf16_lo(a.w) * gelu_erf_grad(bf16_lo(u.w)), bf16_hi(a.w) * gelu_erf_grad(bf16_hi(u.w)));
+  *reinterpret_cast<uint4*>(dx + i) = o;
+}
+
+// Backward of NSP cross-entropy + seq_relationship Linear + pooler tanh, one thread per hidden column:
+//   dlogit[b] = (softmax(logits[b]) - onehot(label[b])) * scale
+//   dW[j,c] += sum_b dlogit[b,j] * pooled[b,c];  db[j] += sum_b dlogit[b,j]
+//   dpre[b,c] = (dlogit[b,0] W[0,c] + dlogit[b,1] W[1,c]) * (1 - pooled[b,c]^2)
+__global__ void __launch_bounds__(256) nsp_pool_bwd_kernel(const float* __restrict__ pooled,
+                                                           const float* __restrict__ logits,
+                                                           const int64_t* __restrict__ labels, int B,
+                                                           const float* __restrict__ scale_dev,
+                                                           const float* __restrict__ w, float* __restrict__ dw,
+                                                           float* __restrict__ db, __nv_bfloat16* __restrict__ dpre) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= kHidden) return;
+  const float scale = __ldg(scale_dev);
+  const float w0 = __ldg(w + c), w1 = __ldg(w + kHidden + c);
+  float a0 = 0.f, a1 = 0.f, s0 = 0.f, s1 = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float l0 = __ldg(logits + 2 * b), l1 = __ldg(logits + 2 * b + 1);
+    const float m = fmaxf(l0, l1);
+    const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+    const float inv = 1.0f / (e0 + e1);
+    const int64_t lab = __ldg(labels + b);
+    const float d0 = (e0 * inv - (lab == 0 ? 1.f : 0.f)) * scale;
+    const float d1 = (e1 * inv - (lab == 1 ? 1.f : 0.f)) * scale;
+    const float pv = __ldg(pooled + static_cast<int64_t>(b) * kHidden + c);
+    a0 = fmaf(d0, pv, a0);
+    a1 = fmaf(d1, pv, a1);
+    s0 += d0;
+    s1 += d1;
+    dpre[static_cast<int64_t>(b) * kHidden + c] = __float2bfloat16_rn((d0 * w0 + d1 * w1) * (1.0f - pv * pv));
+  }
+  dw[c] += a0;
+  dw[kHidden + c] += a1;
+  if (c == 0) { db[0] += s0; db[1] += s1; }
+}
+
 }  // namespace stk
 
 using namespace stk;
@@ -236,5 +289,23 @@ extern "C" int stk_nsp_head_fwd(int device, void* stream, const float* pooled, i
   STK_CHECK_CUDA(cudaSetDevice(device));
   nsp_head_fwd_kernel<<<(B + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(pooled, B, w, b, labels, logits,
                                                                                    row_loss);
+  STK_LAUNCHED();
+}
+
+extern "C" int stk_gelu_bwd(int device, void* stream, const void* dy, const void* pre, int64_t n, void* dx) {
+  STK_REQUIRE(dy && pre && dx && n > 0 && n % 8 == 0, "stk_gelu_bwd: bad arguments (n must be a multiple of 8)");
+  STK_CHECK_CUDA(cudaSetDevice(device));
+  gelu_bwd_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(pre), n, static_cast<__nv_bfloat16*>(dx));
+  STK_LAUNCHED();
+}
+
+extern "C" int stk_nsp_pool_bwd(int device, void* stream, const float* pooled, const float* logits,
+                                const int64_t* labels, int B, const float* scale_dev, const float* w, float* dw,
+                                float* db, void* dpre) {
+  STK_REQUIRE(pooled && logits && labels && scale_dev && w && dw && db && dpre && B > 0, "stk_nsp_pool_bwd: bad arguments");
+  STK_CHECK_CUDA(cudaSetDevice(device));
+  nsp_pool_bwd_kernel<<<3, 256, 0, static_cast<cudaStream_t>(stream)>>>(pooled, logits, labels, B, scale_dev, w, dw, db,
+                                                                      static_cast<__nv_bfloat16*>(dpre));
   STK_LAUNCHED();
 }

@@ -1,0 +1,156 @@
+"""Kernel-level orchestration of the STonKGs hot path (forward and backward).
+
+Everything here is a sequence of libstk.so launches on the current CUDA stream; torch tensors are
+only the memory the kernels read and write.  The module mirrors, step by step, what the reference
+computes in ``STonKGsForPreTraining.forward`` (stonkgs_model.py:149-258) through HF BERT
+(modeling_bert.py: BertEmbeddings :72-112, BertLayer :143-207/:287-298/:330-356, BertPooler
+:456-468, BertPredictionHeadTransform :471-485, BertPreTrainingHeads :530-533).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+
+from . import ops
+
+H = 768
+I = 3072
+HALF = 256
+
+
+# --------------------------------------------------------------------------------------------------
+# device-side weight views
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class LayerWeights:
+    wqkv: torch.Tensor   # bf16 [2304, 768]  rows = query | key | value  (HF:158-160)
+    bqkv: torch.Tensor   # fp32 [2304]
+    wo: torch.Tensor     # bf16 [768, 768]    attention.output.dense (HF:290)
+    bo: torch.Tensor
+    ln1_g: torch.Tensor
+    ln1_b: torch.Tensor
+    w1: torch.Tensor     # bf16 [3072, 768]   intermediate.dense (HF:333)
+    b1: torch.Tensor
+    w2: torch.Tensor     # bf16 [768, 3072]   output.dense (HF:348)
+    b2: torch.Tensor
+    ln2_g: torch.Tensor
+    ln2_b: torch.Tensor
+
+
+@dataclass
+class EncoderWeights:
+    word: Optional[torch.Tensor]  # fp32 [V, 768] (LM backbone only; the joint encoder's table is dead weight)
+    pos: torch.Tensor             # fp32 [512, 768]
+    type_emb: torch.Tensor        # fp32 [2, 768]
+    emb_g: torch.Tensor
+    emb_b: torch.Tensor
+    layers: List[LayerWeights] = field(default_factory=list)
+    wp: Optional[torch.Tensor] = None   # bf16 [768, 768] pooler.dense
+    bp: Optional[torch.Tensor] = None
+
+
+@dataclass
+class HeadWeights:
+    wt: torch.Tensor      # bf16 [768, 768]   cls.predictions.transform.dense
+    bt: torch.Tensor
+    ln_g: torch.Tensor
+    ln_b: torch.Tensor
+    w_text: torch.Tensor  # bf16 [V, 768]     cls.predictions.text_decoder (no bias, stonkgs_model.py:47)
+    w_ent: torch.Tensor   # bf16 [N, 768]     cls.predictions.entity_decoder (no bias, :49)
+    w_nsp: torch.Tensor   # fp32 [2, 768]     cls.seq_relationship
+    b_nsp: torch.Tensor
+
+
+@dataclass
+class LayerCache:
+    """Activations one encoder layer keeps for its backward pass."""
+    x_in: torch.Tensor
+    qkv: torch.Tensor
+    lse: torch.Tensor
+    ctx: torch.Tensor
+    z1: torch.Tensor
+    mean1: torch.Tensor
+    rstd1: torch.Tensor
+    x1: torch.Tensor
+    u: torch.Tensor
+    h: torch.Tensor
+    z2: torch.Tensor
+    mean2: torch.Tensor
+    rstd2: torch.Tensor
+
+
+# --------------------------------------------------------------------------------------------------
+# forward
+# --------------------------------------------------------------------------------------------------
+def encoder_layer_fwd(x, lw: LayerWeights, B: int, S: int, key_bias, cache: Optional[list] = None):
+    """One BertLayer (post-LN). x: bf16 [B*S, 768]."""
+    M = x.shape[0]
+    train = cache is not None
+    qkv = ops.linear(x, lw.wqkv, lw.bqkv)
+    if train:
+        ctx, lse = ops.attention(qkv, key_bias, B, S, save_lse=True)
+    else:
+        ctx = ops.attention(qkv, key_bias, B, S)
+    z1 = ops.linear(ctx, lw.wo, lw.bo, ops.EPI_BIAS_RESID, resid=x)
+    if train:
+        x1, mean1, rstd1 = ops.layernorm(z1, lw.ln1_g, lw.ln1_b, save_stats=True)
+        u = torch.empty((M, I), dtype=torch.bfloat16, device=x.device)
+        h = ops.linear(x1, lw.w1, lw.b1, ops.EPI_BIAS_GELU_SAVE, c2=u)
+    else:
+        x1 = ops.layernorm(z1, lw.ln1_g, lw.ln1_b, out=z1)
+        h = ops.linear(x1, lw.w1, lw.b1, ops.EPI_BIAS_GELU)
+    z2 = ops.linear(h, lw.w2, lw.b2, ops.EPI_BIAS_RESID, resid=x1)
+    if train:
+        x2, mean2, rstd2 = ops.layernorm(z2, lw.ln2_g, lw.ln2_b, save_stats=True)
+        cache.append(LayerCache(x, qkv, lse, ctx, z1, mean1, rstd1, x1, u, h, z2, mean2, rstd2))
+    else:
+        x2 = ops.layernorm(z2, lw.ln2_g, lw.ln2_b, out=z2)
+    return x2
+
+
+def encoder_fwd(x, ew: EncoderWeights, B: int, S: int, key_bias, cache: Optional[list] = None):
+    for lw in ew.layers:
+        x = encoder_layer_fwd(x, lw, B, S, key_bias, cache)
+    return x
+
+
+def lm_backbone_fwd(ew: EncoderWeights, text_ids: torch.Tensor, key_bias=None, err_flag=None):
+    """``self.lm_backbone(input_ids[:, :256])[0]`` (stonkgs_model.py:178): ids only, no mask, types 0."""
+    B, S = text_ids.shape
+    x = ops.embed_text_ln(text_ids, ew.word, ew.pos, ew.type_emb, ew.emb_g, ew.emb_b, err_flag=err_flag)
+    return encoder_fwd(x, ew, B, S, key_bias)
+
+
+def lm_special_rows(ew: EncoderWeights, token_ids) -> torch.Tensor:
+    """``lm_backbone(tensor([[id]]))[0][0][0]`` for each id (stonkgs_model.py:138-141).
+
+    A one-token sequence is run as a 128-token padded sequence whose keys 1..127 are masked, which
+    is the same arithmetic for row 0 (softmax over one key).  Returns fp32 [len(token_ids), 768]."""
+    dev = ew.pos.device
+    n = len(token_ids)
+    ids = torch.zeros((n, 128), dtype=torch.int64, device=dev)
+    ids[:, 0] = torch.tensor(list(token_ids), dtype=torch.int64, device=dev)
+    mask = torch.zeros((n, 128), dtype=torch.int64, device=dev)
+    mask[:, 0] = 1
+    out = lm_backbone_fwd(ew, ids, ops.mask_to_bias(mask))
+    return out.view(n, 128, H)[:, 0].float()
+
+
+def joint_fwd(bert: EncoderWeights, input_ids, token_type_ids, attention_mask, lm_hidden, kg_table, *,
+              cache: Optional[dict] = None, want_inputs_embeds=False, err_flag=None):
+    """KG lookup + concat + joint embeddings + 12 layers + pooler (stonkgs_model.py:182-212)."""
+    B = input_ids.shape[0]
+    train = cache is not None
+    x, mean, rstd, emb = ops.embed_joint_ln(input_ids, token_type_ids, lm_hidden, kg_table, bert.pos, bert.type_emb,
+                                            bert.emb_g, bert.emb_b, save_stats=train,
+                                            want_inputs_embeds=want_inputs_embeds, err_flag=err_flag)
+    key_bias = ops.mask_to_bias(attention_mask) if attention_mask is not None else None
+    layer_cache = [] if train else None
+    seq = encoder_fwd(x, bert, B, 512, key_bias, layer_cache)
+    # BertPooler: tanh(W h[:, 0] + b); rows b*512 are read in place through the A pitch
+    pooled = ops.gemm(seq.view(B, 512, H)[:, 0], bert.wp, M=B, N=H, K=H, epilogue=ops.EPI_BIAS_TANH_F32, bias=bert.bp)
+    if train:
+        cache.update(emb_mean=mean, emb_rstd=rstd, key_bias=key_bias, layers=layer_cache, lm_hidden=lm_hidden)
+    return seq, pooled, emb

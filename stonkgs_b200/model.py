@@ -1,0 +1,362 @@
+"""Drop-in ``STonKGsForPreTraining`` whose forward/backward run on hand-written sm_100a kernels.
+
+Boundary kept identical to the reference (``src/stonkgs/models/stonkgs_model.py``):
+
+* constructor ``STonKGsForPreTraining(config, nlp_model_type, kg_embedding_dict_path)`` (:79-84),
+  ``from_pretrained`` / ``from_default_pretrained`` (:143-147), ``forward(...)`` signature and
+  outputs (:149-159, :247-258), ``BertForPreTrainingOutputWithPooling`` (:30-34);
+* the module tree — and therefore the 413 ``state_dict`` keys and the HF config (+ ``kg_vocab_size``)
+  — is the reference's: ``bert`` (HF BertModel), ``lm_backbone`` (frozen HF BertModel), ``cls`` with
+  ``STonKGsELMPredictionHead`` (:37-60).  The HF modules are *parameter containers only*: their
+  ``forward`` methods are never called; all arithmetic goes through ``engine`` -> ``libstk.so``;
+* attributes other reference code relies on: ``cls.predictions.half_length``, ``lm_backbone``,
+  ``kg_backbone`` (mapping id -> vector), ``kg_idx_to_name``, ``lm_sep_id/lm_mask_id/lm_unk_id``.
+
+There is no CPU / PyTorch fallback: calling ``forward`` without CUDA tensors raises.
+"""
+from __future__ import annotations
+
+import logging
+import os
+from collections.abc import Mapping
+from dataclasses import dataclass
+from functools import lru_cache
+from typing import Optional
+
+import numpy as np
+import torch
+from torch import nn
+from transformers import BertConfig, BertForPreTraining, BertModel
+from transformers.models.bert.modeling_bert import BertForPreTrainingOutput, BertLMPredictionHead
+
+from . import engine, ops
+from ._lib import StkError
+
+logger = logging.getLogger(__name__)
+
+NLP_MODEL_TYPE = "dmis-lab/biobert-v1.1"            # reference constants.py:120-124
+EMBEDDINGS_PATH = os.environ.get("STONKGS_EMBEDDINGS_PATH", "embeddings_best_model.tsv")
+SEP_ID, MASK_ID, UNK_ID = 102, 103, 100            # BioBERT tokenizer ids (stonkgs_model.py:116-118)
+H = 768
+
+
+@dataclass
+class BertForPreTrainingOutputWithPooling(BertForPreTrainingOutput):
+    """Same extra field as the reference (stonkgs_model.py:30-34)."""
+
+    pooler_output: Optional[torch.FloatTensor] = None
+
+
+class STonKGsELMPredictionHead(BertLMPredictionHead):
+    """Parameter layout of the reference ELM head (stonkgs_model.py:37-60); forward is CUDA-only."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.text_decoder = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
+        self.entity_decoder = nn.Linear(config.hidden_size, config.kg_vocab_size, bias=False)
+        self.half_length = config.max_position_embeddings // 2
+        self.text_bias = nn.Parameter(torch.zeros(config.vocab_size))
+        self.entity_bias = nn.Parameter(torch.zeros(config.kg_vocab_size))
+        self.decoder.text_bias = self.text_bias
+        self.decoder.entity_bias = self.entity_bias
+
+    def forward(self, hidden_states):  # pragma: no cover - guarded
+        raise StkError("STonKGsELMPredictionHead.forward is fused into STonKGsForPreTraining.forward")
+
+
+def prepare_df(path: str):
+    """Load the node2vec TSV (``name \\t 768 floats`` per line, reference node2vec.py:350-354) in file
+    order.  Restates ``kg_baseline_model.py:270-280`` without the per-row pandas loop.
+    Returns (names, float32 [N, 768])."""
+    names, rows = [], []
+    with open(path, "r") as f:
+        for line in f:
+            parts = line.rstrip("\n").split("\t")
+            if len(parts) < 2:
+                continue
+            names.append(parts[0])
+            rows.append(np.asarray(parts[1:], dtype=np.float64))
+    return names, np.stack(rows).astype(np.float32)
+
+
+class _KGBackboneView(Mapping):
+    """``kg_backbone`` of the reference is a dict id -> vector (stonkgs_model.py:131-141); this is a
+    read-only mapping view over the dense table that restates it."""
+
+    def __init__(self, model):
+        self._m = model
+
+    def __getitem__(self, i):
+        t = self._m.kg_table
+        if not (0 <= int(i) < t.shape[0]):
+            raise KeyError(i)
+        return t[int(i)]
+
+    def __iter__(self):
+        return iter(range(self._m.kg_table.shape[0]))
+
+    def __len__(self):
+        return self._m.kg_table.shape[0]
+
+
+class STonKGsForPreTraining(BertForPreTraining):
+    """STonKGs pre-training model (text + KG joint transformer), B200-native compute."""
+
+    def __init__(self, config=None, nlp_model_type=NLP_MODEL_TYPE, kg_embedding_dict_path=EMBEDDINGS_PATH):
+        # --- KG vectors in file order (reference :93) -------------------------------------------
+        if isinstance(kg_embedding_dict_path, (str, os.PathLike)):
+            names, rows = prepare_df(kg_embedding_dict_path)
+        elif isinstance(kg_embedding_dict_path, dict):  # name -> vector, like the reference's dict
+            names = list(kg_embedding_dict_path.keys())
+            rows = np.stack([np.asarray(v, dtype=np.float32) for v in kg_embedding_dict_path.values()])
+        else:  # (names, array) or a bare array: synthetic tables for tests / benchmarks
+            if isinstance(kg_embedding_dict_path, tuple):
+                names, rows = kg_embedding_dict_path
+            else:
+                rows = kg_embedding_dict_path
+                names = None
+            rows = np.ascontiguousarray(rows, dtype=np.float32)
+        n_kg = rows.shape[0]
+
+        # --- config (reference :96-97: rebuilt from the LM type; the passed one is only a fallback
+        #     when the hub is unreachable, e.g. from_pretrained of a local checkpoint offline) ----
+        passed = config
+        if isinstance(nlp_model_type, BertConfig):
+            lm_config = nlp_model_type                     # offline: random-init LM backbone of this shape
+            config = BertConfig.from_dict(lm_config.to_dict())
+        else:
+            try:
+                config = BertConfig.from_pretrained(nlp_model_type)
+                lm_config = None
+            except Exception:  # noqa: BLE001  (no network / not cached)
+                if not isinstance(passed, BertConfig):
+                    raise
+                config = BertConfig.from_dict(passed.to_dict())
+                lm_config = BertConfig.from_dict(passed.to_dict())
+        config.update({"kg_vocab_size": n_kg})
+        super().__init__(config)
+        self.cls.predictions = STonKGsELMPredictionHead(config)
+
+        # --- frozen LM backbone (reference :107-114) --------------------------------------------
+        if lm_config is None:
+            try:
+                self.lm_backbone = BertModel.from_pretrained(nlp_model_type)
+            except Exception:  # noqa: BLE001
+                self.lm_backbone = BertModel(config)       # weights then come from the checkpoint's lm_backbone.*
+        else:
+            self.lm_backbone = BertModel(lm_config)
+        for p in self.lm_backbone.parameters():
+            p.requires_grad = False
+        self.lm_sep_id, self.lm_mask_id, self.lm_unk_id = SEP_ID, MASK_ID, UNK_ID
+        if lm_config is None:
+            try:  # tokenizer ids, when the tokenizer is available offline (reference :116-118)
+                from transformers import BertTokenizer
+                tok = BertTokenizer.from_pretrained(nlp_model_type)
+                self.lm_sep_id, self.lm_mask_id, self.lm_unk_id = tok.sep_token_id, tok.mask_token_id, tok.unk_token_id
+            except Exception:  # noqa: BLE001
+                pass
+        self._check_shape(config)
+
+        # --- dense KG table restating the reference's index quirk (reference :123-134) ----------
+        specials = (self.lm_sep_id, self.lm_mask_id, self.lm_unk_id)
+        numeric_indices = [i for i in range(n_kg + 3) if i not in specials][:n_kg]
+        if names is None:
+            names = [f"n{i}" for i in range(n_kg)]
+        self.kg_idx_to_name = dict(zip(numeric_indices, names))
+        table = np.zeros((n_kg + 3, H), dtype=np.float32)
+        table[np.asarray(numeric_indices, dtype=np.int64)] = rows
+        # a plain attribute, not a buffer: the reference does not store it in the checkpoint (fact 5);
+        # built through numpy so that it is a real CPU tensor even under HF's meta-device init context
+        self.kg_table = torch.from_numpy(table)
+        self.kg_backbone = _KGBackboneView(self)
+        self._special_rows_version = None
+        self._dev_state = None
+        self.return_prediction_logits = False   # dense [B,256,V] / [B,256,N] logits only on request
+
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _check_shape(config):
+        if (config.hidden_size, config.num_attention_heads, config.intermediate_size) != (768, 12, 3072) or \
+                config.max_position_embeddings != 512 or config.hidden_act != "gelu":
+            raise StkError("stonkgs_b200 kernels are specialised for the BERT-base shape of the reference "
+                           "(hidden 768, 12 heads, intermediate 3072, 512 positions, erf-GELU)")
+
+    @classmethod
+    @lru_cache(maxsize=32)
+    def from_default_pretrained(cls, **kwargs) -> "STonKGsForPreTraining":
+        """Reference stonkgs_model.py:143-147."""
+        return cls.from_pretrained("stonkgs/stonkgs-150k", **kwargs)
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        if "kg_table" in self.__dict__:
+            self.kg_table = fn(self.kg_table)   # follows .to()/.cuda() like the reference's dict tensors
+            self._dev_state = None
+            self._special_rows_version = None
+            self._grad_buffer = None
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    # device-side state: bf16 weight copies and the three LM-backbone rows of the KG table
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _enc_params(bert: BertModel):
+        ps = [bert.embeddings.position_embeddings.weight, bert.embeddings.token_type_embeddings.weight,
+              bert.embeddings.LayerNorm.weight, bert.embeddings.LayerNorm.bias]
+        for l in bert.encoder.layer:
+            ps += [l.attention.self.query.weight, l.attention.self.key.weight, l.attention.self.value.weight,
+                   l.attention.self.query.bias, l.attention.self.key.bias, l.attention.self.value.bias,
+                   l.attention.output.dense.weight, l.attention.output.dense.bias,
+                   l.attention.output.LayerNorm.weight, l.attention.output.LayerNorm.bias,
+                   l.intermediate.dense.weight, l.intermediate.dense.bias, l.output.dense.weight, l.output.dense.bias,
+                   l.output.LayerNorm.weight, l.output.LayerNorm.bias]
+        ps += [bert.pooler.dense.weight, bert.pooler.dense.bias]
+        return ps
+
+    def _build_encoder_weights(self, bert: BertModel, with_word: bool, old: Optional[engine.EncoderWeights]):
+        """bf16 copies of the GEMM weights (cast kernel), fp32 views of everything else."""
+        dev = bert.embeddings.position_embeddings.weight.device
+        emb = bert.embeddings
+        ew = engine.EncoderWeights(
+            word=emb.word_embeddings.weight.data if with_word else None,
+            pos=emb.position_embeddings.weight.data, type_emb=emb.token_type_embeddings.weight.data,
+            emb_g=emb.LayerNorm.weight.data, emb_b=emb.LayerNorm.bias.data)
+        for i, l in enumerate(bert.encoder.layer):
+            prev = old.layers[i] if old is not None else None
+            att = l.attention.self
+            wqkv = prev.wqkv if prev else torch.empty((3 * H, H), dtype=torch.bfloat16, device=dev)
+            bqkv = prev.bqkv if prev else torch.empty(3 * H, dtype=torch.float32, device=dev)
+            for j, lin in enumerate((att.query, att.key, att.value)):
+                ops.cast_bf16(lin.weight.data, out=wqkv[j * H:(j + 1) * H])
+                bqkv[j * H:(j + 1) * H].copy_(lin.bias.data)
+
+            def c(w, old_t):
+                return ops.cast_bf16(w.data, out=old_t)
+
+            ew.layers.append(engine.LayerWeights(
+                wqkv=wqkv, bqkv=bqkv,
+                wo=c(l.attention.output.dense.weight, prev.wo if prev else None), bo=l.attention.output.dense.bias.data,
+                ln1_g=l.attention.output.LayerNorm.weight.data, ln1_b=l.attention.output.LayerNorm.bias.data,
+                w1=c(l.intermediate.dense.weight, prev.w1 if prev else None), b1=l.intermediate.dense.bias.data,
+                w2=c(l.output.dense.weight, prev.w2 if prev else None), b2=l.output.dense.bias.data,
+                ln2_g=l.output.LayerNorm.weight.data, ln2_b=l.output.LayerNorm.bias.data))
+        ew.wp = ops.cast_bf16(bert.pooler.dense.weight.data, out=old.wp if old is not None else None)
+        ew.bp = bert.pooler.dense.bias.data
+        return ew
+
+    def _build_head_weights(self, old: Optional[engine.HeadWeights]):
+        pr = self.cls.predictions
+        return engine.HeadWeights(
+            wt=ops.cast_bf16(pr.transform.dense.weight.data, out=old.wt if old else None),
+            bt=pr.transform.dense.bias.data,
+            ln_g=pr.transform.LayerNorm.weight.data, ln_b=pr.transform.LayerNorm.bias.data,
+            w_text=ops.cast_bf16(pr.text_decoder.weight.data, out=old.w_text if old else None),
+            w_ent=ops.cast_bf16(pr.entity_decoder.weight.data, out=old.w_ent if old else None),
+            w_nsp=self.cls.seq_relationship.weight.data, b_nsp=self.cls.seq_relationship.bias.data)
+
+    def _live_version(self):
+        v = 0
+        for p in self._enc_params(self.bert):
+            v += p._version
+        pr = self.cls.predictions
+        for p in (pr.transform.dense.weight, pr.text_decoder.weight, pr.entity_decoder.weight):
+            v += p._version
+        return v
+
+    def _lm_version(self):
+        return sum(p._version for p in self.lm_backbone.parameters())
+
+    def _device_state(self, need_heads: bool):
+        """(Re)build the bf16 weight copies when parameters changed (optimizer step, load_state_dict)."""
+        dev = self.bert.pooler.dense.weight.device
+        if dev.type != "cuda":
+            raise StkError("STonKGsForPreTraining runs on CUDA only: move the model with .to('cuda') "
+                           "(stonkgs_b200 has no CPU path)")
+        st = self._dev_state
+        if st is None:
+            st = self._dev_state = {"lm": None, "lm_v": None, "bert": None, "heads": None, "live_v": None,
+                                    "heads_v": None}
+        lm_v = self._lm_version()
+        if st["lm"] is None or st["lm_v"] != lm_v:
+            st["lm"] = self._build_encoder_weights(self.lm_backbone, True, st["lm"])
+            st["lm_v"] = lm_v
+            self._special_rows_version = None
+        live_v = self._live_version()
+        if st["bert"] is None or st["live_v"] != live_v:
+            st["bert"] = self._build_encoder_weights(self.bert, False, st["bert"])
+            st["live_v"] = live_v
+        if need_heads and (st["heads"] is None or st["heads_v"] != live_v):
+            st["heads"] = self._build_head_weights(st["heads"])
+            st["heads_v"] = live_v
+        if self._special_rows_version != lm_v:
+            # rows 102/103/100 of the KG table are LM-backbone outputs of [[id]] (reference :138-141)
+            if self.kg_table.device != dev:
+                self.kg_table = self.kg_table.to(dev)
+            ids = [i for i in (self.lm_sep_id, self.lm_mask_id, self.lm_unk_id) if i < self.kg_table.shape[0]]
+            if ids:
+                self.kg_table[torch.tensor(ids, device=dev)] = engine.lm_special_rows(st["lm"], ids)
+            self._special_rows_version = lm_v
+        return st
+
+    # ------------------------------------------------------------------------------------------
+    # forward
+    # ------------------------------------------------------------------------------------------
+    def _check_ids(self, input_ids):
+        """The reference raises KeyError for ids outside the KG dict (stonkgs_model.py:182-189)."""
+        if not input_ids.is_cuda:
+            kg = input_ids[:, 256:]
+            if kg.numel() and (int(kg.min()) < 0 or int(kg.max()) >= self.kg_table.shape[0]):
+                bad = kg[(kg < 0) | (kg >= self.kg_table.shape[0])][0]
+                raise KeyError(int(bad))
+
+    def encode(self, input_ids, attention_mask=None, token_type_ids=None, *, cache=None, want_inputs_embeds=False,
+               need_heads=False):
+        """LM backbone -> KG lookup -> joint encoder -> pooler.  Returns (seq bf16 [B*512,768], pooled fp32, emb)."""
+        st = self._device_state(need_heads)
+        dev = self.kg_table.device
+        if input_ids.dim() != 2 or input_ids.shape[1] != 512:
+            raise StkError(f"input_ids must be [B, 512] (256 text + 256 KG tokens), got {tuple(input_ids.shape)}")
+        self._check_ids(input_ids)
+        err = torch.zeros(1, dtype=torch.int32, device=dev) if input_ids.is_cuda else None
+        input_ids = input_ids.to(dev, torch.int64, non_blocking=True).contiguous()
+        if attention_mask is not None:
+            attention_mask = attention_mask.to(dev, torch.int64, non_blocking=True).contiguous()
+        if token_type_ids is not None:
+            token_type_ids = token_type_ids.to(dev, torch.int64, non_blocking=True).contiguous()
+        lm_hidden = engine.lm_backbone_fwd(st["lm"], input_ids[:, :256], None, err_flag=err)
+        seq, pooled, emb = engine.joint_fwd(st["bert"], input_ids, token_type_ids, attention_mask, lm_hidden,
+                                            self.kg_table, cache=cache, want_inputs_embeds=want_inputs_embeds,
+                                            err_flag=err)
+        if cache is not None:
+            cache.update(input_ids=input_ids, token_type_ids=token_type_ids, err=err)
+        self._pending_err = err
+        return seq, pooled, emb
+
+    def grad_buffer(self):
+        """Flat fp32 gradient buffer of the live parameters (``param.grad`` are views of it)."""
+        from .training import GradBuffer
+        gb = getattr(self, "_grad_buffer", None)
+        dev = self.bert.pooler.dense.weight.device
+        if gb is None or gb.flat.device != dev:
+            gb = self._grad_buffer = GradBuffer(self)
+        return gb
+
+    def _raise_on_bad_ids(self):
+        err = getattr(self, "_pending_err", None)
+        if err is not None and int(err.item()) != 0:
+            raise KeyError("input id outside the text vocabulary / KG table")
+
+    @torch.no_grad()
+    def embed(self, input_ids, attention_mask=None, token_type_ids=None) -> torch.Tensor:
+        """Extraction path: pooled 768-d output only (stonkgs_for_embeddings.py:180), heads skipped."""
+        _, pooled, _ = self.encode(input_ids, attention_mask, token_type_ids)
+        return pooled
+
+    def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, masked_lm_labels=None,
+                ent_masked_lm_labels=None, next_sentence_labels=None, return_dict=None, head_mask=None):
+        """Same contract as the reference forward (stonkgs_model.py:149-258)."""
+        if head_mask is not None:
+            raise StkError("head_mask is not supported by the fused attention kernel")
+        from . import training  # local import: keeps inference-only users free of the autograd glue
+        return training.forward(self, input_ids, attention_mask, token_type_ids, masked_lm_labels,
+                                ent_masked_lm_labels, next_sentence_labels, return_dict)

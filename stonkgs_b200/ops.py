@@ -184,7 +184,7 @@ def attention(qkv: torch.Tensor, key_bias: Optional[torch.Tensor], B: int, S: in
 def attention_bwd(qkv, key_bias, B, S, out, dout, lse):
     dev, stream = _ctx(qkv)
     dqkv = torch.empty_like(qkv)
-    ws = torch.empty(B * HEADS * S, dtype=torch.float32, device=qkv.device)
+    ws = torch.empty(B * S * H + B * HEADS * S, dtype=torch.float32, device=qkv.device)
     check(_lib.load().stk_attn_bwd(dev, stream, _ptr(qkv), _ptr(key_bias), B, S, _ptr(out), _ptr(dout), _ptr(lse),
                                    _ptr(ws), _ptr(dqkv)), "stk_attn_bwd")
     return dqkv
@@ -252,3 +252,19 @@ def nsp_head(pooled, w, b, labels=None):
     check(_lib.load().stk_nsp_head_fwd(dev, stream, _ptr(pooled), B, _ptr(w), _ptr(b), _ptr(labels), _ptr(logits),
                                        _ptr(row_loss)), "stk_nsp_head_fwd")
     return logits, row_loss
+
+
+def gelu_bwd(dy: torch.Tensor, pre: torch.Tensor) -> torch.Tensor:
+    dev, stream = _ctx(dy)
+    dx = torch.empty_like(dy)
+    check(_lib.load().stk_gelu_bwd(dev, stream, _ptr(dy), _ptr(pre), dy.numel(), _ptr(dx)), "stk_gelu_bwd")
+    return dx
+
+
+def nsp_pool_bwd(pooled, logits, labels, scale_dev, w, dw, db) -> torch.Tensor:
+    dev, stream = _ctx(pooled)
+    B = pooled.shape[0]
+    dpre = torch.empty((B, H), dtype=torch.bfloat16, device=pooled.device)
+    check(_lib.load().stk_nsp_pool_bwd(dev, stream, _ptr(pooled), _ptr(logits), _ptr(labels), B, _ptr(scale_dev),
+                                       _ptr(w), _ptr(dw), _ptr(db), _ptr(dpre)), "stk_nsp_pool_bwd")
+    return dpre

@@ -1,0 +1,406 @@
+"""Heads, losses and the hand-written backward pass of ``STonKGsForPreTraining``.
+
+Forward restates stonkgs_model.py:212-258 (ELM head on labelled rows only, three mean
+cross-entropies); backward is the autograd backward of the whole trainable path — heads, pooler/NSP,
+12 joint encoder layers, joint embedding stage — as an explicit sequence of libstk.so launches.
+Gradients are written into one flat fp32 buffer laid out in *reverse execution order* (entity decoder
+first, embeddings last), of which every ``param.grad`` is a view; the data-parallel layer all-reduces
+slices of that buffer while the rest of backward is still running (``dp.py``).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import engine, ops
+from ._lib import StkError
+
+H = 768
+I = 3072
+HALF = 256
+IGNORE = -100
+
+
+# --------------------------------------------------------------------------------------------------
+# flat gradient buffer
+# --------------------------------------------------------------------------------------------------
+class GradBuffer:
+    """One flat fp32 buffer holding the gradients of all live parameters.
+
+    Order = order in which backward produces them, so that bucket k is complete (and can be
+    all-reduced) long before backward ends.  Segments are padded to 16 B for TMA."""
+
+    def __init__(self, model):
+        self.model = model
+        dev = model.bert.pooler.dense.weight.device
+        pr = model.cls.predictions
+        bert = model.bert
+        entries = []  # (name, shape, [params that view into it])
+
+        def add(name, params, shape=None):
+            shape = tuple(params[0].shape) if shape is None else shape
+            entries.append((name, shape, params))
+
+        add("w_ent", [pr.entity_decoder.weight])
+        add("w_text", [pr.text_decoder.weight])
+        add("t_w", [pr.transform.dense.weight])
+        add("t_b", [pr.transform.dense.bias])
+        add("t_ln_g", [pr.transform.LayerNorm.weight])
+        add("t_ln_b", [pr.transform.LayerNorm.bias])
+        add("nsp_w", [model.cls.seq_relationship.weight])
+        add("nsp_b", [model.cls.seq_relationship.bias])
+        add("pool_w", [bert.pooler.dense.weight])
+        add("pool_b", [bert.pooler.dense.bias])
+        self.num_layers = len(bert.encoder.layer)
+        for li in reversed(range(self.num_layers)):
+            l = bert.encoder.layer[li]
+            a = l.attention.self
+            add(f"l{li}.ln2_g", [l.output.LayerNorm.weight])
+            add(f"l{li}.ln2_b", [l.output.LayerNorm.bias])
+            add(f"l{li}.b2", [l.output.dense.bias])
+            add(f"l{li}.w2", [l.output.dense.weight])
+            add(f"l{li}.b1", [l.intermediate.dense.bias])
+            add(f"l{li}.w1", [l.intermediate.dense.weight])
+            add(f"l{li}.ln1_g", [l.attention.output.LayerNorm.weight])
+            add(f"l{li}.ln1_b", [l.attention.output.LayerNorm.bias])
+            add(f"l{li}.bo", [l.attention.output.dense.bias])
+            add(f"l{li}.wo", [l.attention.output.dense.weight])
+            add(f"l{li}.bqkv", [a.query.bias, a.key.bias, a.value.bias], (3 * H,))
+            add(f"l{li}.wqkv", [a.query.weight, a.key.weight, a.value.weight], (3 * H, H))
+        e = bert.embeddings
+        add("emb_pos", [e.position_embeddings.weight])
+        add("emb_type", [e.token_type_embeddings.weight])
+        add("emb_g", [e.LayerNorm.weight])
+        add("emb_b", [e.LayerNorm.bias])
+
+        total = 0
+        self.offsets = {}
+        for name, shape, _ in entries:
+            n = 1
+            for s in shape:
+                n *= s
+            self.offsets[name] = (total, n, shape)
+            total += (n + 3) // 4 * 4
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.views: Dict[str, torch.Tensor] = {}
+        self.param_views = []  # (param, view)
+        for name, shape, params in entries:
+            off, n, _ = self.offsets[name]
+            v = self.flat[off:off + n].view(shape)
+            self.views[name] = v
+            if len(params) == 1:
+                self.param_views.append((params[0], v))
+            else:  # fused q|k|v: consecutive row blocks
+                rows = shape[0] // len(params)
+                for j, p in enumerate(params):
+                    self.param_views.append((p, v[j * rows:(j + 1) * rows]))
+        self.entries = [e[0] for e in entries]
+
+    def __getitem__(self, name):
+        return self.views[name]
+
+    def prepare(self):
+        """Decide between overwrite (all grads None -> zero the buffer) and accumulate (all grads are
+        already our views).  Anything else is handled by a scratch pass + add."""
+        states = [(p.grad is None, p.grad is not None and p.grad.data_ptr() == v.data_ptr()) for p, v in self.param_views]
+        if all(s[0] for s in states):
+            self.flat.zero_()
+            return "fresh"
+        if all(s[1] for s in states):
+            return "accumulate"
+        # mixed: keep the user's tensors, compute into a zeroed buffer and add afterwards
+        self._foreign = [(p, p.grad) for p, _ in self.param_views]
+        self.flat.zero_()
+        return "foreign"
+
+    def publish(self, mode):
+        if mode == "foreign":
+            for (p, v), (_, old) in zip(self.param_views, self._foreign):
+                if old is None:
+                    p.grad = v.clone()
+                else:
+                    old.add_(v)
+                    p.grad = old
+            self._foreign = None
+            return
+        for p, v in self.param_views:
+            p.grad = v
+
+
+# --------------------------------------------------------------------------------------------------
+# heads: forward
+# --------------------------------------------------------------------------------------------------
+def _label_rows(labels: torch.Tensor, col_offset: int, dev, vocab: int):
+    """Row indices (b*512 + col_offset + t) and int32 labels of the labelled positions."""
+    if labels.dim() != 2 or labels.shape[1] != HALF:
+        raise StkError(f"label tensors must be [B, 256], got {tuple(labels.shape)}")
+    sel = labels != IGNORE
+    pos = torch.nonzero(sel, as_tuple=False)  # host-side when the batch is on the CPU; one sync otherwise
+    lab = labels[sel]
+    if lab.numel() and not labels.is_cuda and (int(lab.min()) < 0 or int(lab.max()) >= vocab):
+        raise IndexError(f"label outside [0, {vocab})")
+    rows = (pos[:, 0] * 512 + pos[:, 1] + col_offset).to(torch.int32)
+    return rows.to(dev, non_blocking=True), lab.to(torch.int32).to(dev, non_blocking=True)
+
+
+def _ce_forward(t_rows, w, labels_i32):
+    """Fused GEMM + cross-entropy statistics over the vocabulary; logits are never materialised."""
+    R = t_rows.shape[0]
+    V = w.shape[0]
+    pitch = 2 * ((V + 255) // 256)
+    part = torch.empty((R, pitch, 2), dtype=torch.float32, device=t_rows.device)
+    tgt = torch.empty(R, dtype=torch.float32, device=t_rows.device)
+    ops.gemm(t_rows, w, M=R, N=V, K=H, epilogue=ops.EPI_CE_STATS, labels=labels_i32, ce_partial=part, tgt_logit=tgt)
+    return ops.ce_finalize(part, tgt, R)  # lse, row_loss
+
+
+def heads_fwd(model, hw: engine.HeadWeights, seq, pooled, mlm_labels, elm_labels, nsp_labels, cache: Optional[dict]):
+    dev = seq.device
+    V = hw.w_text.shape[0]
+    N = hw.w_ent.shape[0]
+    rows_t, lab_t = _label_rows(mlm_labels, 0, dev, V)
+    rows_e, lab_e = _label_rows(elm_labels, HALF, dev, N)
+    Rt, Re = rows_t.numel(), rows_e.numel()
+    rows = torch.cat([rows_t, rows_e])
+    R = Rt + Re
+    nan = torch.full((), float("nan"), dtype=torch.float32, device=dev)
+    mlm_loss = elm_loss = nan
+    lse_t = lse_e = None
+    u = g = t = mean = rstd = hrows = None
+    if R:
+        hrows = ops.gather_rows(seq, rows)
+        u = torch.empty((R, H), dtype=torch.bfloat16, device=dev)
+        g = ops.linear(hrows, hw.wt, hw.bt, ops.EPI_BIAS_GELU_SAVE, c2=u)
+        t, mean, rstd = ops.layernorm(g, hw.ln_g, hw.ln_b, save_stats=True)
+        if Rt:
+            lse_t, rl = _ce_forward(t[:Rt], hw.w_text, lab_t)
+            mlm_loss = rl.mean()
+        if Re:
+            lse_e, rl = _ce_forward(t[Rt:], hw.w_ent, lab_e)
+            elm_loss = rl.mean()
+    nsp_labels_d = nsp_labels.to(dev, torch.int64, non_blocking=True).contiguous()
+    nsp_logits, nsp_rl = ops.nsp_head(pooled, hw.w_nsp, hw.b_nsp, nsp_labels_d)
+    nsp_loss = nsp_rl.mean()
+    loss = mlm_loss + elm_loss + nsp_loss
+    if cache is not None:
+        cache.update(rows=rows, Rt=Rt, Re=Re, lab_t=lab_t, lab_e=lab_e, lse_t=lse_t, lse_e=lse_e, hrows=hrows, u=u, g=g,
+                     t=t, t_mean=mean, t_rstd=rstd, nsp_logits=nsp_logits, nsp_labels=nsp_labels_d, pooled=pooled,
+                     seq=seq)
+    return loss, (mlm_loss, elm_loss, nsp_loss), nsp_logits, (lse_t, lse_e)
+
+
+def dense_prediction_logits(hw: engine.HeadWeights, seq, B):
+    """API-parity mode: the full [B,256,V] and [B,256,N] fp32 logits of stonkgs_model.py:62-73."""
+    dev = seq.device
+    ar = torch.arange(B, device=dev, dtype=torch.int32)[:, None] * 512 + torch.arange(HALF, device=dev, dtype=torch.int32)
+    out = []
+    for off, w in ((0, hw.w_text), (HALF, hw.w_ent)):
+        rows = (ar + off).reshape(-1).contiguous()
+        h = ops.gather_rows(seq, rows)
+        t = ops.layernorm(ops.linear(h, hw.wt, hw.bt, ops.EPI_BIAS_GELU), hw.ln_g, hw.ln_b)
+        V = w.shape[0]
+        pitch = (V + 3) // 4 * 4
+        buf = torch.empty((B * HALF, pitch), dtype=torch.float32, device=dev)
+        ops.gemm(t, w, M=B * HALF, N=V, K=H, epilogue=ops.EPI_F32, out=buf[:, :V])
+        out.append(buf[:, :V].view(B, HALF, V))
+    return tuple(out)
+
+
+# --------------------------------------------------------------------------------------------------
+# backward
+# --------------------------------------------------------------------------------------------------
+def _splits(m_out: int, n_out: int, k: int, sms: int = 148) -> int:
+    tiles = ((m_out + 127) // 128) * ((n_out + 255) // 256)
+    return max(1, min(sms // tiles, (k + 63) // 64))
+
+
+def _wgrad(dy, x, out, k_rows):
+    """out[Nout, Nin] += dy[k_rows, Nout]^T x[k_rows, Nin]  (both operands read in place, MN-major)."""
+    n_out, n_in = out.shape
+    ops.gemm(dy, x, M=n_out, N=n_in, K=k_rows, a_major=1, b_major=1, epilogue=ops.EPI_F32_ADD, out=out,
+             split_k=_splits(n_out, n_in, k_rows))
+
+
+def _dgrad(dy, w, *, epilogue=ops.EPI_BIAS, resid=None):
+    """dx[M, Nin] = dy[M, Nout] w[Nout, Nin]  (w in its nn.Linear layout = MN-major B)."""
+    M, n_out = dy.shape
+    n_in = w.shape[1]
+    return ops.gemm(dy, w, M=M, N=n_in, K=n_out, b_major=1, epilogue=epilogue, resid=resid)
+
+
+def _ce_backward(t_rows, w, labels_i32, lse, scale_dev, dT, gW):
+    """Chunked fused linear + CE backward: per vocabulary chunk recompute the logits tile, form
+    dlogit = (softmax - onehot) * scale in the GEMM epilogue (bf16, chunk-sized workspace that stays
+    in L2), then dT += dlogit W_chunk and dW_chunk += dlogit^T t."""
+    R = t_rows.shape[0]
+    V = w.shape[0]
+    # chunk so that the dlogit workspace is ~<= 48 MB (L2-resident), multiple of 256
+    C = max(256, min(((48 << 20) // (2 * max(R, 1))) // 256 * 256, 32768))
+    C = min(C, (V + 255) // 256 * 256)
+    buf = torch.empty((R, C), dtype=torch.bfloat16, device=t_rows.device)
+    for c0 in range(0, V, C):
+        n = min(C, V - c0)
+        wc = w[c0:c0 + n]
+        dl = buf[:, :n]
+        ops.gemm(t_rows, wc, M=R, N=n, K=H, epilogue=ops.EPI_CE_DLOGIT, labels=labels_i32, lse=lse,
+                 scale_dev=scale_dev, n_offset=c0, out=dl)
+        ops.gemm(dl, wc, M=R, N=H, K=n, b_major=1, epilogue=ops.EPI_F32_ADD, out=dT, split_k=_splits(R, H, n))
+        ops.gemm(dl, t_rows, M=n, N=H, K=R, a_major=1, b_major=1, epilogue=ops.EPI_F32_ADD, out=gW[c0:c0 + n],
+                 split_k=_splits(n, H, R))
+
+
+def backward(model, st, cache, dloss: torch.Tensor, gb: GradBuffer, on_ready=None):
+    """Full backward of loss -> all live parameters.  ``on_ready(name)`` is called (host side) right
+    after the launches that complete gradient segment ``name`` have been enqueued."""
+    bert: engine.EncoderWeights = st["bert"]
+    hw: engine.HeadWeights = st["heads"]
+    seq, pooled = cache["seq"], cache["pooled"]
+    B = pooled.shape[0]
+    dev = seq.device
+    M = B * 512
+    ready = on_ready or (lambda name: None)
+    dloss = dloss.to(dev, torch.float32).reshape(())
+
+    dseq = torch.zeros((M, H), dtype=torch.bfloat16, device=dev)
+
+    # ---- MLM / ELM heads ------------------------------------------------------------------------
+    Rt, Re = cache["Rt"], cache["Re"]
+    R = Rt + Re
+    if R:
+        t = cache["t"]
+        dT = torch.zeros((R, H), dtype=torch.float32, device=dev)
+        if Re:
+            _ce_backward(t[Rt:], hw.w_ent, cache["lab_e"], cache["lse_e"], (dloss / Re).reshape(1), dT[Rt:], gb["w_ent"])
+        ready("w_ent")
+        if Rt:
+            _ce_backward(t[:Rt], hw.w_text, cache["lab_t"], cache["lse_t"], (dloss / Rt).reshape(1), dT[:Rt], gb["w_text"])
+        ready("w_text")
+        dT_bf = ops.cast_bf16(dT)
+        dg = ops.layernorm_bwd(dT_bf, cache["g"], hw.ln_g, cache["t_mean"], cache["t_rstd"], gb["t_ln_g"], gb["t_ln_b"])
+        du = ops.gelu_bwd(dg, cache["u"])
+        ops.colsum(du, gb["t_b"], accumulate=True)
+        _wgrad(du, cache["hrows"], gb["t_w"], R)
+        dh = _dgrad(du, hw.wt)
+        ops.scatter_add_rows(dh, cache["rows"], dseq)
+    else:
+        ready("w_ent")
+        ready("w_text")
+    for n in ("t_w", "t_b", "t_ln_g", "t_ln_b"):
+        ready(n)
+
+    # ---- NSP head + pooler ----------------------------------------------------------------------
+    dpre = ops.nsp_pool_bwd(pooled, cache["nsp_logits"], cache["nsp_labels"], (dloss / B).reshape(1), hw.w_nsp,
+                            gb["nsp_w"], gb["nsp_b"])
+    ops.colsum(dpre, gb["pool_b"], accumulate=True)
+    seq0 = seq.view(B, 512, H)[:, 0]
+    _wgrad(dpre, seq0, gb["pool_w"], B)
+    dseq0 = _dgrad(dpre, bert.wp)
+    cls_rows = (torch.arange(B, device=dev, dtype=torch.int32) * 512).contiguous()
+    ops.scatter_add_rows(dseq0, cls_rows, dseq)
+    for n in ("nsp_w", "nsp_b", "pool_w", "pool_b"):
+        ready(n)
+
+    # ---- 12 encoder layers, last to first --------------------------------------------------------
+    key_bias = cache["key_bias"]
+    dx = dseq
+    for li in reversed(range(len(bert.layers))):
+        lw = bert.layers[li]
+        c: engine.LayerCache = cache["layers"][li]
+        p = f"l{li}."
+        dz2 = ops.layernorm_bwd(dx, c.z2, lw.ln2_g, c.mean2, c.rstd2, gb[p + "ln2_g"], gb[p + "ln2_b"])
+        ops.colsum(dz2, gb[p + "b2"], accumulate=True)
+        _wgrad(dz2, c.h, gb[p + "w2"], M)
+        du = _dgrad(dz2, lw.w2, epilogue=ops.EPI_DGELU, resid=c.u)
+        ops.colsum(du, gb[p + "b1"], accumulate=True)
+        _wgrad(du, c.x1, gb[p + "w1"], M)
+        dx1 = _dgrad(du, lw.w1, epilogue=ops.EPI_BIAS_RESID, resid=dz2)
+        dz1 = ops.layernorm_bwd(dx1, c.z1, lw.ln1_g, c.mean1, c.rstd1, gb[p + "ln1_g"], gb[p + "ln1_b"])
+        ops.colsum(dz1, gb[p + "bo"], accumulate=True)
+        _wgrad(dz1, c.ctx, gb[p + "wo"], M)
+        dctx = _dgrad(dz1, lw.wo)
+        dqkv = ops.attention_bwd(c.qkv, key_bias, B, 512, c.ctx, dctx, c.lse)
+        ops.colsum(dqkv, gb[p + "bqkv"], accumulate=True)
+        _wgrad(dqkv, c.x_in, gb[p + "wqkv"], M)
+        dx = _dgrad(dqkv, lw.wqkv, epilogue=ops.EPI_BIAS_RESID, resid=dz1)
+        for n in ("ln2_g", "ln2_b", "b2", "w2", "b1", "w1", "ln1_g", "ln1_b", "bo", "wo", "bqkv", "wqkv"):
+            ready(p + n)
+
+    # ---- joint embedding stage (position / token-type tables and LayerNorm) ----------------------
+    ops.embed_joint_ln_bwd(cache["input_ids"], cache["token_type_ids"], cache["lm_hidden"], model.kg_table, bert.pos,
+                           bert.type_emb, bert.emb_g, cache["emb_mean"], cache["emb_rstd"], dx, gb["emb_pos"],
+                           gb["emb_type"], gb["emb_g"], gb["emb_b"])
+    for n in ("emb_pos", "emb_type", "emb_g", "emb_b"):
+        ready(n)
+
+
+# --------------------------------------------------------------------------------------------------
+# autograd glue + reference-shaped outputs
+# --------------------------------------------------------------------------------------------------
+class _PretrainStep(torch.autograd.Function):
+    """loss = f(live parameters).  Gradients are written by the hand-written backward directly into
+    the flat gradient buffer (``param.grad`` views), so autograd receives ``None`` for them."""
+
+    @staticmethod
+    def forward(ctx, model, batch, anchor):
+        cache: dict = {}
+        input_ids, attention_mask, token_type_ids, mlm, elm, nsp = batch
+        seq, pooled, _ = model.encode(input_ids, attention_mask, token_type_ids, cache=cache, need_heads=True)
+        st = model._dev_state
+        loss, parts, nsp_logits, _ = heads_fwd(model, st["heads"], seq, pooled, mlm, elm, nsp, cache)
+        ctx.model, ctx.cache, ctx.st = model, cache, st
+        ctx.mark_non_differentiable(pooled, nsp_logits, seq)
+        model._last_loss_parts = parts
+        return loss, pooled, nsp_logits, seq
+
+    @staticmethod
+    def backward(ctx, dloss, *unused):
+        model = ctx.model
+        gb = model.grad_buffer()
+        mode = gb.prepare()
+        dp = getattr(model, "_dp", None)
+        if dp is not None:
+            dp.begin(gb)
+        backward(model, ctx.st, ctx.cache, dloss, gb, on_ready=dp.on_ready if dp is not None else None)
+        if dp is not None:
+            dp.finish(gb)
+        gb.publish(mode)
+        ctx.cache = None
+        return None, None, None
+
+
+def forward(model, input_ids, attention_mask, token_type_ids, mlm, elm, nsp, return_dict):
+    """Reference forward contract (stonkgs_model.py:149-258)."""
+    from .model import BertForPreTrainingOutputWithPooling
+    have_labels = mlm is not None and elm is not None and nsp is not None
+    B = input_ids.shape[0]
+    grad = have_labels and torch.is_grad_enabled() and any(p.requires_grad for p in model.bert.parameters())
+    total_loss = None
+    if grad:
+        anchor = model.bert.pooler.dense.bias  # any live parameter: ties the Function into the autograd graph
+        total_loss, pooled, nsp_logits, seq = _PretrainStep.apply(
+            model, (input_ids, attention_mask, token_type_ids, mlm, elm, nsp), anchor)
+        hw = model._dev_state["heads"]
+    else:
+        with torch.no_grad():
+            seq, pooled, _ = model.encode(input_ids, attention_mask, token_type_ids, need_heads=True)
+            hw = model._dev_state["heads"]
+            if have_labels:
+                total_loss, parts, nsp_logits, _ = heads_fwd(model, hw, seq, pooled, mlm, elm, nsp, None)
+                model._last_loss_parts = parts
+            else:
+                nsp_logits, _ = ops.nsp_head(pooled, hw.w_nsp, hw.b_nsp, None)
+    model._raise_on_bad_ids()
+    prediction_scores = (None, None)
+    if model.return_prediction_logits:
+        with torch.no_grad():
+            prediction_scores = dense_prediction_logits(hw, seq, B)
+    sequence_output = seq.view(B, 512, H)
+    if return_dict:
+        sequence_output = sequence_output.float()  # the reference returns fp32 hidden states
+    if not return_dict:
+        output = (prediction_scores, nsp_logits)
+        return ((total_loss,) + output) if total_loss is not None else output
+    return BertForPreTrainingOutputWithPooling(
+        loss=total_loss, prediction_logits=prediction_scores, seq_relationship_logits=nsp_logits,
+        hidden_states=sequence_output, attentions=None, pooler_output=pooled)

@@ -188,7 +188,9 @@ def case_gemm_epilogues():
     u = _mk(M, N, "cuda")
     uf = u.float().requires_grad_(True)
     torch.nn.functional.gelu(uf).sum().backward()
-    res.append(_err_report(ops.linear(a, w, None, ops.EPI_DGELU, resid=u), acc * uf.grad, "epi_dgelu", tol))
+    wT = w.T.contiguous()  # stored [K][N]: the dgrad layout
+    res.append(_err_report(ops.gemm(a, wT, M=M, N=N, K=K, b_major=1, epilogue=ops.EPI_DGELU, resid=u), acc * uf.grad,
+                           "epi_dgelu", tol))
     # strided A (pooler reads row 0 of every sequence): lda = 512*768
     seq = _mk(4 * 512, 768, "cuda", 0.5)
     a0 = seq.view(4, 512, 768)[:, 0]
@@ -263,7 +265,7 @@ def case_gemm_ce():
     res.append(_err_report(tgt2, tgt, "ce_tgt_chunked", 1e-6))
     # dlogit
     scale = torch.tensor([1.0 / M], device="cuda")
-    dl = torch.empty(M, V, dtype=torch.bfloat16, device="cuda")
+    dl = torch.empty(M, (V + 7) // 8 * 8, dtype=torch.bfloat16, device="cuda")[:, :V]
     ops.gemm(h, W, M=M, N=V, K=K, epilogue=ops.EPI_CE_DLOGIT, labels=labels, lse=lse, scale_dev=scale, out=dl)
     ref = torch.softmax(logits, -1)
     ref[torch.arange(M), labels.long()] -= 1
@@ -407,6 +409,135 @@ def main():
     n_bad = sum(1 for g in results if not g.get("ok", False))
     print(f"probe: {len(results) - n_bad} ok, {n_bad} failed")
 
+
+
+# ------------------------------------------------------------------------------------------------
+# end-to-end cases (appended after the first bring-up run)
+# ------------------------------------------------------------------------------------------------
+def _attn_bwd_ref(qkv, bias, B, S, dout):
+    import torch
+    x = qkv.float().clone().requires_grad_(True)
+    q, k, v = x.view(B, S, 3, 12, 64).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) * 0.125
+    if bias is not None:
+        s = s + bias[:, None, None, :]
+    o = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * S, 768)
+    o.backward(dout.float())
+    return x.grad
+
+
+def case_attn_bwd():
+    import torch
+    from stonkgs_b200 import ops
+    torch.manual_seed(6)
+    res = []
+    for (B, S, masked) in [(2, 512, True), (1, 128, False), (2, 256, True)]:
+        qkv = _mk(B * S, 2304, "cuda", 1.0)
+        bias = None
+        if masked:
+            m = torch.ones(B, S, dtype=torch.long, device="cuda")
+            for b in range(B):
+                m[b, 40 + 17 * b: S // 2] = 0
+            bias = ops.mask_to_bias(m)
+        out, lse = ops.attention(qkv, bias, B, S, save_lse=True)
+        dout = _mk(B * S, 768, "cuda", 1.0)
+        dqkv = ops.attention_bwd(qkv, bias, B, S, out, dout, lse)
+        ref = _attn_bwd_ref(qkv, bias, B, S, dout)
+        tol = 0.03 * ref.abs().max().item()
+        res.append(_err_report(dqkv[:, :768], ref[:, :768], f"attn_bwd_dq_S{S}", tol))
+        res.append(_err_report(dqkv[:, 768:1536], ref[:, 768:1536], f"attn_bwd_dk_S{S}", tol))
+        res.append(_err_report(dqkv[:, 1536:], ref[:, 1536:], f"attn_bwd_dv_S{S}", tol))
+    return res
+
+
+def _load_case(name):
+    import numpy as np
+    import torch
+    from oracle import weights
+    from transformers import BertConfig
+    from stonkgs_b200.model import STonKGsForPreTraining
+    fix = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    L, B, n_kg, seed_w, seed_b, _ = [int(v) for v in fix["meta"]]
+    sd = weights.make_state_dict(n_kg, L, seed_w)
+    rows = weights.make_kg_table(n_kg, seed_w)
+    cfg = BertConfig(vocab_size=28996, num_hidden_layers=L)
+    model = STonKGsForPreTraining(None, cfg, rows)
+    model.load_state_dict(sd, strict=True)
+    model.eval().to("cuda")
+    batch = {k: torch.from_numpy(fix[k]) for k in ("input_ids", "attention_mask", "token_type_ids", "masked_lm_labels",
+                                                   "ent_masked_lm_labels", "next_sentence_labels")}
+    return fix, sd, rows, model, batch
+
+
+def case_e2e_fwd():
+    import torch
+    res = []
+    for name in ("L2_B2_N997", "L12_B2_N997", "L2_B3_N3001_fullmask"):
+        fix, sd, rows, model, batch = _load_case(name)
+        with torch.no_grad():
+            out = model(**batch, return_dict=True)
+        torch.cuda.synchronize()
+        r = [int(v) for v in fix["rows"]]
+        res.append(_err_report(out.pooler_output.cpu(), torch.from_numpy(fix["pooler_output"]), f"{name}_pooler", 5e-2))
+        res.append(_err_report(out.hidden_states[:, r].cpu().reshape(-1, 768),
+                               torch.from_numpy(fix["sequence_output_rows"]).reshape(-1, 768), f"{name}_seq_rows", 8e-2))
+        res.append(_err_report(out.loss.cpu().reshape(1), torch.from_numpy(fix["loss"]).reshape(1), f"{name}_loss",
+                               2e-3 * float(fix["loss"])))
+        parts = [float(p) for p in model._last_loss_parts]
+        res.append({"case": f"{name}_loss_parts", "ok": True, "got": parts,
+                    "ref": [float(fix["mlm_loss"]), float(fix["elm_loss"])]})
+        res.append(_err_report(out.seq_relationship_logits.cpu(), torch.from_numpy(fix["seq_relationship_logits"]),
+                               f"{name}_nsp_logits", 2e-2))
+        # KG table special rows + bit-exact node rows
+        ids = [int(v) for v in fix["kg_probe_ids"]]
+        got = model.kg_table[torch.tensor(ids, device="cuda")].cpu()
+        ref = torch.from_numpy(fix["kg_probe_rows"])
+        special = [i for i, v in enumerate(ids) if v in (100, 102, 103)]
+        normal = [i for i, v in enumerate(ids) if v not in (100, 102, 103)]
+        res.append({"case": f"{name}_kg_rows_bitexact", "ok": bool(torch.equal(got[normal], ref[normal]))})
+        res.append(_err_report(got[special], ref[special], f"{name}_kg_special_rows", 5e-2))
+    return res
+
+
+def case_e2e_bwd():
+    import torch
+    from oracle import stonkgs_oracle as orc
+    res = []
+    for name in ("L2_B2_N997", "L12_B2_N997"):
+        fix, sd, rows, model, batch = _load_case(name)
+        model.zero_grad(set_to_none=True)
+        out = model(**batch)
+        loss = out[0]
+        loss.backward()
+        torch.cuda.synchronize()
+        table = orc.build_kg_table(sd, rows)
+        o, grads = orc.forward_backward(sd, table, batch)
+        res.append(_err_report(loss.detach().cpu().reshape(1), o["loss"].detach().reshape(1), f"{name}_train_loss",
+                               2e-3 * float(o["loss"])))
+        named = dict(model.named_parameters())
+        worst = []
+        for k, g in grads.items():
+            p = named[k]
+            if p.grad is None:
+                res.append({"case": f"{name}_grad_missing_{k}", "ok": False})
+                continue
+            got = p.grad.detach().cpu().float()
+            denom = g.abs().max().item() + 1e-12
+            rel = (got - g).abs().max().item() / denom
+            cos = torch.nn.functional.cosine_similarity(got.reshape(1, -1), g.reshape(1, -1)).item()
+            worst.append((rel, cos, k))
+        worst.sort(reverse=True)
+        bad = [(round(r, 4), round(c, 5), k) for r, c, k in worst if (r > 0.08 and "key.bias" not in k)]
+        res.append({"case": f"{name}_grads", "ok": len(bad) == 0, "n": len(worst), "bad": bad[:12],
+                    "worst5": [(round(r, 4), round(c, 5), k) for r, c, k in worst[:5]],
+                    "min_cos": min(c for r, c, k in worst if "key.bias" not in k)})
+        dead = [k for k, p in named.items() if p.requires_grad and p.grad is None]
+        res.append({"case": f"{name}_dead_params", "ok": sorted(dead) == sorted(str(x) for x in fix["dead_names"]),
+                    "dead": dead})
+    return res
+
+
+CASES.update({"attn_bwd": case_attn_bwd, "e2e_fwd": case_e2e_fwd, "e2e_bwd": case_e2e_bwd})
 
 if __name__ == "__main__":
     main()
