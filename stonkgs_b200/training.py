@@ -320,7 +320,10 @@ def backward(model, st, cache, dloss: torch.Tensor, gb: GradBuffer, on_ready=Non
         _wgrad(dz1, c.ctx, gb[p + "wo"], M)
         dctx = _dgrad(dz1, lw.wo)
         dqkv = ops.attention_bwd(c.qkv, key_bias, B, 512, c.ctx, dctx, c.lse)
-        ops.colsum(dqkv, gb[p + "bqkv"], accumulate=True)
+        # bias gradients of query and value; the key-bias gradient is analytically zero (softmax is
+        # invariant to a per-query shift of the scores), so its segment stays exactly 0
+        ops.colsum(dqkv[:, :H], gb[p + "bqkv"][:H], accumulate=True)
+        ops.colsum(dqkv[:, 2 * H:], gb[p + "bqkv"][2 * H:], accumulate=True)
         _wgrad(dqkv, c.x_in, gb[p + "wqkv"], M)
         dx = _dgrad(dqkv, lw.wqkv, epilogue=ops.EPI_BIAS_RESID, resid=dz1)
         for n in ("ln2_g", "ln2_b", "b2", "w2", "b1", "w1", "ln1_g", "ln1_b", "bo", "wo", "bqkv", "wqkv"):
