@@ -41,6 +41,38 @@ def launch_count() -> int:
     return int(_lib.load().stk_launch_count())
 
 
+class LaunchProfiler:
+    """Optional per-launch CUDA-event timing of the GEMM / attention wrappers (bench.py roofline).
+    Events are recorded on the launching stream; nothing is synchronised until ``summary()``."""
+
+    def __init__(self):
+        self.records = []  # (name, work, start_event, end_event)
+
+    def span(self, name, work):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        self.records.append((name, work, e0, e1))
+        return e0, e1
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, work, e0, e1 in self.records:
+            a = agg.setdefault(name, {"ms": 0.0, "work": 0.0, "launches": 0})
+            a["ms"] += e0.elapsed_time(e1)
+            a["work"] += work
+            a["launches"] += 1
+        return agg
+
+
+_PROFILER: Optional[LaunchProfiler] = None
+
+
+def set_profiler(p: Optional[LaunchProfiler]) -> None:
+    global _PROFILER
+    _PROFILER = p
+
+
 # --------------------------------------------------------------------------------------------------
 # embedding stages / LayerNorm
 # --------------------------------------------------------------------------------------------------
@@ -157,8 +189,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: int, N: int, K: int, a_major: i
         ldc = out.stride(0)
     else:
         ldc = 0
+    prof = _PROFILER
+    if prof is not None:
+        e0, e1 = prof.span(f"gemm_a{a_major}b{b_major}_epi{epilogue}", 2.0 * M * N * K)
+        e0.record()
     check(_lib.load().stk_gemm(dev, stream, a_major, b_major, _ptr(a), a.stride(0), _ptr(b), b.stride(0), M, N, K,
                                epilogue, _ptr(out), ldc, ctypes.byref(epi), split_k), "stk_gemm")
+    if prof is not None:
+        e1.record()
     return out
 
 
@@ -176,8 +214,14 @@ def attention(qkv: torch.Tensor, key_bias: Optional[torch.Tensor], B: int, S: in
     dev, stream = _ctx(qkv)
     ctx = torch.empty((B * S, H), dtype=torch.bfloat16, device=qkv.device) if out is None else out
     lse = torch.empty((B, HEADS, S), dtype=torch.float32, device=qkv.device) if save_lse else None
+    prof = _PROFILER
+    if prof is not None:
+        e0, e1 = prof.span("attn_fwd", 4.0 * B * HEADS * S * S * 64)
+        e0.record()
     check(_lib.load().stk_attn_fwd(dev, stream, _ptr(qkv), _ptr(key_bias), B, S, _ptr(ctx), _ptr(lse)),
           "stk_attn_fwd")
+    if prof is not None:
+        e1.record()
     return (ctx, lse) if save_lse else ctx
 
 

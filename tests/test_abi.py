@@ -1,0 +1,38 @@
+"""CPU: the C-ABI library loads and exports every symbol include/stk.h declares; argument
+validation returns error codes (no compute is launched without a GPU)."""
+import ctypes
+import os
+import re
+
+from stonkgs_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_in_header():
+    src = open(os.path.join(ROOT, "include", "stk.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(?:int|long long)\s+(stk_\w+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    assert declared_in_header() == _lib.declared_symbols()
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared_in_header():
+        assert hasattr(lib, name), name
+    assert _lib.load().stk_version() == _lib.STK_VERSION
+
+
+def test_error_codes_and_text():
+    lib = _lib.load()
+    epi = _lib.GemmEpilogue()
+    rc = lib.stk_gemm(0, None, 0, 0, None, 8, None, 8, 128, 256, 64, 0, None, 8, ctypes.byref(epi), 1)
+    assert rc == -1 and "null operand" in _lib.last_error()
+    rc = lib.stk_gemm(0, None, 0, 0, None, 8, None, 8, 0, 256, 64, 0, None, 8, ctypes.byref(epi), 1)
+    assert rc == -1 and "empty problem" in _lib.last_error()
+    rc = lib.stk_attn_fwd(0, None, ctypes.c_void_p(16), None, 1, 100, ctypes.c_void_p(16), None)
+    assert rc == -1 and "S must be" in _lib.last_error()
+    assert lib.stk_launch_count() == 0

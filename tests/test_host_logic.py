@@ -1,0 +1,101 @@
+"""CPU: host-side mirror of the reference interface — module layout, checkpoint keys, KG table
+index quirk, input contract, gradient-buffer layout, sharding."""
+import numpy as np
+import pytest
+import torch
+
+from _util import build_model, load_fixture, seeded_weights
+from oracle import weights
+from stonkgs_b200 import StkError, synthetic
+from stonkgs_b200.embeddings import shard_bounds
+
+
+@pytest.fixture(scope="module")
+def small():
+    fix, meta, batch = load_fixture("L2_B2_N997")
+    sd, rows = seeded_weights(meta)
+    return fix, meta, batch, sd, rows, build_model(meta, sd, rows)
+
+
+def test_state_dict_layout_matches_reference(small):
+    _, meta, _, sd, _, model = small
+    assert sorted(model.state_dict().keys()) == sorted(sd.keys())      # exactly the reference key set
+    assert len(weights.all_keys(175003, 12)) == 413                    # 413 keys at 12 layers
+    assert model.config.kg_vocab_size == meta["n_kg"]
+    assert model.cls.predictions.half_length == 256
+    assert all(not p.requires_grad for p in model.lm_backbone.parameters())
+    assert model.cls.predictions.text_decoder.bias is None and model.cls.predictions.entity_decoder.bias is None
+
+
+def test_kg_table_index_quirk(small):
+    fix, meta, _, _, rows, model = small
+    n = meta["n_kg"]
+    assert model.kg_table.shape == (n + 3, 768)
+    # file row j sits at numeric_indices[j] = j-th element of range(N+3) \ {100,102,103}
+    assert torch.equal(model.kg_table[99], torch.from_numpy(rows[99]))
+    assert torch.equal(model.kg_table[101], torch.from_numpy(rows[100]))   # shift 1 at 101
+    assert torch.equal(model.kg_table[104], torch.from_numpy(rows[101]))   # shift 3 from 104 on
+    assert torch.equal(model.kg_table[n + 2], torch.from_numpy(rows[n - 1]))
+    ids = [int(v) for v in fix["kg_probe_ids"]]
+    normal = [i for i, v in enumerate(ids) if v not in (100, 102, 103)]
+    assert np.array_equal(model.kg_table[ids].numpy()[normal], fix["kg_probe_rows"][normal])
+    assert model.kg_idx_to_name[104] == "n101" and len(model.kg_backbone) == n + 3
+    with pytest.raises(KeyError):
+        model.kg_backbone[n + 3]
+
+
+def test_out_of_table_id_raises_keyerror_like_reference(small):
+    _, meta, batch, _, _, model = small
+    bad = batch["input_ids"].clone()
+    bad[0, 300] = meta["n_kg"] + 3
+    with pytest.raises(KeyError):
+        model._check_ids(bad)
+
+
+def test_no_cpu_fallback(small):
+    _, _, batch, _, _, model = small
+    with pytest.raises(StkError):
+        model(**batch)
+
+
+def test_synthetic_batch_follows_input_contract():
+    b = synthetic.make_batch(4, 5000, seed=3)
+    ids, mask, tt = b["input_ids"], b["attention_mask"], b["token_type_ids"]
+    assert ids.shape == (4, 512) and ids.dtype == torch.int64
+    assert (ids[:, 0] == 101).all() and (ids[:, 256 + 127] == 102).all() and (ids[:, 511] == 102).all()
+    assert (mask[:, 256:] == 1).all() and (tt[:, :256] == 0).all() and (tt[:, 256:] == 1).all()
+    lens = mask[:, :256].sum(1)
+    for r in range(4):
+        assert ids[r, lens[r] - 1] == 102 and (ids[r, lens[r]:256] == 0).all()
+    assert ((b["masked_lm_labels"] != -100).sum(1) == 38).all() and ((b["ent_masked_lm_labels"] != -100).sum(1) == 38).all()
+    assert ids[:, 256:].max() < 5003
+
+
+def test_grad_buffer_layout(small):
+    from stonkgs_b200.training import GradBuffer
+    _, _, _, _, _, model = small
+    gb = GradBuffer(model)
+    live = {id(p) for p, _ in gb.param_views}
+    from oracle import stonkgs_oracle as orc
+    named = dict(model.named_parameters())
+    assert live == {id(named[k]) for k in orc.live_keys(dict(model.state_dict()))}
+    assert gb.entries[0] == "w_ent" and gb.entries[-1] == "emb_b"          # reverse execution order
+    for name, (off, n, shape) in gb.offsets.items():
+        assert off % 4 == 0                                                # 16-byte aligned segments (TMA)
+    q = model.bert.encoder.layer[0].attention.self
+    vq = [v for p, v in gb.param_views if p is q.query.weight][0]
+    vk = [v for p, v in gb.param_views if p is q.key.weight][0]
+    assert vk.data_ptr() - vq.data_ptr() == 768 * 768 * 4                  # q|k|v grads are one fused block
+    assert gb.prepare() == "fresh"
+    gb.publish("fresh")
+    assert q.query.weight.grad.data_ptr() == vq.data_ptr() and gb.prepare() == "accumulate"
+    model.zero_grad(set_to_none=True)
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 7, 256, 1000):
+        for w in (1, 2, 3, 8):
+            spans = [shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
