@@ -5,16 +5,18 @@
 // the frozen LM backbone (S = 256, no mask; stonkgs_model.py:178) and the joint encoder
 // (S = 512, additive key-padding mask; stonkgs_model.py:204-210, HF:666-672).
 //
-// Forward, one CTA per (128-query tile, head, batch element), 288 threads:
-//   warp 8      TMA loads of Q, K, V head slices straight out of the fused QKV activation
-//               [B*S, 2304] (128B-swizzled boxes), and the single-thread tcgen05.mma issue:
-//               S = Q K^T  -> TMEM (128 lanes x S fp32 columns: the whole score row block lives
-//               in tensor memory, S <= 512 = all TMEM columns), later O = P V -> TMEM cols 0..63
-//   warps 0-7   softmax: each query row is owned by two threads (one per column half); pass 1 reads
-//               the scores from TMEM for the exact row max, pass 2 re-reads, exponentiates, sums in
-//               fp32 and writes bf16 P into shared memory in the K-major 128B-swizzled UMMA layout
-//               (overlaying the dead Q/K tiles); after the PV MMA the same threads scale by 1/sum
-//               and store the context rows.
+// Forward, one CTA per (128-query tile, head, batch element), 288 threads, TWO CTAs per SM
+// (~100 KB shared memory, 256 TMEM columns each) so that one CTA's tensor-core phases overlap the
+// other CTA's softmax phases:
+//   warp 8      TMA: Q once, K_j / V_j key blocks of 128 double-buffered, straight out of the fused QKV
+//               activation [B*S, 2304] (128B-swizzled boxes); single-thread tcgen05.mma issue:
+//               S_j = Q K_j^T -> TMEM cols [0,128), O += P_j V_j -> TMEM cols [128,192)
+//   warps 0-7   online softmax in the log2 domain, two threads per query row (64 key columns each):
+//               ONE tcgen05.ld pass over S_j, block max exchanged through shared memory, P_j written as
+//               bf16 into the K-major 128B-swizzled UMMA layout (first half over the dead K_j tile),
+//               fp32 running sum; the running max is only advanced — and the O accumulator rescaled
+//               in TMEM (tcgen05.ld/st) — when it grows by more than 8 in log2 units ("lazy
+//               rescale": P stays <= 256, exact after the final 1/sum normalisation).
 // No S x S tensor ever goes to HBM.  Row log-sum-exp can be saved for the backward pass.
 #include <atomic>
 
@@ -27,50 +29,55 @@ extern std::atomic<long long> g_launches;
 
 constexpr int ATT_THREADS = 288;
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
+// sQ 16K | sK 2x16K | sV 2x16K | sPx 16K | bias 2K | max/sum exchange 2K | barriers
+constexpr int ATT_SMEM = 16384 * 6 + 2048 + 2048 + 128;
 
-__host__ __device__ constexpr int attn_smem_bytes(int S) {
-  // [P (overlays Q,K)] S*256 | [V] S*128 | [bias] S*4 | [row max/sum exchange] 2 KB | barriers 64 | align slack
-  return 1024 + S * 256 + S * 128 + S * 4 + 2048 + 64;
-}
-
-__global__ void __launch_bounds__(ATT_THREADS)
+__global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __restrict__ key_bias, int S,
-                __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out, uint32_t tmem_cols) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sP = smem;                 // [S/64][128 rows][128 B]   (after the score MMA)
-  uint8_t* sQ = smem;                 // [128][128 B]
-  uint8_t* sK = smem + 16384;         // [S][128 B]
-  uint8_t* sV = smem + S * 256;       // [S][128 B]
-  float* sBias = reinterpret_cast<float*>(sV + S * 128);
-  float* sMax = sBias + S;            // [2][128]
-  float* sSum = sMax + 256;           // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + 256);
-  uint64_t* bar_qk = bars;
-  uint64_t* bar_v = bars + 1;
-  uint64_t* bar_s = bars + 2;
-  uint64_t* bar_p = bars + 3;
-  uint64_t* bar_o = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+                __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 16384;        // [2][128 keys][128 B]; K_j, later the first 64-key chunk of P_j
+  uint8_t* sV = smem + 49152;        // [2][128 keys][128 B]
+  uint8_t* sPx = smem + 81920;       // second 64-key chunk of P_j: [128 rows][128 B]
+  float* sBias = reinterpret_cast<float*>(smem + 98304);   // [S] additive key bias * log2e (clamped finite)
+  float* sXch = sBias + 512;         // [2 parity][2 halves][128 rows] block-max exchange (also final sums)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sXch + 512);
+  uint64_t* bar_q = bars;
+  uint64_t* bar_k = bars + 1;   // [2]
+  uint64_t* bar_v = bars + 3;   // [2]
+  uint64_t* bar_s = bars + 5;
+  uint64_t* bar_p = bars + 6;
+  uint64_t* bar_pv = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int row_base = b * S;
+  const int nblk = S >> 7;
+  constexpr uint32_t T_S = 0, T_O = 128;
 
   if (warp == 8) {
     if (lane == 0) {
+      if ((smem_u32(smem) & 1023u) != 0) { printf("stk attn: smem base not 1024-aligned\n"); __trap(); }
       tma_prefetch_desc(&map_qkv);
-      mbar_init(bar_qk, 1);
-      mbar_init(bar_v, 1);
+      mbar_init(bar_q, 1);
+      mbar_init(bar_k, 1); mbar_init(bar_k + 1, 1);
+      mbar_init(bar_v, 1); mbar_init(bar_v + 1, 1);
       mbar_init(bar_s, 1);
       mbar_init(bar_p, 256);
-      mbar_init(bar_o, 1);
+      mbar_init(bar_pv, 1);
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_alloc(tmem_slot, 256);
   } else {
-    for (int i = threadIdx.x; i < S; i += 256) sBias[i] = key_bias ? __ldg(key_bias + static_cast<int64_t>(b) * S + i) : 0.f;
+    for (int i = threadIdx.x; i < S; i += 256) {
+      const float bz = key_bias ? __ldg(key_bias + static_cast<int64_t>(b) * S + i) * kLog2e : 0.f;
+      sBias[i] = fmaxf(bz, -3.402823466e38f);   // finfo.min * log2e overflows to -inf: keep it finite
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -79,101 +86,134 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
 
   if (warp == 8) {
     if (lane == 0) {
-      const int nblk = S >> 7;
-      mbar_arrive_expect_tx(bar_qk, 16384 + S * 128);
-      tma_load_2d(&map_qkv, bar_qk, sQ, h * 64, row_base + q0);
-      for (int i = 0; i < nblk; ++i) tma_load_2d(&map_qkv, bar_qk, sK + i * 16384, 768 + h * 64, row_base + i * 128);
-      mbar_arrive_expect_tx(bar_v, S * 128);
-      for (int i = 0; i < nblk; ++i) tma_load_2d(&map_qkv, bar_v, sV + i * 16384, 1536 + h * 64, row_base + i * 128);
-
-      // ---- scores: S[128, S] = Q[128,64] K[S,64]^T, 128 key columns per instruction group ----
-      mbar_wait(bar_qk, 0);
-      tc_fence_after();
+      mbar_arrive_expect_tx(bar_q, 16384);
+      tma_load_2d(&map_qkv, bar_q, sQ, h * 64, row_base + q0);
+      for (int j = 0; j < 2 && j < nblk; ++j) {
+        mbar_arrive_expect_tx(bar_k + j, 16384);
+        tma_load_2d(&map_qkv, bar_k + j, sK + j * 16384, 768 + h * 64, row_base + j * 128);
+        mbar_arrive_expect_tx(bar_v + j, 16384);
+        tma_load_2d(&map_qkv, bar_v + j, sV + j * 16384, 1536 + h * 64, row_base + j * 128);
+      }
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-      const uint64_t q_desc = umma_smem_desc(smem_u32(sQ), 16, 1024);
-      for (int nc = 0; nc < nblk; ++nc) {
-        const uint64_t k_desc = umma_smem_desc(smem_u32(sK + nc * 16384), 16, 1024);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + nc * 128, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k > 0);
-      }
-      umma_commit(bar_s);
-
-      // ---- context: O[128,64] = P[128,S] V[S,64]  (P K-major from smem, V MN-major) ----
-      mbar_wait(bar_p, 0);
-      mbar_wait(bar_v, 0);
-      tc_fence_after();
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
-      for (int kb = 0; kb < (S >> 6); ++kb) {
-        const uint64_t p_desc = umma_smem_desc(smem_u32(sP + kb * 16384), 16, 1024);
-        const uint64_t v_desc = umma_smem_desc(smem_u32(sV + kb * 8192), 8192, 1024);
+      const uint64_t q_desc = umma_smem_desc(smem_u32(sQ), 16, 1024);
+      auto issue_scores = [&](int j) {
+        const uint64_t k_desc = umma_smem_desc(smem_u32(sK + (j & 1) * 16384), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base, p_desc + 2 * k, v_desc + k * (2048 >> 4), idesc_o, (kb | k) > 0);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + T_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k > 0);
+        umma_commit(bar_s);
+      };
+      mbar_wait(bar_q, 0);
+      mbar_wait(bar_k, 0);
+      tc_fence_after();
+      issue_scores(0);
+      for (int j = 0; j < nblk; ++j) {
+        const int bf = j & 1;
+        mbar_wait(bar_p, j & 1);             // P_j is in smem, S_j has been read, O rescaled if needed
+        mbar_wait(bar_v + bf, (j >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint64_t p_desc = umma_smem_desc(smem_u32(kb == 0 ? sK + bf * 16384 : sPx), 16, 1024);
+          const uint64_t v_desc = umma_smem_desc(smem_u32(sV + bf * 16384 + kb * 8192), 8192, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + T_O, p_desc + 2 * k, v_desc + k * 128, idesc_o, (j | kb | k) > 0);
+        }
+        umma_commit(bar_pv);
+        if (j + 1 < nblk) {                  // scores of the next block queue right behind P_j V_j
+          mbar_wait(bar_k + (bf ^ 1), ((j + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_scores(j + 1);
+        }
+        if (j + 2 < nblk) {                  // refill this K/V buffer once P_j V_j has consumed it
+          mbar_wait(bar_pv, j & 1);
+          mbar_arrive_expect_tx(bar_k + bf, 16384);
+          tma_load_2d(&map_qkv, bar_k + bf, sK + bf * 16384, 768 + h * 64, row_base + (j + 2) * 128);
+          mbar_arrive_expect_tx(bar_v + bf, 16384);
+          tma_load_2d(&map_qkv, bar_v + bf, sV + bf * 16384, 1536 + h * 64, row_base + (j + 2) * 128);
+        }
       }
-      umma_commit(bar_o);
     }
     __syncwarp();
   } else {
     // ================================ softmax warps ================================
     const int q = warp & 3, half = warp >> 2;
     const int row = q * 32 + lane;
-    const int cols = S >> 1;               // columns owned by this thread
-    const int col0 = half * cols;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const float scale = 0.125f;            // 1/sqrt(64)  (HF:156 attention_head_size ** -0.5)
+    const float k1 = 0.125f * kLog2e;      // 1/sqrt(64) (HF:156) folded with log2(e)
+    float m2 = -INFINITY;                  // running (lazily advanced) row max, log2 domain
+    float l = 0.f;                         // running sum of exp2(x2 - m2) over this thread's columns
 
-    mbar_wait(bar_s, 0);
-    tc_fence_after();
-    float mx = -INFINITY;
-#pragma unroll 1
-    for (int c = 0; c < cols; c += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(t_row + col0 + c, r);
-      tmem_ld_wait();
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(bar_s, j & 1);
+      tc_fence_after();
+      float x[64];
+      {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32b_x32(t_row + T_S + half * 64, r0);
+        tmem_ld_32x32b_x32(t_row + T_S + half * 64 + 32, r1);
+        tmem_ld_wait();
+        const float* bz = sBias + j * 128 + half * 64;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaf(__uint_as_float(r[j]), scale, sBias[col0 + c + j]));
-    }
-    sMax[half * 128 + row] = mx;
-    named_bar_sync(1, 256);
-    mx = fmaxf(sMax[row], sMax[128 + row]);
-
-    float sum = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < cols; c += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(t_row + col0 + c, r);
-      tmem_ld_wait();
-      const int k0 = col0 + c;  // first key of this group of 32
-      uint8_t* prow = sP + (k0 >> 6) * 16384 + row * 128;
-      const int c16 = (k0 & 63) >> 3;
+        for (int c = 0; c < 32; ++c) {
+          x[c] = fmaf(__uint_as_float(r0[c]), k1, bz[c]);
+          x[32 + c] = fmaf(__uint_as_float(r1[c]), k1, bz[32 + c]);
+        }
+      }
+      float bm = x[0];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
+      for (int c = 1; c < 64; ++c) bm = fmaxf(bm, x[c]);
+      float* xch = sXch + (j & 1) * 256;
+      xch[half * 128 + row] = bm;
+      named_bar_sync(1, 256);
+      bm = fmaxf(xch[row], xch[128 + row]);
+      if (j > 0) {
+        // P_{j-1} V_{j-1} must be complete before O is touched and before sPx / sK is overwritten
+        mbar_wait(bar_pv, (j - 1) & 1);
+        tc_fence_after();
+      }
+      if (bm > m2 + kRescaleThreshold) {    // also true for j == 0 (m2 = -inf)
+        if (j > 0) {
+          const float alpha = fast_exp2(m2 - bm);
+          l *= alpha;
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(t_row + T_O + half * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+          tmem_st_32x32b_x32(t_row + T_O + half * 32, o);
+          tmem_st_wait();
+        }
+        m2 = bm;
+      }
+      uint8_t* prow = (half == 0 ? sK + (j & 1) * 16384 : sPx) + row * 128;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
         uint32_t w[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int j = g * 8 + i * 2;
-          const float x0 = fmaf(__uint_as_float(r[j]), scale, sBias[k0 + j]);
-          const float x1 = fmaf(__uint_as_float(r[j + 1]), scale, sBias[k0 + j + 1]);
-          const float p0 = fast_exp2((x0 - mx) * kLog2e);
-          const float p1 = fast_exp2((x1 - mx) * kLog2e);
-          sum += p0 + p1;
+          const float p0 = fast_exp2(x[g * 8 + 2 * i] - m2);
+          const float p1 = fast_exp2(x[g * 8 + 2 * i + 1] - m2);
+          l += p0 + p1;
           w[i] = pack_bf16x2(p0, p1);
         }
-        *reinterpret_cast<uint4*>(prow + (((c16 + g) ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(prow + ((g ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
+      fence_proxy_async_smem();   // P (generic-proxy stores) -> visible to the tensor core (async proxy)
+      tc_fence_before();          // S_j reads and the O rescale are ordered before the next MMAs
+      mbar_arrive(bar_p);
     }
-    sSum[half * 128 + row] = sum;
-    fence_proxy_async_smem();   // P (generic-proxy stores) -> visible to the tensor core (async proxy)
-    tc_fence_before();          // all TMEM reads of the scores are done before the PV MMA overwrites cols 0..63
-    mbar_arrive(bar_p);
 
-    mbar_wait(bar_o, 0);
+    mbar_wait(bar_pv, (nblk - 1) & 1);
     tc_fence_after();
-    named_bar_sync(1, 256);     // sSum of the partner thread is visible
-    const float total = sSum[row] + sSum[128 + row];
+    float* xch = sXch + (nblk & 1) * 256;
+    xch[half * 128 + row] = l;
+    named_bar_sync(1, 256);
+    const float total = xch[row] + xch[128 + row];
     const float inv = 1.0f / total;
     uint32_t r[32];
-    tmem_ld_32x32b_x32(t_row + half * 32, r);
+    tmem_ld_32x32b_x32(t_row + T_O + half * 32, r);
     tmem_ld_wait();
     uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(row_base + q0 + row)) * kHidden + h * 64 + half * 32);
 #pragma unroll
@@ -185,14 +225,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
       dst[g] = make_uint4(w[0], w[1], w[2], w[3]);
     }
     if (lse_out && half == 0)
-      lse_out[(static_cast<int64_t>(b) * kHeads + h) * S + q0 + row] = mx + logf(total);
+      lse_out[(static_cast<int64_t>(b) * kHeads + h) * S + q0 + row] = (m2 + log2f(total)) * kLn2;
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 8) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
+    tmem_dealloc(tmem_base, 256);
   }
 }
 
@@ -209,15 +249,13 @@ extern "C" int stk_attn_fwd(int device, void* stream, const void* qkv, const flo
   int rc = make_tmap_2d(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, 3 * kHidden, static_cast<uint64_t>(B) * S,
                         3 * kHidden * 2, 64, 128);
   if (rc) return rc;
-  const int smem = attn_smem_bytes(S);
-  static int configured[64] = {};
-  if (configured[device & 63] < smem) {
-    STK_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes(512)));
-    configured[device & 63] = attn_smem_bytes(512);
+  static bool configured[64] = {};
+  if (!configured[device & 63]) {
+    STK_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    configured[device & 63] = true;
   }
-  const uint32_t tmem_cols = S <= 128 ? 128 : (S <= 256 ? 256 : 512);
-  attn_fwd_kernel<<<dim3(S / 128, kHeads, B), ATT_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
-      map, key_bias, S, static_cast<__nv_bfloat16*>(out), lse, tmem_cols);
+  attn_fwd_kernel<<<dim3(S / 128, kHeads, B), ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(
+      map, key_bias, S, static_cast<__nv_bfloat16*>(out), lse);
   STK_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return STK_OK;

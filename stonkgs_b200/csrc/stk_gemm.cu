@@ -197,6 +197,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       const int m0 = (tile / p.n_tiles) * BM;
       const int m = m0 + row;
       const bool m_ok = m < p.M;
+      // Residual / saved pre-activation rows do not depend on the accumulator: fetch both 64-column
+      // chunks of this thread's row now so the global-load latency hides behind the MMA of this tile.
+      constexpr bool kPrefetchExtra = EPI == STK_EPI_BIAS_RESID || EPI == STK_EPI_DGELU;
+      uint4 ex_pre[2][8];
+      if (kPrefetchExtra) {
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          const int ncp = n0 + g * 128 + ch * 64;
+          const bool okp = m_ok && ncp + 64 <= p.N;
+          const uint4* pp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.resid) +
+                                                           static_cast<int64_t>(m) * e.ldr + ncp);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) ex_pre[ch][c] = okp ? __ldg(pp + c) : make_uint4(0, 0, 0, 0);
+        }
+      }
       mbar_wait(tfull_bar + as, as_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + g * 128;
@@ -210,7 +225,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         if (EPI == STK_EPI_CE_DLOGIT && m_ok) row_lse = __ldg(e.lse + m);
       }
 
-#pragma unroll 1
+#pragma unroll
       for (int chunk = 0; chunk < 2; ++chunk) {  // 64 accumulator columns per step
         uint32_t r[2][32];
         tmem_ld_32x32b_x32(t_row + chunk * 64, r[0]);
@@ -280,11 +295,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                                   EPI == STK_EPI_BIAS_GELU_SAVE || EPI == STK_EPI_BIAS_RESID;
         constexpr bool kHasExtra = EPI == STK_EPI_BIAS_RESID || EPI == STK_EPI_DGELU;
         const bool bias_vec = kHasBias && e.bias != nullptr && nc + 64 <= p.N;
-        const bool extra_ok = kHasExtra && m_ok && nc + 64 <= p.N;
-        const uint4* extra_p = nullptr;
-        if (kHasExtra)
-          extra_p = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.resid) +
-                                                   static_cast<int64_t>(m) * e.ldr + nc);
         uint4 data[8];
         uint4 data2[8];
 #pragma unroll
@@ -304,7 +314,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             }
           }
           uint4 ex4 = make_uint4(0, 0, 0, 0);
-          if (kHasExtra && extra_ok) ex4 = __ldg(extra_p + c);
+          if (kHasExtra) ex4 = ex_pre[chunk][c];
           const uint32_t ex[4] = {ex4.x, ex4.y, ex4.z, ex4.w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
