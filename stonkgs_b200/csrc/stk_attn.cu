@@ -31,7 +31,7 @@ constexpr int ATT_THREADS = 288;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
-// sQ 16K | sK 2x16K | sV 2x16K | sPx 16K | bias 2K | max/sum exchange 2K | barriers
+// sQ 16K | sK 2x16K | sV 16K | sP 32K | bias 2K | max/sum exchange 2K | barriers
 constexpr int ATT_SMEM = 16384 * 6 + 2048 + 2048 + 128;
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
@@ -39,18 +39,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
                 __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + 16384;        // [2][128 keys][128 B]; K_j, later the first 64-key chunk of P_j
-  uint8_t* sV = smem + 49152;        // [2][128 keys][128 B]
-  uint8_t* sPx = smem + 81920;       // second 64-key chunk of P_j: [128 rows][128 B]
+  uint8_t* sK = smem + 16384;        // [2][128 keys][128 B]
+  uint8_t* sV = smem + 49152;        // [128 keys][128 B]
+  uint8_t* sP = smem + 65536;        // [2 chunks of 64 keys][128 rows][128 B]
   float* sBias = reinterpret_cast<float*>(smem + 98304);   // [S] additive key bias * log2e (clamped finite)
   float* sXch = sBias + 512;         // [2 parity][2 halves][128 rows] block-max exchange (also final sums)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sXch + 512);
   uint64_t* bar_q = bars;
-  uint64_t* bar_k = bars + 1;   // [2]
-  uint64_t* bar_v = bars + 3;   // [2]
-  uint64_t* bar_s = bars + 5;
-  uint64_t* bar_p = bars + 6;
-  uint64_t* bar_pv = bars + 7;
+  uint64_t* bar_k = bars + 1;     // [2]
+  uint64_t* bar_v = bars + 3;
+  uint64_t* bar_s = bars + 4;     // S_j is in TMEM
+  uint64_t* bar_sread = bars + 5; // every softmax thread holds S_j in registers: TMEM columns + K buffer free
+  uint64_t* bar_p = bars + 6;     // P_j is in shared memory (and O has been rescaled if needed)
+  uint64_t* bar_pv = bars + 7;    // O += P_j V_j has completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -65,8 +66,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
       tma_prefetch_desc(&map_qkv);
       mbar_init(bar_q, 1);
       mbar_init(bar_k, 1); mbar_init(bar_k + 1, 1);
-      mbar_init(bar_v, 1); mbar_init(bar_v + 1, 1);
+      mbar_init(bar_v, 1);
       mbar_init(bar_s, 1);
+      mbar_init(bar_sread, 256);
       mbar_init(bar_p, 256);
       mbar_init(bar_pv, 1);
       fence_barrier_init();
@@ -91,9 +93,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
       for (int j = 0; j < 2 && j < nblk; ++j) {
         mbar_arrive_expect_tx(bar_k + j, 16384);
         tma_load_2d(&map_qkv, bar_k + j, sK + j * 16384, 768 + h * 64, row_base + j * 128);
-        mbar_arrive_expect_tx(bar_v + j, 16384);
-        tma_load_2d(&map_qkv, bar_v + j, sV + j * 16384, 1536 + h * 64, row_base + j * 128);
       }
+      mbar_arrive_expect_tx(bar_v, 16384);
+      tma_load_2d(&map_qkv, bar_v, sV, 1536 + h * 64, row_base);
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
       const uint64_t q_desc = umma_smem_desc(smem_u32(sQ), 16, 1024);
@@ -109,29 +111,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
       issue_scores(0);
       for (int j = 0; j < nblk; ++j) {
         const int bf = j & 1;
-        mbar_wait(bar_p, j & 1);             // P_j is in smem, S_j has been read, O rescaled if needed
-        mbar_wait(bar_v + bf, (j >> 1) & 1);
+        mbar_wait(bar_sread, j & 1);         // S_j sits in registers: the S columns and K buffer bf are free
+        tc_fence_after();
+        if (j + 2 < nblk) {
+          mbar_arrive_expect_tx(bar_k + bf, 16384);
+          tma_load_2d(&map_qkv, bar_k + bf, sK + bf * 16384, 768 + h * 64, row_base + (j + 2) * 128);
+        }
+        if (j + 1 < nblk) {                  // next scores run on the tensor core while softmax j is still busy
+          mbar_wait(bar_k + (bf ^ 1), ((j + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_scores(j + 1);
+        }
+        mbar_wait(bar_p, j & 1);             // P_j is in smem, O rescaled if needed
+        mbar_wait(bar_v, j & 1);
         tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t p_desc = umma_smem_desc(smem_u32(kb == 0 ? sK + bf * 16384 : sPx), 16, 1024);
-          const uint64_t v_desc = umma_smem_desc(smem_u32(sV + bf * 16384 + kb * 8192), 8192, 1024);
+          const uint64_t p_desc = umma_smem_desc(smem_u32(sP + kb * 16384), 16, 1024);
+          const uint64_t v_desc = umma_smem_desc(smem_u32(sV + kb * 8192), 8192, 1024);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16(tmem_base + T_O, p_desc + 2 * k, v_desc + k * 128, idesc_o, (j | kb | k) > 0);
         }
         umma_commit(bar_pv);
-        if (j + 1 < nblk) {                  // scores of the next block queue right behind P_j V_j
-          mbar_wait(bar_k + (bf ^ 1), ((j + 1) >> 1) & 1);
-          tc_fence_after();
-          issue_scores(j + 1);
-        }
-        if (j + 2 < nblk) {                  // refill this K/V buffer once P_j V_j has consumed it
+        if (j + 1 < nblk) {                  // V is single-buffered: refill once P_j V_j has consumed it
           mbar_wait(bar_pv, j & 1);
-          mbar_arrive_expect_tx(bar_k + bf, 16384);
-          tma_load_2d(&map_qkv, bar_k + bf, sK + bf * 16384, 768 + h * 64, row_base + (j + 2) * 128);
-          mbar_arrive_expect_tx(bar_v + bf, 16384);
-          tma_load_2d(&map_qkv, bar_v + bf, sV + bf * 16384, 1536 + h * 64, row_base + (j + 2) * 128);
+          mbar_arrive_expect_tx(bar_v, 16384);
+          tma_load_2d(&map_qkv, bar_v, sV, 1536 + h * 64, row_base + (j + 1) * 128);
         }
       }
     }
@@ -143,7 +149,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float k1 = 0.125f * kLog2e;      // 1/sqrt(64) (HF:156) folded with log2(e)
     float m2 = -INFINITY;                  // running (lazily advanced) row max, log2 domain
-    float l = 0.f;                         // running sum of exp2(x2 - m2) over this thread's columns
+    float l0 = 0.f, l1 = 0.f;              // running sums of exp2(x2 - m2) over this thread's columns
 
     for (int j = 0; j < nblk; ++j) {
       mbar_wait(bar_s, j & 1);
@@ -154,29 +160,43 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
         tmem_ld_32x32b_x32(t_row + T_S + half * 64, r0);
         tmem_ld_32x32b_x32(t_row + T_S + half * 64 + 32, r1);
         tmem_ld_wait();
-        const float* bz = sBias + j * 128 + half * 64;
+        tc_fence_before();
+        mbar_arrive(bar_sread);
+        const float4* bz = reinterpret_cast<const float4*>(sBias + j * 128 + half * 64);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          x[c] = fmaf(__uint_as_float(r0[c]), k1, bz[c]);
-          x[32 + c] = fmaf(__uint_as_float(r1[c]), k1, bz[32 + c]);
+        for (int c = 0; c < 8; ++c) {
+          const float4 b0 = bz[c], b1 = bz[8 + c];
+          x[4 * c] = fmaf(__uint_as_float(r0[4 * c]), k1, b0.x);
+          x[4 * c + 1] = fmaf(__uint_as_float(r0[4 * c + 1]), k1, b0.y);
+          x[4 * c + 2] = fmaf(__uint_as_float(r0[4 * c + 2]), k1, b0.z);
+          x[4 * c + 3] = fmaf(__uint_as_float(r0[4 * c + 3]), k1, b0.w);
+          x[32 + 4 * c] = fmaf(__uint_as_float(r1[4 * c]), k1, b1.x);
+          x[32 + 4 * c + 1] = fmaf(__uint_as_float(r1[4 * c + 1]), k1, b1.y);
+          x[32 + 4 * c + 2] = fmaf(__uint_as_float(r1[4 * c + 2]), k1, b1.z);
+          x[32 + 4 * c + 3] = fmaf(__uint_as_float(r1[4 * c + 3]), k1, b1.w);
         }
       }
-      float bm = x[0];
+      float mx[4] = {x[0], x[1], x[2], x[3]};   // four independent chains instead of one of length 64
 #pragma unroll
-      for (int c = 1; c < 64; ++c) bm = fmaxf(bm, x[c]);
+      for (int c = 4; c < 64; c += 4) {
+        mx[0] = fmaxf(mx[0], x[c]); mx[1] = fmaxf(mx[1], x[c + 1]);
+        mx[2] = fmaxf(mx[2], x[c + 2]); mx[3] = fmaxf(mx[3], x[c + 3]);
+      }
+      float bm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
       float* xch = sXch + (j & 1) * 256;
       xch[half * 128 + row] = bm;
       named_bar_sync(1, 256);
       bm = fmaxf(xch[row], xch[128 + row]);
       if (j > 0) {
-        // P_{j-1} V_{j-1} must be complete before O is touched and before sPx / sK is overwritten
+        // P_{j-1} V_{j-1} must be complete before O is touched and before sP is overwritten
         mbar_wait(bar_pv, (j - 1) & 1);
         tc_fence_after();
       }
       if (bm > m2 + kRescaleThreshold) {    // also true for j == 0 (m2 = -inf)
         if (j > 0) {
           const float alpha = fast_exp2(m2 - bm);
-          l *= alpha;
+          l0 *= alpha;
+          l1 *= alpha;
           uint32_t o[32];
           tmem_ld_32x32b_x32(t_row + T_O + half * 32, o);
           tmem_ld_wait();
@@ -187,7 +207,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
         }
         m2 = bm;
       }
-      uint8_t* prow = (half == 0 ? sK + (j & 1) * 16384 : sPx) + row * 128;
+      uint8_t* prow = sP + half * 16384 + row * 128;
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         uint32_t w[4];
@@ -195,20 +215,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
         for (int i = 0; i < 4; ++i) {
           const float p0 = fast_exp2(x[g * 8 + 2 * i] - m2);
           const float p1 = fast_exp2(x[g * 8 + 2 * i + 1] - m2);
-          l += p0 + p1;
+          l0 += p0;
+          l1 += p1;
           w[i] = pack_bf16x2(p0, p1);
         }
         *reinterpret_cast<uint4*>(prow + ((g ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
       fence_proxy_async_smem();   // P (generic-proxy stores) -> visible to the tensor core (async proxy)
-      tc_fence_before();          // S_j reads and the O rescale are ordered before the next MMAs
+      tc_fence_before();          // the O rescale is ordered before the next MMA
       mbar_arrive(bar_p);
     }
 
     mbar_wait(bar_pv, (nblk - 1) & 1);
     tc_fence_after();
     float* xch = sXch + (nblk & 1) * 256;
-    xch[half * 128 + row] = l;
+    xch[half * 128 + row] = l0 + l1;
     named_bar_sync(1, 256);
     const float total = xch[row] + xch[128 + row];
     const float inv = 1.0f / total;
