@@ -31,19 +31,22 @@ constexpr int ATT_THREADS = 288;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
-// sQ 16K | sK 2x16K | sV 16K | sP 32K | bias 2K | max/sum exchange 2K | barriers
-constexpr int ATT_SMEM = 16384 * 6 + 2048 + 2048 + 128;
+// sQ 16K | sK 2x16K | sV 16K | sP 32K | bias 2x2K | max/sum exchange 2K | barriers
+constexpr int ATT_SMEM = 16384 * 6 + 4096 + 2048 + 128;
 
+// Persistent: grid = 2 CTAs per SM; every CTA walks work items (q-tile, head, batch) with the q-tile
+// index fastest, so CTAs that run together share K/V in L2, and the loads of the next item's
+// Q / K_0 / K_1 are issued while the current item's last key block is still in its softmax.
 __global__ void __launch_bounds__(ATT_THREADS, 2)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __restrict__ key_bias, int S,
+attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __restrict__ key_bias, int S, int num_items,
                 __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = smem + 16384;        // [2][128 keys][128 B]
   uint8_t* sV = smem + 49152;        // [128 keys][128 B]
   uint8_t* sP = smem + 65536;        // [2 chunks of 64 keys][128 rows][128 B]
-  float* sBias = reinterpret_cast<float*>(smem + 98304);   // [S] additive key bias * log2e (clamped finite)
-  float* sXch = sBias + 512;         // [2 parity][2 halves][128 rows] block-max exchange (also final sums)
+  float* sBias = reinterpret_cast<float*>(smem + 98304);   // [2 item parity][512] key bias * log2e (clamped finite)
+  float* sXch = sBias + 1024;        // [2 parity][2 halves][128 rows] block-max exchange (also final sums)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sXch + 512);
   uint64_t* bar_q = bars;
   uint64_t* bar_k = bars + 1;     // [2]
@@ -55,9 +58,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-  const int row_base = b * S;
-  const int nblk = S >> 7;
+  const int nblk = S >> 7;          // key blocks per item == q-tiles per (head, batch)
   constexpr uint32_t T_S = 0, T_O = 128;
 
   if (warp == 8) {
@@ -75,11 +76,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
     }
     __syncwarp();
     tmem_alloc(tmem_slot, 256);
-  } else {
-    for (int i = threadIdx.x; i < S; i += 256) {
-      const float bz = key_bias ? __ldg(key_bias + static_cast<int64_t>(b) * S + i) * kLog2e : 0.f;
-      sBias[i] = fmaxf(bz, -3.402823466e38f);   // finfo.min * log2e overflows to -inf: keep it finite
-    }
   }
   tc_fence_before();
   __syncthreads();
@@ -88,56 +84,95 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
 
   if (warp == 8) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(bar_q, 16384);
-      tma_load_2d(&map_qkv, bar_q, sQ, h * 64, row_base + q0);
-      for (int j = 0; j < 2 && j < nblk; ++j) {
-        mbar_arrive_expect_tx(bar_k + j, 16384);
-        tma_load_2d(&map_qkv, bar_k + j, sK + j * 16384, 768 + h * 64, row_base + j * 128);
-      }
-      mbar_arrive_expect_tx(bar_v, 16384);
-      tma_load_2d(&map_qkv, bar_v, sV, 1536 + h * 64, row_base);
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
       const uint64_t q_desc = umma_smem_desc(smem_u32(sQ), 16, 1024);
-      auto issue_scores = [&](int j) {
-        const uint64_t k_desc = umma_smem_desc(smem_u32(sK + (j & 1) * 16384), 16, 1024);
+      // running use counters -> mbarrier parities
+      uint32_t n_q = 0, n_k[2] = {0, 0}, n_v = 0, n_sread = 0, n_p = 0, n_pv = 0;
+      uint32_t kload = 0;   // total K blocks loaded so far (buffer = kload & 1)
+      auto coords = [&](int item, int& hh, int& rb, int& qq) {
+        const int qt = item % nblk, rest = item / nblk;
+        hh = rest % kHeads;
+        rb = (rest / kHeads) * S;
+        qq = qt * 128;
+      };
+      auto load_q = [&](int item) {
+        int hh, rb, qq; coords(item, hh, rb, qq);
+        mbar_arrive_expect_tx(bar_q, 16384);
+        tma_load_2d(&map_qkv, bar_q, sQ, hh * 64, rb + qq);
+      };
+      auto load_k = [&](int item, int j) {
+        int hh, rb, qq; coords(item, hh, rb, qq);
+        const int bf = kload & 1;
+        mbar_arrive_expect_tx(bar_k + bf, 16384);
+        tma_load_2d(&map_qkv, bar_k + bf, sK + bf * 16384, 768 + hh * 64, rb + j * 128);
+        ++kload;
+      };
+      auto load_v = [&](int item, int j) {
+        int hh, rb, qq; coords(item, hh, rb, qq);
+        mbar_arrive_expect_tx(bar_v, 16384);
+        tma_load_2d(&map_qkv, bar_v, sV, 1536 + hh * 64, rb + j * 128);
+      };
+      uint32_t kuse = 0;    // total K blocks consumed by score MMAs so far
+      auto issue_scores = [&]() {
+        const int bf = kuse & 1;
+        mbar_wait(bar_k + bf, n_k[bf] & 1);
+        ++n_k[bf];
+        tc_fence_after();
+        const uint64_t k_desc = umma_smem_desc(smem_u32(sK + bf * 16384), 16, 1024);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + T_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k > 0);
         umma_commit(bar_s);
+        ++kuse;
       };
-      mbar_wait(bar_q, 0);
-      mbar_wait(bar_k, 0);
-      tc_fence_after();
-      issue_scores(0);
-      for (int j = 0; j < nblk; ++j) {
-        const int bf = j & 1;
-        mbar_wait(bar_sread, j & 1);         // S_j sits in registers: the S columns and K buffer bf are free
-        tc_fence_after();
-        if (j + 2 < nblk) {
-          mbar_arrive_expect_tx(bar_k + bf, 16384);
-          tma_load_2d(&map_qkv, bar_k + bf, sK + bf * 16384, 768 + h * 64, row_base + (j + 2) * 128);
-        }
-        if (j + 1 < nblk) {                  // next scores run on the tensor core while softmax j is still busy
-          mbar_wait(bar_k + (bf ^ 1), ((j + 1) >> 1) & 1);
+
+      int item = blockIdx.x;
+      if (item < num_items) {
+        load_q(item);
+        load_k(item, 0);
+        if (nblk > 1) load_k(item, 1);
+        load_v(item, 0);
+        mbar_wait(bar_q, n_q & 1); ++n_q;
+        issue_scores();
+      }
+      for (; item < num_items; item += gridDim.x) {
+        const int next = item + gridDim.x;
+        for (int j = 0; j < nblk; ++j) {
+          mbar_wait(bar_sread, n_sread & 1); ++n_sread;   // S_j is in registers: S columns + its K buffer are free
           tc_fence_after();
-          issue_scores(j + 1);
-        }
-        mbar_wait(bar_p, j & 1);             // P_j is in smem, O rescaled if needed
-        mbar_wait(bar_v, j & 1);
-        tc_fence_after();
+          if (j + 2 < nblk) {
+            load_k(item, j + 2);
+          } else if (next < num_items) {   // tail of this item: start fetching the next item's Q / K
+            if (j + 1 == nblk) {           // last block: every score MMA of this item is done -> Q is free too
+              load_q(next);
+              load_k(next, (nblk > 1) ? 1 : 0);
+            } else {                       // j + 2 == nblk: this buffer will hold the next item's K_0
+              load_k(next, 0);
+            }
+          }
+          if (j + 1 < nblk) {
+            issue_scores();                // next scores run on the tensor core while softmax j is still busy
+          } else if (next < num_items) {
+            mbar_wait(bar_q, n_q & 1); ++n_q;
+            issue_scores();                // first scores of the next item
+          }
+          mbar_wait(bar_p, n_p & 1); ++n_p;              // P_j is in smem, O rescaled if needed
+          mbar_wait(bar_v, n_v & 1); ++n_v;
+          tc_fence_after();
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t p_desc = umma_smem_desc(smem_u32(sP + kb * 16384), 16, 1024);
-          const uint64_t v_desc = umma_smem_desc(smem_u32(sV + kb * 8192), 8192, 1024);
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint64_t p_desc = umma_smem_desc(smem_u32(sP + kb * 16384), 16, 1024);
+            const uint64_t v_desc = umma_smem_desc(smem_u32(sV + kb * 8192), 8192, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + T_O, p_desc + 2 * k, v_desc + k * 128, idesc_o, (j | kb | k) > 0);
-        }
-        umma_commit(bar_pv);
-        if (j + 1 < nblk) {                  // V is single-buffered: refill once P_j V_j has consumed it
-          mbar_wait(bar_pv, j & 1);
-          mbar_arrive_expect_tx(bar_v, 16384);
-          tma_load_2d(&map_qkv, bar_v, sV, 1536 + h * 64, row_base + (j + 1) * 128);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + T_O, p_desc + 2 * k, v_desc + k * 128, idesc_o, (j | kb | k) > 0);
+          }
+          umma_commit(bar_pv);
+          if (j + 1 < nblk || next < num_items) {   // V is single-buffered: refill once P_j V_j has consumed it
+            mbar_wait(bar_pv, n_pv & 1);
+            if (j + 1 < nblk) load_v(item, j + 1); else load_v(next, 0);
+          }
+          ++n_pv;
         }
       }
     }
@@ -148,105 +183,120 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
     const int row = q * 32 + lane;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float k1 = 0.125f * kLog2e;      // 1/sqrt(64) (HF:156) folded with log2(e)
-    float m2 = -INFINITY;                  // running (lazily advanced) row max, log2 domain
-    float l0 = 0.f, l1 = 0.f;              // running sums of exp2(x2 - m2) over this thread's columns
+    uint32_t n_s = 0, n_pv = 0, n_x = 0, it = 0;
 
-    for (int j = 0; j < nblk; ++j) {
-      mbar_wait(bar_s, j & 1);
-      tc_fence_after();
-      float x[64];
-      {
-        uint32_t r0[32], r1[32];
-        tmem_ld_32x32b_x32(t_row + T_S + half * 64, r0);
-        tmem_ld_32x32b_x32(t_row + T_S + half * 64 + 32, r1);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(bar_sread);
-        const float4* bz = reinterpret_cast<const float4*>(sBias + j * 128 + half * 64);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 b0 = bz[c], b1 = bz[8 + c];
-          x[4 * c] = fmaf(__uint_as_float(r0[4 * c]), k1, b0.x);
-          x[4 * c + 1] = fmaf(__uint_as_float(r0[4 * c + 1]), k1, b0.y);
-          x[4 * c + 2] = fmaf(__uint_as_float(r0[4 * c + 2]), k1, b0.z);
-          x[4 * c + 3] = fmaf(__uint_as_float(r0[4 * c + 3]), k1, b0.w);
-          x[32 + 4 * c] = fmaf(__uint_as_float(r1[4 * c]), k1, b1.x);
-          x[32 + 4 * c + 1] = fmaf(__uint_as_float(r1[4 * c + 1]), k1, b1.y);
-          x[32 + 4 * c + 2] = fmaf(__uint_as_float(r1[4 * c + 2]), k1, b1.z);
-          x[32 + 4 * c + 3] = fmaf(__uint_as_float(r1[4 * c + 3]), k1, b1.w);
-        }
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int qt = item % nblk, rest = item / nblk;
+      const int h = rest % kHeads, b = rest / kHeads;
+      const int row_base = b * S, q0 = qt * 128;
+      // key bias of this item's batch element (double-buffered by item parity; the per-block named
+      // barrier below orders these writes before any read)
+      float* bias_it = sBias + (it & 1) * 512;
+      for (int i = threadIdx.x; i < S; i += 256) {
+        const float bz = key_bias ? __ldg(key_bias + static_cast<int64_t>(b) * S + i) * kLog2e : 0.f;
+        bias_it[i] = fmaxf(bz, -3.402823466e38f);   // finfo.min * log2e overflows to -inf: keep it finite
       }
-      float mx[4] = {x[0], x[1], x[2], x[3]};   // four independent chains instead of one of length 64
-#pragma unroll
-      for (int c = 4; c < 64; c += 4) {
-        mx[0] = fmaxf(mx[0], x[c]); mx[1] = fmaxf(mx[1], x[c + 1]);
-        mx[2] = fmaxf(mx[2], x[c + 2]); mx[3] = fmaxf(mx[3], x[c + 3]);
-      }
-      float bm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-      float* xch = sXch + (j & 1) * 256;
-      xch[half * 128 + row] = bm;
       named_bar_sync(1, 256);
-      bm = fmaxf(xch[row], xch[128 + row]);
-      if (j > 0) {
-        // P_{j-1} V_{j-1} must be complete before O is touched and before sP is overwritten
-        mbar_wait(bar_pv, (j - 1) & 1);
+      float m2 = -INFINITY;                // running (lazily advanced) row max, log2 domain
+      float l0 = 0.f, l1 = 0.f;            // running sums of exp2(x2 - m2) over this thread's columns
+
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(bar_s, n_s & 1); ++n_s;
         tc_fence_after();
-      }
-      if (bm > m2 + kRescaleThreshold) {    // also true for j == 0 (m2 = -inf)
-        if (j > 0) {
-          const float alpha = fast_exp2(m2 - bm);
-          l0 *= alpha;
-          l1 *= alpha;
-          uint32_t o[32];
-          tmem_ld_32x32b_x32(t_row + T_O + half * 32, o);
+        float x[64];
+        {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(t_row + T_S + half * 64, r0);
+          tmem_ld_32x32b_x32(t_row + T_S + half * 64 + 32, r1);
           tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(bar_sread);
+          const float4* bz = reinterpret_cast<const float4*>(bias_it + j * 128 + half * 64);
 #pragma unroll
-          for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-          tmem_st_32x32b_x32(t_row + T_O + half * 32, o);
-          tmem_st_wait();
+          for (int c = 0; c < 8; ++c) {
+            const float4 b0 = bz[c], b1 = bz[8 + c];
+            x[4 * c] = fmaf(__uint_as_float(r0[4 * c]), k1, b0.x);
+            x[4 * c + 1] = fmaf(__uint_as_float(r0[4 * c + 1]), k1, b0.y);
+            x[4 * c + 2] = fmaf(__uint_as_float(r0[4 * c + 2]), k1, b0.z);
+            x[4 * c + 3] = fmaf(__uint_as_float(r0[4 * c + 3]), k1, b0.w);
+            x[32 + 4 * c] = fmaf(__uint_as_float(r1[4 * c]), k1, b1.x);
+            x[32 + 4 * c + 1] = fmaf(__uint_as_float(r1[4 * c + 1]), k1, b1.y);
+            x[32 + 4 * c + 2] = fmaf(__uint_as_float(r1[4 * c + 2]), k1, b1.z);
+            x[32 + 4 * c + 3] = fmaf(__uint_as_float(r1[4 * c + 3]), k1, b1.w);
+          }
         }
-        m2 = bm;
-      }
-      uint8_t* prow = sP + half * 16384 + row * 128;
+        float mx[4] = {x[0], x[1], x[2], x[3]};   // four independent chains instead of one of length 64
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
+        for (int c = 4; c < 64; c += 4) {
+          mx[0] = fmaxf(mx[0], x[c]); mx[1] = fmaxf(mx[1], x[c + 1]);
+          mx[2] = fmaxf(mx[2], x[c + 2]); mx[3] = fmaxf(mx[3], x[c + 3]);
+        }
+        float bm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        float* xch = sXch + (n_x & 1) * 256; ++n_x;
+        xch[half * 128 + row] = bm;
+        named_bar_sync(1, 256);
+        bm = fmaxf(xch[row], xch[128 + row]);
+        if (j > 0) {
+          // P_{j-1} V_{j-1} must be complete before O is touched and before sP is overwritten
+          mbar_wait(bar_pv, n_pv & 1); ++n_pv;
+          tc_fence_after();
+        }
+        if (bm > m2 + kRescaleThreshold) {    // also true for j == 0 (m2 = -inf)
+          if (j > 0) {
+            const float alpha = fast_exp2(m2 - bm);
+            l0 *= alpha;
+            l1 *= alpha;
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(t_row + T_O + half * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+            tmem_st_32x32b_x32(t_row + T_O + half * 32, o);
+            tmem_st_wait();
+          }
+          m2 = bm;
+        }
+        uint8_t* prow = sP + half * 16384 + row * 128;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float p0 = fast_exp2(x[g * 8 + 2 * i] - m2);
+            const float p1 = fast_exp2(x[g * 8 + 2 * i + 1] - m2);
+            l0 += p0;
+            l1 += p1;
+            w[i] = pack_bf16x2(p0, p1);
+          }
+          *reinterpret_cast<uint4*>(prow + ((g ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        fence_proxy_async_smem();   // P (generic-proxy stores) -> visible to the tensor core (async proxy)
+        tc_fence_before();          // the O rescale is ordered before the next MMA
+        mbar_arrive(bar_p);
+      }
+
+      mbar_wait(bar_pv, n_pv & 1); ++n_pv;
+      tc_fence_after();
+      float* xch = sXch + (n_x & 1) * 256; ++n_x;
+      xch[half * 128 + row] = l0 + l1;
+      named_bar_sync(1, 256);
+      const float total = xch[row] + xch[128 + row];
+      const float inv = 1.0f / total;
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_row + T_O + half * 32, r);
+      tmem_ld_wait();
+      uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(row_base + q0 + row)) * kHidden + h * 64 + half * 32);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
         uint32_t w[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float p0 = fast_exp2(x[g * 8 + 2 * i] - m2);
-          const float p1 = fast_exp2(x[g * 8 + 2 * i + 1] - m2);
-          l0 += p0;
-          l1 += p1;
-          w[i] = pack_bf16x2(p0, p1);
-        }
-        *reinterpret_cast<uint4*>(prow + ((g ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int i = 0; i < 4; ++i)
+          w[i] = pack_bf16x2(__uint_as_float(r[g * 8 + 2 * i]) * inv, __uint_as_float(r[g * 8 + 2 * i + 1]) * inv);
+        dst[g] = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      fence_proxy_async_smem();   // P (generic-proxy stores) -> visible to the tensor core (async proxy)
-      tc_fence_before();          // the O rescale is ordered before the next MMA
-      mbar_arrive(bar_p);
+      if (lse_out && half == 0)
+        lse_out[(static_cast<int64_t>(b) * kHeads + h) * S + q0 + row] = (m2 + log2f(total)) * kLn2;
     }
-
-    mbar_wait(bar_pv, (nblk - 1) & 1);
-    tc_fence_after();
-    float* xch = sXch + (nblk & 1) * 256;
-    xch[half * 128 + row] = l0 + l1;
-    named_bar_sync(1, 256);
-    const float total = xch[row] + xch[128 + row];
-    const float inv = 1.0f / total;
-    uint32_t r[32];
-    tmem_ld_32x32b_x32(t_row + T_O + half * 32, r);
-    tmem_ld_wait();
-    uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(row_base + q0 + row)) * kHidden + h * 64 + half * 32);
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      uint32_t w[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        w[i] = pack_bf16x2(__uint_as_float(r[g * 8 + 2 * i]) * inv, __uint_as_float(r[g * 8 + 2 * i + 1]) * inv);
-      dst[g] = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-    if (lse_out && half == 0)
-      lse_out[(static_cast<int64_t>(b) * kHeads + h) * S + q0 + row] = (m2 + log2f(total)) * kLn2;
   }
 
   tc_fence_before();
@@ -275,8 +325,10 @@ extern "C" int stk_attn_fwd(int device, void* stream, const void* qkv, const flo
     STK_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     configured[device & 63] = true;
   }
-  attn_fwd_kernel<<<dim3(S / 128, kHeads, B), ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(
-      map, key_bias, S, static_cast<__nv_bfloat16*>(out), lse);
+  const int num_items = (S / 128) * kHeads * B;
+  const int grid = num_items < 2 * num_sms(device) ? num_items : 2 * num_sms(device);
+  attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(
+      map, key_bias, S, num_items, static_cast<__nv_bfloat16*>(out), lse);
   STK_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return STK_OK;
