@@ -8,17 +8,19 @@
 // Forward, one CTA per (128-query tile, head, batch element), 288 threads, TWO CTAs per SM
 // (~100 KB shared memory, 256 TMEM columns each) so that one CTA's tensor-core phases overlap the
 // other CTA's softmax phases:
-//   warp 8      TMA: Q once, K_j / V_j key blocks of 128 double-buffered, straight out of the fused QKV
-//               activation [B*S, 2304] (128B-swizzled boxes); single-thread tcgen05.mma issue:
-//               S_j = Q K_j^T -> TMEM cols [0,128), O += P_j V_j -> TMEM cols [128,192)
+//   warp 8      TMA: Q, then K_j / V_j key blocks of 128 through a 3-deep / 2-deep ring, straight out of
+//               the fused QKV activation [B*S, 2304] (128B-swizzled boxes); single-thread
+//               tcgen05.mma issue: S_j = Q K_j^T -> TMEM cols [0,128) (A, B from shared memory),
+//               O += P_j V_j -> TMEM cols [192,256) with the A operand P_j read FROM TENSOR MEMORY
 //   warps 0-7   online softmax in the log2 domain, two threads per query row (64 key columns each):
-//               ONE tcgen05.ld pass over S_j, block max exchanged through shared memory, P_j written as
-//               bf16 into the K-major 128B-swizzled UMMA layout (first half over the dead K_j tile),
-//               fp32 running sum; the running max is only advanced — and the O accumulator rescaled
-//               in TMEM (tcgen05.ld/st) — when it grows by more than 8 in log2 units ("lazy
+//               ONE tcgen05.ld pass over S_j, block max exchanged through shared memory, P_j packed to
+//               bf16 and written with one tcgen05.st per thread into TMEM cols [128,192) (no shared
+//               memory round trip), fp32 running sum; the running max is only advanced — and the O
+//               accumulator rescaled in TMEM — when it grows by more than 8 in log2 units ("lazy
 //               rescale": P stays <= 256, exact after the final 1/sum normalisation).
 // No S x S tensor ever goes to HBM.  Row log-sum-exp can be saved for the backward pass.
 #include <atomic>
+#include <stdlib.h>
 
 #include "stk_common.cuh"
 #include "stk_host.h"
@@ -31,46 +33,50 @@ constexpr int ATT_THREADS = 288;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
-// sQ 16K | sK 2x16K | sV 16K | sP 32K | bias 2x2K | max/sum exchange 2K | barriers
+// sQ 16K | sK 3x16K | sV 2x16K | bias 2x2K | max/sum exchange 2K | barriers
+constexpr int ATT_KSTAGES = 3, ATT_VSTAGES = 2;
 constexpr int ATT_SMEM = 16384 * 6 + 4096 + 2048 + 128;
 
 // Persistent: grid = 2 CTAs per SM; every CTA walks work items (q-tile, head, batch) with the q-tile
 // index fastest, so CTAs that run together share K/V in L2, and the loads of the next item's
 // Q / K_0 / K_1 are issued while the current item's last key block is still in its softmax.
+// DBG is a bring-up bit mask (env STK_ATTN_DEBUG; 0 in production) used to attribute time to hardware
+// units: 1 skip exp2 (MUFU), 2 skip the TMEM score loads, 4 skip the P stores, 8 skip fence.proxy.async,
+// 16 one mbarrier arrival per warp instead of per thread, 32 skip the block-max exchange barrier.
+template <int DBG>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __restrict__ key_bias, int S, int num_items,
                 __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + 16384;        // [2][128 keys][128 B]
-  uint8_t* sV = smem + 49152;        // [128 keys][128 B]
-  uint8_t* sP = smem + 65536;        // [2 chunks of 64 keys][128 rows][128 B]
+  uint8_t* sK = smem + 16384;        // [3][128 keys][128 B]
+  uint8_t* sV = smem + 65536;        // [2][128 keys][128 B]
   float* sBias = reinterpret_cast<float*>(smem + 98304);   // [2 item parity][512] key bias * log2e (clamped finite)
   float* sXch = sBias + 1024;        // [2 parity][2 halves][128 rows] block-max exchange (also final sums)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sXch + 512);
   uint64_t* bar_q = bars;
-  uint64_t* bar_k = bars + 1;     // [2]
-  uint64_t* bar_v = bars + 3;
-  uint64_t* bar_s = bars + 4;     // S_j is in TMEM
-  uint64_t* bar_sread = bars + 5; // every softmax thread holds S_j in registers: TMEM columns + K buffer free
-  uint64_t* bar_p = bars + 6;     // P_j is in shared memory (and O has been rescaled if needed)
-  uint64_t* bar_pv = bars + 7;    // O += P_j V_j has completed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bar_k = bars + 1;     // [3]
+  uint64_t* bar_v = bars + 4;     // [2]
+  uint64_t* bar_s = bars + 6;     // S_j is in TMEM
+  uint64_t* bar_sread = bars + 7; // every softmax thread holds S_j in registers: TMEM columns + K buffer free
+  uint64_t* bar_p = bars + 8;     // P_j is in tensor memory (and O has been rescaled if needed)
+  uint64_t* bar_pv = bars + 9;    // O += P_j V_j has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = S >> 7;          // key blocks per item == q-tiles per (head, batch)
-  constexpr uint32_t T_S = 0, T_O = 128;
+  constexpr uint32_t T_S = 0, T_P = 128, T_O = 192;
 
   if (warp == 8) {
     if (lane == 0) {
       if ((smem_u32(smem) & 1023u) != 0) { printf("stk attn: smem base not 1024-aligned\n"); __trap(); }
       tma_prefetch_desc(&map_qkv);
       mbar_init(bar_q, 1);
-      mbar_init(bar_k, 1); mbar_init(bar_k + 1, 1);
-      mbar_init(bar_v, 1);
+      for (int i = 0; i < ATT_KSTAGES; ++i) mbar_init(bar_k + i, 1);
+      for (int i = 0; i < ATT_VSTAGES; ++i) mbar_init(bar_v + i, 1);
       mbar_init(bar_s, 1);
-      mbar_init(bar_sread, 256);
-      mbar_init(bar_p, 256);
+      mbar_init(bar_sread, (DBG & 16) ? 8 : 256);
+      mbar_init(bar_p, (DBG & 16) ? 8 : 256);
       mbar_init(bar_pv, 1);
       fence_barrier_init();
     }
@@ -87,92 +93,72 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
       const uint64_t q_desc = umma_smem_desc(smem_u32(sQ), 16, 1024);
-      // running use counters -> mbarrier parities
-      uint32_t n_q = 0, n_k[2] = {0, 0}, n_v = 0, n_sread = 0, n_p = 0, n_pv = 0;
-      uint32_t kload = 0;   // total K blocks loaded so far (buffer = kload & 1)
-      auto coords = [&](int item, int& hh, int& rb, int& qq) {
+      // Flat stream of key blocks over all of this CTA's items: block g = (item index i, key block j).
+      // K_g goes to ring slot g % 3, V_g to slot g % 2; a slot's mbarrier parity is (g / stages) & 1.
+      const int my_items = (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+      const int total = my_items * nblk;
+      auto coords = [&](int g, int& hh, int& rb, int& qq, int& j) {
+        const int item = static_cast<int>(blockIdx.x) + (g / nblk) * static_cast<int>(gridDim.x);
+        j = g % nblk;
         const int qt = item % nblk, rest = item / nblk;
         hh = rest % kHeads;
         rb = (rest / kHeads) * S;
         qq = qt * 128;
       };
-      auto load_q = [&](int item) {
-        int hh, rb, qq; coords(item, hh, rb, qq);
+      auto load_q = [&](int g) {
+        int hh, rb, qq, j; coords(g, hh, rb, qq, j);
         mbar_arrive_expect_tx(bar_q, 16384);
         tma_load_2d(&map_qkv, bar_q, sQ, hh * 64, rb + qq);
       };
-      auto load_k = [&](int item, int j) {
-        int hh, rb, qq; coords(item, hh, rb, qq);
-        const int bf = kload & 1;
-        mbar_arrive_expect_tx(bar_k + bf, 16384);
-        tma_load_2d(&map_qkv, bar_k + bf, sK + bf * 16384, 768 + hh * 64, rb + j * 128);
-        ++kload;
+      auto load_k = [&](int g) {
+        if (g >= total) return;
+        int hh, rb, qq, j; coords(g, hh, rb, qq, j);
+        const int sl = g % ATT_KSTAGES;
+        mbar_arrive_expect_tx(bar_k + sl, 16384);
+        tma_load_2d(&map_qkv, bar_k + sl, sK + sl * 16384, 768 + hh * 64, rb + j * 128);
       };
-      auto load_v = [&](int item, int j) {
-        int hh, rb, qq; coords(item, hh, rb, qq);
-        mbar_arrive_expect_tx(bar_v, 16384);
-        tma_load_2d(&map_qkv, bar_v, sV, 1536 + hh * 64, rb + j * 128);
+      auto load_v = [&](int g) {
+        if (g >= total) return;
+        int hh, rb, qq, j; coords(g, hh, rb, qq, j);
+        const int sl = g % ATT_VSTAGES;
+        mbar_arrive_expect_tx(bar_v + sl, 16384);
+        tma_load_2d(&map_qkv, bar_v + sl, sV + sl * 16384, 1536 + hh * 64, rb + j * 128);
       };
-      uint32_t kuse = 0;    // total K blocks consumed by score MMAs so far
-      auto issue_scores = [&]() {
-        const int bf = kuse & 1;
-        mbar_wait(bar_k + bf, n_k[bf] & 1);
-        ++n_k[bf];
+      uint32_t n_q = 0;
+      auto issue_scores = [&](int g) {   // S_g = Q K_g^T ; the first block of an item waits for its Q tile
+        if (g % nblk == 0) { mbar_wait(bar_q, n_q & 1); ++n_q; }
+        const int sl = g % ATT_KSTAGES;
+        mbar_wait(bar_k + sl, (g / ATT_KSTAGES) & 1);
         tc_fence_after();
-        const uint64_t k_desc = umma_smem_desc(smem_u32(sK + bf * 16384), 16, 1024);
+        const uint64_t k_desc = umma_smem_desc(smem_u32(sK + sl * 16384), 16, 1024);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + T_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k > 0);
         umma_commit(bar_s);
-        ++kuse;
       };
 
-      int item = blockIdx.x;
-      if (item < num_items) {
-        load_q(item);
-        load_k(item, 0);
-        if (nblk > 1) load_k(item, 1);
-        load_v(item, 0);
-        mbar_wait(bar_q, n_q & 1); ++n_q;
-        issue_scores();
+      if (total > 0) {
+        load_q(0);
+        for (int g = 0; g < ATT_KSTAGES; ++g) load_k(g);
+        for (int g = 0; g < ATT_VSTAGES; ++g) load_v(g);
+        issue_scores(0);
       }
-      for (; item < num_items; item += gridDim.x) {
-        const int next = item + gridDim.x;
-        for (int j = 0; j < nblk; ++j) {
-          mbar_wait(bar_sread, n_sread & 1); ++n_sread;   // S_j is in registers: S columns + its K buffer are free
-          tc_fence_after();
-          if (j + 2 < nblk) {
-            load_k(item, j + 2);
-          } else if (next < num_items) {   // tail of this item: start fetching the next item's Q / K
-            if (j + 1 == nblk) {           // last block: every score MMA of this item is done -> Q is free too
-              load_q(next);
-              load_k(next, (nblk > 1) ? 1 : 0);
-            } else {                       // j + 2 == nblk: this buffer will hold the next item's K_0
-              load_k(next, 0);
-            }
-          }
-          if (j + 1 < nblk) {
-            issue_scores();                // next scores run on the tensor core while softmax j is still busy
-          } else if (next < num_items) {
-            mbar_wait(bar_q, n_q & 1); ++n_q;
-            issue_scores();                // first scores of the next item
-          }
-          mbar_wait(bar_p, n_p & 1); ++n_p;              // P_j is in smem, O rescaled if needed
-          mbar_wait(bar_v, n_v & 1); ++n_v;
-          tc_fence_after();
+      for (int g = 0; g < total; ++g) {
+        mbar_wait(bar_sread, g & 1);         // S_g sits in registers: the S columns and K slot g % 3 are free
+        tc_fence_after();
+        load_k(g + ATT_KSTAGES);
+        if ((g + 1) % nblk == 0 && g + 1 < total) load_q(g + 1);   // last block of an item: Q is free as well
+        if (g + 1 < total) issue_scores(g + 1);                      // runs while softmax g is still busy
+        mbar_wait(bar_p, g & 1);             // P_g is in tensor memory, O rescaled if needed
+        mbar_wait(bar_v + (g % ATT_VSTAGES), (g / ATT_VSTAGES) & 1);
+        tc_fence_after();
+        const uint64_t v_desc = umma_smem_desc(smem_u32(sV + (g % ATT_VSTAGES) * 16384), 8192, 1024);
 #pragma unroll
-          for (int kb = 0; kb < 2; ++kb) {
-            const uint64_t p_desc = umma_smem_desc(smem_u32(sP + kb * 16384), 16, 1024);
-            const uint64_t v_desc = umma_smem_desc(smem_u32(sV + kb * 8192), 8192, 1024);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base + T_O, p_desc + 2 * k, v_desc + k * 128, idesc_o, (j | kb | k) > 0);
-          }
-          umma_commit(bar_pv);
-          if (j + 1 < nblk || next < num_items) {   // V is single-buffered: refill once P_j V_j has consumed it
-            mbar_wait(bar_pv, n_pv & 1);
-            if (j + 1 < nblk) load_v(item, j + 1); else load_v(next, 0);
-          }
-          ++n_pv;
+        for (int k = 0; k < 8; ++k)          // 8 x (K = 16 keys): A = P columns [8k, 8k+8), B = V rows [16k, 16k+16)
+          umma_bf16_ts(tmem_base + T_O, tmem_base + T_P + 8 * k, v_desc + k * 128, idesc_o, ((g % nblk) | k) > 0);
+        umma_commit(bar_pv);
+        if (g + ATT_VSTAGES < total) {       // refill this V slot once P_g V_g has consumed it
+          mbar_wait(bar_pv, g & 1);
+          load_v(g + ATT_VSTAGES);
         }
       }
     }
@@ -183,7 +169,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
     const int row = q * 32 + lane;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float k1 = 0.125f * kLog2e;      // 1/sqrt(64) (HF:156) folded with log2(e)
-    uint32_t n_s = 0, n_pv = 0, n_x = 0, it = 0;
+    uint32_t n_blk = 0, n_x = 0, it = 0;   // n_blk = flat key-block counter (mbarrier parities)
 
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       const int qt = item % nblk, rest = item / nblk;
@@ -201,44 +187,43 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
       float l0 = 0.f, l1 = 0.f;            // running sums of exp2(x2 - m2) over this thread's columns
 
       for (int j = 0; j < nblk; ++j) {
-        mbar_wait(bar_s, n_s & 1); ++n_s;
+        mbar_wait(bar_s, n_blk & 1);
         tc_fence_after();
-        float x[64];
-        {
-          uint32_t r0[32], r1[32];
+        // The raw scores stay in registers as loaded (r0 | r1 = this thread's 64 columns); the biased,
+        // scaled score x2 = s * k1 + bias2 is recomputed in the exp pass instead of being kept, which
+        // halves the live register set (2 CTAs/SM leave ~96 registers per thread).
+        uint32_t r0[32], r1[32];
+        if (DBG & 2) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) { r0[c] = lane + c; r1[c] = row + c; }
+        } else {
           tmem_ld_32x32b_x32(t_row + T_S + half * 64, r0);
           tmem_ld_32x32b_x32(t_row + T_S + half * 64 + 32, r1);
           tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive(bar_sread);
-          const float4* bz = reinterpret_cast<const float4*>(bias_it + j * 128 + half * 64);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 b0 = bz[c], b1 = bz[8 + c];
-            x[4 * c] = fmaf(__uint_as_float(r0[4 * c]), k1, b0.x);
-            x[4 * c + 1] = fmaf(__uint_as_float(r0[4 * c + 1]), k1, b0.y);
-            x[4 * c + 2] = fmaf(__uint_as_float(r0[4 * c + 2]), k1, b0.z);
-            x[4 * c + 3] = fmaf(__uint_as_float(r0[4 * c + 3]), k1, b0.w);
-            x[32 + 4 * c] = fmaf(__uint_as_float(r1[4 * c]), k1, b1.x);
-            x[32 + 4 * c + 1] = fmaf(__uint_as_float(r1[4 * c + 1]), k1, b1.y);
-            x[32 + 4 * c + 2] = fmaf(__uint_as_float(r1[4 * c + 2]), k1, b1.z);
-            x[32 + 4 * c + 3] = fmaf(__uint_as_float(r1[4 * c + 3]), k1, b1.w);
-          }
         }
-        float mx[4] = {x[0], x[1], x[2], x[3]};   // four independent chains instead of one of length 64
+        tc_fence_before();
+        if (DBG & 16) { __syncwarp(); if (lane == 0) mbar_arrive(bar_sread); } else mbar_arrive(bar_sread);
+        const float4* bz = reinterpret_cast<const float4*>(bias_it + j * 128 + half * 64);
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
 #pragma unroll
-        for (int c = 4; c < 64; c += 4) {
-          mx[0] = fmaxf(mx[0], x[c]); mx[1] = fmaxf(mx[1], x[c + 1]);
-          mx[2] = fmaxf(mx[2], x[c + 2]); mx[3] = fmaxf(mx[3], x[c + 3]);
+        for (int c = 0; c < 8; ++c) {
+          const float4 b0 = bz[c], b1 = bz[8 + c];
+          mx[0] = fmaxf(mx[0], fmaxf(fmaf(__uint_as_float(r0[4 * c]), k1, b0.x), fmaf(__uint_as_float(r1[4 * c]), k1, b1.x)));
+          mx[1] = fmaxf(mx[1], fmaxf(fmaf(__uint_as_float(r0[4 * c + 1]), k1, b0.y), fmaf(__uint_as_float(r1[4 * c + 1]), k1, b1.y)));
+          mx[2] = fmaxf(mx[2], fmaxf(fmaf(__uint_as_float(r0[4 * c + 2]), k1, b0.z), fmaf(__uint_as_float(r1[4 * c + 2]), k1, b1.z)));
+          mx[3] = fmaxf(mx[3], fmaxf(fmaf(__uint_as_float(r0[4 * c + 3]), k1, b0.w), fmaf(__uint_as_float(r1[4 * c + 3]), k1, b1.w)));
         }
         float bm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
         float* xch = sXch + (n_x & 1) * 256; ++n_x;
-        xch[half * 128 + row] = bm;
-        named_bar_sync(1, 256);
-        bm = fmaxf(xch[row], xch[128 + row]);
-        if (j > 0) {
-          // P_{j-1} V_{j-1} must be complete before O is touched and before sP is overwritten
-          mbar_wait(bar_pv, n_pv & 1); ++n_pv;
+        if (!(DBG & 32)) {
+          xch[half * 128 + row] = bm;
+          named_bar_sync(1, 256);
+          bm = fmaxf(xch[row], xch[128 + row]);
+        }
+        if (n_blk > 0) {
+          // the previous P V product (possibly the previous item's last) must be complete before O is
+          // touched and before the P columns are overwritten
+          mbar_wait(bar_pv, (n_blk - 1) & 1);
           tc_fence_after();
         }
         if (bm > m2 + kRescaleThreshold) {    // also true for j == 0 (m2 = -inf)
@@ -246,36 +231,51 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
             const float alpha = fast_exp2(m2 - bm);
             l0 *= alpha;
             l1 *= alpha;
-            uint32_t o[32];
-            tmem_ld_32x32b_x32(t_row + T_O + half * 32, o);
-            tmem_ld_wait();
+#pragma unroll 1
+            for (int c0 = 0; c0 < 32; c0 += 8) {   // 8 columns at a time keeps the register peak low
+              uint32_t o[8];
+              tmem_ld_32x32b_x8(t_row + T_O + half * 32 + c0, o);
+              tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-            tmem_st_32x32b_x32(t_row + T_O + half * 32, o);
+              for (int c = 0; c < 8; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+              tmem_st_32x32b_x8(t_row + T_O + half * 32 + c0, o);
+            }
             tmem_st_wait();
           }
           m2 = bm;
         }
-        uint8_t* prow = sP + half * 16384 + row * 128;
+        uint32_t pk[32];   // this thread's 64 probabilities as bf16 pairs = 32 TMEM columns of the A operand
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          uint32_t w[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float p0 = fast_exp2(x[g * 8 + 2 * i] - m2);
-            const float p1 = fast_exp2(x[g * 8 + 2 * i + 1] - m2);
-            l0 += p0;
-            l1 += p1;
-            w[i] = pack_bf16x2(p0, p1);
-          }
-          *reinterpret_cast<uint4*>(prow + ((g ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int g = 0; g < 8; ++g) {   // 8 columns per step
+          const float4 ba = bz[2 * g], bb = bz[2 * g + 1];
+          const uint32_t* rr = (g < 4) ? (r0 + 8 * g) : (r1 + 8 * (g - 4));
+#define fast_exp2(v) ((DBG & 1) ? (v) : fast_exp2(v))
+          const float p0 = fast_exp2(fmaf(__uint_as_float(rr[0]), k1, ba.x - m2));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(rr[1]), k1, ba.y - m2));
+          const float p2 = fast_exp2(fmaf(__uint_as_float(rr[2]), k1, ba.z - m2));
+          const float p3 = fast_exp2(fmaf(__uint_as_float(rr[3]), k1, ba.w - m2));
+          const float p4 = fast_exp2(fmaf(__uint_as_float(rr[4]), k1, bb.x - m2));
+          const float p5 = fast_exp2(fmaf(__uint_as_float(rr[5]), k1, bb.y - m2));
+          const float p6 = fast_exp2(fmaf(__uint_as_float(rr[6]), k1, bb.z - m2));
+          const float p7 = fast_exp2(fmaf(__uint_as_float(rr[7]), k1, bb.w - m2));
+#undef fast_exp2
+          l0 += (p0 + p2) + (p4 + p6);
+          l1 += (p1 + p3) + (p5 + p7);
+          pk[4 * g] = pack_bf16x2(p0, p1);
+          pk[4 * g + 1] = pack_bf16x2(p2, p3);
+          pk[4 * g + 2] = pack_bf16x2(p4, p5);
+          pk[4 * g + 3] = pack_bf16x2(p6, p7);
         }
-        fence_proxy_async_smem();   // P (generic-proxy stores) -> visible to the tensor core (async proxy)
-        tc_fence_before();          // the O rescale is ordered before the next MMA
-        mbar_arrive(bar_p);
+        if (!(DBG & 4)) {
+          tmem_st_32x32b_x32(t_row + T_P + half * 32, pk);
+          tmem_st_wait();
+        }
+        tc_fence_before();          // P store and O rescale are ordered before the next MMA
+        if (DBG & 16) { __syncwarp(); if (lane == 0) mbar_arrive(bar_p); } else mbar_arrive(bar_p);
+        ++n_blk;
       }
 
-      mbar_wait(bar_pv, n_pv & 1); ++n_pv;
+      mbar_wait(bar_pv, (n_blk - 1) & 1);
       tc_fence_after();
       float* xch = sXch + (n_x & 1) * 256; ++n_x;
       xch[half * 128 + row] = l0 + l1;
@@ -320,15 +320,31 @@ extern "C" int stk_attn_fwd(int device, void* stream, const void* qkv, const flo
   int rc = make_tmap_2d(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, 3 * kHidden, static_cast<uint64_t>(B) * S,
                         3 * kHidden * 2, 64, 128);
   if (rc) return rc;
-  static bool configured[64] = {};
-  if (!configured[device & 63]) {
-    STK_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    configured[device & 63] = true;
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("STK_ATTN_DEBUG");
+    dbg = e ? atoi(e) : 0;
   }
   const int num_items = (S / 128) * kHeads * B;
   const int grid = num_items < 2 * num_sms(device) ? num_items : 2 * num_sms(device);
-  attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(
-      map, key_bias, S, num_items, static_cast<__nv_bfloat16*>(out), lse);
+  auto go = [&](auto kern) -> int {
+    STK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    kern<<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(
+        map, key_bias, S, num_items, static_cast<__nv_bfloat16*>(out), lse);
+    return STK_OK;
+  };
+  switch (dbg) {
+    case 1: rc = go(attn_fwd_kernel<1>); break;
+    case 2: rc = go(attn_fwd_kernel<2>); break;
+    case 4: rc = go(attn_fwd_kernel<4>); break;
+    case 8: rc = go(attn_fwd_kernel<8>); break;
+    case 16: rc = go(attn_fwd_kernel<16>); break;
+    case 32: rc = go(attn_fwd_kernel<32>); break;
+    case 24: rc = go(attn_fwd_kernel<24>); break;
+    case 63: rc = go(attn_fwd_kernel<63>); break;
+    default: rc = go(attn_fwd_kernel<0>); break;
+  }
+  if (rc) return rc;
   STK_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return STK_OK;
