@@ -124,16 +124,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a pipeline bug must never hang the GPU box.  After ~4 s the kernel traps
-// (sticky launch failure reported to the host) instead of spinning forever.
+// Bounded wait: a pipeline bug must never hang the GPU box.  mbarrier.try_wait already suspends the
+// thread for a hardware-defined interval, so the loop polls it directly; the (cheap, SM-local)
+// cycle counter is only consulted every 1024 failed polls, and after ~2^33 cycles (> 4 s) the kernel
+// traps (sticky launch failure reported to the host) instead of spinning forever.
+// NOTE: %globaltimer must not be read on this path — it costs on the order of a microsecond.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = global_timer_ns();
+  uint32_t polls = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (global_timer_ns() - t0 > 4000000000ull) {
-      printf("stk: mbarrier wait timeout (block %d thread %d bar %p parity %u)\n", blockIdx.x, threadIdx.x,
-             (void*)bar, parity);
-      __trap();
+    if ((++polls & 1023u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > (1ll << 33)) {
+        printf("stk: mbarrier wait timeout (block %d thread %d bar %p parity %u)\n", blockIdx.x, threadIdx.x,
+               (void*)bar, parity);
+        __trap();
+      }
     }
   }
 }
