@@ -5,12 +5,13 @@
 // the frozen LM backbone (S = 256, no mask; stonkgs_model.py:178) and the joint encoder
 // (S = 512, additive key-padding mask; stonkgs_model.py:204-210, HF:666-672).
 //
-// Forward, one CTA per (128-query tile, head, batch element), 288 threads, TWO CTAs per SM
+// Forward, persistent CTAs over (128-query tile, head, batch element) items, 320 threads, TWO CTAs per SM
 // (~100 KB shared memory, 256 TMEM columns each) so that one CTA's tensor-core phases overlap the
 // other CTA's softmax phases:
-//   warp 8      TMA: Q, then K_j / V_j key blocks of 128 through a 3-deep / 2-deep ring, straight out of
-//               the fused QKV activation [B*S, 2304] (128B-swizzled boxes); single-thread
-//               tcgen05.mma issue: S_j = Q K_j^T -> TMEM cols [0,128) (A, B from shared memory),
+//   warp 8      TMA producer: Q, then K_j / V_j key blocks of 128 through a 3-deep / 2-deep ring, straight
+//               out of the fused QKV activation [B*S, 2304] (128B-swizzled boxes)
+//   warp 9      tcgen05.mma issuer (warp-uniform control flow, one elected lane issues):
+//               S_j = Q K_j^T -> TMEM cols [0,128) (A, B from shared memory),
 //               O += P_j V_j -> TMEM cols [192,256) with the A operand P_j read FROM TENSOR MEMORY
 //   warps 0-7   online softmax in the log2 domain, two threads per query row (64 key columns each):
 //               ONE tcgen05.ld pass over S_j, block max exchanged through shared memory, P_j packed to
@@ -29,7 +30,8 @@ namespace stk {
 
 extern std::atomic<long long> g_launches;
 
-constexpr int ATT_THREADS = 288;
+constexpr int ATT_THREADS = 320;   // 8 softmax warps + TMA warp + MMA warp
+__device__ long long g_attn_timeline[4096];   // bring-up only (DBG & 64): clock64 stamps of CTA 0
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
@@ -88,81 +90,124 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // this CTA's items: blockIdx.x, blockIdx.x + gridDim.x, ...; flat key-block index g = item_idx * nblk + j
+  const int my_items = (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int total = my_items * nblk;
+
   if (warp == 8) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
-      const uint64_t q_desc = umma_smem_desc(smem_u32(sQ), 16, 1024);
-      // Flat stream of key blocks over all of this CTA's items: block g = (item index i, key block j).
-      // K_g goes to ring slot g % 3, V_g to slot g % 2; a slot's mbarrier parity is (g / stages) & 1.
-      const int my_items = (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-      const int total = my_items * nblk;
-      auto coords = [&](int g, int& hh, int& rb, int& qq, int& j) {
-        const int item = static_cast<int>(blockIdx.x) + (g / nblk) * static_cast<int>(gridDim.x);
-        j = g % nblk;
-        const int qt = item % nblk, rest = item / nblk;
-        hh = rest % kHeads;
-        rb = (rest / kHeads) * S;
-        qq = qt * 128;
-      };
-      auto load_q = [&](int g) {
-        int hh, rb, qq, j; coords(g, hh, rb, qq, j);
+    // ================================ TMA producer ================================
+    // K_g -> ring slot g % 3 (free once S_g has been read out of TMEM: bar_sread(g - 3 + ...)),
+    // V_g -> ring slot g % 2 (free once P V of block g - 2 has completed), Q once per item (free once
+    // the item's last score block has been read).  Loads are issued in consumption order.
+    const bool leader = elect_one();
+    int item = blockIdx.x;
+    int hh = 0, rb = 0, qq = 0;
+    auto set_item = [&](int it) {
+      const int qt = it % nblk, rest = it / nblk;
+      hh = rest % kHeads;
+      rb = (rest / kHeads) * S;
+      qq = qt * 128;
+    };
+    // kq/vq: next K / V block to load; their item coordinates advance independently
+    int kg = 0, k_j = 0, k_item = item, k_hh, k_rb;
+    int vg = 0, v_j = 0, v_item = item, v_hh, v_rb;
+    set_item(item); k_hh = v_hh = hh; k_rb = v_rb = rb;
+    auto load_k = [&]() {
+      if (kg >= total) return;
+      const int sl = kg % ATT_KSTAGES;
+      if (leader) {
+        mbar_arrive_expect_tx(bar_k + sl, 16384);
+        tma_load_2d(&map_qkv, bar_k + sl, sK + sl * 16384, 768 + k_hh * 64, k_rb + k_j * 128);
+      }
+      ++kg;
+      if (++k_j == nblk) { k_j = 0; k_item += gridDim.x; if (kg < total) { set_item(k_item); k_hh = hh; k_rb = rb; } }
+    };
+    auto load_v = [&]() {
+      if (vg >= total) return;
+      const int sl = vg % ATT_VSTAGES;
+      if (leader) {
+        mbar_arrive_expect_tx(bar_v + sl, 16384);
+        tma_load_2d(&map_qkv, bar_v + sl, sV + sl * 16384, 1536 + v_hh * 64, v_rb + v_j * 128);
+      }
+      ++vg;
+      if (++v_j == nblk) { v_j = 0; v_item += gridDim.x; if (vg < total) { set_item(v_item); v_hh = hh; v_rb = rb; } }
+    };
+    auto load_q = [&](int it) {
+      set_item(it);
+      if (leader) {
         mbar_arrive_expect_tx(bar_q, 16384);
         tma_load_2d(&map_qkv, bar_q, sQ, hh * 64, rb + qq);
-      };
-      auto load_k = [&](int g) {
-        if (g >= total) return;
-        int hh, rb, qq, j; coords(g, hh, rb, qq, j);
-        const int sl = g % ATT_KSTAGES;
-        mbar_arrive_expect_tx(bar_k + sl, 16384);
-        tma_load_2d(&map_qkv, bar_k + sl, sK + sl * 16384, 768 + hh * 64, rb + j * 128);
-      };
-      auto load_v = [&](int g) {
-        if (g >= total) return;
-        int hh, rb, qq, j; coords(g, hh, rb, qq, j);
-        const int sl = g % ATT_VSTAGES;
-        mbar_arrive_expect_tx(bar_v + sl, 16384);
-        tma_load_2d(&map_qkv, bar_v + sl, sV + sl * 16384, 1536 + hh * 64, rb + j * 128);
-      };
-      uint32_t n_q = 0;
-      auto issue_scores = [&](int g) {   // S_g = Q K_g^T ; the first block of an item waits for its Q tile
-        if (g % nblk == 0) { mbar_wait(bar_q, n_q & 1); ++n_q; }
-        const int sl = g % ATT_KSTAGES;
-        mbar_wait(bar_k + sl, (g / ATT_KSTAGES) & 1);
-        tc_fence_after();
-        const uint64_t k_desc = umma_smem_desc(smem_u32(sK + sl * 16384), 16, 1024);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + T_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k > 0);
-        umma_commit(bar_s);
-      };
-
-      if (total > 0) {
-        load_q(0);
-        for (int g = 0; g < ATT_KSTAGES; ++g) load_k(g);
-        for (int g = 0; g < ATT_VSTAGES; ++g) load_v(g);
-        issue_scores(0);
       }
-      for (int g = 0; g < total; ++g) {
-        mbar_wait(bar_sread, g & 1);         // S_g sits in registers: the S columns and K slot g % 3 are free
-        tc_fence_after();
-        load_k(g + ATT_KSTAGES);
-        if ((g + 1) % nblk == 0 && g + 1 < total) load_q(g + 1);   // last block of an item: Q is free as well
-        if (g + 1 < total) issue_scores(g + 1);                      // runs while softmax g is still busy
-        mbar_wait(bar_p, g & 1);             // P_g is in tensor memory, O rescaled if needed
-        mbar_wait(bar_v + (g % ATT_VSTAGES), (g / ATT_VSTAGES) & 1);
-        tc_fence_after();
-        const uint64_t v_desc = umma_smem_desc(smem_u32(sV + (g % ATT_VSTAGES) * 16384), 8192, 1024);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)          // 8 x (K = 16 keys): A = P columns [8k, 8k+8), B = V rows [16k, 16k+16)
-          umma_bf16_ts(tmem_base + T_O, tmem_base + T_P + 8 * k, v_desc + k * 128, idesc_o, ((g % nblk) | k) > 0);
-        umma_commit(bar_pv);
-        if (g + ATT_VSTAGES < total) {       // refill this V slot once P_g V_g has consumed it
-          mbar_wait(bar_pv, g & 1);
-          load_v(g + ATT_VSTAGES);
-        }
+    };
+    if (total > 0) {
+      load_q(item);
+      for (int i = 0; i < ATT_KSTAGES; ++i) load_k();
+      for (int i = 0; i < ATT_VSTAGES; ++i) load_v();
+    }
+    int j = 0;
+    for (int g = 0; g < total; ++g) {
+      mbar_wait(bar_sread, g & 1);           // S_g has been read: K slot g % 3 is free (and Q after an item's last block)
+      load_k();
+      if (++j == nblk) {
+        j = 0;
+        item += gridDim.x;
+        if (g + 1 < total) load_q(item);
+      }
+      if (g + ATT_VSTAGES < total) {
+        mbar_wait(bar_pv, g & 1);            // P_g V_g done: V slot g % 2 is free
+        load_v();
       }
     }
     __syncwarp();
+  } else if (warp == 9) {
+    // ================================ MMA issuer ================================
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
+    const bool leader = elect_one();
+    const uint64_t q_desc = umma_smem_desc(smem_u32(sQ), 16, 1024);
+    const uint64_t k_desc0 = umma_smem_desc(smem_u32(sK), 16, 1024);
+    const uint64_t v_desc0 = umma_smem_desc(smem_u32(sV), 8192, 1024);
+    uint32_t n_q = 0;
+    int ks = 0, kph = 0;        // K ring slot / parity of the next score block
+    int sj = 0;                 // key block index within the item of the next score block
+    auto issue_scores = [&]() { // S = Q K^T for the next block; the first block of an item waits for its Q tile
+      if (sj == 0) { mbar_wait(bar_q, n_q & 1); ++n_q; }
+      mbar_wait(bar_k + ks, kph);
+      tc_fence_after();
+      if (leader) {
+        const uint64_t k_desc = k_desc0 + static_cast<uint64_t>(ks * (16384 >> 4));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + T_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k > 0);
+        umma_commit(bar_s);
+      }
+      __syncwarp();
+      if (++ks == ATT_KSTAGES) { ks = 0; kph ^= 1; }
+      if (++sj == nblk) sj = 0;
+    };
+    if (total > 0) issue_scores();
+    int vs = 0, vph = 0, pj = 0;
+    for (int g = 0; g < total; ++g) {
+      if (g + 1 < total) {
+        mbar_wait(bar_sread, g & 1);         // S_g sits in registers: the S columns are free
+        tc_fence_after();
+        issue_scores();                      // next scores run while softmax g is still busy
+      }
+      mbar_wait(bar_p, g & 1);               // P_g is in tensor memory, O rescaled if needed
+      mbar_wait(bar_v + vs, vph);
+      tc_fence_after();
+      if (leader) {
+        const uint64_t v_desc = v_desc0 + static_cast<uint64_t>(vs * (16384 >> 4));
+        // 8 x (K = 16 keys): A = P columns [8k, 8k+8), B = V rows [16k, 16k+16)
+        if (pj == 0) umma_bf16_ts(tmem_base + T_O, tmem_base + T_P, v_desc, idesc_o, 0u);
+        else umma_bf16_ts(tmem_base + T_O, tmem_base + T_P, v_desc, idesc_o, 1u);
+#pragma unroll
+        for (int k = 1; k < 8; ++k) umma_bf16_ts(tmem_base + T_O, tmem_base + T_P + 8 * k, v_desc + k * 128, idesc_o, 1u);
+        umma_commit(bar_pv);
+      }
+      __syncwarp();
+      if (++vs == ATT_VSTAGES) { vs = 0; vph ^= 1; }
+      if (++pj == nblk) pj = 0;
+    }
   } else {
     // ================================ softmax warps ================================
     const int q = warp & 3, half = warp >> 2;
@@ -187,8 +232,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
       float l0 = 0.f, l1 = 0.f;            // running sums of exp2(x2 - m2) over this thread's columns
 
       for (int j = 0; j < nblk; ++j) {
+        const bool st = (DBG & 64) && blockIdx.x == 0 && threadIdx.x == 0 && n_blk < 64;
+        if (st) g_attn_timeline[n_blk * 16 + 8] = clock64();
         mbar_wait(bar_s, n_blk & 1);
         tc_fence_after();
+        if (st) g_attn_timeline[n_blk * 16 + 9] = clock64();
         // The raw scores stay in registers as loaded (r0 | r1 = this thread's 64 columns); the biased,
         // scaled score x2 = s * k1 + bias2 is recomputed in the exp pass instead of being kept, which
         // halves the live register set (2 CTAs/SM leave ~96 registers per thread).
@@ -220,6 +268,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
           named_bar_sync(1, 256);
           bm = fmaxf(xch[row], xch[128 + row]);
         }
+        if (st) g_attn_timeline[n_blk * 16 + 10] = clock64();
         if (n_blk > 0) {
           // the previous P V product (possibly the previous item's last) must be complete before O is
           // touched and before the P columns are overwritten
@@ -270,6 +319,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
           tmem_st_32x32b_x32(t_row + T_P + half * 32, pk);
           tmem_st_wait();
         }
+        if (st) g_attn_timeline[n_blk * 16 + 11] = clock64();
         tc_fence_before();          // P store and O rescale are ordered before the next MMA
         if (DBG & 16) { __syncwarp(); if (lane == 0) mbar_arrive(bar_p); } else mbar_arrive(bar_p);
         ++n_blk;
@@ -342,6 +392,8 @@ extern "C" int stk_attn_fwd(int device, void* stream, const void* qkv, const flo
     case 32: rc = go(attn_fwd_kernel<32>); break;
     case 24: rc = go(attn_fwd_kernel<24>); break;
     case 63: rc = go(attn_fwd_kernel<63>); break;
+    case 64: rc = go(attn_fwd_kernel<64>); break;
+    case 127: rc = go(attn_fwd_kernel<127>); break;
     default: rc = go(attn_fwd_kernel<0>); break;
   }
   if (rc) return rc;
@@ -351,3 +403,8 @@ extern "C" int stk_attn_fwd(int device, void* stream, const void* qkv, const flo
 }
 
 // (backward kernel: see stk_attn_bwd.cu)
+
+// bring-up only: copy the clock64 timeline recorded by CTA 0 of the last STK_ATTN_DEBUG&64 launch
+extern "C" __attribute__((visibility("default"))) int stk_debug_attn_timeline(long long* host, int n) {
+  return cudaMemcpyFromSymbol(host, stk::g_attn_timeline, sizeof(long long) * n) == cudaSuccess ? 0 : -2;
+}
