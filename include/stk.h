@@ -171,6 +171,12 @@ int stk_gelu_bwd(int device, void* stream, const void* dy_bf16, const void* pre_
 int stk_nsp_pool_bwd(int device, void* stream, const float* pooled, const float* logits, const int64_t* labels,
                      int B, const float* scale_dev, const float* w, float* dw, float* db, void* dpre_bf16);
 
+/* Data-parallel bucket helpers (the producer / consumer kernels around the NCCL all-reduce that
+ * replaces torch DDP's Reducer, reference stonkgs_pretraining.py:147-168,215-223):
+ *   pack   = stk_cast_f32_to_bf16 on a slice of the flat gradient buffer (bf16 on the wire)
+ *   unpack = dst[i] = float(src[i]) * scale   (scale = 1 / world size: gradient mean) */
+int stk_unpack_scale(int device, void* stream, const void* src_bf16, float* dst, int64_t n, float scale);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,7 @@ _SIGNATURES = {
     "stk_ce_finalize": (c_int, [c_int, _P, _P, c_int64, _P, c_int, _P, _P]),
     "stk_nsp_head_fwd": (c_int, [c_int, _P, _P, c_int, _P, _P, _P, _P, _P]),
     "stk_gelu_bwd": (c_int, [c_int, _P, _P, _P, c_int64, _P]),
+    "stk_unpack_scale": (c_int, [c_int, _P, _P, _P, c_int64, c_float]),
     "stk_nsp_pool_bwd": (c_int, [c_int, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P]),
 }
 

@@ -209,6 +209,23 @@ __global__ void __launch_bounds__(256) nsp_pool_bwd_kernel(const float* __restri
   if (c == 0) { db[0] += s0; db[1] += s1; }
 }
 
+
+// dst[i] = float(src[i]) * scale : gradient bucket coming back from the bf16 all-reduce (mean = sum / world)
+__global__ void unpack_scale_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int64_t n,
+                                    float scale) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 8;
+  for (int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + i));
+      float4* d = reinterpret_cast<float4*>(dst + i);
+      d[0] = make_float4(bf16_lo(v.x) * scale, bf16_hi(v.x) * scale, bf16_lo(v.y) * scale, bf16_hi(v.y) * scale);
+      d[1] = make_float4(bf16_lo(v.z) * scale, bf16_hi(v.z) * scale, bf16_lo(v.w) * scale, bf16_hi(v.w) * scale);
+    } else {
+      for (int64_t j = i; j < n; ++j) dst[j] = __bfloat162float(src[j]) * scale;
+    }
+  }
+}
+
 }  // namespace stk
 
 using namespace stk;
@@ -307,5 +324,19 @@ extern "C" int stk_nsp_pool_bwd(int device, void* stream, const float* pooled, c
   STK_CHECK_CUDA(cudaSetDevice(device));
   nsp_pool_bwd_kernel<<<3, 256, 0, static_cast<cudaStream_t>(stream)>>>(pooled, logits, labels, B, scale_dev, w, dw, db,
                                                                       static_cast<__nv_bfloat16*>(dpre));
+  STK_LAUNCHED();
+}
+
+extern "C" int stk_unpack_scale(int device, void* stream, const void* src_bf16, float* dst, int64_t n, float scale) {
+  STK_REQUIRE(src_bf16 && dst && n > 0, "stk_unpack_scale: bad arguments");
+  STK_REQUIRE((reinterpret_cast<uintptr_t>(src_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+              "stk_unpack_scale: pointers must be 16-byte aligned");
+  STK_CHECK_CUDA(cudaSetDevice(device));
+  int64_t blocks = (n / 8 + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(num_sms(device)) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  unpack_scale_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src_bf16), dst, n, scale);
   STK_LAUNCHED();
 }

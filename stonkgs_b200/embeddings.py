@@ -52,10 +52,11 @@ def embed_arrays(model: STonKGsForPreTraining, input_ids: np.ndarray, attention_
 
 def get_stonkgs_embeddings(preprocessed_df: pd.DataFrame, pretrained_stonkgs_model_name: Optional[str] = None,
                            list_of_indices: Optional[List] = None, *, model: Optional[STonKGsForPreTraining] = None,
-                           batch_size: int = 256) -> pd.DataFrame:
+                           batch_size: int = 256, _embed_fn=None) -> pd.DataFrame:
     """Reference signature (stonkgs_for_embeddings.py:158-162) plus two keyword-only extras:
-    an already constructed ``model`` and the ``batch_size``."""
-    if model is None:
+    an already constructed ``model`` and the ``batch_size`` (``_embed_fn`` lets the CPU test-suite
+    exercise the sharding / gathering logic without a GPU)."""
+    if model is None and _embed_fn is None:
         if pretrained_stonkgs_model_name is not None:
             model = STonKGsForPreTraining.from_pretrained(pretrained_stonkgs_model_name)
         else:
@@ -71,8 +72,8 @@ def get_stonkgs_embeddings(preprocessed_df: pd.DataFrame, pretrained_stonkgs_mod
     world = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
     rank = torch.distributed.get_rank() if world > 1 else 0
     lo, hi = shard_bounds(len(indices), rank, world)
-    local = embed_arrays(model, ids[lo:hi], None if mask is None else mask[lo:hi],
-                         None if types is None else types[lo:hi], batch_size)
+    embed = _embed_fn if _embed_fn is not None else (lambda *a: embed_arrays(model, *a, batch_size))
+    local = embed(ids[lo:hi], None if mask is None else mask[lo:hi], None if types is None else types[lo:hi])
     if world > 1:
         gathered = [None] * world
         torch.distributed.all_gather_object(gathered, local)

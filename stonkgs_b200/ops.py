@@ -229,8 +229,14 @@ def attention_bwd(qkv, key_bias, B, S, out, dout, lse):
     dev, stream = _ctx(qkv)
     dqkv = torch.empty_like(qkv)
     ws = torch.empty(B * S * H + B * HEADS * S, dtype=torch.float32, device=qkv.device)
+    prof = _PROFILER
+    if prof is not None:
+        e0, e1 = prof.span("attn_bwd", 10.0 * B * HEADS * S * S * 64)
+        e0.record()
     check(_lib.load().stk_attn_bwd(dev, stream, _ptr(qkv), _ptr(key_bias), B, S, _ptr(out), _ptr(dout), _ptr(lse),
                                    _ptr(ws), _ptr(dqkv)), "stk_attn_bwd")
+    if prof is not None:
+        e1.record()
     return dqkv
 
 
@@ -312,3 +318,9 @@ def nsp_pool_bwd(pooled, logits, labels, scale_dev, w, dw, db) -> torch.Tensor:
     check(_lib.load().stk_nsp_pool_bwd(dev, stream, _ptr(pooled), _ptr(logits), _ptr(labels), B, _ptr(scale_dev),
                                        _ptr(w), _ptr(dw), _ptr(db), _ptr(dpre)), "stk_nsp_pool_bwd")
     return dpre
+
+
+def unpack_scale(src_bf16: torch.Tensor, dst_f32: torch.Tensor, scale: float) -> None:
+    dev, stream = _ctx(src_bf16)
+    check(_lib.load().stk_unpack_scale(dev, stream, _ptr(src_bf16), _ptr(dst_f32), src_bf16.numel(), float(scale)),
+          "stk_unpack_scale")
