@@ -105,18 +105,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int split = item % p.splits;
-        const int tile = item / p.splits;
-        const int n0 = (tile % p.n_tiles) * BN;
-        const int m0 = (tile / p.n_tiles) * BM;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(empty_bar + stage, phase ^ 1);
+    // Warp-uniform control flow (all lanes walk the loop and poll the barriers, so addresses and
+    // coordinates stay on the uniform datapath); one elected lane issues the TMA instructions.
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int split = item % p.splits;
+      const int tile = item / p.splits;
+      const int n0 = (tile % p.n_tiles) * BN;
+      const int m0 = (tile / p.n_tiles) * BM;
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(empty_bar + stage, phase ^ 1);
+        if (leader) {
           mbar_arrive_expect_tx(full_bar + stage, A_STAGE_BYTES + B_STAGE_BYTES);
           uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
           uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
@@ -133,48 +136,52 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           } else {
             tma_load_2d(&map_b, full_bar + stage, sb, k0, n0);
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
-      // K-major: 8-row groups 1024 B apart, +32 B per 16-wide k step.
-      // MN-major: 64-wide chunks 8192 B apart (LBO), 8 k-rows 1024 B apart (SBO), +2048 B per k step.
-      const uint64_t a_desc0 = umma_smem_desc(smem_u32(smem_a), A_MN ? 8192 : 16, 1024);
-      const uint64_t b_desc0 = umma_smem_desc(smem_u32(smem_b), B_MN ? 8192 : 16, 1024);
-      constexpr uint32_t a_kstep = (A_MN ? 2048 : 32) >> 4;
-      constexpr uint32_t b_kstep = (B_MN ? 2048 : 32) >> 4;
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t as_phase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int split = item % p.splits;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
-        mbar_wait(tempty_bar + as, as_phase ^ 1);  // epilogue has drained this accumulator stage
+    // Same structure: the whole warp tracks the pipeline state, one elected lane issues tcgen05.mma /
+    // tcgen05.commit, so descriptor arithmetic is uniform and no per-instruction R2UR chain forms.
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    // K-major: 8-row groups 1024 B apart, +32 B per 16-wide k step.
+    // MN-major: 64-wide chunks 8192 B apart (LBO), 8 k-rows 1024 B apart (SBO), +2048 B per k step.
+    const uint64_t a_desc0 = umma_smem_desc(smem_u32(smem_a), A_MN ? 8192 : 16, 1024);
+    const uint64_t b_desc0 = umma_smem_desc(smem_u32(smem_b), B_MN ? 8192 : 16, 1024);
+    constexpr uint32_t a_kstep = (A_MN ? 2048 : 32) >> 4;
+    constexpr uint32_t b_kstep = (B_MN ? 2048 : 32) >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t as_phase = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int split = item % p.splits;
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+      mbar_wait(tempty_bar + as, as_phase ^ 1);  // epilogue has drained this accumulator stage
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar + stage, phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(full_bar + stage, phase);
-          tc_fence_after();
+        if (leader) {
           const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((stage * A_STAGE_BYTES) >> 4);
           const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((stage * B_STAGE_BYTES) >> 4);
+          if (kb == kb0) umma_bf16(d_tmem, a_desc, b_desc, idesc, 0u);
+          else umma_bf16(d_tmem, a_desc, b_desc, idesc, 1u);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(d_tmem, a_desc + k * a_kstep, b_desc + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int k = 1; k < BK / 16; ++k) umma_bf16(d_tmem, a_desc + k * a_kstep, b_desc + k * b_kstep, idesc, 1u);
           umma_commit(empty_bar + stage);  // frees the smem slot once these MMAs have read it
           if (kb == kb1 - 1) umma_commit(tfull_bar + as);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (++as == 2) { as = 0; as_phase ^= 1; }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (++as == 2) { as = 0; as_phase ^= 1; }
     }
-    __syncwarp();
   } else {
     // ============================== epilogue warps ==============================
     const int ew = warp - 2;
