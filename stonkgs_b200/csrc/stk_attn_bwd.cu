@@ -8,7 +8,8 @@
 //     dQ = dS K                                   dK = dS^T Q
 //
 // One CTA per (128-key block j, head, batch element) loops over the query blocks i:
-//   warp 8     TMA (K_j, V_j once; Q_i, dO_i double-buffered) + single-thread tcgen05.mma issue
+//   warp 8     TMA producer (K_j, V_j once; Q_i, dO_i double-buffered)
+//   warp 9     tcgen05.mma issuer (warp-uniform control flow, one elected lane issues)
 //   warps 0-7  two threads per query row: read S and dP from TMEM, form P and dS in registers, write
 //              both as bf16 into 128B-swizzled shared tiles that serve BOTH as K-major A operand
 //              (dQ = dS K) and as MN-major A operand (dV = P^T dO, dK = dS^T Q) — no transposes.
@@ -25,7 +26,7 @@ namespace stk {
 
 extern std::atomic<long long> g_launches;
 
-constexpr int ABW_THREADS = 288;
+constexpr int ABW_THREADS = 320;   // 8 compute warps + TMA warp + MMA warp
 constexpr float kL2e = 1.4426950408889634f;
 constexpr int ABW_SMEM = 1024 + 16384 * 2 + 32768 * 4 + 512 + 128;
 
@@ -118,64 +119,88 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
   constexpr uint32_t T_S = 0, T_DP = 128, T_DV = 256, T_DK = 320, T_DQ = 384;
 
   if (warp == 8) {
-    if (lane == 0) {
+    // ================================ TMA producer ================================
+    const bool leader = elect_one();
+    if (leader) {
       mbar_arrive_expect_tx(bar_kv, 32768);
       tma_load_2d(&map_qkv, bar_kv, sK, 768 + h * 64, row_base + j * 128);
       tma_load_2d(&map_qkv, bar_kv, sV, 1536 + h * 64, row_base + j * 128);
       mbar_arrive_expect_tx(bar_q, 32768);
       tma_load_2d(&map_qkv, bar_q, sQ, h * 64, row_base);
       tma_load_2d(&map_do, bar_q, sdO, h * 64, row_base);
-      mbar_wait(bar_kv, 0);
-
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S, dP
-      constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64, 1, 1);    // dV = P^T dO, dK = dS^T Q
-      constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64, 0, 1);    // dQ = dS K
-      const uint64_t k_desc = umma_smem_desc(smem_u32(sK), 16, 1024);
-      const uint64_t v_desc = umma_smem_desc(smem_u32(sV), 16, 1024);
-      const uint64_t pT_desc = umma_smem_desc(smem_u32(sP), 16384, 1024);
-      const uint64_t dsT_desc = umma_smem_desc(smem_u32(sdS), 16384, 1024);
-
-      for (int i = 0; i < nq; ++i) {
-        const int buf = i & 1;
-        if (i + 1 < nq) {  // prefetch the next query block into the other buffer (free since bar_dq(i-1))
-          mbar_arrive_expect_tx(bar_q + (buf ^ 1), 32768);
-          tma_load_2d(&map_qkv, bar_q + (buf ^ 1), sQ + (buf ^ 1) * 16384, h * 64, row_base + (i + 1) * 128);
-          tma_load_2d(&map_do, bar_q + (buf ^ 1), sdO + (buf ^ 1) * 16384, h * 64, row_base + (i + 1) * 128);
-        }
-        mbar_wait(bar_q + buf, (i >> 1) & 1);
-        tc_fence_after();
-        const uint64_t q_desc = umma_smem_desc(smem_u32(sQ + buf * 16384), 16, 1024);
-        const uint64_t do_desc = umma_smem_desc(smem_u32(sdO + buf * 16384), 16, 1024);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + T_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k > 0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + T_DP, do_desc + 2 * k, v_desc + 2 * k, idesc_s, k > 0);
-        umma_commit(bar_s);
-
-        mbar_wait(bar_p, i & 1);
-        tc_fence_after();
-        // MN-major operands: +2048 B (16 rows of the reduction dimension) per k step
-        const uint64_t doT_desc = umma_smem_desc(smem_u32(sdO + buf * 16384), 8192, 1024);
-        const uint64_t qT_desc = umma_smem_desc(smem_u32(sQ + buf * 16384), 8192, 1024);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_bf16(tmem_base + T_DV, pT_desc + k * 128, doT_desc + k * 128, idesc_t, (i > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_bf16(tmem_base + T_DK, dsT_desc + k * 128, qT_desc + k * 128, idesc_t, (i > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t ds_desc = umma_smem_desc(smem_u32(sdS + kb * 16384), 16, 1024);
-          const uint64_t kT_desc = umma_smem_desc(smem_u32(sK + kb * 8192), 8192, 1024);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + T_DQ, ds_desc + 2 * k, kT_desc + k * 128, idesc_q, (kb | k) > 0);
-        }
-        umma_commit(bar_dq);
-        mbar_wait(bar_dq, i & 1);  // Q/dO[buf], P and dS tiles are free again
-      }
     }
     __syncwarp();
+    for (int i = 0; i + 1 < nq; ++i) {
+      // buffer (i+1)&1 was last read by the MMAs of iteration i-1
+      if (i > 0) mbar_wait(bar_dq, (i - 1) & 1);
+      const int nb = (i + 1) & 1;
+      if (leader) {
+        mbar_arrive_expect_tx(bar_q + nb, 32768);
+        tma_load_2d(&map_qkv, bar_q + nb, sQ + nb * 16384, h * 64, row_base + (i + 1) * 128);
+        tma_load_2d(&map_do, bar_q + nb, sdO + nb * 16384, h * 64, row_base + (i + 1) * 128);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 9) {
+    // ================================ MMA issuer ================================
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S, dP
+    constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64, 1, 1);    // dV = P^T dO, dK = dS^T Q
+    constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64, 0, 1);    // dQ = dS K
+    const uint64_t k_desc = umma_smem_desc(smem_u32(sK), 16, 1024);
+    const uint64_t v_desc = umma_smem_desc(smem_u32(sV), 16, 1024);
+    const uint64_t kT_desc = umma_smem_desc(smem_u32(sK), 8192, 1024);
+    const uint64_t pT_desc = umma_smem_desc(smem_u32(sP), 16384, 1024);
+    const uint64_t dsT_desc = umma_smem_desc(smem_u32(sdS), 16384, 1024);
+    const uint64_t ds_desc = umma_smem_desc(smem_u32(sdS), 16, 1024);
+    const uint64_t q_desc0 = umma_smem_desc(smem_u32(sQ), 16, 1024);
+    const uint64_t do_desc0 = umma_smem_desc(smem_u32(sdO), 16, 1024);
+    const uint64_t qT_desc0 = umma_smem_desc(smem_u32(sQ), 8192, 1024);
+    const uint64_t doT_desc0 = umma_smem_desc(smem_u32(sdO), 8192, 1024);
+    mbar_wait(bar_kv, 0);
+    for (int i = 0; i < nq; ++i) {
+      const int buf = i & 1;
+      const uint64_t boff = static_cast<uint64_t>(buf * (16384 >> 4));
+      mbar_wait(bar_q + buf, (i >> 1) & 1);
+      if (i > 0) mbar_wait(bar_p, (i - 1) & 1);   // (already passed) S / dP columns were read last iteration
+      tc_fence_after();
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + T_S, q_desc0 + boff + 2 * k, k_desc + 2 * k, idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + T_DP, do_desc0 + boff + 2 * k, v_desc + 2 * k, idesc_s, k > 0);
+        umma_commit(bar_s);
+      }
+      __syncwarp();
+      mbar_wait(bar_p, i & 1);
+      tc_fence_after();
+      if (leader) {
+        // MN-major operands: +2048 B (16 rows of the reduction dimension) per k step
+        if (i == 0) {
+          umma_bf16(tmem_base + T_DV, pT_desc, doT_desc0 + boff, idesc_t, 0u);
+        } else {
+          umma_bf16(tmem_base + T_DV, pT_desc, doT_desc0 + boff, idesc_t, 1u);
+        }
+#pragma unroll
+        for (int k = 1; k < 8; ++k) umma_bf16(tmem_base + T_DV, pT_desc + k * 128, doT_desc0 + boff + k * 128, idesc_t, 1u);
+        if (i == 0) {
+          umma_bf16(tmem_base + T_DK, dsT_desc, qT_desc0 + boff, idesc_t, 0u);
+        } else {
+          umma_bf16(tmem_base + T_DK, dsT_desc, qT_desc0 + boff, idesc_t, 1u);
+        }
+#pragma unroll
+        for (int k = 1; k < 8; ++k) umma_bf16(tmem_base + T_DK, dsT_desc + k * 128, qT_desc0 + boff + k * 128, idesc_t, 1u);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + T_DQ, ds_desc + kb * (16384 >> 4) + 2 * k, kT_desc + kb * (8192 >> 4) + k * 128, idesc_q,
+                      (kb | k) > 0);
+        umma_commit(bar_dq);
+      }
+      __syncwarp();
+      mbar_wait(bar_dq, i & 1);  // Q/dO[buf], P and dS tiles are free again; dQ_i can be read
+    }
   } else {
     const int q = warp & 3, half = warp >> 2;
     const int row = q * 32 + lane;
