@@ -28,7 +28,7 @@ extern std::atomic<long long> g_launches;
 
 constexpr int ABW_THREADS = 320;   // 8 compute warps + TMA warp + MMA warp
 constexpr float kL2e = 1.4426950408889634f;
-constexpr int ABW_SMEM = 1024 + 16384 * 2 + 32768 * 4 + 512 + 128;
+constexpr int ABW_SMEM = 1024 + 16384 * 2 + 32768 * 5 + 512 + 128;
 
 // D[b,h,s] = sum_d dO * O : one warp per token row, 16-lane groups own one head
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o,
@@ -78,9 +78,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
   uint8_t* sV = smem + 16384;
   uint8_t* sQ = smem + 32768;    // [2][16 KB]
   uint8_t* sdO = smem + 65536;   // [2][16 KB]
-  uint8_t* sP = smem + 98304;    // [2 key chunks][128 q][128 B]; later the fp32 dQ staging tiles
+  uint8_t* sP = smem + 98304;    // [2 key chunks][128 q][128 B]
   uint8_t* sdS = smem + 131072;
-  float* sBias = reinterpret_cast<float*>(smem + 163840);
+  uint8_t* sStage = smem + 163840;   // fp32 dQ staging: 2 x [128 rows][32 fp32] for the TMA reduce-add
+  float* sBias = reinterpret_cast<float*>(smem + 196608);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 128);
   uint64_t* bar_kv = bars;
   uint64_t* bar_q = bars + 1;  // [2]
@@ -158,11 +159,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     const uint64_t qT_desc0 = umma_smem_desc(smem_u32(sQ), 8192, 1024);
     const uint64_t doT_desc0 = umma_smem_desc(smem_u32(sdO), 8192, 1024);
     mbar_wait(bar_kv, 0);
-    for (int i = 0; i < nq; ++i) {
-      const int buf = i & 1;
-      const uint64_t boff = static_cast<uint64_t>(buf * (16384 >> 4));
-      mbar_wait(bar_q + buf, (i >> 1) & 1);
-      if (i > 0) mbar_wait(bar_p, (i - 1) & 1);   // (already passed) S / dP columns were read last iteration
+    auto issue_scores = [&](int i) {   // S_i = Q_i K_j^T and dP_i = dO_i V_j^T into their TMEM columns
+      const uint64_t boff = static_cast<uint64_t>((i & 1) * (16384 >> 4));
+      mbar_wait(bar_q + (i & 1), (i >> 1) & 1);
       tc_fence_after();
       if (leader) {
 #pragma unroll
@@ -172,7 +171,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
         umma_commit(bar_s);
       }
       __syncwarp();
-      mbar_wait(bar_p, i & 1);
+    };
+    issue_scores(0);
+    for (int i = 0; i < nq; ++i) {
+      const uint64_t boff = static_cast<uint64_t>((i & 1) * (16384 >> 4));
+      mbar_wait(bar_p, i & 1);           // P_i, dS_i are in smem; S_i / dP_i columns have been read
       tc_fence_after();
       if (leader) {
         // MN-major operands: +2048 B (16 rows of the reduction dimension) per k step
@@ -199,7 +202,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
         umma_commit(bar_dq);
       }
       __syncwarp();
-      mbar_wait(bar_dq, i & 1);  // Q/dO[buf], P and dS tiles are free again; dQ_i can be read
+      // the next pair's scores queue right behind: they run while the compute warps drain dQ_i
+      if (i + 1 < nq) issue_scores(i + 1);
     }
   } else {
     const int q = warp & 3, half = warp >> 2;
@@ -212,10 +216,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     for (int i = 0; i < nq; ++i) {
       const float row_lse = __ldg(lse + stat_base + i * 128 + row);
       const float row_D = __ldg(Dws + stat_base + i * 128 + row);
-      if (i > 0) {  // the dQ reduce-add of the previous iteration has finished reading the staging tiles
-        if (issuer) tma_wait_group_read<0>();
-        named_bar_sync(1, 256);
-      }
       mbar_wait(bar_s, i & 1);
       tc_fence_after();
       float p[64];
@@ -265,11 +265,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
 
       mbar_wait(bar_dq, i & 1);
       tc_fence_after();
-      {  // dQ_i partial: my 32 fp32 columns -> swizzled staging tile (overlays P) -> TMA reduce-add
+      {  // dQ_i partial: my 32 fp32 columns -> swizzled staging tile -> TMA reduce-add
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_row + T_DQ + half * 32, r);
         tmem_ld_wait();
-        uint8_t* srow = sP + half * 16384 + row * 128;
+        if (i > 0) {  // the reduce-add of the previous pair has finished reading the staging tiles
+          if (issuer) tma_wait_group_read<0>();
+          named_bar_sync(1, 256);
+        }
+        uint8_t* srow = sStage + half * 16384 + row * 128;
 #pragma unroll
         for (int c = 0; c < 8; ++c)
           *reinterpret_cast<uint4*>(srow + ((c ^ (row & 7)) << 4)) = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
@@ -277,8 +281,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
         tc_fence_before();
         named_bar_sync(1, 256);
         if (issuer) {
-          tma_reduce_add_2d(&map_dq, sP, h * 64, row_base + i * 128);
-          tma_reduce_add_2d(&map_dq, sP + 16384, h * 64 + 32, row_base + i * 128);
+          tma_reduce_add_2d(&map_dq, sStage, h * 64, row_base + i * 128);
+          tma_reduce_add_2d(&map_dq, sStage + 16384, h * 64 + 32, row_base + i * 128);
           tma_commit_group();
         }
       }
