@@ -42,11 +42,13 @@ struct GemmParams {
 // ------------------------------------------------------------------------------------------------
 // Write this thread's 128 B of row data into the swizzled staging tile, then have one thread of the
 // 128-thread group issue the TMA store (or reduce-add) of the [128 x 128B] box at (c0, c1).
-template <bool kReduceAdd>
+template <bool kReduceAdd, bool kAcquired = false>
 __device__ __forceinline__ void stage_and_store(const CUtensorMap* map, uint8_t* buf, int row, const uint4 (&data)[8],
                                                 int c0, int c1, bool store_thread, uint32_t bar_id) {
-  if (store_thread) tma_wait_group_read<0>();  // previous store out of this buffer has been read
-  named_bar_sync(bar_id, 128);
+  if (!kAcquired) {
+    if (store_thread) tma_wait_group_read<0>();  // previous store out of this buffer has been read
+    named_bar_sync(bar_id, 128);
+  }
   uint8_t* rowp = buf + row * 128;
 #pragma unroll
   for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(rowp + ((c ^ (row & 7)) << 4)) = data[c];
@@ -207,16 +209,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       // Residual / saved pre-activation rows do not depend on the accumulator: fetch both 64-column
       // chunks of this thread's row now so the global-load latency hides behind the MMA of this tile.
       constexpr bool kPrefetchExtra = EPI == STK_EPI_BIAS_RESID || EPI == STK_EPI_DGELU;
+      // COALESCED: thread t of the 128-thread group fetches 16-byte piece (t + 128 i) of the
+      // [128 rows x 128 B] residual tile (8 consecutive threads = one full 128-byte row segment); the
+      // pieces are transposed to the thread-per-row accumulator layout through the staging tile later.
       uint4 ex_pre[2][8];
+      const int gt = (ew & 3) * 32 + lane;   // thread index within the epilogue group
       if (kPrefetchExtra) {
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
           const int ncp = n0 + g * 128 + ch * 64;
-          const bool okp = m_ok && ncp + 64 <= p.N;
-          const uint4* pp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.resid) +
-                                                           static_cast<int64_t>(m) * e.ldr + ncp);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) ex_pre[ch][c] = okp ? __ldg(pp + c) : make_uint4(0, 0, 0, 0);
+          for (int i = 0; i < 8; ++i) {
+            const int idx = gt + 128 * i;
+            const int rr = idx >> 3, cc = idx & 7;
+            const bool okp = (m0 + rr) < p.M && ncp + 64 <= p.N;
+            const uint4* pp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.resid) +
+                                                             static_cast<int64_t>(m0 + rr) * e.ldr + ncp) + cc;
+            ex_pre[ch][i] = okp ? __ldg(pp) : make_uint4(0, 0, 0, 0);
+          }
         }
       }
       mbar_wait(tfull_bar + as, as_phase);
@@ -302,6 +312,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                                   EPI == STK_EPI_BIAS_GELU_SAVE || EPI == STK_EPI_BIAS_RESID;
         constexpr bool kHasExtra = EPI == STK_EPI_BIAS_RESID || EPI == STK_EPI_DGELU;
         const bool bias_vec = kHasBias && e.bias != nullptr && nc + 64 <= p.N;
+        if (kHasExtra) {
+          // acquire the staging tile, drop the coalesced residual pieces into it (swizzled), then every
+          // thread picks up its own row below; the result overwrites the same 16-byte slots
+          if (store_thread) tma_wait_group_read<0>();
+          named_bar_sync(bar_id, 128);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int idx = gt + 128 * i;
+            const int rr = idx >> 3, cc = idx & 7;
+            *reinterpret_cast<uint4*>(buf + rr * 128 + ((cc ^ (rr & 7)) << 4)) = ex_pre[chunk][i];
+          }
+          named_bar_sync(bar_id, 128);
+        }
         uint4 data[8];
         uint4 data2[8];
 #pragma unroll
@@ -321,7 +344,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             }
           }
           uint4 ex4 = make_uint4(0, 0, 0, 0);
-          if (kHasExtra) ex4 = ex_pre[chunk][c];
+          if (kHasExtra) ex4 = *reinterpret_cast<const uint4*>(buf + row * 128 + ((c ^ (row & 7)) << 4));
           const uint32_t ex[4] = {ex4.x, ex4.y, ex4.z, ex4.w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -360,7 +383,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           data[c] = make_uint4(w[0], w[1], w[2], w[3]);
           if (EPI == STK_EPI_BIAS_GELU_SAVE) data2[c] = make_uint4(w2[0], w2[1], w2[2], w2[3]);
         }
-        stage_and_store<false>(&map_c, buf, row, data, nc, m0, store_thread, bar_id);
+        stage_and_store<false, kHasExtra>(&map_c, buf, row, data, nc, m0, store_thread, bar_id);
         if (EPI == STK_EPI_BIAS_GELU_SAVE)
           stage_and_store<false>(&map_c2, buf, row, data2, nc, m0, store_thread, bar_id);
       }
