@@ -217,11 +217,15 @@ def main():
     train = args.workload == "pretrain"
     B = args.batch or (TRAIN_BATCH if train else BATCH)
     model = build_model(dev, args.layers)
+    opt = None
     if train:
         model.train()  # the compute path has no dropout (reference parity is defined in eval)
         if world > 1:
             from stonkgs_b200.dp import DataParallel
             DataParallel(model, dist.group.WORLD)
+        from stonkgs_b200.optim import FusedAdamW
+        # HF Trainer defaults of the reference driver: AdamW lr 1e-4, wd 0, max_grad_norm 1.0
+        opt = FusedAdamW(model, lr=1e-4, weight_decay=0.0, max_grad_norm=1.0)
     # distinct batches per step so that no step re-reads the previous step's inputs from L2
     n_batches = 4
     host = [synthetic.make_batch(B, N_KG, seed=100 + rank * 17 + i, with_labels=train) for i in range(n_batches)]
@@ -233,18 +237,20 @@ def main():
     def step_resident(i):
         b = resident[i % n_batches]
         if train:
-            model.zero_grad(set_to_none=True)
+            opt.zero_grad()
             loss = model(**b)[0]
             loss.backward()
+            opt.step()
             return loss
         return model.embed(b["input_ids"], b["attention_mask"], b["token_type_ids"])
 
     def step_e2e(i):
         b = {k: v.to(dev, non_blocking=True) for k, v in host[i % n_batches].items()}
         if train:
-            model.zero_grad(set_to_none=True)
+            opt.zero_grad()
             loss = model(**b)[0]
             loss.backward()
+            opt.step()
             loss_host.copy_(loss.detach(), non_blocking=True)
         else:
             pooled_host.copy_(model.embed(b["input_ids"], b["attention_mask"], b["token_type_ids"]), non_blocking=True)
@@ -316,7 +322,7 @@ def main():
         "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": ("STonKGs-150k-shape pretraining step (fwd+bwd, MLM/ELM/NSP losses, DP grad allreduce)"
+        "config": {"workload": ("STonKGs-150k-shape pretraining step (fwd + bwd + MLM/ELM/NSP losses + DP grad allreduce + clip + AdamW)"
                                 if train else "get_stonkgs_embeddings-style extraction, STonKGs-150k shape"),
                    "batch_per_gpu": B, "global_batch": B * world, "seq_len": "256 text + 256 KG", "layers": f"{args.layers}+{args.layers}",
                    "kg_vocab": N_KG, "parallelism": f"dp{world}" if train else f"batch-sharded x{world}, no comms",

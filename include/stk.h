@@ -177,6 +177,31 @@ int stk_nsp_pool_bwd(int device, void* stream, const float* pooled, const float*
  *   unpack = dst[i] = float(src[i]) * scale   (scale = 1 / world size: gradient mean) */
 int stk_unpack_scale(int device, void* stream, const void* src_bf16, float* dst, int64_t n, float scale);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused clip + AdamW (HF Trainer defaults reached from stonkgs_pretraining.py:171-193)
+ * ---------------------------------------------------------------------------------------------- */
+/* out[0] += sum(x^2): global gradient norm (caller zeroes out first) */
+int stk_sumsq(int device, void* stream, const float* x, int64_t n, float* out);
+
+typedef struct StkAdamSeg {
+  void* p;        /* fp32 parameter [n] (updated in place) */
+  const void* g;  /* fp32 gradient [n] */
+  void* m;        /* fp32 exp_avg [n] */
+  void* v;        /* fp32 exp_avg_sq [n] */
+  void* w16;      /* optional bf16 copy of the updated parameter [n] (GEMM operand), or NULL */
+  void* p32_copy; /* optional second fp32 destination (fused q|k|v bias vector), or NULL */
+  int64_t n;
+} StkAdamSeg;
+
+/* One multi-tensor AdamW step.  segs_dev: device array of segments; chunk_seg_dev / chunk_off_dev:
+ * per 65 536-element chunk the segment index and the element offset inside it (n_chunks blocks).
+ * sumsq_dev: device scalar with the squared global grad norm (NULL = no clipping);
+ * clip coefficient = min(1, max_grad_norm / (sqrt(*sumsq_dev) + 1e-6)) like torch clip_grad_norm_. */
+int stk_adamw_step(int device, void* stream, const StkAdamSeg* segs_dev, const int32_t* chunk_seg_dev,
+                   const int64_t* chunk_off_dev, int n_chunks, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, float bias_correction1, float bias_correction2, const float* sumsq_dev,
+                   float max_grad_norm);
+
 #ifdef __cplusplus
 }
 #endif

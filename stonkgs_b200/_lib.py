@@ -23,6 +23,11 @@ class StkError(RuntimeError):
     pass
 
 
+class AdamSeg(Structure):
+    _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("w16", c_void_p), ("p32_copy", c_void_p),
+                ("n", c_int64)]
+
+
 class GemmEpilogue(Structure):
     _fields_ = [
         ("bias", c_void_p),
@@ -63,6 +68,9 @@ _SIGNATURES = {
     "stk_nsp_head_fwd": (c_int, [c_int, _P, _P, c_int, _P, _P, _P, _P, _P]),
     "stk_gelu_bwd": (c_int, [c_int, _P, _P, _P, c_int64, _P]),
     "stk_unpack_scale": (c_int, [c_int, _P, _P, _P, c_int64, c_float]),
+    "stk_sumsq": (c_int, [c_int, _P, _P, c_int64, _P]),
+    "stk_adamw_step": (c_int, [c_int, _P, _P, _P, _P, c_int, c_float, c_float, c_float, c_float, c_float, c_float,
+                               c_float, _P, c_float]),
     "stk_nsp_pool_bwd": (c_int, [c_int, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P]),
 }
 
