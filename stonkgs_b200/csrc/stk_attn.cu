@@ -56,14 +56,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
   float* sBias = reinterpret_cast<float*>(smem + 98304);   // [2 item parity][512] key bias * log2e (clamped finite)
   float* sXch = sBias + 1024;        // [2 parity][2 halves][128 rows] block-max exchange (also final sums)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sXch + 512);
-  uint64_t* bar_q = bars;
-  uint64_t* bar_k = bars + 1;     // [3]
-  uint64_t* bar_v = bars + 4;     // [2]
+  uint64_t* bar_q = bars;         // Q tile landed
+  uint64_t* bar_k = bars + 1;     // [3] K block landed
+  uint64_t* bar_v = bars + 4;     // [2] V block landed
   uint64_t* bar_s = bars + 6;     // S_j is in TMEM
-  uint64_t* bar_sread = bars + 7; // every softmax thread holds S_j in registers: TMEM columns + K buffer free
+  uint64_t* bar_sread = bars + 7; // every softmax thread holds S_j in registers: the S columns are free
   uint64_t* bar_p = bars + 8;     // P_j is in tensor memory (and O has been rescaled if needed)
   uint64_t* bar_pv = bars + 9;    // O += P_j V_j has completed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  // ring "slot free" barriers with the TMA warp as their only waiter (tcgen05.commit arrives when the
+  // MMAs that read the slot have completed): a producer can never fall two phases behind on these
+  uint64_t* bar_kfree = bars + 10;  // [3]
+  uint64_t* bar_vfree = bars + 13;  // [2]
+  uint64_t* bar_qfree = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = S >> 7;          // key blocks per item == q-tiles per (head, batch)
@@ -74,8 +79,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
       if ((smem_u32(smem) & 1023u) != 0) { printf("stk attn: smem base not 1024-aligned\n"); __trap(); }
       tma_prefetch_desc(&map_qkv);
       mbar_init(bar_q, 1);
-      for (int i = 0; i < ATT_KSTAGES; ++i) mbar_init(bar_k + i, 1);
-      for (int i = 0; i < ATT_VSTAGES; ++i) mbar_init(bar_v + i, 1);
+      for (int i = 0; i < ATT_KSTAGES; ++i) { mbar_init(bar_k + i, 1); mbar_init(bar_kfree + i, 1); }
+      for (int i = 0; i < ATT_VSTAGES; ++i) { mbar_init(bar_v + i, 1); mbar_init(bar_vfree + i, 1); }
+      mbar_init(bar_qfree, 1);
       mbar_init(bar_s, 1);
       mbar_init(bar_sread, (DBG & 16) ? 8 : 256);
       mbar_init(bar_p, (DBG & 16) ? 8 : 256);
@@ -96,9 +102,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
 
   if (warp == 8) {
     // ================================ TMA producer ================================
-    // K_g -> ring slot g % 3 (free once S_g has been read out of TMEM: bar_sread(g - 3 + ...)),
-    // V_g -> ring slot g % 2 (free once P V of block g - 2 has completed), Q once per item (free once
-    // the item's last score block has been read).  Loads are issued in consumption order.
+    // K_g -> ring slot g % 3, V_g -> ring slot g % 2, Q once per item; a slot is refilled as soon as the
+    // MMA warp's tcgen05.commit reports that the MMAs reading it have completed.
     const bool leader = elect_one();
     int item = blockIdx.x;
     int hh = 0, rb = 0, qq = 0;
@@ -139,24 +144,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
         tma_load_2d(&map_qkv, bar_q, sQ, hh * 64, rb + qq);
       }
     };
-    if (total > 0) {
-      load_q(item);
-      for (int i = 0; i < ATT_KSTAGES; ++i) load_k();
-      for (int i = 0; i < ATT_VSTAGES; ++i) load_v();
-    }
-    int j = 0;
+    // Loads are issued in consumption order (Q_item, then K_g, V_g per key block); each waits for its
+    // ring slot to be released by the MMA warp's tcgen05.commit.
+    int j = 0, n_item = 0;
     for (int g = 0; g < total; ++g) {
-      mbar_wait(bar_sread, g & 1);           // S_g has been read: K slot g % 3 is free (and Q after an item's last block)
+      if (g == 0) { load_q(item); ++n_item; }
+      if (g >= ATT_KSTAGES) mbar_wait(bar_kfree + g % ATT_KSTAGES, ((g / ATT_KSTAGES) - 1) & 1);
       load_k();
-      if (++j == nblk) {
-        j = 0;
-        item += gridDim.x;
-        if (g + 1 < total) load_q(item);
+      if (g >= ATT_VSTAGES) mbar_wait(bar_vfree + g % ATT_VSTAGES, ((g / ATT_VSTAGES) - 1) & 1);
+      load_v();
+      if (j == 0 && g > 0) {   // first block of a later item: its K/V are already on their way, now Q
+        mbar_wait(bar_qfree, (n_item - 1) & 1);   // previous item's last score MMA has read Q
+        load_q(item);
+        ++n_item;
       }
-      if (g + ATT_VSTAGES < total) {
-        mbar_wait(bar_pv, g & 1);            // P_g V_g done: V slot g % 2 is free
-        load_v();
-      }
+      if (++j == nblk) { j = 0; item += gridDim.x; }
     }
     __syncwarp();
   } else if (warp == 9) {
@@ -181,6 +183,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + T_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k > 0);
         umma_commit(bar_s);
+        umma_commit(bar_kfree + ks);                    // K slot reusable once these MMAs have read it
+        if (sj == nblk - 1) umma_commit(bar_qfree);     // last score block of the item: Q reusable
       }
       __syncwarp();
       if (++ks == ATT_KSTAGES) { ks = 0; kph ^= 1; }
@@ -213,6 +217,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
 #pragma unroll
         for (int k = 1; k < 8; ++k) umma_bf16_ts(tmem_base + T_O, tmem_base + T_P + 8 * k, v_desc + k * 128, idesc_o, 1u);
         umma_commit(bar_pv);
+        umma_commit(bar_vfree + vs);                    // V slot reusable
       }
       __syncwarp();
       stamp(g, 5);

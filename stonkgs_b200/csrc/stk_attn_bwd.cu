@@ -88,7 +88,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
   uint64_t* bar_s = bars + 3;
   uint64_t* bar_p = bars + 4;
   uint64_t* bar_dq = bars + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* bar_qfree = bars + 6;  // [2] Q_i / dO_i buffer released (only the TMA warp waits on these)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -106,6 +107,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       mbar_init(bar_s, 1);
       mbar_init(bar_p, 256);
       mbar_init(bar_dq, 1);
+      mbar_init(bar_qfree, 1);
+      mbar_init(bar_qfree + 1, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -132,9 +135,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     }
     __syncwarp();
     for (int i = 0; i + 1 < nq; ++i) {
-      // buffer (i+1)&1 was last read by the MMAs of iteration i-1
-      if (i > 0) mbar_wait(bar_dq, (i - 1) & 1);
+      // buffer (i+1)&1 was last read by the MMAs of iteration i-1 (its (i-1)/2-th use)
       const int nb = (i + 1) & 1;
+      if (i > 0) mbar_wait(bar_qfree + nb, ((i - 1) >> 1) & 1);
       if (leader) {
         mbar_arrive_expect_tx(bar_q + nb, 32768);
         tma_load_2d(&map_qkv, bar_q + nb, sQ + nb * 16384, h * 64, row_base + (i + 1) * 128);
@@ -200,6 +203,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
             umma_bf16(tmem_base + T_DQ, ds_desc + kb * (16384 >> 4) + 2 * k, kT_desc + kb * (8192 >> 4) + k * 128, idesc_q,
                       (kb | k) > 0);
         umma_commit(bar_dq);
+        umma_commit(bar_qfree + (i & 1));   // Q_i / dO_i buffer reusable once everything above has completed
       }
       __syncwarp();
       // the next pair's scores queue right behind: they run while the compute warps drain dQ_i
