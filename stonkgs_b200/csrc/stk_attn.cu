@@ -37,7 +37,7 @@ constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 // sQ 16K | sK 3x16K | sV 2x16K | bias 2x2K | max/sum exchange 2K | barriers
 constexpr int ATT_KSTAGES = 3, ATT_VSTAGES = 2;
-constexpr int ATT_SMEM = 16384 * 6 + 4096 + 2048 + 128;
+constexpr int ATT_SMEM = 16384 * 6 + 4096 + 2048 + 256;
 
 // Persistent: grid = 2 CTAs per SM; every CTA walks work items (q-tile, head, batch) with the q-tile
 // index fastest, so CTAs that run together share K/V in L2, and the loads of the next item's
