@@ -292,24 +292,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
           mbar_wait(bar_pv, (n_blk - 1) & 1);
           tc_fence_after();
         }
-        if (bm > m2 + kRescaleThreshold) {    // also true for j == 0 (m2 = -inf)
-          if (j > 0) {
-            const float alpha = fast_exp2(m2 - bm);
-            l0 *= alpha;
-            l1 *= alpha;
+        // Lazy rescale.  The decision is per row, but tcgen05.ld / tcgen05.st are warp-collective
+        // (.sync.aligned): when ANY row of the warp must advance its max, the whole warp runs the O
+        // rescale with a per-lane factor (1.0 for rows that keep their max).
+        const bool advance = bm > m2 + kRescaleThreshold;   // always true for j == 0 (m2 = -inf)
+        if (j > 0 && __any_sync(0xffffffffu, advance)) {
+          const float alpha = advance ? fast_exp2(m2 - bm) : 1.0f;
+          l0 *= alpha;
+          l1 *= alpha;
 #pragma unroll 1
-            for (int c0 = 0; c0 < 32; c0 += 8) {   // 8 columns at a time keeps the register peak low
-              uint32_t o[8];
-              tmem_ld_32x32b_x8(t_row + T_O + half * 32 + c0, o);
-              tmem_ld_wait();
+          for (int c0 = 0; c0 < 32; c0 += 8) {   // 8 columns at a time keeps the register peak low
+            uint32_t o[8];
+            tmem_ld_32x32b_x8(t_row + T_O + half * 32 + c0, o);
+            tmem_ld_wait();
 #pragma unroll
-              for (int c = 0; c < 8; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-              tmem_st_32x32b_x8(t_row + T_O + half * 32 + c0, o);
-            }
-            tmem_st_wait();
+            for (int c = 0; c < 8; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+            tmem_st_32x32b_x8(t_row + T_O + half * 32 + c0, o);
           }
-          m2 = bm;
+          tmem_st_wait();
         }
+        if (advance) m2 = bm;
         uint32_t pk[32];   // this thread's 64 probabilities as bf16 pairs = 32 TMEM columns of the A operand
 #pragma unroll
         for (int g = 0; g < 8; ++g) {   // 8 columns per step

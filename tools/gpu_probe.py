@@ -302,6 +302,20 @@ def case_attn():
         ref, lref = _attn_ref(qkv, bias, B, S)
         res.append(_err_report(out, ref, f"attn_fwd_S{S}_mask{int(masked)}", 2e-2))
         res.append(_err_report(lse, lref, f"attn_lse_S{S}", 2e-3))
+    # large, growing scores: later key blocks dominate -> exercises the lazy O rescale in TMEM
+    B, S = 2, 512
+    qkv = _mk(B * S, 2304, "cuda", 1.0)
+    ramp = torch.linspace(0.5, 6.0, S, device="cuda").repeat(B)[:, None]
+    qkv[:, 768:1536] = (qkv[:, 768:1536].float() * ramp).bfloat16()      # keys grow with position
+    qkv[:, :768] = (qkv[:, :768].float() * 2.0).bfloat16()
+    out, lse = ops.attention(qkv, None, B, S, save_lse=True)
+    ref, lref = _attn_ref(qkv, None, B, S)
+    res.append(_err_report(out, ref, "attn_fwd_rescale_path", 3e-2))
+    res.append(_err_report(lse, lref, "attn_lse_rescale_path", 2e-2))
+    dout = _mk(B * S, 768, "cuda", 1.0)
+    dqkv = ops.attention_bwd(qkv, None, B, S, out, dout, lse)
+    gref = _attn_bwd_ref(qkv, None, B, S, dout)
+    res.append(_err_report(dqkv, gref, "attn_bwd_large_scores", 0.04 * gref.abs().max().item()))
     return res
 
 
