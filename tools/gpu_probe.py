@@ -551,7 +551,29 @@ def case_e2e_bwd():
     return res
 
 
-CASES.update({"attn_bwd": case_attn_bwd, "e2e_fwd": case_e2e_fwd, "e2e_bwd": case_e2e_bwd})
+def case_elm_head_perf():
+    """BASELINE configs[3]: ELM head alone, ~1M entity nodes, batch 128 -> 4 864 labelled rows."""
+    import torch
+    from stonkgs_b200 import training
+    N, R, H = 1_000_003, 128 * 38, 768
+    W = (torch.randn(N, H, device="cuda") * 0.05).bfloat16()
+    t = torch.randn(R, H, device="cuda").bfloat16()
+    labels = torch.randint(0, N, (R,), device="cuda", dtype=torch.int32)
+    ms_f = _time(lambda: training._ce_forward(t, W, labels), iters=5, warm=2)
+    lse, _ = training._ce_forward(t, W, labels)
+    dT = torch.zeros(R, H, dtype=torch.float32, device="cuda")
+    gW = torch.zeros(N, H, dtype=torch.float32, device="cuda")
+    scale = torch.full((1,), 1.0 / R, device="cuda")
+    ms_b = _time(lambda: training._ce_backward(t, W, labels, lse, scale, dT, gW), iters=3, warm=1)
+    fl = 2.0 * R * H * N
+    return [{"case": "elm_head_1M_fwd", "ms": ms_f, "tflops": fl / ms_f / 1e9, "ok": True},
+            {"case": "elm_head_1M_bwd", "ms": ms_b, "tflops": 3 * fl / ms_b / 1e9, "ok": True},
+            {"case": "elm_head_1M_step", "ms": ms_f + ms_b, "tflops": 4 * fl / (ms_f + ms_b) / 1e9,
+             "rows_per_s": R / (ms_f + ms_b) * 1e3, "ok": True}]
+
+
+CASES.update({"attn_bwd": case_attn_bwd, "e2e_fwd": case_e2e_fwd, "e2e_bwd": case_e2e_bwd,
+              "elm_head_perf": case_elm_head_perf})
 
 if __name__ == "__main__":
     main()
