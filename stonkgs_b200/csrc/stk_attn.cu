@@ -244,6 +244,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
         const float bz = key_bias ? __ldg(key_bias + static_cast<int64_t>(b) * S + i) * kLog2e : 0.f;
         bias_it[i] = fmaxf(bz, -3.402823466e38f);   // finfo.min * log2e overflows to -inf: keep it finite
       }
+      // which 128-key blocks hold at least one biased (masked) key: blocks without any take the short
+      // instruction path below (no bias loads / adds)
+      uint32_t blk_biased = 0;
+      if (key_bias) {
+        for (int i = lane; i < S; i += 32)
+          if (__ldg(key_bias + static_cast<int64_t>(b) * S + i) != 0.f) blk_biased |= 1u << (i >> 7);
+        blk_biased = __reduce_or_sync(0xffffffffu, blk_biased);
+      }
       named_bar_sync(1, 256);
       float m2 = -INFINITY;                // running (lazily advanced) row max, log2 domain
       float l0 = 0.f, l1 = 0.f;            // running sums of exp2(x2 - m2) over this thread's columns
@@ -269,16 +277,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
         tc_fence_before();
         if (DBG & 16) { __syncwarp(); if (lane == 0) mbar_arrive(bar_sread); } else mbar_arrive(bar_sread);
         const float4* bz = reinterpret_cast<const float4*>(bias_it + j * 128 + half * 64);
+        const bool biased = (blk_biased >> j) & 1u;   // warp-uniform
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
+        float bm;
+        if (biased) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 b0 = bz[c], b1 = bz[8 + c];
-          mx[0] = fmaxf(mx[0], fmaxf(fmaf(__uint_as_float(r0[4 * c]), k1, b0.x), fmaf(__uint_as_float(r1[4 * c]), k1, b1.x)));
-          mx[1] = fmaxf(mx[1], fmaxf(fmaf(__uint_as_float(r0[4 * c + 1]), k1, b0.y), fmaf(__uint_as_float(r1[4 * c + 1]), k1, b1.y)));
-          mx[2] = fmaxf(mx[2], fmaxf(fmaf(__uint_as_float(r0[4 * c + 2]), k1, b0.z), fmaf(__uint_as_float(r1[4 * c + 2]), k1, b1.z)));
-          mx[3] = fmaxf(mx[3], fmaxf(fmaf(__uint_as_float(r0[4 * c + 3]), k1, b0.w), fmaf(__uint_as_float(r1[4 * c + 3]), k1, b1.w)));
+          for (int c = 0; c < 8; ++c) {
+            const float4 b0 = bz[c], b1 = bz[8 + c];
+            mx[0] = fmaxf(mx[0], fmaxf(fmaf(__uint_as_float(r0[4 * c]), k1, b0.x), fmaf(__uint_as_float(r1[4 * c]), k1, b1.x)));
+            mx[1] = fmaxf(mx[1], fmaxf(fmaf(__uint_as_float(r0[4 * c + 1]), k1, b0.y), fmaf(__uint_as_float(r1[4 * c + 1]), k1, b1.y)));
+            mx[2] = fmaxf(mx[2], fmaxf(fmaf(__uint_as_float(r0[4 * c + 2]), k1, b0.z), fmaf(__uint_as_float(r1[4 * c + 2]), k1, b1.z)));
+            mx[3] = fmaxf(mx[3], fmaxf(fmaf(__uint_as_float(r0[4 * c + 3]), k1, b0.w), fmaf(__uint_as_float(r1[4 * c + 3]), k1, b1.w)));
+          }
+          bm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        } else {   // max(s * k1) = k1 * max(s): one FMNMX per element (3-input max where available)
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            mx[0] = fmaxf(mx[0], fmaxf(__uint_as_float(r0[c]), __uint_as_float(r1[c])));
+            mx[1] = fmaxf(mx[1], fmaxf(__uint_as_float(r0[c + 1]), __uint_as_float(r1[c + 1])));
+            mx[2] = fmaxf(mx[2], fmaxf(__uint_as_float(r0[c + 2]), __uint_as_float(r1[c + 2])));
+            mx[3] = fmaxf(mx[3], fmaxf(__uint_as_float(r0[c + 3]), __uint_as_float(r1[c + 3])));
+          }
+          bm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * k1;
         }
-        float bm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
         float* xch = sXch + (n_x & 1) * 256; ++n_x;
         if (!(DBG & 32)) {
           xch[half * 128 + row] = bm;
@@ -313,26 +334,46 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
         }
         if (advance) m2 = bm;
         uint32_t pk[32];   // this thread's 64 probabilities as bf16 pairs = 32 TMEM columns of the A operand
+        if (biased) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {   // 8 columns per step
-          const float4 ba = bz[2 * g], bb = bz[2 * g + 1];
-          const uint32_t* rr = (g < 4) ? (r0 + 8 * g) : (r1 + 8 * (g - 4));
-#define fast_exp2(v) ((DBG & 1) ? (v) : fast_exp2(v))
-          const float p0 = fast_exp2(fmaf(__uint_as_float(rr[0]), k1, ba.x - m2));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(rr[1]), k1, ba.y - m2));
-          const float p2 = fast_exp2(fmaf(__uint_as_float(rr[2]), k1, ba.z - m2));
-          const float p3 = fast_exp2(fmaf(__uint_as_float(rr[3]), k1, ba.w - m2));
-          const float p4 = fast_exp2(fmaf(__uint_as_float(rr[4]), k1, bb.x - m2));
-          const float p5 = fast_exp2(fmaf(__uint_as_float(rr[5]), k1, bb.y - m2));
-          const float p6 = fast_exp2(fmaf(__uint_as_float(rr[6]), k1, bb.z - m2));
-          const float p7 = fast_exp2(fmaf(__uint_as_float(rr[7]), k1, bb.w - m2));
-#undef fast_exp2
-          l0 += (p0 + p2) + (p4 + p6);
-          l1 += (p1 + p3) + (p5 + p7);
-          pk[4 * g] = pack_bf16x2(p0, p1);
-          pk[4 * g + 1] = pack_bf16x2(p2, p3);
-          pk[4 * g + 2] = pack_bf16x2(p4, p5);
-          pk[4 * g + 3] = pack_bf16x2(p6, p7);
+          for (int g = 0; g < 8; ++g) {   // 8 columns per step
+            const float4 ba = bz[2 * g], bb = bz[2 * g + 1];
+            const uint32_t* rr = (g < 4) ? (r0 + 8 * g) : (r1 + 8 * (g - 4));
+            const float p0 = fast_exp2(fmaf(__uint_as_float(rr[0]), k1, ba.x - m2));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(rr[1]), k1, ba.y - m2));
+            const float p2 = fast_exp2(fmaf(__uint_as_float(rr[2]), k1, ba.z - m2));
+            const float p3 = fast_exp2(fmaf(__uint_as_float(rr[3]), k1, ba.w - m2));
+            const float p4 = fast_exp2(fmaf(__uint_as_float(rr[4]), k1, bb.x - m2));
+            const float p5 = fast_exp2(fmaf(__uint_as_float(rr[5]), k1, bb.y - m2));
+            const float p6 = fast_exp2(fmaf(__uint_as_float(rr[6]), k1, bb.z - m2));
+            const float p7 = fast_exp2(fmaf(__uint_as_float(rr[7]), k1, bb.w - m2));
+            l0 += (p0 + p2) + (p4 + p6);
+            l1 += (p1 + p3) + (p5 + p7);
+            pk[4 * g] = pack_bf16x2(p0, p1);
+            pk[4 * g + 1] = pack_bf16x2(p2, p3);
+            pk[4 * g + 2] = pack_bf16x2(p4, p5);
+            pk[4 * g + 3] = pack_bf16x2(p6, p7);
+          }
+        } else {
+          const float nm2 = -m2;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {   // FFMA + MUFU.EX2 + FADD per element
+            const uint32_t* rr = (g < 4) ? (r0 + 8 * g) : (r1 + 8 * (g - 4));
+            const float p0 = fast_exp2(fmaf(__uint_as_float(rr[0]), k1, nm2));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(rr[1]), k1, nm2));
+            const float p2 = fast_exp2(fmaf(__uint_as_float(rr[2]), k1, nm2));
+            const float p3 = fast_exp2(fmaf(__uint_as_float(rr[3]), k1, nm2));
+            const float p4 = fast_exp2(fmaf(__uint_as_float(rr[4]), k1, nm2));
+            const float p5 = fast_exp2(fmaf(__uint_as_float(rr[5]), k1, nm2));
+            const float p6 = fast_exp2(fmaf(__uint_as_float(rr[6]), k1, nm2));
+            const float p7 = fast_exp2(fmaf(__uint_as_float(rr[7]), k1, nm2));
+            l0 += (p0 + p2) + (p4 + p6);
+            l1 += (p1 + p3) + (p5 + p7);
+            pk[4 * g] = pack_bf16x2(p0, p1);
+            pk[4 * g + 1] = pack_bf16x2(p2, p3);
+            pk[4 * g + 2] = pack_bf16x2(p4, p5);
+            pk[4 * g + 3] = pack_bf16x2(p6, p7);
+          }
         }
         if (!(DBG & 4)) {
           tmem_st_32x32b_x32(t_row + T_P + half * 32, pk);
