@@ -51,7 +51,7 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed regions."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -65,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -283,10 +283,10 @@ def main():
     launches0 = ops.launch_count()
     ms = timed(step_resident, args.steps)
     launches = ops.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     for i in range(2):
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline of the dominant kernel: one profiled step, CUDA events around every GEMM/attention launch
     prof = ops.LaunchProfiler()
@@ -297,18 +297,33 @@ def main():
     peaks = measured_peaks()
     total_ms = sum(a["ms"] for a in agg.values())
     gemm = {k: v for k, v in agg.items() if k.startswith("gemm")}
-    dom_name = max(agg, key=lambda k: agg[k]["ms"]) if agg else None
+    dom_name = max(gemm, key=lambda k: gemm[k]["ms"]) if gemm else None   # dominant kernel instantiation
+    dom = gemm[dom_name] if dom_name else None
     g_ms = sum(a["ms"] for a in gemm.values())
     g_fl = sum(a["work"] for a in gemm.values())
-    achieved = g_fl / g_ms / 1e9 if g_ms else None
+    achieved = dom["work"] / dom["ms"] / 1e9 if dom else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if dom_name and os.path.exists(tpath):
+        t = json.load(open(tpath)).get(dom_name)
+        if t:   # ncu-measured DRAM bytes of one captured launch, scaled to this run's average launch
+            traffic = t["dram_bytes"] * (dom["work"] / dom["launches"]) / t["flops"]
+    names = {"gemm_a0b0_epi0": "fused QKV projection", "gemm_a0b0_epi1": "FFN1 + erf-GELU epilogue",
+             "gemm_a0b0_epi3": "Wo / FFN2 + residual epilogue", "gemm_a1b1_epi6": "wgrad (split-K reduce-add)",
+             "gemm_a0b1_epi3": "dgrad + residual", "gemm_a0b1_epi5": "dgrad * GELU'"}
     roofline = {
-        "bound": "tensor", "kernel": "stk::gemm_kernel (tcgen05 GEMM, all epilogues)", "achieved": achieved,
-        "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": (achieved / peaks["bf16_sustained"]) if achieved else None,
-        "peak_source": f"{peaks['source']} cuBLAS bf16 sustained", "traffic": None,
-        "share_of_profiled_step": g_ms / total_ms if total_ms else None,
+        "bound": "tensor",
+        "kernel": f"stk::gemm_kernel<{dom_name}> ({names.get(dom_name, 'tcgen05 GEMM')})" if dom_name else None,
+        "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+        "frac": (achieved / peaks["bf16_sustained"]) if achieved else None,
+        "peak_source": f"{peaks['source']} cuBLAS bf16 sustained (kernel timed inside a long step)",
+        "traffic": traffic,
+        "algorithmic_flops_per_launch": (dom["work"] / dom["launches"]) if dom else None,
+        "launches": dom["launches"] if dom else None, "ms_per_launch": (dom["ms"] / dom["launches"]) if dom else None,
+        "share_of_profiled_step": (dom["ms"] / total_ms) if dom and total_ms else None,
+        "gemm_family": {"achieved": g_fl / g_ms / 1e9 if g_ms else None, "share_of_profiled_step": g_ms / total_ms if total_ms else None},
         "per_kernel": {k: {"ms": round(v["ms"], 3), "tflops": round(v["work"] / v["ms"] / 1e9, 1), "launches": v["launches"]}
                        for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])},
-        "dominant_single": dom_name,
     }
 
     pairs = world * B * args.steps
