@@ -5,20 +5,21 @@
 // the frozen LM backbone (S = 256, no mask; stonkgs_model.py:178) and the joint encoder
 // (S = 512, additive key-padding mask; stonkgs_model.py:204-210, HF:666-672).
 //
-// Forward, persistent CTAs over (128-query tile, head, batch element) items, 320 threads, TWO CTAs per SM
+// Forward, persistent CTAs over (128-query tile, head, batch element) items, 192 threads, TWO CTAs per SM
 // (~100 KB shared memory, 256 TMEM columns each) so that one CTA's tensor-core phases overlap the
 // other CTA's softmax phases:
-//   warp 8      TMA producer: Q, then K_j / V_j key blocks of 128 through a 3-deep / 2-deep ring, straight
+//   warp 4      TMA producer: Q, then K_j / V_j key blocks of 128 through a 3-deep / 2-deep ring, straight
 //               out of the fused QKV activation [B*S, 2304] (128B-swizzled boxes)
-//   warp 9      tcgen05.mma issuer (warp-uniform control flow, one elected lane issues):
+//   warp 5      tcgen05.mma issuer (warp-uniform control flow, one elected lane issues):
 //               S_j = Q K_j^T -> TMEM cols [0,128) (A, B from shared memory),
 //               O += P_j V_j -> TMEM cols [192,256) with the A operand P_j read FROM TENSOR MEMORY
-//   warps 0-7   online softmax in the log2 domain, two threads per query row (64 key columns each):
-//               ONE tcgen05.ld pass over S_j, block max exchanged through shared memory, P_j packed to
-//               bf16 and written with one tcgen05.st per thread into TMEM cols [128,192) (no shared
-//               memory round trip), fp32 running sum; the running max is only advanced — and the O
-//               accumulator rescaled in TMEM — when it grows by more than 8 in log2 units ("lazy
-//               rescale": P stays <= 256, exact after the final 1/sum normalisation).
+//   warps 0-3   online softmax in the log2 domain, ONE thread per query row (all 128 key columns of the
+//               block live in its registers: no cross-thread exchange, no block-wide barrier in the
+//               loop): one tcgen05.ld pass over S_j, P_j packed to bf16 and written with tcgen05.st into
+//               TMEM cols [128,192) (no shared-memory round trip), fp32 running sum; the running max is
+//               only advanced — and the O accumulator rescaled in TMEM — when it grows by more than 8
+//               in log2 units ("lazy rescale": P stays <= 256, exact after the final 1/sum).
+//               The two co-resident CTAs play the role of the two ping-pong tiles of FlashAttention-4.
 // No S x S tensor ever goes to HBM.  Row log-sum-exp can be saved for the backward pass.
 #include <atomic>
 #include <stdlib.h>
@@ -30,7 +31,7 @@ namespace stk {
 
 extern std::atomic<long long> g_launches;
 
-constexpr int ATT_THREADS = 320;   // 8 softmax warps + TMA warp + MMA warp
+constexpr int ATT_THREADS = 192;   // 4 softmax warps (one thread per query row) + TMA warp + MMA warp
 __device__ long long g_attn_timeline[4096];   // bring-up only (DBG & 64): clock64 stamps of CTA 0
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -54,7 +55,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
   uint8_t* sK = smem + 16384;        // [3][128 keys][128 B]
   uint8_t* sV = smem + 65536;        // [2][128 keys][128 B]
   float* sBias = reinterpret_cast<float*>(smem + 98304);   // [2 item parity][512] key bias * log2e (clamped finite)
-  float* sXch = sBias + 1024;        // [2 parity][2 halves][128 rows] block-max exchange (also final sums)
+  float* sXch = sBias + 1024;        // (unused scratch)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sXch + 512);
   uint64_t* bar_q = bars;         // Q tile landed
   uint64_t* bar_k = bars + 1;     // [3] K block landed
@@ -74,7 +75,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
   const int nblk = S >> 7;          // key blocks per item == q-tiles per (head, batch)
   constexpr uint32_t T_S = 0, T_P = 128, T_O = 192;
 
-  if (warp == 8) {
+  if (warp == 4) {
     if (lane == 0) {
       if ((smem_u32(smem) & 1023u) != 0) { printf("stk attn: smem base not 1024-aligned\n"); __trap(); }
       tma_prefetch_desc(&map_qkv);
@@ -83,8 +84,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
       for (int i = 0; i < ATT_VSTAGES; ++i) { mbar_init(bar_v + i, 1); mbar_init(bar_vfree + i, 1); }
       mbar_init(bar_qfree, 1);
       mbar_init(bar_s, 1);
-      mbar_init(bar_sread, (DBG & 16) ? 8 : 256);
-      mbar_init(bar_p, (DBG & 16) ? 8 : 256);
+      mbar_init(bar_sread, 128);
+      mbar_init(bar_p, 128);
       mbar_init(bar_pv, 1);
       fence_barrier_init();
     }
@@ -100,7 +101,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
   const int my_items = (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const int total = my_items * nblk;
 
-  if (warp == 8) {
+  if (warp == 4) {
     // ================================ TMA producer ================================
     // K_g -> ring slot g % 3, V_g -> ring slot g % 2, Q once per item; a slot is refilled as soon as the
     // MMA warp's tcgen05.commit reports that the MMAs reading it have completed.
@@ -161,7 +162,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
       if (++j == nblk) { j = 0; item += gridDim.x; }
     }
     __syncwarp();
-  } else if (warp == 9) {
+  } else if (warp == 5) {
     // ================================ MMA issuer ================================
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
@@ -227,20 +228,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
     }
   } else {
     // ================================ softmax warps ================================
-    const int q = warp & 3, half = warp >> 2;
-    const int row = q * 32 + lane;
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int row = warp * 32 + lane;      // warp w may touch TMEM lanes 32w .. 32w+31
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     const float k1 = 0.125f * kLog2e;      // 1/sqrt(64) (HF:156) folded with log2(e)
-    uint32_t n_blk = 0, n_x = 0, it = 0;   // n_blk = flat key-block counter (mbarrier parities)
+    uint32_t n_blk = 0, it = 0;            // n_blk = flat key-block counter (mbarrier parities)
 
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       const int qt = item % nblk, rest = item / nblk;
       const int h = rest % kHeads, b = rest / kHeads;
       const int row_base = b * S, q0 = qt * 128;
-      // key bias of this item's batch element (double-buffered by item parity; the per-block named
-      // barrier below orders these writes before any read)
+      // key bias of this item's batch element (double-buffered by item parity)
       float* bias_it = sBias + (it & 1) * 512;
-      for (int i = threadIdx.x; i < S; i += 256) {
+      for (int i = threadIdx.x; i < S; i += 128) {
         const float bz = key_bias ? __ldg(key_bias + static_cast<int64_t>(b) * S + i) * kLog2e : 0.f;
         bias_it[i] = fmaxf(bz, -3.402823466e38f);   // finfo.min * log2e overflows to -inf: keep it finite
       }
@@ -252,9 +251,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
           if (__ldg(key_bias + static_cast<int64_t>(b) * S + i) != 0.f) blk_biased |= 1u << (i >> 7);
         blk_biased = __reduce_or_sync(0xffffffffu, blk_biased);
       }
-      named_bar_sync(1, 256);
+      named_bar_sync(1, 128);
       float m2 = -INFINITY;                // running (lazily advanced) row max, log2 domain
-      float l0 = 0.f, l1 = 0.f;            // running sums of exp2(x2 - m2) over this thread's columns
+      float l0 = 0.f, l1 = 0.f;            // running sums of exp2(x2 - m2)
 
       for (int j = 0; j < nblk; ++j) {
         const bool st = (DBG & 64) && blockIdx.x == 0 && threadIdx.x == 0 && n_blk < 64;
@@ -262,49 +261,40 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
         mbar_wait(bar_s, n_blk & 1);
         tc_fence_after();
         if (st) g_attn_timeline[n_blk * 16 + 9] = clock64();
-        // The raw scores stay in registers as loaded (r0 | r1 = this thread's 64 columns); the biased,
-        // scaled score x2 = s * k1 + bias2 is recomputed in the exp pass instead of being kept, which
-        // halves the live register set (2 CTAs/SM leave ~96 registers per thread).
-        uint32_t r0[32], r1[32];
-        if (DBG & 2) {
+        // the whole score row of this key block: 4 x 32 columns, one TMEM pass
+        uint32_t r[4][32];
 #pragma unroll
-          for (int c = 0; c < 32; ++c) { r0[c] = lane + c; r1[c] = row + c; }
-        } else {
-          tmem_ld_32x32b_x32(t_row + T_S + half * 64, r0);
-          tmem_ld_32x32b_x32(t_row + T_S + half * 64 + 32, r1);
-          tmem_ld_wait();
-        }
+        for (int g = 0; g < 4; ++g) tmem_ld_32x32b_x32(t_row + T_S + g * 32, r[g]);
+        tmem_ld_wait();
         tc_fence_before();
-        if (DBG & 16) { __syncwarp(); if (lane == 0) mbar_arrive(bar_sread); } else mbar_arrive(bar_sread);
-        const float4* bz = reinterpret_cast<const float4*>(bias_it + j * 128 + half * 64);
+        mbar_arrive(bar_sread);
+        const float4* bz = reinterpret_cast<const float4*>(bias_it + j * 128);
         const bool biased = (blk_biased >> j) & 1u;   // warp-uniform
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
         float bm;
         if (biased) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 b0 = bz[c], b1 = bz[8 + c];
-            mx[0] = fmaxf(mx[0], fmaxf(fmaf(__uint_as_float(r0[4 * c]), k1, b0.x), fmaf(__uint_as_float(r1[4 * c]), k1, b1.x)));
-            mx[1] = fmaxf(mx[1], fmaxf(fmaf(__uint_as_float(r0[4 * c + 1]), k1, b0.y), fmaf(__uint_as_float(r1[4 * c + 1]), k1, b1.y)));
-            mx[2] = fmaxf(mx[2], fmaxf(fmaf(__uint_as_float(r0[4 * c + 2]), k1, b0.z), fmaf(__uint_as_float(r1[4 * c + 2]), k1, b1.z)));
-            mx[3] = fmaxf(mx[3], fmaxf(fmaf(__uint_as_float(r0[4 * c + 3]), k1, b0.w), fmaf(__uint_as_float(r1[4 * c + 3]), k1, b1.w)));
-          }
-          bm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-        } else {   // max(s * k1) = k1 * max(s): one FMNMX per element (3-input max where available)
+          for (int g = 0; g < 4; ++g)
 #pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            mx[0] = fmaxf(mx[0], fmaxf(__uint_as_float(r0[c]), __uint_as_float(r1[c])));
-            mx[1] = fmaxf(mx[1], fmaxf(__uint_as_float(r0[c + 1]), __uint_as_float(r1[c + 1])));
-            mx[2] = fmaxf(mx[2], fmaxf(__uint_as_float(r0[c + 2]), __uint_as_float(r1[c + 2])));
-            mx[3] = fmaxf(mx[3], fmaxf(__uint_as_float(r0[c + 3]), __uint_as_float(r1[c + 3])));
-          }
+            for (int c = 0; c < 8; ++c) {
+              const float4 b0 = bz[g * 8 + c];
+              mx[0] = fmaxf(mx[0], fmaf(__uint_as_float(r[g][4 * c]), k1, b0.x));
+              mx[1] = fmaxf(mx[1], fmaf(__uint_as_float(r[g][4 * c + 1]), k1, b0.y));
+              mx[2] = fmaxf(mx[2], fmaf(__uint_as_float(r[g][4 * c + 2]), k1, b0.z));
+              mx[3] = fmaxf(mx[3], fmaf(__uint_as_float(r[g][4 * c + 3]), k1, b0.w));
+            }
+          bm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        } else {   // max(s * k1) = k1 * max(s)
+#pragma unroll
+          for (int g = 0; g < 4; g += 2)
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+              mx[0] = fmaxf(mx[0], fmaxf(__uint_as_float(r[g][c]), __uint_as_float(r[g + 1][c])));
+              mx[1] = fmaxf(mx[1], fmaxf(__uint_as_float(r[g][c + 1]), __uint_as_float(r[g + 1][c + 1])));
+              mx[2] = fmaxf(mx[2], fmaxf(__uint_as_float(r[g][c + 2]), __uint_as_float(r[g + 1][c + 2])));
+              mx[3] = fmaxf(mx[3], fmaxf(__uint_as_float(r[g][c + 3]), __uint_as_float(r[g + 1][c + 3])));
+            }
           bm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * k1;
-        }
-        float* xch = sXch + (n_x & 1) * 256; ++n_x;
-        if (!(DBG & 32)) {
-          xch[half * 128 + row] = bm;
-          named_bar_sync(1, 256);
-          bm = fmaxf(xch[row], xch[128 + row]);
         }
         if (st) g_attn_timeline[n_blk * 16 + 10] = clock64();
         if (n_blk > 0) {
@@ -322,96 +312,72 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
           l0 *= alpha;
           l1 *= alpha;
 #pragma unroll 1
-          for (int c0 = 0; c0 < 32; c0 += 8) {   // 8 columns at a time keeps the register peak low
+          for (int c0 = 0; c0 < 64; c0 += 8) {   // 8 columns at a time keeps the register peak low
             uint32_t o[8];
-            tmem_ld_32x32b_x8(t_row + T_O + half * 32 + c0, o);
+            tmem_ld_32x32b_x8(t_row + T_O + c0, o);
             tmem_ld_wait();
 #pragma unroll
             for (int c = 0; c < 8; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-            tmem_st_32x32b_x8(t_row + T_O + half * 32 + c0, o);
+            tmem_st_32x32b_x8(t_row + T_O + c0, o);
           }
           tmem_st_wait();
         }
         if (advance) m2 = bm;
-        uint32_t pk[32];   // this thread's 64 probabilities as bf16 pairs = 32 TMEM columns of the A operand
-        if (biased) {
+        const float nm2 = -m2;
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {   // 8 columns per step
-            const float4 ba = bz[2 * g], bb = bz[2 * g + 1];
-            const uint32_t* rr = (g < 4) ? (r0 + 8 * g) : (r1 + 8 * (g - 4));
-            const float p0 = fast_exp2(fmaf(__uint_as_float(rr[0]), k1, ba.x - m2));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(rr[1]), k1, ba.y - m2));
-            const float p2 = fast_exp2(fmaf(__uint_as_float(rr[2]), k1, ba.z - m2));
-            const float p3 = fast_exp2(fmaf(__uint_as_float(rr[3]), k1, ba.w - m2));
-            const float p4 = fast_exp2(fmaf(__uint_as_float(rr[4]), k1, bb.x - m2));
-            const float p5 = fast_exp2(fmaf(__uint_as_float(rr[5]), k1, bb.y - m2));
-            const float p6 = fast_exp2(fmaf(__uint_as_float(rr[6]), k1, bb.z - m2));
-            const float p7 = fast_exp2(fmaf(__uint_as_float(rr[7]), k1, bb.w - m2));
-            l0 += (p0 + p2) + (p4 + p6);
-            l1 += (p1 + p3) + (p5 + p7);
-            pk[4 * g] = pack_bf16x2(p0, p1);
-            pk[4 * g + 1] = pack_bf16x2(p2, p3);
-            pk[4 * g + 2] = pack_bf16x2(p4, p5);
-            pk[4 * g + 3] = pack_bf16x2(p6, p7);
-          }
-        } else {
-          const float nm2 = -m2;
+        for (int g = 0; g < 4; ++g) {      // 32 keys -> 16 packed TMEM columns of the A operand
+          uint32_t pk[16];
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {   // FFMA + MUFU.EX2 + FADD per element
-            const uint32_t* rr = (g < 4) ? (r0 + 8 * g) : (r1 + 8 * (g - 4));
-            const float p0 = fast_exp2(fmaf(__uint_as_float(rr[0]), k1, nm2));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(rr[1]), k1, nm2));
-            const float p2 = fast_exp2(fmaf(__uint_as_float(rr[2]), k1, nm2));
-            const float p3 = fast_exp2(fmaf(__uint_as_float(rr[3]), k1, nm2));
-            const float p4 = fast_exp2(fmaf(__uint_as_float(rr[4]), k1, nm2));
-            const float p5 = fast_exp2(fmaf(__uint_as_float(rr[5]), k1, nm2));
-            const float p6 = fast_exp2(fmaf(__uint_as_float(rr[6]), k1, nm2));
-            const float p7 = fast_exp2(fmaf(__uint_as_float(rr[7]), k1, nm2));
-            l0 += (p0 + p2) + (p4 + p6);
-            l1 += (p1 + p3) + (p5 + p7);
-            pk[4 * g] = pack_bf16x2(p0, p1);
-            pk[4 * g + 1] = pack_bf16x2(p2, p3);
-            pk[4 * g + 2] = pack_bf16x2(p4, p5);
-            pk[4 * g + 3] = pack_bf16x2(p6, p7);
+          for (int c = 0; c < 8; ++c) {
+            float a0 = nm2, a1 = nm2, a2 = nm2, a3 = nm2;
+            if (biased) {
+              const float4 b0 = bz[g * 8 + c];
+              a0 += b0.x; a1 += b0.y; a2 += b0.z; a3 += b0.w;
+            }
+            const float p0 = fast_exp2(fmaf(__uint_as_float(r[g][4 * c]), k1, a0));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(r[g][4 * c + 1]), k1, a1));
+            const float p2 = fast_exp2(fmaf(__uint_as_float(r[g][4 * c + 2]), k1, a2));
+            const float p3 = fast_exp2(fmaf(__uint_as_float(r[g][4 * c + 3]), k1, a3));
+            l0 += p0 + p2;
+            l1 += p1 + p3;
+            pk[2 * c] = pack_bf16x2(p0, p1);
+            pk[2 * c + 1] = pack_bf16x2(p2, p3);
           }
+          tmem_st_32x32b_x16(t_row + T_P + g * 16, pk);
         }
-        if (!(DBG & 4)) {
-          tmem_st_32x32b_x32(t_row + T_P + half * 32, pk);
-          tmem_st_wait();
-        }
+        tmem_st_wait();
         if (st) g_attn_timeline[n_blk * 16 + 11] = clock64();
         tc_fence_before();          // P store and O rescale are ordered before the next MMA
-        if (DBG & 16) { __syncwarp(); if (lane == 0) mbar_arrive(bar_p); } else mbar_arrive(bar_p);
+        mbar_arrive(bar_p);
         ++n_blk;
       }
 
       mbar_wait(bar_pv, (n_blk - 1) & 1);
       tc_fence_after();
-      float* xch = sXch + (n_x & 1) * 256; ++n_x;
-      xch[half * 128 + row] = l0 + l1;
-      named_bar_sync(1, 256);
-      const float total = xch[row] + xch[128 + row];
+      const float total = l0 + l1;
       const float inv = 1.0f / total;
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(t_row + T_O + half * 32, r);
-      tmem_ld_wait();
-      uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(row_base + q0 + row)) * kHidden + h * 64 + half * 32);
+      uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(row_base + q0 + row)) * kHidden + h * 64);
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint32_t w[4];
+      for (int hh2 = 0; hh2 < 2; ++hh2) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(t_row + T_O + hh2 * 32, o);
+        tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          w[i] = pack_bf16x2(__uint_as_float(r[g * 8 + 2 * i]) * inv, __uint_as_float(r[g * 8 + 2 * i + 1]) * inv);
-        dst[g] = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int g = 0; g < 4; ++g) {
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            w[i] = pack_bf16x2(__uint_as_float(o[g * 8 + 2 * i]) * inv, __uint_as_float(o[g * 8 + 2 * i + 1]) * inv);
+          dst[hh2 * 4 + g] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
       }
-      if (lse_out && half == 0)
-        lse_out[(static_cast<int64_t>(b) * kHeads + h) * S + q0 + row] = (m2 + log2f(total)) * kLn2;
+      if (lse_out) lse_out[(static_cast<int64_t>(b) * kHeads + h) * S + q0 + row] = (m2 + log2f(total)) * kLn2;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
