@@ -102,6 +102,14 @@ class _KGBackboneView(Mapping):
 class STonKGsForPreTraining(BertForPreTraining):
     """STonKGs pre-training model (text + KG joint transformer), B200-native compute."""
 
+    # The reference registers text_bias / entity_bias a second time on the inherited decoder
+    # (stonkgs_model.py:58-60), i.e. the same Parameter under two state-dict keys.  Declaring the
+    # aliases lets the installed transformers (safetensors refuses aliased tensors) save and re-tie them.
+    _stk_alias_keys = {
+        "cls.predictions.decoder.text_bias": "cls.predictions.text_bias",
+        "cls.predictions.decoder.entity_bias": "cls.predictions.entity_bias",
+    }
+
     def __init__(self, config=None, nlp_model_type=NLP_MODEL_TYPE, kg_embedding_dict_path=EMBEDDINGS_PATH):
         # --- KG vectors in file order (reference :93) -------------------------------------------
         if isinstance(kg_embedding_dict_path, (str, os.PathLike)):
@@ -136,6 +144,10 @@ class STonKGsForPreTraining(BertForPreTraining):
         config.update({"kg_vocab_size": n_kg})
         super().__init__(config)
         self.cls.predictions = STonKGsELMPredictionHead(config)
+        # the head swap happens after HF's post_init(): register the two extra aliases now
+        self._tied_weights_keys = {**(type(self)._tied_weights_keys or {}), **self._stk_alias_keys}
+        if hasattr(self, "get_expanded_tied_weights_keys"):
+            self.all_tied_weights_keys = self.get_expanded_tied_weights_keys(all_submodels=False)
 
         # --- frozen LM backbone (reference :107-114) --------------------------------------------
         if lm_config is None:

@@ -99,3 +99,23 @@ def test_shard_bounds_cover_everything():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_checkpoint_round_trip_hf_layout(tmp_path, small):
+    """save_pretrained -> from_pretrained (offline) keeps every weight; the HF config carries kg_vocab_size
+    (reference stonkgs_model.py:96-97) and extra kwargs reach __init__ like in the reference (api/api.py:107-110)."""
+    import json
+    from stonkgs_b200.model import STonKGsForPreTraining
+    _, meta, _, sd, rows, model = small
+    model.save_pretrained(tmp_path)
+    cfg = json.load(open(tmp_path / "config.json"))
+    assert cfg["kg_vocab_size"] == meta["n_kg"] and cfg["architectures"] == ["STonKGsForPreTraining"]
+    again = STonKGsForPreTraining.from_pretrained(tmp_path, kg_embedding_dict_path=rows)
+    sd2 = again.state_dict()
+    assert sorted(sd2) == sorted(sd) and all(torch.equal(sd[k], sd2[k]) for k in sd)
+    assert again.kg_table.device.type == "cpu" and torch.equal(again.kg_table, model.kg_table)
+    # the reference's legacy format: a plain state dict with all aliased keys
+    torch.save(model.state_dict(), tmp_path / "pytorch_model.bin")
+    fresh = build_model(meta, weights.make_state_dict(meta["n_kg"], meta["layers"], seed=5), rows)
+    missing, unexpected = fresh.load_state_dict(torch.load(tmp_path / "pytorch_model.bin"), strict=True)
+    assert not missing and not unexpected
