@@ -18,6 +18,7 @@
 // dQ_i partial products go out as fp32 TMA reduce-adds into a workspace (summed over the key
 // blocks in L2) and are converted to bf16 by a small tail kernel.
 #include <atomic>
+#include <stdlib.h>
 
 #include "stk_common.cuh"
 #include "stk_host.h"
@@ -26,6 +27,7 @@ namespace stk {
 
 extern std::atomic<long long> g_launches;
 
+__device__ long long g_abw_timeline[2048];   // bring-up only (STK_ATTN_DEBUG=64): clock64 stamps of CTA 0
 constexpr int ABW_THREADS = 320;   // 8 compute warps + TMA warp + MMA warp
 constexpr float kL2e = 1.4426950408889634f;
 constexpr int ABW_SMEM = 1024 + 16384 * 2 + 32768 * 5 + 512 + 128;
@@ -67,6 +69,7 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_cast_kernel(const float* __re
       make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
 }
 
+template <int DBG>
 __global__ void __launch_bounds__(ABW_THREADS)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
                 const __grid_constant__ CUtensorMap map_dq, const float* __restrict__ key_bias,
@@ -89,7 +92,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
   uint64_t* bar_p = bars + 4;
   uint64_t* bar_dq = bars + 5;
   uint64_t* bar_qfree = bars + 6;  // [2] Q_i / dO_i buffer released (only the TMA warp waits on these)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bar_dvdk = bars + 8;   // dV / dK MMAs of pair i have completed: the P / dS tiles may be rewritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -109,12 +113,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       mbar_init(bar_dq, 1);
       mbar_init(bar_qfree, 1);
       mbar_init(bar_qfree + 1, 1);
+      mbar_init(bar_dvdk, 1);
       fence_barrier_init();
     }
     __syncwarp();
     tmem_alloc(tmem_slot, 512);
   } else if (threadIdx.x < 128) {
-    sBias[threadIdx.x] = key_bias ? __ldg(key_bias + static_cast<int64_t>(b) * S + j * 128 + threadIdx.x) : 0.f;
+    // additive key bias in the log2 domain, clamped finite (finfo.min * log2e would overflow to -inf)
+    sBias[threadIdx.x] = key_bias ? fmaxf(__ldg(key_bias + static_cast<int64_t>(b) * S + j * 128 + threadIdx.x) * kL2e,
+                                          -3.402823466e38f) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -175,12 +182,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       }
       __syncwarp();
     };
+    auto stamp = [&](int i, int slot) {
+      if ((DBG & 64) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && leader) g_abw_timeline[i * 16 + slot] = clock64();
+    };
+    stamp(0, 0);
     issue_scores(0);
     for (int i = 0; i < nq; ++i) {
       const uint64_t boff = static_cast<uint64_t>((i & 1) * (16384 >> 4));
+      stamp(i, 1);
       mbar_wait(bar_p, i & 1);           // P_i, dS_i are in smem; S_i / dP_i columns have been read
       tc_fence_after();
+      stamp(i, 2);
       if (leader) {
+        // dQ_i first: the compute warps are waiting for it (they drain it while dV / dK run)
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + T_DQ, ds_desc + kb * (16384 >> 4) + 2 * k, kT_desc + kb * (8192 >> 4) + k * 128, idesc_q,
+                      (kb | k) > 0);
+        umma_commit(bar_dq);
         // MN-major operands: +2048 B (16 rows of the reduction dimension) per k step
         if (i == 0) {
           umma_bf16(tmem_base + T_DV, pT_desc, doT_desc0 + boff, idesc_t, 0u);
@@ -196,16 +217,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
         }
 #pragma unroll
         for (int k = 1; k < 8; ++k) umma_bf16(tmem_base + T_DK, dsT_desc + k * 128, qT_desc0 + boff + k * 128, idesc_t, 1u);
-#pragma unroll
-        for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + T_DQ, ds_desc + kb * (16384 >> 4) + 2 * k, kT_desc + kb * (8192 >> 4) + k * 128, idesc_q,
-                      (kb | k) > 0);
-        umma_commit(bar_dq);
+        umma_commit(bar_dvdk);              // P / dS tiles reusable
         umma_commit(bar_qfree + (i & 1));   // Q_i / dO_i buffer reusable once everything above has completed
       }
       __syncwarp();
+      stamp(i, 3);
       // the next pair's scores queue right behind: they run while the compute warps drain dQ_i
       if (i + 1 < nq) issue_scores(i + 1);
     }
@@ -220,55 +236,55 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     for (int i = 0; i < nq; ++i) {
       const float row_lse = __ldg(lse + stat_base + i * 128 + row);
       const float row_D = __ldg(Dws + stat_base + i * 128 + row);
+      const bool st = (DBG & 64) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
+      if (st) g_abw_timeline[i * 16 + 8] = clock64();
       mbar_wait(bar_s, i & 1);
       tc_fence_after();
-      float p[64];
+      if (st) g_abw_timeline[i * 16 + 9] = clock64();
       uint8_t* prow = sP + half * 16384 + row * 128;
       uint8_t* dsrow = sdS + half * 16384 + row * 128;
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_row + T_S + half * 64 + hh * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t w[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int c = hh * 32 + g * 8 + t * 2;
-            const float x0 = fmaf(__uint_as_float(r[g * 8 + t * 2]), scale, sBias[half * 64 + c]);
-            const float x1 = fmaf(__uint_as_float(r[g * 8 + t * 2 + 1]), scale, sBias[half * 64 + c + 1]);
-            p[c] = fast_exp2((x0 - row_lse) * kL2e);
-            p[c + 1] = fast_exp2((x1 - row_lse) * kL2e);
-            w[t] = pack_bf16x2(p[c], p[c + 1]);
-          }
-          *reinterpret_cast<uint4*>(prow + (((hh * 4 + g) ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
+      const float lse2 = row_lse * kL2e;
+      const float k1 = scale * kL2e;
+      const float nDs = -row_D * scale;
+      if (i > 0) {   // dV / dK of the previous pair have finished reading the P / dS tiles
+        mbar_wait(bar_dvdk, (i - 1) & 1);
       }
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_row + T_DP + half * 64 + hh * 32, r);
+      for (int hh = 0; hh < 2; ++hh) {   // 32 key columns at a time: S and dP loaded together
+        uint32_t rs[32], rd[32];
+        tmem_ld_32x32b_x32(t_row + T_S + half * 64 + hh * 32, rs);
+        tmem_ld_32x32b_x32(t_row + T_DP + half * 64 + hh * 32, rd);
         tmem_ld_wait();
+        const float4* bz = reinterpret_cast<const float4*>(sBias + half * 64 + hh * 32);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          uint32_t w[4];
+          const float4 ba = bz[2 * g], bb = bz[2 * g + 1];
+          const float bias8[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+          uint32_t wp[4], wd[4];
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            const int c = hh * 32 + g * 8 + t * 2;
-            const float d0 = p[c] * (__uint_as_float(r[g * 8 + t * 2]) - row_D) * scale;
-            const float d1 = p[c + 1] * (__uint_as_float(r[g * 8 + t * 2 + 1]) - row_D) * scale;
-            w[t] = pack_bf16x2(d0, d1);
+            const int e = g * 8 + t * 2;
+            // p = exp(s/8 + bias - lse) in the log2 domain; dS = p * (dP - D) / 8
+            const float p0 = fast_exp2(fmaf(__uint_as_float(rs[e]), k1, bias8[2 * t] - lse2));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(rs[e + 1]), k1, bias8[2 * t + 1] - lse2));
+            const float d0 = p0 * fmaf(__uint_as_float(rd[e]), scale, nDs);
+            const float d1 = p1 * fmaf(__uint_as_float(rd[e + 1]), scale, nDs);
+            wp[t] = pack_bf16x2(p0, p1);
+            wd[t] = pack_bf16x2(d0, d1);
           }
-          *reinterpret_cast<uint4*>(dsrow + (((hh * 4 + g) ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          const int off = ((hh * 4 + g) ^ (row & 7)) << 4;
+          *reinterpret_cast<uint4*>(prow + off) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
+          *reinterpret_cast<uint4*>(dsrow + off) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
         }
       }
       fence_proxy_async_smem();
       tc_fence_before();
+      if (st) g_abw_timeline[i * 16 + 10] = clock64();
       mbar_arrive(bar_p);
 
       mbar_wait(bar_dq, i & 1);
       tc_fence_after();
+      if (st) g_abw_timeline[i * 16 + 11] = clock64();
       {  // dQ_i partial: my 32 fp32 columns -> swizzled staging tile -> TMA reduce-add
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_row + T_DQ + half * 32, r);
@@ -289,6 +305,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
           tma_reduce_add_2d(&map_dq, sStage + 16384, h * 64 + 32, row_base + i * 128);
           tma_commit_group();
         }
+        if (st) g_abw_timeline[i * 16 + 12] = clock64();
       }
     }
     if (issuer) tma_wait_group<0>();
@@ -343,17 +360,28 @@ extern "C" int stk_attn_bwd(int device, void* stream_, const void* qkv, const fl
   attn_bwd_prep_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), B, S, Dws);
   STK_CHECK_CUDA(cudaGetLastError());
-  static bool configured[64] = {};
-  if (!configured[device & 63]) {
-    STK_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ABW_SMEM));
-    configured[device & 63] = true;
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("STK_ATTN_DEBUG");
+    dbg = e ? atoi(e) : 0;
   }
-  attn_bwd_kernel<<<dim3(S / 128, kHeads, B), ABW_THREADS, ABW_SMEM, stream>>>(
-      map_qkv, map_do, map_dq, key_bias, lse, Dws, S, static_cast<__nv_bfloat16*>(dqkv));
+  auto go = [&](auto kern) -> int {
+    STK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ABW_SMEM));
+    kern<<<dim3(S / 128, kHeads, B), ABW_THREADS, ABW_SMEM, stream>>>(map_qkv, map_do, map_dq, key_bias, lse, Dws, S,
+                                                                     static_cast<__nv_bfloat16*>(dqkv));
+    return STK_OK;
+  };
+  rc = (dbg == 64) ? go(attn_bwd_kernel<64>) : go(attn_bwd_kernel<0>);
+  if (rc) return rc;
   STK_CHECK_CUDA(cudaGetLastError());
   attn_bwd_dq_cast_kernel<<<static_cast<unsigned>((rows * (kHidden / 8) + 255) / 256), 256, 0, stream>>>(
       dq_acc, rows, static_cast<__nv_bfloat16*>(dqkv));
   STK_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(3, std::memory_order_relaxed);
   return STK_OK;
+}
+
+// bring-up only: clock64 timeline of CTA (0,0,0) of the last STK_ATTN_DEBUG=64 backward launch
+extern "C" __attribute__((visibility("default"))) int stk_debug_attn_bwd_timeline(long long* host, int n) {
+  return cudaMemcpyFromSymbol(host, stk::g_abw_timeline, sizeof(long long) * n) == cudaSuccess ? 0 : -2;
 }
