@@ -202,6 +202,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
             umma_bf16(tmem_base + T_DQ, ds_desc + kb * (16384 >> 4) + 2 * k, kT_desc + kb * (8192 >> 4) + k * 128, idesc_q,
                       (kb | k) > 0);
         umma_commit(bar_dq);
+      }
+      __syncwarp();
+      // the next pair's scores come next (the compute warps need them right after draining dQ_i) ...
+      if (i + 1 < nq) issue_scores(i + 1);
+      // ... and dV / dK of this pair last: nobody waits for them until the P / dS tiles are rewritten
+      if (leader) {
         // MN-major operands: +2048 B (16 rows of the reduction dimension) per k step
         if (i == 0) {
           umma_bf16(tmem_base + T_DV, pT_desc, doT_desc0 + boff, idesc_t, 0u);
@@ -222,8 +228,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       }
       __syncwarp();
       stamp(i, 3);
-      // the next pair's scores queue right behind: they run while the compute warps drain dQ_i
-      if (i + 1 < nq) issue_scores(i + 1);
     }
   } else {
     const int q = warp & 3, half = warp >> 2;
@@ -246,15 +250,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       const float lse2 = row_lse * kL2e;
       const float k1 = scale * kL2e;
       const float nDs = -row_D * scale;
-      if (i > 0) {   // dV / dK of the previous pair have finished reading the P / dS tiles
-        mbar_wait(bar_dvdk, (i - 1) & 1);
-      }
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {   // 32 key columns at a time: S and dP loaded together
         uint32_t rs[32], rd[32];
         tmem_ld_32x32b_x32(t_row + T_S + half * 64 + hh * 32, rs);
         tmem_ld_32x32b_x32(t_row + T_DP + half * 64 + hh * 32, rd);
         tmem_ld_wait();
+        if (hh == 0 && i > 0) {   // dV / dK of the previous pair have finished reading the P / dS tiles
+          mbar_wait(bar_dvdk, (i - 1) & 1);
+        }
         const float4* bz = reinterpret_cast<const float4*>(sBias + half * 64 + hh * 32);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
