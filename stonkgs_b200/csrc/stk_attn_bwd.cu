@@ -313,7 +313,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       }
     }
     if (issuer) tma_wait_group<0>();
-    // dV_j, dK_j: accumulated over all query blocks; lane = key row
+    // dV_j, dK_j: accumulated over all query blocks; lane = key row.  Their last MMAs are issued after
+    // the dQ MMAs, so wait for the dV / dK commit of the final pair before reading the accumulators.
+    mbar_wait(bar_dvdk, (nq - 1) & 1);
+    tc_fence_after();
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
       uint32_t r[32];
