@@ -29,7 +29,7 @@ extern "C" {
 #define STK_ERR_CUDA (-2)
 #define STK_ERR_UNSUPPORTED (-3)
 
-#define STK_VERSION 100
+#define STK_VERSION 101
 
 /* library version (STK_VERSION) */
 int stk_version(void);
@@ -104,7 +104,10 @@ enum {
   STK_EPI_F32_ADD = 6,       /* C(fp32) += acc   (TMA reduce-add; split-K and grad accumulation)      */
   STK_EPI_F32 = 7,           /* C(fp32) = acc                                                          */
   STK_EPI_CE_STATS = 8,      /* no C: per-row (max, sum exp) partials + target logit (A9+A10 fwd)     */
-  STK_EPI_CE_DLOGIT = 9      /* C(bf16) = (exp(acc - lse[m]) - [n+n_offset == label[m]]) * *scale_dev   */
+  STK_EPI_CE_DLOGIT = 9,     /* C(bf16) = (exp(acc - lse[m]) - [n+n_offset == label[m]]) * *scale_dev   */
+  STK_EPI_BIAS_RESID_LN = 10 /* z = acc + bias + R;  C(bf16) = LayerNorm_768(z) * gamma + beta  (HF:294-298,352-356);
+                                N must be 768 (rows are normalised across a 3-CTA cluster through distributed
+                                shared memory); optional C2(bf16) = z and ln_mean/ln_rstd[m] for the backward */
 };
 
 typedef struct StkGemmEpilogue {
@@ -120,6 +123,10 @@ typedef struct StkGemmEpilogue {
   int64_t ce_pitch;       /* number of slabs in the full vocabulary = 2 * ceil(N_full / 256) */
   float* tgt_logit;       /* CE_STATS: [M] logit of the target column (written by the owning slab) */
   int32_t n_offset;       /* CE: first vocabulary column of this call's B block (multiple of 256) */
+  const float* ln_gamma;  /* BIAS_RESID_LN: [768] LayerNorm weight */
+  const float* ln_beta;   /* BIAS_RESID_LN: [768] LayerNorm bias */
+  float* ln_mean;         /* BIAS_RESID_LN: optional [M] row mean of z (saved for the backward) */
+  float* ln_rstd;         /* BIAS_RESID_LN: optional [M] 1/sqrt(var + 1e-12) */
 } StkGemmEpilogue;
 
 int stk_gemm(int device, void* stream, int a_major, int b_major, const void* A_bf16, int64_t lda,

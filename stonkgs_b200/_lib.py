@@ -12,11 +12,11 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libstk.so")
 
-STK_VERSION = 100
+STK_VERSION = 101
 
 # epilogue ids (include/stk.h)
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GELU_SAVE, EPI_BIAS_RESID, EPI_BIAS_TANH_F32 = 0, 1, 2, 3, 4
-EPI_DGELU, EPI_F32_ADD, EPI_F32, EPI_CE_STATS, EPI_CE_DLOGIT = 5, 6, 7, 8, 9
+EPI_DGELU, EPI_F32_ADD, EPI_F32, EPI_CE_STATS, EPI_CE_DLOGIT, EPI_BIAS_RESID_LN = 5, 6, 7, 8, 9, 10
 
 
 class StkError(RuntimeError):
@@ -42,6 +42,10 @@ class GemmEpilogue(Structure):
         ("ce_pitch", c_int64),
         ("tgt_logit", c_void_p),
         ("n_offset", c_int32),
+        ("ln_gamma", c_void_p),
+        ("ln_beta", c_void_p),
+        ("ln_mean", c_void_p),
+        ("ln_rstd", c_void_p),
     ]
 
 

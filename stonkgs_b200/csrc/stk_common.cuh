@@ -43,6 +43,42 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+// Packed fp32x2 arithmetic (sm_100: one FADD2 / FMUL2 / FFMA2 instruction per pair of lanes' values):
+// halves the instruction count of elementwise epilogue math.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack_f32x2(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(f32x2_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t add_f32x2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t mul_f32x2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t fma_f32x2(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// bf16x2 word -> two fp32 values (exact)
+__device__ __forceinline__ f32x2_t bf16x2_to_f32x2(uint32_t v) {
+  return pack_f32x2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t f32x2_to_bf16x2(f32x2_t v) {
+  float lo, hi;
+  unpack_f32x2(v, lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -147,6 +183,80 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// thread-block clusters / distributed shared memory
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// address of the same shared-memory location in CTA `rank` of this cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32x2(uint32_t cluster_addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
+}
+// Asynchronous distributed-shared-memory store that also completes 8 transaction bytes on an mbarrier of
+// the destination CTA: the data is visible to whoever observes that barrier's phase complete, with no
+// fence on the sending side (a release.cluster arrive costs a MEMBAR.ALL.GPU, ~2000 cycles under load).
+__device__ __forceinline__ void st_async_f32x2(uint32_t cluster_addr, float a, float b, uint32_t cluster_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(
+                   cluster_addr),
+               "f"(a), "f"(b), "r"(cluster_mbar)
+               : "memory");
+}
+// arrive on an mbarrier of a peer CTA; release at cluster scope publishes this thread's earlier
+// (and, through __syncwarp, its warp's) distributed-shared-memory stores to the waiter
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded like mbar_wait (a protocol bug must trap, not hang the box)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  uint32_t polls = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++polls & 1023u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > (1ll << 33)) {
+        printf("stk: cluster mbarrier wait timeout (block %d thread %d bar %p parity %u)\n", blockIdx.x, threadIdx.x,
+               (void*)bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -18,24 +18,45 @@
 // forward, dgrad and wgrad read the tensors where they lie — no transposed copies.
 // Tails in M, N and K are handled by TMA (zero fill on load, clipping on store).
 #include <atomic>
+#include <stdlib.h>
 
 #include "stk_common.cuh"
 #include "stk_host.h"
 
 namespace stk {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
-constexpr int EPI_BUF_BYTES = 128 * 128;    // [128 rows][128 B] staging tile per epilogue group
-constexpr int GEMM_THREADS = 320;
-constexpr int GEMM_SMEM_BYTES = 1024 /*align slack*/ + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 2 * EPI_BUF_BYTES + 256;
+constexpr int EPI_BUF_BYTES = 128 * 128;    // [128 rows][128 B] staging tile
+
+// Per-epilogue kernel geometry.  The fused residual + LayerNorm epilogue (STK_EPI_BIAS_RESID_LN) runs as
+// clusters of three CTAs (one per 256-column slab of the 768-wide row) with an extra I/O warp that moves
+// the residual in and the results out through FOUR staging tiles by TMA; it pays for the extra staging
+// and the statistics exchange buffers with one ring stage.
+template <int EPI>
+struct GemmCfg {
+  static constexpr bool kLN = EPI == STK_EPI_BIAS_RESID_LN;
+  static constexpr int kStages = kLN ? 3 : 4;
+  static constexpr int kThreads = kLN ? 384 : 320;
+  static constexpr int kEpiBufs = kLN ? 4 : 2;
+  static constexpr int kStatsBytes = kLN ? 2 * 6 * 128 * 8 : 0;   // [parity][slab half][row] (mean, M2)
+  static constexpr int kParamBytes = kLN ? 3 * 256 * 4 : 256 * 4;  // bias (+ gamma, beta) of this CTA's columns
+  static constexpr int kSmem = 1024 /*align slack*/ + kStages * (A_STAGE_BYTES + B_STAGE_BYTES) +
+                               kEpiBufs * EPI_BUF_BYTES + kStatsBytes + kParamBytes + 512 /*barriers*/;
+};
+constexpr int LN_CLUSTER = 3;
 
 struct GemmParams {
   int M, N, K;
   int m_tiles, n_tiles, splits, kb_total, kb_per_split;
+  int dbg;   // bring-up only (env STK_GEMM_DEBUG): CTA 0 records a clock64 timeline of its first tiles
   StkGemmEpilogue epi;
 };
+
+__device__ long long g_gemm_timeline[4096];   // bring-up only: [tile][16] clock64 stamps of CTA 0
+#define STK_GEMM_STAMP(cond, t, slot) \
+  do { if (p.dbg && blockIdx.x < 3 && (cond) && (t) < 64) g_gemm_timeline[blockIdx.x * 1024 + (t) * 16 + (slot)] = clock64(); } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // epilogue helpers
@@ -64,21 +85,32 @@ __device__ __forceinline__ void stage_and_store(const CUtensorMap* map, uint8_t*
 }
 
 template <int A_MN, int B_MN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GemmCfg<EPI>::kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c2,
-            const GemmParams p) {
+            const __grid_constant__ CUtensorMap map_r, const GemmParams p) {
+  using Cfg = GemmCfg<EPI>;
+  constexpr bool kLN = Cfg::kLN;
+  constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
   uint8_t* smem_epi = smem_b + STAGES * B_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + 2 * EPI_BUF_BYTES);
+  float2* s_stats = reinterpret_cast<float2*>(smem_epi + Cfg::kEpiBufs * EPI_BUF_BYTES);   // LN only
+  float* s_par = reinterpret_cast<float*>(smem_epi + Cfg::kEpiBufs * EPI_BUF_BYTES + Cfg::kStatsBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_par) + Cfg::kParamBytes);
   uint64_t* full_bar = bars;                 // [STAGES]
-  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* empty_bar = bars + 4;            // [STAGES]
+  uint64_t* tfull_bar = bars + 8;            // [2]
+  uint64_t* tempty_bar = bars + 10;          // [2]
+  // LN epilogue only:
+  uint64_t* rfull_bar = bars + 12;           // [4] residual chunk landed in staging tile L
+  uint64_t* staged_bar = bars + 16;          // [4] normalised output written to staging tile L
+  uint64_t* zstaged_bar = bars + 20;         // [4] pre-LN sum written to staging tile L (training: saved for backward)
+  uint64_t* zdone_bar = bars + 24;           // [4] ... and read out by its TMA store
+  uint64_t* stats_bar = bars + 28;           // [2] row statistics of all three slabs have arrived (cluster scope)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -95,12 +127,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       mbar_init(tfull_bar + i, 1);
       mbar_init(tempty_bar + i, 8);  // one arrive per epilogue warp
     }
+    if (kLN) {
+      for (int i = 0; i < 4; ++i) {
+        mbar_init(rfull_bar + i, 1);
+        mbar_init(staged_bar + i, 4);    // one arrive per warp of the 128-thread group
+        mbar_init(zstaged_bar + i, 4);
+        mbar_init(zdone_bar + i, 1);
+      }
+      for (int i = 0; i < 2; ++i) mbar_init(stats_bar + i, 1);   // one local arrive.expect_tx + 6 x 128 x 8 B of st.async
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (kLN) cluster_sync_all();   // peers' barriers are initialised before anyone arrives on them remotely
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_items = p.m_tiles * p.n_tiles * p.splits;
@@ -121,6 +163,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(empty_bar + stage, phase ^ 1);
+        if (kb == kb0 && !kLN) STK_GEMM_STAMP(leader, (item - blockIdx.x) / gridDim.x, 12);
         if (leader) {
           mbar_arrive_expect_tx(full_bar + stage, A_STAGE_BYTES + B_STAGE_BYTES);
           uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
@@ -166,9 +209,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       mbar_wait(tempty_bar + as, as_phase ^ 1);  // epilogue has drained this accumulator stage
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
+      STK_GEMM_STAMP(leader, (item - blockIdx.x) / gridDim.x, 0);
+      long long waited = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(full_bar + stage, phase);
+        if (p.dbg) {
+          const long long t0 = clock64();
+          mbar_wait(full_bar + stage, phase);
+          waited += clock64() - t0;
+        } else {
+          mbar_wait(full_bar + stage, phase);
+        }
         tc_fence_after();
+        if (kb == kb0) STK_GEMM_STAMP(leader, (item - blockIdx.x) / gridDim.x, 13);
+        if (kb == kb1 - 1) STK_GEMM_STAMP(leader, (item - blockIdx.x) / gridDim.x, 1);
         if (leader) {
           const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((stage * A_STAGE_BYTES) >> 4);
           const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((stage * B_STAGE_BYTES) >> 4);
@@ -181,6 +234,243 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (p.dbg && blockIdx.x == 0 && leader && (item - blockIdx.x) / gridDim.x < 64)
+        g_gemm_timeline[((item - blockIdx.x) / gridDim.x) * 16 + 14] = waited;   // cycles starved for operands
+      if (++as == 2) { as = 0; as_phase ^= 1; }
+    }
+  } else if (kLN && warp >= 10) {
+    // ============================== epilogue I/O warps (LN variant) ==============================
+    // Warp 10 + g serves column half g of this CTA's 128 x 256 slab through its two staging tiles
+    // (64-column chunks): residual chunk in by TMA, (training: pre-LN sum out,) normalised rows out, next
+    // tile's residual in.  The epilogue math warps never touch global memory for these tensors.
+    if (lane == 0) {
+      const int g = warp - 10;
+      const int L0 = g * 2, L1 = g * 2 + 1;
+      uint8_t* ebuf0 = smem_epi + L0 * EPI_BUF_BYTES;
+      uint8_t* ebuf1 = smem_epi + L1 * EPI_BUF_BYTES;
+      const bool save_z = p.epi.c2 != nullptr;
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int n_col = (item % p.n_tiles) * BN + g * 128;
+        const int m0 = (item / p.n_tiles) * BM;
+        if (it == 0) {
+          mbar_arrive_expect_tx(rfull_bar + L0, EPI_BUF_BYTES);
+          tma_load_2d(&map_r, rfull_bar + L0, ebuf0, n_col, m0);
+          mbar_arrive_expect_tx(rfull_bar + L1, EPI_BUF_BYTES);
+          tma_load_2d(&map_r, rfull_bar + L1, ebuf1, n_col + 64, m0);
+        }
+        if (save_z) {
+          mbar_wait(zstaged_bar + L0, it & 1);
+          tma_store_2d(&map_c2, ebuf0, n_col, m0);
+          tma_commit_group();
+          mbar_wait(zstaged_bar + L1, it & 1);
+          tma_store_2d(&map_c2, ebuf1, n_col + 64, m0);
+          tma_commit_group();
+          tma_wait_group_read<1>();
+          mbar_arrive(zdone_bar + L0);
+          tma_wait_group_read<0>();
+          mbar_arrive(zdone_bar + L1);
+        }
+        mbar_wait(staged_bar + L0, it & 1);
+        tma_store_2d(&map_c, ebuf0, n_col, m0);
+        tma_commit_group();
+        mbar_wait(staged_bar + L1, it & 1);
+        tma_store_2d(&map_c, ebuf1, n_col + 64, m0);
+        tma_commit_group();
+        STK_GEMM_STAMP(g == 0, static_cast<int>(it), 10);
+        const int next = item + gridDim.x;
+        const int m0n = (next / p.n_tiles) * BM;
+        tma_wait_group_read<1>();
+        if (next < num_items) {
+          mbar_arrive_expect_tx(rfull_bar + L0, EPI_BUF_BYTES);
+          tma_load_2d(&map_r, rfull_bar + L0, ebuf0, n_col, m0n);
+        }
+        tma_wait_group_read<0>();
+        if (next < num_items) {
+          mbar_arrive_expect_tx(rfull_bar + L1, EPI_BUF_BYTES);
+          tma_load_2d(&map_r, rfull_bar + L1, ebuf1, n_col + 64, m0n);
+        }
+        STK_GEMM_STAMP(g == 0, static_cast<int>(it), 15);
+      }
+      tma_wait_group<0>();
+    }
+    __syncwarp();
+  } else if (kLN) {
+    // ============================== epilogue warps, fused bias + residual + LayerNorm ==============================
+    // HF BertSelfOutput / BertOutput (modeling_bert.py:294-298, 352-356): y = LN(dense(x) + residual), eps 1e-12.
+    // The 768-wide row is spread over the three CTAs of the cluster.  Every thread owns one row x 128
+    // columns: pass 1 forms z = acc + bias + residual and its (mean, M2) over those columns; the six
+    // partials of a row are exchanged through distributed shared memory (every thread pushes its partial
+    // into all three CTAs with st.async, which completes transaction bytes on the receiver's mbarrier:
+    // no fences), merged with the parallel-variance formula, and pass 2 normalises the bf16 z kept in
+    // registers.
+    const int ew = warp - 2;
+    const int q = warp & 3;   // TMEM lane quarter this warp may access
+    const int g = ew >> 2;    // column half of the 256-wide accumulator
+    const int row = q * 32 + lane;
+    const StkGemmEpilogue& e = p.epi;
+    const uint32_t rank = cluster_ctarank();   // == n-tile index of this CTA (grid is a multiple of the cluster size)
+    {
+      const int t = ew * 32 + lane;            // 0..255: column of this CTA's slab
+      const int n = static_cast<int>(rank) * BN + t;
+      s_par[t] = e.bias ? __ldg(e.bias + n) : 0.f;
+      s_par[256 + t] = __ldg(e.ln_gamma + n);
+      s_par[512 + t] = __ldg(e.ln_beta + n);
+    }
+    named_bar_sync(3, 256);
+    const bool save_z = e.c2 != nullptr;
+    const uint32_t stats_bar_addr[2] = {smem_u32(stats_bar), smem_u32(stats_bar + 1)};
+
+    int as = 0;
+    uint32_t as_phase = 0, it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int m0 = (item / p.n_tiles) * BM;
+      const int m = m0 + row;
+      const int dbg_t = static_cast<int>(it);
+      const bool dbg_thr = threadIdx.x == 64;
+      STK_GEMM_STAMP(dbg_thr, dbg_t, 2);
+      mbar_wait(tfull_bar + as, as_phase);
+      tc_fence_after();
+      STK_GEMM_STAMP(dbg_thr, dbg_t, 3);
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + g * 128;
+
+      uint4 zpk[2][8];
+      float cmean[2], cm2[2];
+#pragma unroll
+      for (int chunk = 0; chunk < 2; ++chunk) {
+        uint32_t r[2][32];
+        tmem_ld_32x32b_x32(t_row + chunk * 64, r[0]);
+        tmem_ld_32x32b_x32(t_row + chunk * 64 + 32, r[1]);
+        tmem_ld_wait();
+        if (chunk == 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar + as);
+        }
+        const int L = g * 2 + chunk;
+        uint8_t* ebuf = smem_epi + L * EPI_BUF_BYTES;
+        mbar_wait(rfull_bar + L, it & 1);
+        STK_GEMM_STAMP(dbg_thr, dbg_t, 4 + chunk * 4);
+        const float4* bias4 = reinterpret_cast<const float4*>(s_par + g * 128 + chunk * 64);
+        // packed fp32x2 math: v[k] = (z[2k], z[2k+1])
+        f32x2_t v[32];
+        f32x2_t s2 = pack_f32x2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 ex4 = *reinterpret_cast<const uint4*>(ebuf + row * 128 + ((c ^ (row & 7)) << 4));
+          const uint32_t ex[4] = {ex4.x, ex4.y, ex4.z, ex4.w};
+          const float4 b0 = bias4[2 * c], b1 = bias4[2 * c + 1];
+          const f32x2_t bv[4] = {pack_f32x2(b0.x, b0.y), pack_f32x2(b0.z, b0.w), pack_f32x2(b1.x, b1.y),
+                                 pack_f32x2(b1.z, b1.w)};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int j = c * 8 + i * 2;
+            const f32x2_t acc = pack_f32x2(__uint_as_float(r[j >> 5][j & 31]), __uint_as_float(r[(j + 1) >> 5][(j + 1) & 31]));
+            const f32x2_t z2 = add_f32x2(add_f32x2(acc, bv[i]), bf16x2_to_f32x2(ex[i]));
+            v[c * 4 + i] = z2;
+            s2 = add_f32x2(s2, z2);
+          }
+        }
+        float sa, sb;
+        unpack_f32x2(s2, sa, sb);
+        const float mu = (sa + sb) * (1.0f / 64.0f);
+        const f32x2_t nmu2 = pack_f32x2(-mu, -mu);
+        f32x2_t q2 = pack_f32x2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const f32x2_t d2 = add_f32x2(v[c * 4 + i], nmu2);
+            q2 = fma_f32x2(d2, d2, q2);
+            w[i] = f32x2_to_bf16x2(v[c * 4 + i]);
+          }
+          zpk[chunk][c] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        float q0, q1;
+        unpack_f32x2(q2, q0, q1);
+        cmean[chunk] = mu;
+        cm2[chunk] = q0 + q1;
+        if (save_z) {   // training: z is kept for the LayerNorm backward (second output, row pitch ldc2)
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(ebuf + row * 128 + ((c ^ (row & 7)) << 4)) = zpk[chunk][c];
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(zstaged_bar + L);
+        }
+        STK_GEMM_STAMP(dbg_thr, dbg_t, 5 + chunk * 4);
+      }
+
+      // ---- row statistics: merge the two 64-column chunks, publish to the cluster, merge six partials ----
+      const uint32_t par = it & 1;
+      {
+        const float d = cmean[1] - cmean[0];
+        const float mean_t = 0.5f * (cmean[0] + cmean[1]);
+        const float m2_t = cm2[0] + cm2[1] + d * d * 32.0f;   // n_a n_b / (n_a + n_b) = 32
+        const uint32_t slot = smem_u32(s_stats + (par * 6 + rank * 2 + g) * 128 + row);
+        if (ew == 0 && lane == 0) mbar_arrive_expect_tx(stats_bar + par, 6 * 128 * 8);
+#pragma unroll
+        for (uint32_t peer = 0; peer < LN_CLUSTER; ++peer)
+          st_async_f32x2(map_to_cta(slot, peer), mean_t, m2_t, map_to_cta(stats_bar_addr[par], peer));
+      }
+      STK_GEMM_STAMP(dbg_thr, dbg_t, 12);
+      mbar_wait(stats_bar + par, (it >> 1) & 1);
+      STK_GEMM_STAMP(dbg_thr, dbg_t, 6);
+      float mean, rstd;
+      {
+        float2 pt[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) pt[k] = s_stats[(par * 6 + k) * 128 + row];
+        float sm = 0.f;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) sm += pt[k].x;
+        mean = sm * (1.0f / 6.0f);
+        float m2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const float d = pt[k].x - mean;
+          m2 += pt[k].y + 128.0f * d * d;
+        }
+        rstd = rsqrtf(m2 * (1.0f / 768.0f) + kLnEps);
+      }
+      if (e.ln_mean != nullptr && rank == 0 && g == 0 && m < p.M) {
+        e.ln_mean[m] = mean;
+        e.ln_rstd[m] = rstd;
+      }
+
+      // ---- pass 2: normalise, scale, shift; hand the staging tile to the I/O warp ----
+#pragma unroll
+      for (int chunk = 0; chunk < 2; ++chunk) {
+        const int L = g * 2 + chunk;
+        uint8_t* ebuf = smem_epi + L * EPI_BUF_BYTES;
+        const float4* gam4 = reinterpret_cast<const float4*>(s_par + 256 + g * 128 + chunk * 64);
+        const float4* bet4 = reinterpret_cast<const float4*>(s_par + 512 + g * 128 + chunk * 64);
+        if (save_z) mbar_wait(zdone_bar + L, it & 1);   // the z store has read the tile: it may be overwritten
+        const f32x2_t rstd2 = pack_f32x2(rstd, rstd);
+        const f32x2_t nmr2 = pack_f32x2(-mean * rstd, -mean * rstd);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t zz[4] = {zpk[chunk][c].x, zpk[chunk][c].y, zpk[chunk][c].z, zpk[chunk][c].w};
+          const float4 g0 = gam4[2 * c], g1 = gam4[2 * c + 1];
+          const float4 h0 = bet4[2 * c], h1 = bet4[2 * c + 1];
+          const f32x2_t gv[4] = {pack_f32x2(g0.x, g0.y), pack_f32x2(g0.z, g0.w), pack_f32x2(g1.x, g1.y),
+                                 pack_f32x2(g1.z, g1.w)};
+          const f32x2_t hv[4] = {pack_f32x2(h0.x, h0.y), pack_f32x2(h0.z, h0.w), pack_f32x2(h1.x, h1.y),
+                                 pack_f32x2(h1.z, h1.w)};
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const f32x2_t t2 = fma_f32x2(bf16x2_to_f32x2(zz[i]), rstd2, nmr2);   // (z - mean) * rstd
+            w[i] = f32x2_to_bf16x2(fma_f32x2(t2, gv[i], hv[i]));
+          }
+          *reinterpret_cast<uint4*>(ebuf + row * 128 + ((c ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(staged_bar + L);
+        STK_GEMM_STAMP(dbg_thr, dbg_t, 7 + chunk * 4);
       }
       if (++as == 2) { as = 0; as_phase ^= 1; }
     }
@@ -196,6 +486,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const StkGemmEpilogue& e = p.epi;
     float ce_scale = 0.f;
     if (EPI == STK_EPI_CE_DLOGIT) ce_scale = __ldg(e.scale_dev);
+    constexpr bool kHasBias = EPI == STK_EPI_BIAS || EPI == STK_EPI_BIAS_GELU || EPI == STK_EPI_BIAS_GELU_SAVE ||
+                              EPI == STK_EPI_BIAS_RESID || EPI == STK_EPI_BIAS_TANH_F32;
+    const int gt = (ew & 3) * 32 + lane;   // thread index within the epilogue group
+    float* s_bias = s_par + g * 128;       // bias of this group's 128 columns of the current tile (0 beyond N)
 
     int as = 0;
     uint32_t as_phase = 0;
@@ -206,6 +500,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       const int m0 = (tile / p.n_tiles) * BM;
       const int m = m0 + row;
       const bool m_ok = m < p.M;
+      const int dbg_t = (item - blockIdx.x) / gridDim.x;
+      const bool dbg_thr = threadIdx.x == 64;
+      STK_GEMM_STAMP(dbg_thr, dbg_t, 2);
+      if (kHasBias) {
+        // every thread of the previous tile is past its last read of s_bias (the staging barriers of
+        // its final chunk come after the math), so the vector can be replaced now
+        const int n = n0 + g * 128 + gt;
+        s_bias[gt] = (e.bias != nullptr && n < p.N) ? __ldg(e.bias + n) : 0.f;
+        named_bar_sync(bar_id, 128);
+      }
       // Residual / saved pre-activation rows do not depend on the accumulator: fetch both 64-column
       // chunks of this thread's row now so the global-load latency hides behind the MMA of this tile.
       constexpr bool kPrefetchExtra = EPI == STK_EPI_BIAS_RESID || EPI == STK_EPI_DGELU;
@@ -213,7 +517,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       // [128 rows x 128 B] residual tile (8 consecutive threads = one full 128-byte row segment); the
       // pieces are transposed to the thread-per-row accumulator layout through the staging tile later.
       uint4 ex_pre[2][8];
-      const int gt = (ew & 3) * 32 + lane;   // thread index within the epilogue group
       if (kPrefetchExtra) {
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
@@ -231,6 +534,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       }
       mbar_wait(tfull_bar + as, as_phase);
       tc_fence_after();
+      STK_GEMM_STAMP(dbg_thr, dbg_t, 3);
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + g * 128;
 
       // per-row CE state
@@ -248,6 +552,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         tmem_ld_32x32b_x32(t_row + chunk * 64, r[0]);
         tmem_ld_32x32b_x32(t_row + chunk * 64 + 32, r[1]);
         tmem_ld_wait();
+        STK_GEMM_STAMP(dbg_thr, dbg_t, 4 + chunk * 4);
         if (chunk == 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -293,11 +598,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 v[i] = __uint_as_float(r[h][c * 4 + i]);
-                if (EPI == STK_EPI_BIAS_TANH_F32) {
-                  const int n = nc + h * 32 + c * 4 + i;
-                  const float b = (e.bias != nullptr && n < p.N) ? __ldg(e.bias + n) : 0.f;
-                  v[i] = tanhf(v[i] + b);
-                }
+                if (EPI == STK_EPI_BIAS_TANH_F32) v[i] = tanhf(v[i] + s_bias[chunk * 64 + h * 32 + c * 4 + i]);
               }
               data[c] = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]),
                                    __float_as_uint(v[3]));
@@ -308,10 +609,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
 
         // bf16 outputs
-        constexpr bool kHasBias = EPI == STK_EPI_BIAS || EPI == STK_EPI_BIAS_GELU ||
-                                  EPI == STK_EPI_BIAS_GELU_SAVE || EPI == STK_EPI_BIAS_RESID;
         constexpr bool kHasExtra = EPI == STK_EPI_BIAS_RESID || EPI == STK_EPI_DGELU;
-        const bool bias_vec = kHasBias && e.bias != nullptr && nc + 64 <= p.N;
         if (kHasExtra) {
           // acquire the staging tile, drop the coalesced residual pieces into it (swizzled), then every
           // thread picks up its own row below; the result overwrites the same 16-byte slots
@@ -325,23 +623,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           }
           named_bar_sync(bar_id, 128);
         }
+        STK_GEMM_STAMP(dbg_thr, dbg_t, 5 + chunk * 4);
         uint4 data[8];
         uint4 data2[8];
+        const float4* bias4 = reinterpret_cast<const float4*>(s_bias + chunk * 64);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           uint32_t w[4], w2[4];
           float bias_v[8];
-          if (kHasBias) {
-            if (bias_vec) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + nc) + 2 * c);
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(e.bias + nc) + 2 * c + 1);
-              bias_v[0] = b0.x; bias_v[1] = b0.y; bias_v[2] = b0.z; bias_v[3] = b0.w;
-              bias_v[4] = b1.x; bias_v[5] = b1.y; bias_v[6] = b1.z; bias_v[7] = b1.w;
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                bias_v[i] = (e.bias != nullptr && nc + c * 8 + i < p.N) ? __ldg(e.bias + nc + c * 8 + i) : 0.f;
-            }
+          if (kHasBias) {   // broadcast shared-memory reads: no global loads, no tail predicates on the hot path
+            const float4 b0 = bias4[2 * c], b1 = bias4[2 * c + 1];
+            bias_v[0] = b0.x; bias_v[1] = b0.y; bias_v[2] = b0.z; bias_v[3] = b0.w;
+            bias_v[4] = b1.x; bias_v[5] = b1.y; bias_v[6] = b1.z; bias_v[7] = b1.w;
           }
           uint4 ex4 = make_uint4(0, 0, 0, 0);
           if (kHasExtra) ex4 = *reinterpret_cast<const uint4*>(buf + row * 128 + ((c ^ (row & 7)) << 4));
@@ -383,9 +676,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           data[c] = make_uint4(w[0], w[1], w[2], w[3]);
           if (EPI == STK_EPI_BIAS_GELU_SAVE) data2[c] = make_uint4(w2[0], w2[1], w2[2], w2[3]);
         }
+        STK_GEMM_STAMP(dbg_thr, dbg_t, 6 + chunk * 4);
         stage_and_store<false, kHasExtra>(&map_c, buf, row, data, nc, m0, store_thread, bar_id);
         if (EPI == STK_EPI_BIAS_GELU_SAVE)
           stage_and_store<false>(&map_c2, buf, row, data2, nc, m0, store_thread, bar_id);
+        STK_GEMM_STAMP(dbg_thr, dbg_t, 7 + chunk * 4);
       }
 
       if (EPI == STK_EPI_CE_STATS && m_ok) {
@@ -400,6 +695,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
   tc_fence_before();
   __syncthreads();
+  if (kLN) cluster_sync_all();   // no CTA leaves while a peer may still write into its shared memory
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -413,16 +709,46 @@ extern std::atomic<long long> g_launches;
 
 template <int A_MN, int B_MN, int EPI>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mc2,
-                  const GemmParams& p, int grid, cudaStream_t stream) {
+                  const CUtensorMap& mr, const GemmParams& p, int grid, cudaStream_t stream) {
+  using Cfg = GemmCfg<EPI>;
   auto kern = gemm_kernel<A_MN, B_MN, EPI>;
   static bool configured[64] = {};
+  static int max_clusters[64] = {};
   int dev = 0;
   STK_CHECK_CUDA(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
-    STK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    STK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     configured[dev & 63] = true;
   }
-  kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(ma, mb, mc, mc2, p);
+  if (!Cfg::kLN) {
+    kern<<<grid, Cfg::kThreads, Cfg::kSmem, stream>>>(ma, mb, mc, mc2, mr, p);
+  } else {
+    // clusters of three CTAs (one per 256-column slab of the 768-wide rows), persistent over the row tiles
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = LN_CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(Cfg::kThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmem;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (max_clusters[dev & 63] == 0) {
+      cfg.gridDim = dim3(LN_CLUSTER * 64);
+      int n = 0;
+      STK_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+      if (n <= 0) {
+        set_error("stk_gemm: no %d-CTA cluster of the LayerNorm epilogue fits on this device", LN_CLUSTER);
+        return STK_ERR_UNSUPPORTED;
+      }
+      max_clusters[dev & 63] = n;
+    }
+    const int clusters = p.m_tiles < max_clusters[dev & 63] ? p.m_tiles : max_clusters[dev & 63];
+    cfg.gridDim = dim3(LN_CLUSTER * clusters);
+    STK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, mc2, mr, p));
+  }
   STK_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return STK_OK;
@@ -454,6 +780,12 @@ extern "C" int stk_gemm(int device, void* stream_, int a_major, int b_major, con
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   if (epi) p.epi = *epi;
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("STK_GEMM_DEBUG");
+    dbg = e ? atoi(e) : 0;
+  }
+  p.dbg = dbg;
 
   const bool f32_out = epilogue == STK_EPI_F32 || epilogue == STK_EPI_F32_ADD || epilogue == STK_EPI_BIAS_TANH_F32;
   const bool has_c = epilogue != STK_EPI_CE_STATS;
@@ -461,6 +793,15 @@ extern "C" int stk_gemm(int device, void* stream_, int a_major, int b_major, con
     STK_REQUIRE(epi && epi->resid && epi->ldr % 8 == 0 && N % 64 == 0, "stk_gemm: residual epilogue needs resid, ldr%%8==0, N%%64==0");
   }
   if (epilogue == STK_EPI_BIAS_GELU_SAVE) STK_REQUIRE(epi && epi->c2 && epi->ldc2 % 8 == 0, "stk_gemm: GELU_SAVE needs c2");
+  if (epilogue == STK_EPI_BIAS_RESID_LN) {
+    STK_REQUIRE(N == kHidden && a_major == 0 && b_major == 0, "stk_gemm: the LayerNorm epilogue needs N == 768 and K-major operands");
+    STK_REQUIRE(epi && epi->resid && epi->ldr % 8 == 0 && epi->ln_gamma && epi->ln_beta,
+                "stk_gemm: the LayerNorm epilogue needs resid (ldr%%8==0), ln_gamma and ln_beta");
+    STK_REQUIRE((reinterpret_cast<uintptr_t>(epi->resid) & 15) == 0, "stk_gemm: resid must be 16-byte aligned");
+    STK_REQUIRE(epi->c2 == nullptr || (epi->ldc2 % 8 == 0 && (reinterpret_cast<uintptr_t>(epi->c2) & 15) == 0),
+                "stk_gemm: c2 (pre-LayerNorm output) must be 16-byte aligned with ldc2%%8==0");
+    STK_REQUIRE((epi->ln_mean == nullptr) == (epi->ln_rstd == nullptr), "stk_gemm: ln_mean and ln_rstd come together");
+  }
   if (epilogue == STK_EPI_CE_STATS)
     STK_REQUIRE(epi && epi->labels && epi->ce_partial && epi->tgt_logit && epi->n_offset % 256 == 0, "stk_gemm: CE_STATS args");
   if (epilogue == STK_EPI_CE_DLOGIT)
@@ -470,7 +811,7 @@ extern "C" int stk_gemm(int device, void* stream_, int a_major, int b_major, con
     STK_REQUIRE(ldc % (f32_out ? 4 : 8) == 0, "stk_gemm: ldc must be a multiple of 16 bytes");
   }
 
-  CUtensorMap ma, mb, mc, mc2;
+  CUtensorMap ma, mb, mc, mc2, mr;
   int rc;
   // A: K-major -> stored [M][K], box {64 k, 128 m};  MN-major -> stored [K][M], box {64 m, 64 k}
   if (a_major == 0) rc = make_tmap_2d(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, K, M, lda * 2, 64, BM);
@@ -487,8 +828,13 @@ extern "C" int stk_gemm(int device, void* stream_, int a_major, int b_major, con
     mc = ma;
   }
   mc2 = mc;
-  if (epilogue == STK_EPI_BIAS_GELU_SAVE) {
+  mr = mc;
+  if (epilogue == STK_EPI_BIAS_GELU_SAVE || (epilogue == STK_EPI_BIAS_RESID_LN && epi->c2)) {
     rc = make_tmap_2d(&mc2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, epi->c2, N, M, epi->ldc2 * 2, 64, 128);
+    if (rc) return rc;
+  }
+  if (epilogue == STK_EPI_BIAS_RESID_LN) {
+    rc = make_tmap_2d(&mr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, epi->resid, N, M, epi->ldr * 2, 64, 128);
     if (rc) return rc;
   }
   const int items = p.m_tiles * p.n_tiles * p.splits;
@@ -497,11 +843,12 @@ extern "C" int stk_gemm(int device, void* stream_, int a_major, int b_major, con
 
 #define STK_GEMM_CASE(AM, BMJ, E)                                   \
   if (a_major == AM && b_major == BMJ && epilogue == E)             \
-    return launch<AM, BMJ, E>(ma, mb, mc, mc2, p, grid, stream);
+    return launch<AM, BMJ, E>(ma, mb, mc, mc2, mr, p, grid, stream);
   STK_GEMM_CASE(0, 0, STK_EPI_BIAS)
   STK_GEMM_CASE(0, 0, STK_EPI_BIAS_GELU)
   STK_GEMM_CASE(0, 0, STK_EPI_BIAS_GELU_SAVE)
   STK_GEMM_CASE(0, 0, STK_EPI_BIAS_RESID)
+  STK_GEMM_CASE(0, 0, STK_EPI_BIAS_RESID_LN)
   STK_GEMM_CASE(0, 0, STK_EPI_BIAS_TANH_F32)
   STK_GEMM_CASE(0, 0, STK_EPI_F32)
   STK_GEMM_CASE(0, 0, STK_EPI_CE_STATS)
@@ -516,4 +863,9 @@ extern "C" int stk_gemm(int device, void* stream_, int a_major, int b_major, con
 #undef STK_GEMM_CASE
   set_error("stk_gemm: unsupported combination a_major=%d b_major=%d epilogue=%d", a_major, b_major, epilogue);
   return STK_ERR_UNSUPPORTED;
+}
+
+// bring-up only: copy the clock64 timeline recorded by CTA 0 of the last STK_GEMM_DEBUG launch
+extern "C" __attribute__((visibility("default"))) int stk_debug_gemm_timeline(long long* host, int n) {
+  return cudaMemcpyFromSymbol(host, stk::g_gemm_timeline, sizeof(long long) * n) == cudaSuccess ? 0 : -2;
 }

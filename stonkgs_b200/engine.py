@@ -8,6 +8,7 @@ computes in ``STonKGsForPreTraining.forward`` (stonkgs_model.py:149-258) through
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -18,6 +19,9 @@ from . import ops
 H = 768
 I = 3072
 HALF = 256
+# bias + residual + LayerNorm fused into the Wo / FFN2 GEMM epilogues (STK_EPI_BIAS_RESID_LN); the switch
+# exists only so that profiling tools can time the unfused pair (GEMM + LayerNorm kernel) beside it
+FUSED_LN = os.environ.get("STK_FUSED_LN", "1") != "0"
 
 
 # --------------------------------------------------------------------------------------------------
@@ -93,6 +97,18 @@ def encoder_layer_fwd(x, lw: LayerWeights, B: int, S: int, key_bias, cache: Opti
         ctx, lse = ops.attention(qkv, key_bias, B, S, save_lse=True)
     else:
         ctx = ops.attention(qkv, key_bias, B, S)
+    if FUSED_LN:
+        if train:
+            x1, z1, mean1, rstd1 = ops.linear_resid_ln(ctx, lw.wo, lw.bo, x, lw.ln1_g, lw.ln1_b, save_for_backward=True)
+            u = torch.empty((M, I), dtype=torch.bfloat16, device=x.device)
+            h = ops.linear(x1, lw.w1, lw.b1, ops.EPI_BIAS_GELU_SAVE, c2=u)
+            x2, z2, mean2, rstd2 = ops.linear_resid_ln(h, lw.w2, lw.b2, x1, lw.ln2_g, lw.ln2_b, save_for_backward=True)
+            cache.append(LayerCache(x, qkv, lse, ctx, z1, mean1, rstd1, x1, u, h, z2, mean2, rstd2))
+        else:
+            x1 = ops.linear_resid_ln(ctx, lw.wo, lw.bo, x, lw.ln1_g, lw.ln1_b)
+            h = ops.linear(x1, lw.w1, lw.b1, ops.EPI_BIAS_GELU)
+            x2 = ops.linear_resid_ln(h, lw.w2, lw.b2, x1, lw.ln2_g, lw.ln2_b)
+        return x2
     z1 = ops.linear(ctx, lw.wo, lw.bo, ops.EPI_BIAS_RESID, resid=x)
     if train:
         x1, mean1, rstd1 = ops.layernorm(z1, lw.ln1_g, lw.ln1_b, save_stats=True)

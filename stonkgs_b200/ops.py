@@ -11,8 +11,8 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GELU_SAVE, EPI_BIAS_RESID, EPI_BIAS_TANH_F32, EPI_CE_DLOGIT,
-                   EPI_CE_STATS, EPI_DGELU, EPI_F32, EPI_F32_ADD, GemmEpilogue, check)
+from ._lib import (EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GELU_SAVE, EPI_BIAS_RESID, EPI_BIAS_RESID_LN, EPI_BIAS_TANH_F32,
+                   EPI_CE_DLOGIT, EPI_CE_STATS, EPI_DGELU, EPI_F32, EPI_F32_ADD, GemmEpilogue, check)
 
 H = 768
 HEADS = 12
@@ -155,7 +155,8 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, out=None):
 # --------------------------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, b: torch.Tensor, *, M: int, N: int, K: int, a_major: int = 0, b_major: int = 0,
          epilogue: int = EPI_BIAS, out: Optional[torch.Tensor] = None, bias=None, resid=None, c2=None, labels=None,
-         lse=None, scale_dev=None, ce_partial=None, tgt_logit=None, n_offset: int = 0, split_k: int = 1):
+         lse=None, scale_dev=None, ce_partial=None, tgt_logit=None, n_offset: int = 0, split_k: int = 1,
+         ln_gamma=None, ln_beta=None, ln_mean=None, ln_rstd=None):
     """C[M,N] = epilogue(A[M,K] B[N,K]^T); a/b are 2-D bf16 tensors in the stored layout
     (K-major: [M,K] / [N,K]; MN-major: [K,M] / [K,N]); row stride = leading dimension."""
     _req(a, torch.bfloat16, "A")
@@ -181,6 +182,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: int, N: int, K: int, a_major: i
         epi.ce_pitch = ce_partial.shape[1]
     epi.tgt_logit = tgt_logit.data_ptr() if tgt_logit is not None else None
     epi.n_offset = n_offset
+    epi.ln_gamma = ln_gamma.data_ptr() if ln_gamma is not None else None
+    epi.ln_beta = ln_beta.data_ptr() if ln_beta is not None else None
+    epi.ln_mean = ln_mean.data_ptr() if ln_mean is not None else None
+    epi.ln_rstd = ln_rstd.data_ptr() if ln_rstd is not None else None
     if epilogue != EPI_CE_STATS:
         if out is None:
             dt = torch.float32 if epilogue in _F32_EPIS else torch.bfloat16
@@ -198,6 +203,21 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: int, N: int, K: int, a_major: i
     if prof is not None:
         e1.record()
     return out
+
+
+def linear_resid_ln(x, w, bias, resid, gamma, beta, *, save_for_backward=False):
+    """y = LayerNorm(x @ w.T + bias + resid) * gamma + beta in ONE kernel (HF:294-298, 352-356).
+    Returns y, or (y, z, mean, rstd) with z the pre-LayerNorm sum when ``save_for_backward``."""
+    M = x.shape[0]
+    assert w.shape[0] == H
+    z = mean = rstd = None
+    if save_for_backward:
+        z = torch.empty((M, H), dtype=torch.bfloat16, device=x.device)
+        mean = torch.empty(M, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+    y = gemm(x, w, M=M, N=H, K=x.shape[1], bias=bias, epilogue=EPI_BIAS_RESID_LN, resid=resid, c2=z, ln_gamma=gamma,
+             ln_beta=beta, ln_mean=mean, ln_rstd=rstd)
+    return (y, z, mean, rstd) if save_for_backward else y
 
 
 def linear(x, w, bias=None, epilogue=EPI_BIAS, **kw):

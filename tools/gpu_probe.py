@@ -199,6 +199,48 @@ def case_gemm_epilogues():
     return res
 
 
+def case_gemm_ln():
+    """Fused bias + residual + LayerNorm epilogue (3-CTA clusters, DSMEM row statistics) vs torch fp32."""
+    import torch
+    from stonkgs_b200 import ops
+    torch.manual_seed(7)
+    res = []
+    for (M, K) in [(128, 768), (520, 768), (1000, 3072), (128 * 160 + 37, 768)]:
+        N = 768
+        a = _mk(M, K, "cuda", 0.5)
+        w = _mk(N, K, "cuda", 0.05)
+        bias = torch.randn(N, device="cuda") * 0.5
+        r = _mk(M, N, "cuda")
+        gamma = 1.0 + 0.2 * torch.randn(N, device="cuda")
+        beta = 0.3 * torch.randn(N, device="cuda")
+        zref = _gemm_ref(a, w, 0, 0) + bias + r.float()
+        yref = torch.nn.functional.layer_norm(zref, (N,), gamma, beta, 1e-12)
+        y = ops.linear_resid_ln(a, w, bias, r, gamma, beta)
+        torch.cuda.synchronize()
+        res.append(_err_report(y, yref, f"ln_infer_{M}x{K}", 6e-2))
+        y2, z, mean, rstd = ops.linear_resid_ln(a, w, bias, r, gamma, beta, save_for_backward=True)
+        torch.cuda.synchronize()
+        res.append(_err_report(y2, yref, f"ln_train_y_{M}x{K}", 6e-2))
+        res.append(_err_report(z, zref, f"ln_train_z_{M}x{K}", 5e-2))
+        res.append(_err_report(mean, zref.mean(1), f"ln_train_mean_{M}x{K}", 2e-3))
+        res.append(_err_report(rstd, (zref.var(1, unbiased=False) + 1e-12).rsqrt(), f"ln_train_rstd_{M}x{K}", 2e-3))
+        res.append({"case": f"ln_same_{M}x{K}", "ok": bool(torch.equal(y, y2))})
+    # a row with a large common offset: the chunked (mean, M2) merge must not cancel catastrophically
+    M, K, N = 256, 768, 768
+    a = _mk(M, K, "cuda", 0.5)
+    w = _mk(N, K, "cuda", 0.05)
+    r = (torch.randn(M, N, device="cuda") + 40.0).bfloat16()
+    gamma = torch.ones(N, device="cuda")
+    beta = torch.zeros(N, device="cuda")
+    zref = _gemm_ref(a, w, 0, 0) + r.float()
+    yref = torch.nn.functional.layer_norm(zref, (N,), gamma, beta, 1e-12)
+    y = ops.linear_resid_ln(a, w, None, r, gamma, beta)
+    torch.cuda.synchronize()
+    res.append(_err_report(y, yref, "ln_offset40", 0.3))   # z itself is rounded to bf16 at |z| ~ 40 (ulp 0.25)
+    return res
+
+
+
 def case_gemm_majors():
     """dgrad (B MN-major) and wgrad (A and B MN-major, split-K reduce-add)."""
     import torch
@@ -373,6 +415,7 @@ CASES = {
     "gemm_basic": case_gemm_basic,
     "gemm_epilogues": case_gemm_epilogues,
     "gemm_majors": case_gemm_majors,
+    "gemm_ln": case_gemm_ln,
     "gemm_ce": case_gemm_ce,
     "attn": case_attn,
     "perf": case_perf,
