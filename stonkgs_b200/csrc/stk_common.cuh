@@ -163,6 +163,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (never suspends the thread): look-ahead polls between tcgen05.mma issues
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a pipeline bug must never hang the GPU box.  mbarrier.try_wait already suspends the
 // thread for a hardware-defined interval, so the loop polls it directly; the (cheap, SM-local)
 // cycle counter is only consulted every 1024 failed polls, and after ~2^33 cycles (> 4 s) the kernel
@@ -321,6 +333,94 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Whole-warp forms: every lane of a converged warp executes the statement and elect.sync picks the issuing
+// lane INSIDE it, so ptxas emits a plain `ELECT P; @P UTCHMMA` with uniform-register operands.  (Branching
+// on an elect result cached in a register hides from ptxas that exactly one lane is active: it then wraps
+// each tcgen05 instruction in an elect / issue / "any lane left?" loop and re-broadcasts its operands.)
+__device__ __forceinline__ void umma_bf16_warp(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair_warp(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                    uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_warp(uint64_t* bar, uint32_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t.reg .b16 lo, hi;\n\t"
+      "mov.b32 {lo, hi}, %1;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], lo;\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta_mask)
+      : "memory");
+}
+// One k-block (four K=16 steps) of a GEMM mainloop as ONE statement: a single elect, four MMAs, a
+// non-blocking probe of the next slot's "full" barrier between them (returned), and the commit that frees
+// this slot.  Keeps the issuing warp's instruction count per k-block minimal — it shares its scheduler with
+// epilogue warps, and every cycle it waits for an issue slot beyond the 128 of the MMA in flight idles the
+// tensor pipe.  PAIR selects the cta_group::2 forms (commit multicast to both CTAs of the pair).
+template <bool PAIR>
+__device__ __forceinline__ bool umma_kblock_warp(uint32_t d_tmem, uint64_t a0, uint64_t b0, uint64_t a1, uint64_t b1,
+                                                 uint64_t a2, uint64_t b2, uint64_t a3, uint64_t b3, uint32_t idesc,
+                                                 uint32_t acc_first, uint64_t* slot_free_bar, uint32_t cta_mask,
+                                                 uint64_t* next_full_bar, uint32_t next_parity) {
+  uint32_t ready;
+  if (PAIR) {
+    asm volatile(
+        "{\n\t.reg .pred p, e, r;\n\t.reg .b16 lo, hi;\n\t"
+        "mov.b32 {lo, hi}, %13;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %11, 0;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%1], %2, %3, %10, p;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%1], %4, %5, %10, 1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 r, [%14], %15;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%1], %6, %7, %10, 1;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%1], %8, %9, %10, 1;\n\t"
+        "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%12], lo;\n\t"
+        "selp.u32 %0, 1, 0, r;\n\t}"
+        : "=r"(ready)
+        : "r"(d_tmem), "l"(a0), "l"(b0), "l"(a1), "l"(b1), "l"(a2), "l"(b2), "l"(a3), "l"(b3), "r"(idesc),
+          "r"(acc_first), "r"(smem_u32(slot_free_bar)), "r"(cta_mask), "r"(smem_u32(next_full_bar)), "r"(next_parity)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, e, r;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %11, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %3, %10, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], %4, %5, %10, 1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 r, [%13], %14;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], %6, %7, %10, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%1], %8, %9, %10, 1;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n\t"
+        "selp.u32 %0, 1, 0, r;\n\t}"
+        : "=r"(ready)
+        : "r"(d_tmem), "l"(a0), "l"(b0), "l"(a1), "l"(b1), "l"(a2), "l"(b2), "l"(a3), "l"(b3), "r"(idesc),
+          "r"(acc_first), "r"(smem_u32(slot_free_bar)), "r"(smem_u32(next_full_bar)), "r"(next_parity)
+        : "memory");
+  }
+  return ready != 0;
+}
 // D[tmem] (+)= A[tmem] * B[smem desc]: A operand read from tensor memory (lane = row, each 32-bit
 // column holds two consecutive K elements), e.g. the bf16 softmax probabilities of attention.
 __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
@@ -337,6 +437,50 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster whose ranks differ in bit 0 run ONE 256-row MMA;
+// each holds its 128 rows of A and of the accumulator, and half of B (the halves are exchanged by the
+// tensor cores), which halves the shared-memory operand traffic per SM.  The even CTA issues the MMAs.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the pair-rank bit of a shared::cluster address
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {  // one warp of EACH CTA
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all earlier MMAs of this thread are complete) on the barrier at the same offset in every
+// CTA of the cluster whose rank bit is set in cta_mask
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint32_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .b16 lo, hi;\n\t"
+      "mov.b32 {lo, hi}, %1;\n\t"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], lo;\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta_mask)
+      : "memory");
+}
+// TMA load issued by either CTA of a pair; the transaction bytes complete on the barrier of the EVEN CTA
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint64_t* bar, void* smem, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+// plain (release.cta) arrive on a barrier of another CTA of the cluster: no GPU-scope fence is emitted
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
 // TMEM -> registers: thread i of the warp reads lane (base_lane + i), 32 consecutive columns.

@@ -27,25 +27,32 @@ namespace stk {
 
 constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
 constexpr int EPI_BUF_BYTES = 128 * 128;    // [128 rows][128 B] staging tile
 
-// Per-epilogue kernel geometry.  The fused residual + LayerNorm epilogue (STK_EPI_BIAS_RESID_LN) runs as
-// clusters of three CTAs (one per 256-column slab of the 768-wide row) with an extra I/O warp that moves
-// the residual in and the results out through FOUR staging tiles by TMA; it pays for the extra staging
-// and the statistics exchange buffers with one ring stage.
-template <int EPI>
+// Kernel geometry per (epilogue, pairing).
+// PAIR: two CTAs of a cluster (ranks 2p, 2p+1) run one 256 x 256 tile with cta_group::2 MMAs: each CTA
+// stages its 128 rows of A and 128 of the 256 rows of B (32 KB per stage instead of 48 KB), the even CTA
+// issues the MMAs for both, each CTA drains its own 128 x 256 accumulator.  Halving the B traffic per SM
+// takes the operand reads + TMA fills under the shared-memory bandwidth that limits the single-CTA form.
+// LN: the fused residual + LayerNorm epilogue (STK_EPI_BIAS_RESID_LN) spreads the 768-wide row over three
+// column slabs (three CTAs, or three pairs) of one cluster, with two extra I/O warps that move the
+// residual in and the results out through FOUR staging tiles by TMA.
+template <int EPI, bool PAIR>
 struct GemmCfg {
   static constexpr bool kLN = EPI == STK_EPI_BIAS_RESID_LN;
-  static constexpr int kStages = kLN ? 3 : 4;
+  static constexpr int kBRows = PAIR ? 128 : 256;                   // rows of B this CTA stages
+  static constexpr int kBStageBytes = kBRows * BK * 2;
+  static constexpr int kStageBytes = A_STAGE_BYTES + kBStageBytes;
+  static constexpr int kStages = PAIR ? (kLN ? 4 : 6) : (kLN ? 3 : 4);
   static constexpr int kThreads = kLN ? 384 : 320;
   static constexpr int kEpiBufs = kLN ? 4 : 2;
   static constexpr int kStatsBytes = kLN ? 2 * 6 * 128 * 8 : 0;   // [parity][slab half][row] (mean, M2)
   static constexpr int kParamBytes = kLN ? 3 * 256 * 4 : 256 * 4;  // bias (+ gamma, beta) of this CTA's columns
-  static constexpr int kSmem = 1024 /*align slack*/ + kStages * (A_STAGE_BYTES + B_STAGE_BYTES) +
-                               kEpiBufs * EPI_BUF_BYTES + kStatsBytes + kParamBytes + 512 /*barriers*/;
+  static constexpr int kCluster = (kLN ? 3 : 1) * (PAIR ? 2 : 1);
+  static constexpr int kTileM = PAIR ? 256 : 128;
+  static constexpr int kSmem = 1024 /*align slack*/ + kStages * kStageBytes + kEpiBufs * EPI_BUF_BYTES + kStatsBytes +
+                               kParamBytes + 512 /*barriers*/;
 };
-constexpr int LN_CLUSTER = 3;
 
 struct GemmParams {
   int M, N, K;
@@ -84,14 +91,16 @@ __device__ __forceinline__ void stage_and_store(const CUtensorMap* map, uint8_t*
   }
 }
 
-template <int A_MN, int B_MN, int EPI>
-__global__ void __launch_bounds__(GemmCfg<EPI>::kThreads, 1)
+template <int A_MN, int B_MN, int EPI, bool PAIR>
+__global__ void __launch_bounds__(GemmCfg<EPI, PAIR>::kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c2,
             const __grid_constant__ CUtensorMap map_r, const GemmParams p) {
-  using Cfg = GemmCfg<EPI>;
+  using Cfg = GemmCfg<EPI, PAIR>;
   constexpr bool kLN = Cfg::kLN;
   constexpr int STAGES = Cfg::kStages;
+  constexpr int B_STAGE_BYTES = Cfg::kBStageBytes;
+  constexpr int TM = Cfg::kTileM;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -100,20 +109,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   float2* s_stats = reinterpret_cast<float2*>(smem_epi + Cfg::kEpiBufs * EPI_BUF_BYTES);   // LN only
   float* s_par = reinterpret_cast<float*>(smem_epi + Cfg::kEpiBufs * EPI_BUF_BYTES + Cfg::kStatsBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_par) + Cfg::kParamBytes);
-  uint64_t* full_bar = bars;                 // [STAGES]
-  uint64_t* empty_bar = bars + 4;            // [STAGES]
-  uint64_t* tfull_bar = bars + 8;            // [2]
-  uint64_t* tempty_bar = bars + 10;          // [2]
+  uint64_t* full_bar = bars;                 // [STAGES]  (PAIR: only the even CTA's are used)
+  uint64_t* empty_bar = bars + 8;            // [STAGES]
+  uint64_t* tfull_bar = bars + 16;           // [2]
+  uint64_t* tempty_bar = bars + 18;          // [2]       (PAIR: only the even CTA's are used)
   // LN epilogue only:
-  uint64_t* rfull_bar = bars + 12;           // [4] residual chunk landed in staging tile L
-  uint64_t* staged_bar = bars + 16;          // [4] normalised output written to staging tile L
-  uint64_t* zstaged_bar = bars + 20;         // [4] pre-LN sum written to staging tile L (training: saved for backward)
-  uint64_t* zdone_bar = bars + 24;           // [4] ... and read out by its TMA store
-  uint64_t* stats_bar = bars + 28;           // [2] row statistics of all three slabs have arrived (cluster scope)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+  uint64_t* rfull_bar = bars + 20;           // [4] residual chunk landed in staging tile L
+  uint64_t* staged_bar = bars + 24;          // [4] normalised output written to staging tile L
+  uint64_t* zstaged_bar = bars + 28;         // [4] pre-LN sum written to staging tile L (training: saved for backward)
+  uint64_t* zdone_bar = bars + 32;           // [4] ... and read out by its TMA store
+  uint64_t* stats_bar = bars + 36;           // [2] row statistics of all three slabs have arrived (cluster scope)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 38);
+  static_assert(STAGES <= 8, "barrier layout");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t crank = Cfg::kCluster > 1 ? cluster_ctarank() : 0u;   // rank in the cluster
+  const uint32_t pr = PAIR ? (crank & 1u) : 0u;                        // rank in the CTA pair (0 issues the MMAs)
+  const uint32_t pair_leader = crank & ~1u;
+  // persistent scheduling unit = CTA or CTA pair
+  const int unit = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int units = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -125,7 +141,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar + i, 1);
-      mbar_init(tempty_bar + i, 8);  // one arrive per epilogue warp
+      mbar_init(tempty_bar + i, PAIR ? 16 : 8);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     if (kLN) {
       for (int i = 0; i < 4; ++i) {
@@ -138,11 +154,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(tmem_slot, 512);
+    else tmem_alloc(tmem_slot, 512);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (kLN) cluster_sync_all();   // peers' barriers are initialised before anyone arrives on them remotely
+  if (Cfg::kCluster > 1) cluster_sync_all();   // peers' barriers are initialised before anyone arrives on them remotely
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_items = p.m_tiles * p.n_tiles * p.splits;
@@ -152,92 +171,136 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     // Warp-uniform control flow (all lanes walk the loop and poll the barriers, so addresses and
     // coordinates stay on the uniform datapath); one elected lane issues the TMA instructions.
     const bool leader = elect_one();
-    int stage = 0;
+    int stage = 0, n_loaded = 0;
     uint32_t phase = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    for (int item = unit; item < num_items; item += units) {
       const int split = item % p.splits;
       const int tile = item / p.splits;
       const int n0 = (tile % p.n_tiles) * BN;
-      const int m0 = (tile / p.n_tiles) * BM;
+      const int m0 = (tile / p.n_tiles) * TM + static_cast<int>(pr) * 128;
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(empty_bar + stage, phase ^ 1);
-        if (kb == kb0 && !kLN) STK_GEMM_STAMP(leader, (item - blockIdx.x) / gridDim.x, 12);
-        if (leader) {
-          mbar_arrive_expect_tx(full_bar + stage, A_STAGE_BYTES + B_STAGE_BYTES);
+        if (kb == kb0 && !kLN) STK_GEMM_STAMP(leader, (item - unit) / units, 12);
+        if ((p.dbg & 4) && n_loaded >= STAGES) {   // bring-up: no loads after the ring's first fill (pure MMA rate)
+          if (leader && (!PAIR || pr == 0)) mbar_arrive(full_bar + stage);
+        } else if (leader) {
+          // PAIR: both CTAs' loads complete on the even CTA's barrier, which expects the bytes of both
+          if (!PAIR || pr == 0) mbar_arrive_expect_tx(full_bar + stage, (PAIR ? 2 : 1) * Cfg::kStageBytes);
           uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
           uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
           const int k0 = kb * BK;
+          const int nb0 = n0 + static_cast<int>(pr) * 128;   // PAIR: this CTA stages rows [nb0, nb0 + 128) of B
+          auto load = [&](const CUtensorMap* m, void* dst, int c0, int c1) {
+            if (PAIR) tma_load_2d_pair(m, full_bar + stage, dst, c0, c1);
+            else tma_load_2d(m, full_bar + stage, dst, c0, c1);
+          };
           if (A_MN) {
 #pragma unroll
-            for (int i = 0; i < BM / 64; ++i) tma_load_2d(&map_a, full_bar + stage, sa + i * 8192, m0 + 64 * i, k0);
+            for (int i = 0; i < BM / 64; ++i) load(&map_a, sa + i * 8192, m0 + 64 * i, k0);
           } else {
-            tma_load_2d(&map_a, full_bar + stage, sa, k0, m0);
+            load(&map_a, sa, k0, m0);
           }
           if (B_MN) {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i) tma_load_2d(&map_b, full_bar + stage, sb + i * 8192, n0 + 64 * i, k0);
+            for (int i = 0; i < Cfg::kBRows / 64; ++i) load(&map_b, sb + i * 8192, nb0 + 64 * i, k0);
           } else {
-            tma_load_2d(&map_b, full_bar + stage, sb, k0, n0);
+            load(&map_b, sb, k0, nb0);
           }
         }
         __syncwarp();
+        ++n_loaded;
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
+    if (PAIR && pr != 0) {
+      // the odd CTA of a pair only lends its shared and tensor memory to the MMAs issued by the even one
+    } else {
     // ============================== MMA issuer ==============================
     // Same structure: the whole warp tracks the pipeline state, one elected lane issues tcgen05.mma /
     // tcgen05.commit, so descriptor arithmetic is uniform and no per-instruction R2UR chain forms.
     const bool leader = elect_one();
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    constexpr uint32_t idesc = umma_idesc_bf16(TM, BN, A_MN, B_MN);   // PAIR: M = 256 across the two CTAs
+    const uint32_t pair_mask = 3u << pair_leader;
     // K-major: 8-row groups 1024 B apart, +32 B per 16-wide k step.
     // MN-major: 64-wide chunks 8192 B apart (LBO), 8 k-rows 1024 B apart (SBO), +2048 B per k step.
     const uint64_t a_desc0 = umma_smem_desc(smem_u32(smem_a), A_MN ? 8192 : 16, 1024);
     const uint64_t b_desc0 = umma_smem_desc(smem_u32(smem_b), B_MN ? 8192 : 16, 1024);
     constexpr uint32_t a_kstep = (A_MN ? 2048 : 32) >> 4;
     constexpr uint32_t b_kstep = (B_MN ? 2048 : 32) >> 4;
+    const uint32_t tmem_base_u = __reduce_max_sync(0xffffffffu, tmem_base);
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
     uint32_t as_phase = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    bool ready = false;
+    for (int item = unit; item < num_items; item += units) {
       const int split = item % p.splits;
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
       mbar_wait(tempty_bar + as, as_phase ^ 1);  // epilogue has drained this accumulator stage
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * BN;
-      STK_GEMM_STAMP(leader, (item - blockIdx.x) / gridDim.x, 0);
+      // warp-uniform by construction (redux result): a per-lane register here makes the compiler wrap every
+      // tcgen05.mma in an elect / R2UR.BROADCAST / branch "waterfall" (~180 cycles per MMA instead of 128)
+      const uint32_t d_tmem = tmem_base_u + as * BN;
+      STK_GEMM_STAMP(leader, (item - unit) / units, 0);
       long long waited = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
-        if (p.dbg) {
-          const long long t0 = clock64();
-          mbar_wait(full_bar + stage, phase);
-          waited += clock64() - t0;
-        } else {
-          mbar_wait(full_bar + stage, phase);
+        // `ready` = the look-ahead probe issued between the previous k-block's MMAs already saw this slot full
+        if (!ready) {
+          if (p.dbg) {
+            const long long t0 = clock64();
+            mbar_wait(full_bar + stage, phase);
+            waited += clock64() - t0;
+          } else {
+            mbar_wait(full_bar + stage, phase);
+          }
         }
         tc_fence_after();
-        if (kb == kb0) STK_GEMM_STAMP(leader, (item - blockIdx.x) / gridDim.x, 13);
-        if (kb == kb1 - 1) STK_GEMM_STAMP(leader, (item - blockIdx.x) / gridDim.x, 1);
-        if (leader) {
+        const long long kb_t0 = p.dbg ? clock64() : 0;
+        if (kb == kb0) STK_GEMM_STAMP(leader, (item - unit) / units, 13);
+        if (kb == kb1 - 1) STK_GEMM_STAMP(leader, (item - unit) / units, 1);
+        {
+          // The whole (converged) warp executes every tcgen05 statement; elect.sync inside the statement picks
+          // the issuing lane, all operands are warp-uniform: ptxas emits ELECT + @P UTCHMMA back to back and
+          // the tensor pipe is fed at its 128-cycle cadence (a branch on a cached elect result costs ~180
+          // cycles per MMA in elect / broadcast / loop overhead — measured with tools/mma_rate.py).
           const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((stage * A_STAGE_BYTES) >> 4);
           const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((stage * B_STAGE_BYTES) >> 4);
-          if (kb == kb0) umma_bf16(d_tmem, a_desc, b_desc, idesc, 0u);
-          else umma_bf16(d_tmem, a_desc, b_desc, idesc, 1u);
-#pragma unroll
-          for (int k = 1; k < BK / 16; ++k) umma_bf16(d_tmem, a_desc + k * a_kstep, b_desc + k * b_kstep, idesc, 1u);
-          umma_commit(empty_bar + stage);  // frees the smem slot once these MMAs have read it
-          if (kb == kb1 - 1) umma_commit(tfull_bar + as);
+          auto commit = [&](uint64_t* bar) {
+            if (PAIR) umma_commit_pair_warp(bar, pair_mask);
+            else umma_commit_warp(bar);
+          };
+          // The tensor pipe buffers about one pending MMA: whatever the warp does between two issues is
+          // hidden only while the previous MMA (128 cycles) executes.  So the NEXT slot's full barrier is
+          // probed (non-blocking) in the middle of this k-block's issues, and the whole k-block — elect,
+          // four MMAs, probe, slot-free commit — is one statement (umma_kblock_warp).
+          const int nstage = stage + 1 == STAGES ? 0 : stage + 1;
+          const uint32_t nphase = stage + 1 == STAGES ? phase ^ 1 : phase;
+          static_assert(BK / 16 == 4, "k-steps per stage");
+          if (!(p.dbg & 8)) {   // bring-up bit 8: no MMAs (pure TMA fill rate)
+            ready = umma_kblock_warp<PAIR>(d_tmem, a_desc, b_desc, a_desc + a_kstep, b_desc + b_kstep,
+                                           a_desc + 2 * a_kstep, b_desc + 2 * b_kstep, a_desc + 3 * a_kstep,
+                                           b_desc + 3 * b_kstep, idesc, kb != kb0 ? 1u : 0u, empty_bar + stage, pair_mask,
+                                           full_bar + nstage, nphase);
+          } else {
+            ready = false;
+            commit(empty_bar + stage);
+          }
+          if (kb == kb1 - 1) commit(tfull_bar + as);
+          if (p.dbg && blockIdx.x == 0 && leader && (item - unit) / units == 2 && kb - kb0 < 64) {
+            g_gemm_timeline[3072 + (kb - kb0) * 2] = kb_t0;          // k-block operands ready
+            g_gemm_timeline[3072 + (kb - kb0) * 2 + 1] = clock64();  // its MMAs + commits issued
+          }
         }
-        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      if (p.dbg && blockIdx.x == 0 && leader && (item - blockIdx.x) / gridDim.x < 64)
-        g_gemm_timeline[((item - blockIdx.x) / gridDim.x) * 16 + 14] = waited;   // cycles starved for operands
+      if (p.dbg && blockIdx.x < 3 && leader && (item - unit) / units < 64)
+        g_gemm_timeline[blockIdx.x * 1024 + ((item - unit) / units) * 16 + 14] = waited;   // cycles starved for operands
       if (++as == 2) { as = 0; as_phase ^= 1; }
+    }
     }
   } else if (kLN && warp >= 10) {
     // ============================== epilogue I/O warps (LN variant) ==============================
@@ -251,9 +314,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       uint8_t* ebuf1 = smem_epi + L1 * EPI_BUF_BYTES;
       const bool save_z = p.epi.c2 != nullptr;
       uint32_t it = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      for (int item = unit; item < num_items; item += units, ++it) {
         const int n_col = (item % p.n_tiles) * BN + g * 128;
-        const int m0 = (item / p.n_tiles) * BM;
+        const int m0 = (item / p.n_tiles) * TM + static_cast<int>(pr) * 128;
         if (it == 0) {
           mbar_arrive_expect_tx(rfull_bar + L0, EPI_BUF_BYTES);
           tma_load_2d(&map_r, rfull_bar + L0, ebuf0, n_col, m0);
@@ -279,8 +342,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         tma_store_2d(&map_c, ebuf1, n_col + 64, m0);
         tma_commit_group();
         STK_GEMM_STAMP(g == 0, static_cast<int>(it), 10);
-        const int next = item + gridDim.x;
-        const int m0n = (next / p.n_tiles) * BM;
+        const int next = item + units;
+        const int m0n = (next / p.n_tiles) * TM + static_cast<int>(pr) * 128;
         tma_wait_group_read<1>();
         if (next < num_items) {
           mbar_arrive_expect_tx(rfull_bar + L0, EPI_BUF_BYTES);
@@ -310,7 +373,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const int g = ew >> 2;    // column half of the 256-wide accumulator
     const int row = q * 32 + lane;
     const StkGemmEpilogue& e = p.epi;
-    const uint32_t rank = cluster_ctarank();   // == n-tile index of this CTA (grid is a multiple of the cluster size)
+    const uint32_t rank = PAIR ? crank >> 1 : crank;   // column slab == n-tile index of this CTA (grid is a multiple of the cluster size)
     {
       const int t = ew * 32 + lane;            // 0..255: column of this CTA's slab
       const int n = static_cast<int>(rank) * BN + t;
@@ -324,8 +387,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
     int as = 0;
     uint32_t as_phase = 0, it = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-      const int m0 = (item / p.n_tiles) * BM;
+    for (int item = unit; item < num_items; item += units, ++it) {
+      const int m0 = (item / p.n_tiles) * TM + static_cast<int>(pr) * 128;
       const int m = m0 + row;
       const int dbg_t = static_cast<int>(it);
       const bool dbg_thr = threadIdx.x == 64;
@@ -346,7 +409,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         if (chunk == 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar + as);
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_remote(map_to_cta(smem_u32(tempty_bar + as), pair_leader));
+            else mbar_arrive(tempty_bar + as);
+          }
         }
         const int L = g * 2 + chunk;
         uint8_t* ebuf = smem_epi + L * EPI_BUF_BYTES;
@@ -412,8 +478,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         const uint32_t slot = smem_u32(s_stats + (par * 6 + rank * 2 + g) * 128 + row);
         if (ew == 0 && lane == 0) mbar_arrive_expect_tx(stats_bar + par, 6 * 128 * 8);
 #pragma unroll
-        for (uint32_t peer = 0; peer < LN_CLUSTER; ++peer)
+        for (uint32_t k = 0; k < 3; ++k) {   // the CTAs holding the other slabs of the same rows (and this one)
+          const uint32_t peer = PAIR ? 2 * k + pr : k;
           st_async_f32x2(map_to_cta(slot, peer), mean_t, m2_t, map_to_cta(stats_bar_addr[par], peer));
+        }
       }
       STK_GEMM_STAMP(dbg_thr, dbg_t, 12);
       mbar_wait(stats_bar + par, (it >> 1) & 1);
@@ -493,14 +561,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
     int as = 0;
     uint32_t as_phase = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    for (int item = unit; item < num_items; item += units) {
       const int tile = item / p.splits;
       const int n_blk = tile % p.n_tiles;
       const int n0 = n_blk * BN;
-      const int m0 = (tile / p.n_tiles) * BM;
+      const int m0 = (tile / p.n_tiles) * TM + static_cast<int>(pr) * 128;
       const int m = m0 + row;
       const bool m_ok = m < p.M;
-      const int dbg_t = (item - blockIdx.x) / gridDim.x;
+      const int dbg_t = (item - unit) / units;
       const bool dbg_thr = threadIdx.x == 64;
       STK_GEMM_STAMP(dbg_thr, dbg_t, 2);
       if (kHasBias) {
@@ -556,9 +624,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         if (chunk == 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar + as);
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_remote(map_to_cta(smem_u32(tempty_bar + as), pair_leader));
+            else mbar_arrive(tempty_bar + as);
+          }
         }
         const int nc = n0 + g * 128 + chunk * 64;  // first global column of this chunk
+        if (p.dbg & 16) continue;   // bring-up: accumulator read only (isolates the epilogue's effect on the MMA rate)
 
         if (EPI == STK_EPI_CE_STATS) {
           float cmax = -INFINITY;
@@ -695,10 +767,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
   tc_fence_before();
   __syncthreads();
-  if (kLN) cluster_sync_all();   // no CTA leaves while a peer may still write into its shared memory
+  if (Cfg::kCluster > 1) cluster_sync_all();   // no CTA leaves while a peer may still touch its shared / tensor memory
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -707,11 +780,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 // ------------------------------------------------------------------------------------------------
 extern std::atomic<long long> g_launches;
 
-template <int A_MN, int B_MN, int EPI>
+template <int A_MN, int B_MN, int EPI, bool PAIR>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mc2,
-                  const CUtensorMap& mr, const GemmParams& p, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<EPI>;
-  auto kern = gemm_kernel<A_MN, B_MN, EPI>;
+                  const CUtensorMap& mr, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<EPI, PAIR>;
+  auto kern = gemm_kernel<A_MN, B_MN, EPI, PAIR>;
   static bool configured[64] = {};
   static int max_clusters[64] = {};
   int dev = 0;
@@ -720,14 +793,17 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
     STK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     configured[dev & 63] = true;
   }
-  if (!Cfg::kLN) {
-    kern<<<grid, Cfg::kThreads, Cfg::kSmem, stream>>>(ma, mb, mc, mc2, mr, p);
+  const int items = p.m_tiles * p.n_tiles * p.splits;
+  if (Cfg::kCluster == 1) {
+    const int sms = num_sms(dev);
+    kern<<<items < sms ? items : sms, Cfg::kThreads, Cfg::kSmem, stream>>>(ma, mb, mc, mc2, mr, p);
   } else {
-    // clusters of three CTAs (one per 256-column slab of the 768-wide rows), persistent over the row tiles
+    // clusters: CTA pairs (cta_group::2 MMAs), three column slabs of a LayerNorm row, or three pairs;
+    // persistent over the tiles, as many clusters as the device can keep resident
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = LN_CLUSTER;
+    attr[0].val.clusterDim.x = Cfg::kCluster;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.blockDim = dim3(Cfg::kThreads);
@@ -736,17 +812,19 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (max_clusters[dev & 63] == 0) {
-      cfg.gridDim = dim3(LN_CLUSTER * 64);
+      cfg.gridDim = dim3(Cfg::kCluster * 32);
       int n = 0;
       STK_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
       if (n <= 0) {
-        set_error("stk_gemm: no %d-CTA cluster of the LayerNorm epilogue fits on this device", LN_CLUSTER);
+        set_error("stk_gemm: no %d-CTA cluster of this kernel fits on the device", Cfg::kCluster);
         return STK_ERR_UNSUPPORTED;
       }
       max_clusters[dev & 63] = n;
     }
-    const int clusters = p.m_tiles < max_clusters[dev & 63] ? p.m_tiles : max_clusters[dev & 63];
-    cfg.gridDim = dim3(LN_CLUSTER * clusters);
+    // work per cluster: a LayerNorm cluster takes whole row tiles (its slabs are the n-tiles), a pair one item
+    const int work = Cfg::kLN ? p.m_tiles : items;
+    const int clusters = work < max_clusters[dev & 63] ? work : max_clusters[dev & 63];
+    cfg.gridDim = dim3(Cfg::kCluster * clusters);
     STK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, mc2, mr, p));
   }
   STK_CHECK_CUDA(cudaGetLastError());
@@ -769,9 +847,16 @@ extern "C" int stk_gemm(int device, void* stream_, int a_major, int b_major, con
   STK_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
               "stk_gemm: operands must be 16-byte aligned");
   STK_CHECK_CUDA(cudaSetDevice(device));
+  // CTA pairs (256-row tiles, cta_group::2) whenever there is more than one 128-row tile of work
+  static int pair_env = -1;
+  if (pair_env < 0) {
+    const char* e = getenv("STK_GEMM_PAIR");
+    pair_env = e ? atoi(e) : 1;
+  }
+  const bool pair = pair_env != 0 && M > BM;
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
-  p.m_tiles = (M + BM - 1) / BM;
+  p.m_tiles = pair ? (M + 2 * BM - 1) / (2 * BM) : (M + BM - 1) / BM;
   p.n_tiles = (N + BN - 1) / BN;
   p.kb_total = (K + BK - 1) / BK;
   int splits = split_k < 1 ? 1 : split_k;
@@ -817,7 +902,7 @@ extern "C" int stk_gemm(int device, void* stream_, int a_major, int b_major, con
   if (a_major == 0) rc = make_tmap_2d(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, K, M, lda * 2, 64, BM);
   else rc = make_tmap_2d(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, M, K, lda * 2, 64, 64);
   if (rc) return rc;
-  if (b_major == 0) rc = make_tmap_2d(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, K, N, ldb * 2, 64, BN);
+  if (b_major == 0) rc = make_tmap_2d(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, K, N, ldb * 2, 64, pair ? BN / 2 : BN);
   else rc = make_tmap_2d(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, N, K, ldb * 2, 64, 64);
   if (rc) return rc;
   if (has_c) {
@@ -837,13 +922,10 @@ extern "C" int stk_gemm(int device, void* stream_, int a_major, int b_major, con
     rc = make_tmap_2d(&mr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, epi->resid, N, M, epi->ldr * 2, 64, 128);
     if (rc) return rc;
   }
-  const int items = p.m_tiles * p.n_tiles * p.splits;
-  const int sms = num_sms(device);
-  const int grid = items < sms ? items : sms;
-
-#define STK_GEMM_CASE(AM, BMJ, E)                                   \
-  if (a_major == AM && b_major == BMJ && epilogue == E)             \
-    return launch<AM, BMJ, E>(ma, mb, mc, mc2, mr, p, grid, stream);
+#define STK_GEMM_CASE(AM, BMJ, E)                                            \
+  if (a_major == AM && b_major == BMJ && epilogue == E)                      \
+    return pair ? launch<AM, BMJ, E, true>(ma, mb, mc, mc2, mr, p, stream)   \
+                : launch<AM, BMJ, E, false>(ma, mb, mc, mc2, mr, p, stream);
   STK_GEMM_CASE(0, 0, STK_EPI_BIAS)
   STK_GEMM_CASE(0, 0, STK_EPI_BIAS_GELU)
   STK_GEMM_CASE(0, 0, STK_EPI_BIAS_GELU_SAVE)

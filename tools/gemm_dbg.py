@@ -40,6 +40,8 @@ def run(name, M, N, K, epi, **kw):
     buf = (ctypes.c_longlong * 4096)()
     lib.stk_debug_gemm_timeline(buf, 4096)
     t0 = buf[2]
+    kbs = [(buf[3072 + 2 * i] - buf[3072], buf[3072 + 2 * i + 1] - buf[3072]) for i in range(min(K // 64, 16))]
+    print("  tile 2 k-blocks (ready, issued):", kbs)
     if kw.get("ln"):
         names = ["mma:start", "mma:lastk", "e:loop", "e:tfull", "e:r0", "e:p1_0", "e:stats", "e:p2_0", "e:r1", "e:p1_1",
                  "io:stored", "e:p2_1", "e:published", "mma:firstk"]
