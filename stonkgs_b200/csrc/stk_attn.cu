@@ -166,7 +166,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
     // ================================ MMA issuer ================================
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
-    const bool leader = elect_one();
+    // Whole-warp issue: every tcgen05 statement is executed by the converged warp and elects its issuing lane
+    // itself (see stk_common.cuh: a branch on a cached elect result costs ~180 cycles per MMA).
+    const bool leader = elect_one();   // timeline stamps only
+    const uint32_t tmem_u = __reduce_max_sync(0xffffffffu, tmem_base);   // provably warp-uniform TMEM base
     const uint64_t q_desc = umma_smem_desc(smem_u32(sQ), 16, 1024);
     const uint64_t k_desc0 = umma_smem_desc(smem_u32(sK), 16, 1024);
     const uint64_t v_desc0 = umma_smem_desc(smem_u32(sV), 8192, 1024);
@@ -179,15 +182,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
       mbar_wait(bar_k + ks, kph);
       tc_fence_after();
       if ((DBG & 64) && blockIdx.x == 0 && leader && n_q < 60) g_attn_timeline[1024 + (dbg_cnt++ & 63)] = clock64();
-      if (leader) {
+      {
         const uint64_t k_desc = k_desc0 + static_cast<uint64_t>(ks * (16384 >> 4));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + T_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k > 0);
-        umma_commit(bar_s);
-        umma_commit(bar_kfree + ks);                    // K slot reusable once these MMAs have read it
-        if (sj == nblk - 1) umma_commit(bar_qfree);     // last score block of the item: Q reusable
+        for (int k = 0; k < 4; ++k) umma_bf16_warp(tmem_u + T_S, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k > 0);
+        umma_commit_warp(bar_s);
+        umma_commit_warp(bar_kfree + ks);                    // K slot reusable once these MMAs have read it
+        if (sj == nblk - 1) umma_commit_warp(bar_qfree);     // last score block of the item: Q reusable
       }
-      __syncwarp();
       if (++ks == ATT_KSTAGES) { ks = 0; kph ^= 1; }
       if (++sj == nblk) sj = 0;
     };
@@ -210,17 +212,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
       mbar_wait(bar_v + vs, vph);
       tc_fence_after();
       stamp(g, 4);
-      if (leader) {
+      {
         const uint64_t v_desc = v_desc0 + static_cast<uint64_t>(vs * (16384 >> 4));
         // 8 x (K = 16 keys): A = P columns [8k, 8k+8), B = V rows [16k, 16k+16)
-        if (pj == 0) umma_bf16_ts(tmem_base + T_O, tmem_base + T_P, v_desc, idesc_o, 0u);
-        else umma_bf16_ts(tmem_base + T_O, tmem_base + T_P, v_desc, idesc_o, 1u);
+        umma_bf16_ts_warp(tmem_u + T_O, tmem_u + T_P, v_desc, idesc_o, pj > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 1; k < 8; ++k) umma_bf16_ts(tmem_base + T_O, tmem_base + T_P + 8 * k, v_desc + k * 128, idesc_o, 1u);
-        umma_commit(bar_pv);
-        umma_commit(bar_vfree + vs);                    // V slot reusable
+        for (int k = 1; k < 8; ++k) umma_bf16_ts_warp(tmem_u + T_O, tmem_u + T_P + 8 * k, v_desc + k * 128, idesc_o, 1u);
+        umma_commit_warp(bar_pv);
+        umma_commit_warp(bar_vfree + vs);                    // V slot reusable
       }
-      __syncwarp();
       stamp(g, 5);
       if (DBG & 64) { mbar_wait(bar_pv, g & 1); stamp(g, 6); }
       if (++vs == ATT_VSTAGES) { vs = 0; vph ^= 1; }

@@ -154,7 +154,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     }
   } else if (warp == 9) {
     // ================================ MMA issuer ================================
-    const bool leader = elect_one();
+    // Whole-warp issue: every tcgen05 statement is executed by the converged warp and elects its issuing lane
+    // itself (see stk_common.cuh: a branch on a cached elect result costs ~180 cycles per MMA).
+    const bool leader = elect_one();   // timeline stamps only
+    const uint32_t tmem_u = __reduce_max_sync(0xffffffffu, tmem_base);   // provably warp-uniform TMEM base
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S, dP
     constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64, 1, 1);    // dV = P^T dO, dK = dS^T Q
     constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64, 0, 1);    // dQ = dS K
@@ -173,14 +176,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       const uint64_t boff = static_cast<uint64_t>((i & 1) * (16384 >> 4));
       mbar_wait(bar_q + (i & 1), (i >> 1) & 1);
       tc_fence_after();
-      if (leader) {
+      {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + T_S, q_desc0 + boff + 2 * k, k_desc + 2 * k, idesc_s, k > 0);
+        for (int k = 0; k < 4; ++k) umma_bf16_warp(tmem_u + T_S, q_desc0 + boff + 2 * k, k_desc + 2 * k, idesc_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + T_DP, do_desc0 + boff + 2 * k, v_desc + 2 * k, idesc_s, k > 0);
-        umma_commit(bar_s);
+        for (int k = 0; k < 4; ++k) umma_bf16_warp(tmem_u + T_DP, do_desc0 + boff + 2 * k, v_desc + 2 * k, idesc_s, k > 0);
+        umma_commit_warp(bar_s);
       }
-      __syncwarp();
     };
     auto stamp = [&](int i, int slot) {
       if ((DBG & 64) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && leader) g_abw_timeline[i * 16 + slot] = clock64();
@@ -193,40 +195,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       mbar_wait(bar_p, i & 1);           // P_i, dS_i are in smem; S_i / dP_i columns have been read
       tc_fence_after();
       stamp(i, 2);
-      if (leader) {
+      {
         // dQ_i first: the compute warps are waiting for it (they drain it while dV / dK run)
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + T_DQ, ds_desc + kb * (16384 >> 4) + 2 * k, kT_desc + kb * (8192 >> 4) + k * 128, idesc_q,
+            umma_bf16_warp(tmem_u + T_DQ, ds_desc + kb * (16384 >> 4) + 2 * k, kT_desc + kb * (8192 >> 4) + k * 128, idesc_q,
                       (kb | k) > 0);
-        umma_commit(bar_dq);
+        umma_commit_warp(bar_dq);
       }
-      __syncwarp();
       // the next pair's scores come next (the compute warps need them right after draining dQ_i) ...
       if (i + 1 < nq) issue_scores(i + 1);
       // ... and dV / dK of this pair last: nobody waits for them until the P / dS tiles are rewritten
-      if (leader) {
+      {
         // MN-major operands: +2048 B (16 rows of the reduction dimension) per k step
-        if (i == 0) {
-          umma_bf16(tmem_base + T_DV, pT_desc, doT_desc0 + boff, idesc_t, 0u);
-        } else {
-          umma_bf16(tmem_base + T_DV, pT_desc, doT_desc0 + boff, idesc_t, 1u);
-        }
+        umma_bf16_warp(tmem_u + T_DV, pT_desc, doT_desc0 + boff, idesc_t, i > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 1; k < 8; ++k) umma_bf16(tmem_base + T_DV, pT_desc + k * 128, doT_desc0 + boff + k * 128, idesc_t, 1u);
-        if (i == 0) {
-          umma_bf16(tmem_base + T_DK, dsT_desc, qT_desc0 + boff, idesc_t, 0u);
-        } else {
-          umma_bf16(tmem_base + T_DK, dsT_desc, qT_desc0 + boff, idesc_t, 1u);
-        }
+        for (int k = 1; k < 8; ++k) umma_bf16_warp(tmem_u + T_DV, pT_desc + k * 128, doT_desc0 + boff + k * 128, idesc_t, 1u);
+        umma_bf16_warp(tmem_u + T_DK, dsT_desc, qT_desc0 + boff, idesc_t, i > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 1; k < 8; ++k) umma_bf16(tmem_base + T_DK, dsT_desc + k * 128, qT_desc0 + boff + k * 128, idesc_t, 1u);
-        umma_commit(bar_dvdk);              // P / dS tiles reusable
-        umma_commit(bar_qfree + (i & 1));   // Q_i / dO_i buffer reusable once everything above has completed
+        for (int k = 1; k < 8; ++k) umma_bf16_warp(tmem_u + T_DK, dsT_desc + k * 128, qT_desc0 + boff + k * 128, idesc_t, 1u);
+        umma_commit_warp(bar_dvdk);              // P / dS tiles reusable
+        umma_commit_warp(bar_qfree + (i & 1));   // Q_i / dO_i buffer reusable once everything above has completed
       }
-      __syncwarp();
       stamp(i, 3);
     }
   } else {

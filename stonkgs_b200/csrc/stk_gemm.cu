@@ -23,6 +23,10 @@
 #include "stk_common.cuh"
 #include "stk_host.h"
 
+#ifndef STK_GEMM_EPI_WARP0
+#define STK_GEMM_EPI_WARP0 0
+#endif
+
 namespace stk {
 
 constexpr int BM = 128, BN = 256, BK = 64;
@@ -53,6 +57,12 @@ struct GemmCfg {
   static constexpr int kSmem = 1024 /*align slack*/ + kStages * kStageBytes + kEpiBufs * EPI_BUF_BYTES + kStatsBytes +
                                kParamBytes + 512 /*barriers*/;
 };
+
+// Warp roles.  The eight epilogue warps come FIRST (warp w drains TMEM lane quarter w % 4, column half w / 4),
+// the TMA producer and the MMA issuer after them.
+constexpr int kEpiWarp0 = STK_GEMM_EPI_WARP0;
+constexpr int kProducerWarp = kEpiWarp0 == 0 ? 8 : 0;
+constexpr int kMmaWarp = kEpiWarp0 == 0 ? 9 : 1;
 
 struct GemmParams {
   int M, N, K;
@@ -131,7 +141,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   const int unit = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int units = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     if (EPI != STK_EPI_CE_STATS) tma_prefetch_desc(&map_c);
@@ -154,7 +164,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     }
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     if (PAIR) tmem_alloc_pair(tmem_slot, 512);
     else tmem_alloc(tmem_slot, 512);
   }
@@ -166,7 +176,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
   const int num_items = p.m_tiles * p.n_tiles * p.splits;
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // ============================== TMA producer ==============================
     // Warp-uniform control flow (all lanes walk the loop and poll the barriers, so addresses and
     // coordinates stay on the uniform datapath); one elected lane issues the TMA instructions.
@@ -214,7 +224,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     if (PAIR && pr != 0) {
       // the odd CTA of a pair only lends its shared and tensor memory to the MMAs issued by the even one
     } else {
@@ -368,7 +378,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     // into all three CTAs with st.async, which completes transaction bytes on the receiver's mbarrier:
     // no fences), merged with the parallel-variance formula, and pass 2 normalises the bf16 z kept in
     // registers.
-    const int ew = warp - 2;
+    const int ew = warp - kEpiWarp0;
     const int q = warp & 3;   // TMEM lane quarter this warp may access
     const int g = ew >> 2;    // column half of the 256-wide accumulator
     const int row = q * 32 + lane;
@@ -391,7 +401,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       const int m0 = (item / p.n_tiles) * TM + static_cast<int>(pr) * 128;
       const int m = m0 + row;
       const int dbg_t = static_cast<int>(it);
-      const bool dbg_thr = threadIdx.x == 64;
+      const bool dbg_thr = threadIdx.x == kEpiWarp0 * 32;
       STK_GEMM_STAMP(dbg_thr, dbg_t, 2);
       mbar_wait(tfull_bar + as, as_phase);
       tc_fence_after();
@@ -544,7 +554,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     }
   } else {
     // ============================== epilogue warps ==============================
-    const int ew = warp - 2;
+    const int ew = warp - kEpiWarp0;
     const int q = warp & 3;   // TMEM lane quarter this warp may access
     const int g = ew >> 2;    // column half of the 256-wide accumulator
     const int row = q * 32 + lane;
@@ -569,7 +579,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       const int m = m0 + row;
       const bool m_ok = m < p.M;
       const int dbg_t = (item - unit) / units;
-      const bool dbg_thr = threadIdx.x == 64;
+      const bool dbg_thr = threadIdx.x == kEpiWarp0 * 32;
       STK_GEMM_STAMP(dbg_thr, dbg_t, 2);
       if (kHasBias) {
         // every thread of the previous tile is past its last read of s_bias (the staging barriers of
@@ -631,6 +641,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
         const int nc = n0 + g * 128 + chunk * 64;  // first global column of this chunk
         if (p.dbg & 16) continue;   // bring-up: accumulator read only (isolates the epilogue's effect on the MMA rate)
+        if ((p.dbg & 32) && q == 1 && EPI == STK_EPI_BIAS_GELU) {   // bring-up: no epilogue math on the MMA warp's scheduler
+          uint4 data[8] = {};
+          stage_and_store<false, false>(&map_c, buf, row, data, nc, m0, store_thread, bar_id);
+          continue;
+        }
 
         if (EPI == STK_EPI_CE_STATS) {
           float cmax = -INFINITY;
@@ -768,7 +783,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   tc_fence_before();
   __syncthreads();
   if (Cfg::kCluster > 1) cluster_sync_all();   // no CTA leaves while a peer may still touch its shared / tensor memory
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     if (PAIR) tmem_dealloc_pair(tmem_base, 512);
     else tmem_dealloc(tmem_base, 512);
