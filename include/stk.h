@@ -178,6 +178,19 @@ int stk_gelu_bwd(int device, void* stream, const void* dy_bf16, const void* pre_
 int stk_nsp_pool_bwd(int device, void* stream, const float* pooled, const float* logits, const int64_t* labels,
                      int B, const float* scale_dev, const float* w, float* dw, float* db, void* dpre_bf16);
 
+/* Sequence-classification head of fine-tuned checkpoints (reference stonkgs_finetuning.py:237-346:
+ * dropout -> Linear(768 -> num_labels) on the pooled output, single-label cross-entropy; num_labels <= 32).
+ * pooled fp32 [B,768]; w [num_labels,768]; logits fp32 [B,num_labels]; labels may be NULL (inference);
+ * err_flag (may be NULL) is set to 1 on a label outside [0, num_labels). */
+int stk_cls_head_fwd(int device, void* stream, const float* pooled, int B, int num_labels, const float* w,
+                     const float* b, const int64_t* labels, float* logits, float* row_loss, int* err_flag);
+/* Backward of the head above and of the pooler's tanh.  scale_dev: device scalar = upstream grad / B.
+ * dlogit_ws: fp32 workspace [B,num_labels]; dw [num_labels,768], db [num_labels] accumulated (+=);
+ * dpre: bf16 [B,768] gradient w.r.t. the pooler's pre-activation. */
+int stk_cls_pool_bwd(int device, void* stream, const float* pooled, const float* logits, const int64_t* labels,
+                     int B, int num_labels, const float* scale_dev, const float* w, float* dlogit_ws, float* dw,
+                     float* db, void* dpre_bf16);
+
 /* Data-parallel bucket helpers (the producer / consumer kernels around the NCCL all-reduce that
  * replaces torch DDP's Reducer, reference stonkgs_pretraining.py:147-168,215-223):
  *   pack   = stk_cast_f32_to_bf16 on a slice of the flat gradient buffer (bf16 on the wire)

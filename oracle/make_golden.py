@@ -121,6 +121,62 @@ def run_case(name, num_layers, batch_size, n_kg, seed_w, seed_b, full_mask):
     np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **fix)
 
 
+# fine-tuning model: name -> (num_layers, batch, n_kg, seed_weights, seed_batch, num_labels)
+CLS_CASES = {
+    "cls_L2_B3_N997_K5": (2, 3, 997, 4, 9, 5),
+}
+
+
+def classifier_state(sd, num_labels, seed):
+    g = torch.Generator().manual_seed(1000 + seed)
+    sd = dict(sd)
+    sd["classifier.weight"] = torch.randn(num_labels, 768, generator=g) * 0.05
+    sd["classifier.bias"] = torch.randn(num_labels, generator=g) * 0.1
+    return sd
+
+
+def run_cls_case(name, num_layers, batch_size, n_kg, seed_w, seed_b, num_labels):
+    """The reference's own STonKGsForSequenceClassification (stonkgs_finetuning.py:237-346), eval(), fwd + bwd."""
+    sd = classifier_state(weights.make_state_dict(n_kg, num_layers, seed_w), num_labels, seed_w)
+    rows = weights.make_kg_table(n_kg, seed_w)
+    b = synthetic.make_batch(batch_size, n_kg, seed_b, with_labels=False)
+    labels = torch.randint(0, num_labels, (batch_size,), generator=torch.Generator().manual_seed(seed_b))
+    ref = ref_shim.load_reference_classifier(sd, rows, num_layers, num_labels)
+    for p in ref.parameters():
+        p.grad = None
+    out = ref(**b, labels=labels, return_dict=True)
+    out.loss.backward()
+    fix = {k: v.numpy() for k, v in b.items()}
+    fix["labels"] = labels.numpy()
+    fix["meta"] = np.array([num_layers, batch_size, n_kg, seed_w, seed_b, num_labels], dtype=np.int64)
+    fix["loss"] = out.loss.detach().numpy()
+    fix["logits"] = out.logits.detach().numpy()
+    names, norms, samples, dead = [], [], [], []
+    for k, p in ref.named_parameters():
+        if not p.requires_grad:
+            continue
+        if p.grad is None:
+            dead.append(k)
+            continue
+        s, _ = sample_grad(p.grad)
+        names.append(k)
+        norms.append(float(p.grad.norm()))
+        samples.append(np.pad(s, (0, 64 - len(s))))
+    fix["grad_names"] = np.array(names)
+    fix["grad_norms"] = np.array(norms, dtype=np.float64)
+    fix["grad_samples"] = np.stack(samples).astype(np.float32)
+    fix["dead_names"] = np.array(dead)
+    table = orc.build_kg_table(sd, rows)
+    o, grads = orc.forward_backward_classifier(sd, table, dict(b, labels=labels))
+    ref_grads = {k: p.grad for k, p in ref.named_parameters() if p.grad is not None}
+    assert sorted(ref_grads) == sorted(grads), set(ref_grads) ^ set(grads)
+    worst = max((g - ref_grads[k]).abs().max().item() / (ref_grads[k].abs().max().item() + 1e-30)
+                for k, g in grads.items() if "attention.self.key.bias" not in k)
+    print(f"[{name}] oracle vs reference: logits max|d|={(o['logits'].detach() - out.logits.detach()).abs().max().item():.3g} "
+          f"|dloss|={abs(o['loss'].item() - out.loss.item()):.3g} worst rel grad diff={worst:.3g} | dead={len(dead)} live={len(names)}")
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **fix)
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     only = sys.argv[1:]
@@ -128,6 +184,10 @@ def main():
         if only and name not in only:
             continue
         run_case(name, *cfg)
+    for name, cfg in CLS_CASES.items():
+        if only and name not in only:
+            continue
+        run_cls_case(name, *cfg)
 
 
 if __name__ == "__main__":

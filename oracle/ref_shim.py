@@ -110,3 +110,27 @@ def load_reference(state_dict, kg_table: np.ndarray, num_layers: int = 12):
     missing, unexpected = model.load_state_dict(state_dict, strict=False)
     assert not missing and not unexpected, (missing, unexpected)
     return model.eval()
+
+
+def load_reference_classifier(state_dict, kg_table: np.ndarray, num_layers: int, num_labels: int):
+    """The reference's ``STonKGsForSequenceClassification`` (stonkgs_finetuning.py:237-346) with the given
+    synthetic checkpoint (pre-training keys + ``classifier.*``)."""
+    sm = _import_reference()
+    import stonkgs.models.stonkgs_finetuning as sf  # noqa: E402  (the reference's own module)
+    from transformers import BertConfig
+    _state["num_layers"] = num_layers
+    _state["lm_sd"] = {k[len("lm_backbone."):]: v for k, v in state_dict.items() if k.startswith("lm_backbone.")}
+    tab64 = kg_table.astype(np.float64)
+    sm.prepare_df = lambda path: {f"n{i}": tab64[i] for i in range(tab64.shape[0])}
+    cfg = BertConfig(vocab_size=28996, num_hidden_layers=num_layers, num_labels=num_labels)
+    cfg._attn_implementation = "eager"
+    cfg.kg_vocab_size = kg_table.shape[0]
+    was_cuda = torch.cuda.is_available
+    torch.cuda.is_available = lambda: False
+    try:
+        model = sf.STonKGsForSequenceClassification(cfg, kg_embedding_dict_path="unused")
+    finally:
+        torch.cuda.is_available = was_cuda
+    missing, unexpected = model.load_state_dict(state_dict, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    return model.eval()

@@ -76,6 +76,8 @@ _SIGNATURES = {
     "stk_adamw_step": (c_int, [c_int, _P, _P, _P, _P, c_int, c_float, c_float, c_float, c_float, c_float, c_float,
                                c_float, _P, c_float]),
     "stk_nsp_pool_bwd": (c_int, [c_int, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P]),
+    "stk_cls_head_fwd": (c_int, [c_int, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P]),
+    "stk_cls_pool_bwd": (c_int, [c_int, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

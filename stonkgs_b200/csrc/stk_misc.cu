@@ -226,6 +226,102 @@ __global__ void unpack_scale_kernel(const __nv_bfloat16* __restrict__ src, float
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Sequence-classification head (fine-tuned checkpoints; reference stonkgs_finetuning.py:237-346):
+//   logits = pooled . W^T + b   (W [L,768], L = num_labels <= 32),  single-label cross-entropy.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxLabels = 32;
+
+// one warp per sample
+__global__ void __launch_bounds__(256) cls_head_fwd_kernel(const float* __restrict__ pooled, int B, int L,
+                                                           const float* __restrict__ w, const float* __restrict__ bias,
+                                                           const int64_t* __restrict__ labels,
+                                                           float* __restrict__ logits, float* __restrict__ row_loss,
+                                                           int* __restrict__ err_flag) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  float x[kHidden / 32];
+#pragma unroll
+  for (int i = 0; i < kHidden / 32; ++i) x[i] = __ldg(pooled + static_cast<int64_t>(b) * kHidden + lane + 32 * i);
+  float mine = 0.f;   // lane j keeps logit j
+  for (int j = 0; j < L; ++j) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kHidden / 32; ++i) s = fmaf(x[i], __ldg(w + static_cast<int64_t>(j) * kHidden + lane + 32 * i), s);
+    s = warp_sum(s) + __ldg(bias + j);
+    if (lane == j) mine = s;
+  }
+  if (lane < L) logits[static_cast<int64_t>(b) * L + lane] = mine;
+  if (labels && row_loss) {
+    const float m = warp_max(lane < L ? mine : -INFINITY);
+    const float e = lane < L ? expf(mine - m) : 0.f;
+    const float lse = m + logf(warp_sum(e));
+    const int64_t lab = __ldg(labels + b);
+    if (lab < 0 || lab >= L) {
+      if (lane == 0) { row_loss[b] = 0.f; if (err_flag) *err_flag = 1; }
+    } else {
+      const float tgt = __shfl_sync(0xffffffffu, mine, static_cast<int>(lab));
+      if (lane == 0) row_loss[b] = lse - tgt;
+    }
+  }
+}
+
+// dlogit[b, j] = (softmax(logits[b])[j] - [j == label[b]]) * scale   (one warp per sample)
+__global__ void __launch_bounds__(256) cls_dlogit_kernel(const float* __restrict__ logits,
+                                                         const int64_t* __restrict__ labels, int B, int L,
+                                                         const float* __restrict__ scale_dev,
+                                                         float* __restrict__ dlogit) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float v = lane < L ? __ldg(logits + static_cast<int64_t>(b) * L + lane) : -INFINITY;
+  const float m = warp_max(v);
+  const float e = lane < L ? expf(v - m) : 0.f;
+  const float inv = 1.0f / warp_sum(e);
+  const int64_t lab = __ldg(labels + b);
+  if (lane < L) dlogit[static_cast<int64_t>(b) * L + lane] = (e * inv - (lane == lab ? 1.f : 0.f)) * __ldg(scale_dev);
+}
+
+// one thread per hidden column c:
+//   dW[j,c] += sum_b dlogit[b,j] pooled[b,c];  db[j] += sum_b dlogit[b,j]
+//   dpre[b,c] = (sum_j dlogit[b,j] W[j,c]) * (1 - pooled[b,c]^2)      (backward of the pooler's tanh, HF:456-468)
+__global__ void __launch_bounds__(256) cls_pool_bwd_kernel(const float* __restrict__ pooled,
+                                                           const float* __restrict__ dlogit, int B, int L,
+                                                           const float* __restrict__ w, float* __restrict__ dw,
+                                                           float* __restrict__ db, __nv_bfloat16* __restrict__ dpre) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= kHidden) return;
+  float wc[kMaxLabels], acc[kMaxLabels], sb[kMaxLabels];
+#pragma unroll
+  for (int j = 0; j < kMaxLabels; ++j) {
+    wc[j] = j < L ? __ldg(w + static_cast<int64_t>(j) * kHidden + c) : 0.f;
+    acc[j] = 0.f;
+    sb[j] = 0.f;
+  }
+  for (int b = 0; b < B; ++b) {
+    const float pv = __ldg(pooled + static_cast<int64_t>(b) * kHidden + c);
+    float dp = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxLabels; ++j) {
+      if (j < L) {
+        const float d = __ldg(dlogit + static_cast<int64_t>(b) * L + j);   // same address across the warp: broadcast
+        acc[j] = fmaf(d, pv, acc[j]);
+        sb[j] += d;
+        dp = fmaf(d, wc[j], dp);
+      }
+    }
+    dpre[static_cast<int64_t>(b) * kHidden + c] = __float2bfloat16_rn(dp * (1.0f - pv * pv));
+  }
+#pragma unroll
+  for (int j = 0; j < kMaxLabels; ++j) {
+    if (j < L) {
+      dw[static_cast<int64_t>(j) * kHidden + c] += acc[j];
+      if (c == 0) db[j] += sb[j];
+    }
+  }
+}
+
 }  // namespace stk
 
 using namespace stk;
@@ -338,5 +434,31 @@ extern "C" int stk_unpack_scale(int device, void* stream, const void* src_bf16, 
   if (blocks < 1) blocks = 1;
   unpack_scale_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(src_bf16), dst, n, scale);
+  STK_LAUNCHED();
+}
+
+extern "C" int stk_cls_head_fwd(int device, void* stream, const float* pooled, int B, int num_labels, const float* w,
+                                const float* b, const int64_t* labels, float* logits, float* row_loss, int* err_flag) {
+  STK_REQUIRE(pooled && w && b && logits && B > 0, "stk_cls_head_fwd: bad arguments");
+  STK_REQUIRE(num_labels >= 1 && num_labels <= kMaxLabels, "stk_cls_head_fwd: num_labels must be in [1, 32] (got %d)", num_labels);
+  STK_CHECK_CUDA(cudaSetDevice(device));
+  cls_head_fwd_kernel<<<(B + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(pooled, B, num_labels, w, b, labels,
+                                                                                 logits, row_loss, err_flag);
+  STK_LAUNCHED();
+}
+
+extern "C" int stk_cls_pool_bwd(int device, void* stream, const float* pooled, const float* logits,
+                                const int64_t* labels, int B, int num_labels, const float* scale_dev, const float* w,
+                                float* dlogit_ws, float* dw, float* db, void* dpre_bf16) {
+  STK_REQUIRE(pooled && logits && labels && scale_dev && w && dlogit_ws && dw && db && dpre_bf16 && B > 0,
+              "stk_cls_pool_bwd: bad arguments");
+  STK_REQUIRE(num_labels >= 1 && num_labels <= kMaxLabels, "stk_cls_pool_bwd: num_labels must be in [1, 32] (got %d)", num_labels);
+  STK_CHECK_CUDA(cudaSetDevice(device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cls_dlogit_kernel<<<(B + 7) / 8, 256, 0, st>>>(logits, labels, B, num_labels, scale_dev, dlogit_ws);
+  STK_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cls_pool_bwd_kernel<<<3, 256, 0, st>>>(pooled, dlogit_ws, B, num_labels, w, dw, db,
+                                          static_cast<__nv_bfloat16*>(dpre_bf16));
   STK_LAUNCHED();
 }

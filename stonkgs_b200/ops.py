@@ -340,6 +340,27 @@ def nsp_pool_bwd(pooled, logits, labels, scale_dev, w, dw, db) -> torch.Tensor:
     return dpre
 
 
+def cls_head(pooled, w, b, labels=None, err_flag=None):
+    """Sequence-classification head: logits fp32 [B, L] (+ per-sample CE when labels are given)."""
+    dev, stream = _ctx(pooled)
+    B, L = pooled.shape[0], w.shape[0]
+    logits = torch.empty((B, L), dtype=torch.float32, device=pooled.device)
+    row_loss = torch.empty(B, dtype=torch.float32, device=pooled.device) if labels is not None else None
+    check(_lib.load().stk_cls_head_fwd(dev, stream, _ptr(pooled), B, L, _ptr(w), _ptr(b), _ptr(labels), _ptr(logits),
+                                       _ptr(row_loss), _ptr(err_flag)), "stk_cls_head_fwd")
+    return logits, row_loss
+
+
+def cls_pool_bwd(pooled, logits, labels, scale_dev, w, dw, db) -> torch.Tensor:
+    dev, stream = _ctx(pooled)
+    B, L = logits.shape
+    dpre = torch.empty((B, H), dtype=torch.bfloat16, device=pooled.device)
+    ws = torch.empty((B, L), dtype=torch.float32, device=pooled.device)
+    check(_lib.load().stk_cls_pool_bwd(dev, stream, _ptr(pooled), _ptr(logits), _ptr(labels), B, L, _ptr(scale_dev),
+                                       _ptr(w), _ptr(ws), _ptr(dw), _ptr(db), _ptr(dpre)), "stk_cls_pool_bwd")
+    return dpre
+
+
 def unpack_scale(src_bf16: torch.Tensor, dst_f32: torch.Tensor, scale: float) -> None:
     dev, stream = _ctx(src_bf16)
     check(_lib.load().stk_unpack_scale(dev, stream, _ptr(src_bf16), _ptr(dst_f32), src_bf16.numel(), float(scale)),

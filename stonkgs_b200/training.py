@@ -42,14 +42,20 @@ class GradBuffer:
             shape = tuple(params[0].shape) if shape is None else shape
             entries.append((name, shape, params))
 
-        add("w_ent", [pr.entity_decoder.weight])
-        add("w_text", [pr.text_decoder.weight])
-        add("t_w", [pr.transform.dense.weight])
-        add("t_b", [pr.transform.dense.bias])
-        add("t_ln_g", [pr.transform.LayerNorm.weight])
-        add("t_ln_b", [pr.transform.LayerNorm.bias])
-        add("nsp_w", [model.cls.seq_relationship.weight])
-        add("nsp_b", [model.cls.seq_relationship.bias])
+        if getattr(model, "classifier", None) is not None:
+            # fine-tuning model (stonkgs_finetuning.py:237-346): only the classifier sits on top of the pooler;
+            # the pre-training heads stay in the checkpoint but receive no gradient
+            add("cls_w", [model.classifier.weight])
+            add("cls_b", [model.classifier.bias])
+        else:
+            add("w_ent", [pr.entity_decoder.weight])
+            add("w_text", [pr.text_decoder.weight])
+            add("t_w", [pr.transform.dense.weight])
+            add("t_b", [pr.transform.dense.bias])
+            add("t_ln_g", [pr.transform.LayerNorm.weight])
+            add("t_ln_b", [pr.transform.LayerNorm.bias])
+            add("nsp_w", [model.cls.seq_relationship.weight])
+            add("nsp_b", [model.cls.seq_relationship.bias])
         add("pool_w", [bert.pooler.dense.weight])
         add("pool_b", [bert.pooler.dense.bias])
         self.num_layers = len(bert.encoder.layer)
@@ -211,8 +217,19 @@ def dense_prediction_logits(hw: engine.HeadWeights, seq, B):
 # backward
 # --------------------------------------------------------------------------------------------------
 def _splits(m_out: int, n_out: int, k: int, sms: int = 148) -> int:
-    tiles = ((m_out + 127) // 128) * ((n_out + 255) // 256)
-    return max(1, min(sms // tiles, (k + 63) // 64))
+    """Split-K factor of a reduce-add GEMM: fill the persistent grid (CTA pairs on 256 x 256 tiles when there
+    is more than one 128-row tile, else single CTAs on 128 x 256) with as few k-splits as possible."""
+    pair = m_out > 128
+    tiles = ((m_out + (255 if pair else 127)) // (256 if pair else 128)) * ((n_out + 255) // 256)
+    units = sms // 2 if pair else sms
+    kb = (k + 63) // 64
+    best, best_eff = 1, 0.0
+    for s in range(1, min(kb, 32) + 1):
+        items = tiles * s
+        eff = items / (-(-items // units) * units)
+        if eff > best_eff + 0.05:   # more splits only for a clearly fuller grid (each split re-reduces the tile)
+            best, best_eff = s, eff
+    return best
 
 
 def _wgrad(dy, x, out, k_rows):
@@ -292,16 +309,30 @@ def backward(model, st, cache, dloss: torch.Tensor, gb: GradBuffer, on_ready=Non
     # ---- NSP head + pooler ----------------------------------------------------------------------
     dpre = ops.nsp_pool_bwd(pooled, cache["nsp_logits"], cache["nsp_labels"], (dloss / B).reshape(1), hw.w_nsp,
                             gb["nsp_w"], gb["nsp_b"])
+    for n in ("nsp_w", "nsp_b"):
+        ready(n)
+    backward_pooler(bert, seq, dpre, dseq, gb, ready)
+    backward_trunk(model, bert, cache, dseq, gb, ready)
+
+
+def backward_pooler(bert: engine.EncoderWeights, seq, dpre, dseq, gb: GradBuffer, ready):
+    """Backward of BertPooler's dense layer (HF:456-468) given the gradient w.r.t. its pre-activation;
+    the [CLS] rows of ``dseq`` receive the result."""
+    B = dpre.shape[0]
     ops.colsum(dpre, gb["pool_b"], accumulate=True)
     seq0 = seq.view(B, 512, H)[:, 0]
     _wgrad(dpre, seq0, gb["pool_w"], B)
     dseq0 = _dgrad(dpre, bert.wp)
-    cls_rows = (torch.arange(B, device=dev, dtype=torch.int32) * 512).contiguous()
+    cls_rows = (torch.arange(B, device=seq.device, dtype=torch.int32) * 512).contiguous()
     ops.scatter_add_rows(dseq0, cls_rows, dseq)
-    for n in ("nsp_w", "nsp_b", "pool_w", "pool_b"):
+    for n in ("pool_w", "pool_b"):
         ready(n)
 
-    # ---- 12 encoder layers, last to first --------------------------------------------------------
+
+def backward_trunk(model, bert: engine.EncoderWeights, cache, dseq, gb: GradBuffer, ready):
+    """12 joint encoder layers (last to first) and the joint embedding stage, given d(loss)/d(sequence output)."""
+    M = dseq.shape[0]
+    B = M // 512
     key_bias = cache["key_bias"]
     dx = dseq
     for li in reversed(range(len(bert.layers))):
@@ -335,6 +366,22 @@ def backward(model, st, cache, dloss: torch.Tensor, gb: GradBuffer, on_ready=Non
                            gb["emb_type"], gb["emb_g"], gb["emb_b"])
     for n in ("emb_pos", "emb_type", "emb_g", "emb_b"):
         ready(n)
+
+
+def backward_classifier(model, st, cache, dloss: torch.Tensor, gb: GradBuffer, on_ready=None):
+    """Backward of the fine-tuning model: classifier CE -> pooler -> trunk (no pre-training heads)."""
+    bert: engine.EncoderWeights = st["bert"]
+    seq, pooled = cache["seq"], cache["pooled"]
+    B = pooled.shape[0]
+    ready = on_ready or (lambda name: None)
+    dloss = dloss.to(seq.device, torch.float32).reshape(())
+    dseq = torch.zeros((B * 512, H), dtype=torch.bfloat16, device=seq.device)
+    dpre = ops.cls_pool_bwd(pooled, cache["cls_logits"], cache["cls_labels"], (dloss / B).reshape(1),
+                            model.classifier.weight.data, gb["cls_w"], gb["cls_b"])
+    for n in ("cls_w", "cls_b"):
+        ready(n)
+    backward_pooler(bert, seq, dpre, dseq, gb, ready)
+    backward_trunk(model, bert, cache, dseq, gb, ready)
 
 
 # --------------------------------------------------------------------------------------------------

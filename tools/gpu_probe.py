@@ -241,6 +241,38 @@ def case_gemm_ln():
 
 
 
+def case_cls_head():
+    """Sequence-classification head fwd / bwd vs torch autograd (fp32)."""
+    import torch
+    from stonkgs_b200 import ops
+    torch.manual_seed(11)
+    res = []
+    for (B, L) in [(3, 5), (64, 2), (130, 32), (7, 1)]:
+        pooled = torch.tanh(torch.randn(B, 768, device="cuda"))
+        w = torch.randn(L, 768, device="cuda") * 0.05
+        b = torch.randn(L, device="cuda") * 0.1
+        labels = torch.randint(0, L, (B,), device="cuda")
+        logits, rl = ops.cls_head(pooled, w, b, labels)
+        pre = torch.atanh(pooled.double().clamp(-0.999999, 0.999999)).float().requires_grad_(True)
+        wr = w.clone().requires_grad_(True)
+        br = b.clone().requires_grad_(True)
+        lr = torch.tanh(pre) @ wr.T + br
+        loss = torch.nn.functional.cross_entropy(lr, labels)
+        loss.backward()
+        res.append(_err_report(logits, (pooled @ w.T + b), f"cls_logits_{B}x{L}", 1e-4))
+        res.append(_err_report(rl.mean().reshape(1), torch.nn.functional.cross_entropy(pooled @ w.T + b, labels).reshape(1), f"cls_loss_{B}x{L}", 1e-4))
+        dw = torch.zeros_like(w)
+        db = torch.zeros_like(b)
+        scale = torch.full((1,), 1.0 / B, device="cuda")
+        dpre = ops.cls_pool_bwd(pooled, logits, labels, scale, w, dw, db)
+        torch.cuda.synchronize()
+        res.append(_err_report(dw, wr.grad, f"cls_dw_{B}x{L}", 1e-4))
+        res.append(_err_report(db, br.grad, f"cls_db_{B}x{L}", 1e-4))
+        res.append(_err_report(dpre, pre.grad, f"cls_dpre_{B}x{L}", 5e-3 * float(pre.grad.abs().max()) + 1e-6))   # dpre is stored in bf16
+    return res
+
+
+
 def case_gemm_majors():
     """dgrad (B MN-major) and wgrad (A and B MN-major, split-K reduce-add)."""
     import torch
@@ -415,6 +447,7 @@ CASES = {
     "gemm_basic": case_gemm_basic,
     "gemm_epilogues": case_gemm_epilogues,
     "gemm_majors": case_gemm_majors,
+    "cls_head": case_cls_head,
     "gemm_ln": case_gemm_ln,
     "gemm_ce": case_gemm_ce,
     "attn": case_attn,
