@@ -191,6 +191,25 @@ int stk_cls_pool_bwd(int device, void* stream, const float* pooled, const float*
                      int B, int num_labels, const float* scale_dev, const float* w, float* dlogit_ws, float* dw,
                      float* db, void* dpre_bf16);
 
+/* ------------------------------------------------------------------------------------------------
+ * Input pipeline for pre-tokenised pairs
+ * ---------------------------------------------------------------------------------------------- */
+/* Joint 512-token inputs of n pairs (reference stonkgs_for_embeddings.py:100-135): text ids / padding mask
+ * int32 [n,256] (mask may be NULL = all ones), node indices int32 [n] into the random-walk table
+ * walks int32 [num_nodes, walk_len] (index outside [0,num_nodes) = unknown node -> UNK walk), KG half =
+ * walk(src) SEP walk(tgt) SEP.  Outputs int64 [n,512]: input_ids, attention_mask, token_type_ids. */
+int stk_assemble_pairs(int device, void* stream, const int32_t* text_ids, const int32_t* text_mask,
+                       const int32_t* src_node, const int32_t* tgt_node, const int32_t* walks, int num_nodes,
+                       int walk_len, int unk_id, int sep_id, int n, int64_t* input_ids, int64_t* attention_mask,
+                       int64_t* token_type_ids);
+/* replace_mlm_tokens (reference indra_for_pretraining.py:33-77) on both halves of input_ids int64 [n,512], in
+ * place: n_pick (= int(256*0.15) = 38) distinct positions per half, 80 % mask_id / 10 % unchanged / 10 % random
+ * id below vocab_len (text) or kg_vocab_len (KG); labels int64 [n,256] = original id at picked positions, -100
+ * elsewhere.  Philox4x32-10, counter (position, first_row + row, half, step), key = seed. */
+int stk_mask_tokens(int device, void* stream, int64_t* input_ids, int64_t* mlm_labels, int64_t* elm_labels, int n,
+                    int vocab_len, int kg_vocab_len, int mask_id, int n_pick, uint64_t seed, uint32_t step,
+                    int64_t first_row);
+
 /* Data-parallel bucket helpers (the producer / consumer kernels around the NCCL all-reduce that
  * replaces torch DDP's Reducer, reference stonkgs_pretraining.py:147-168,215-223):
  *   pack   = stk_cast_f32_to_bf16 on a slice of the flat gradient buffer (bf16 on the wire)

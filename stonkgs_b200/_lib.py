@@ -7,7 +7,8 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_longlong, c_size_t, c_void_p
+from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_longlong, c_size_t, c_uint32, c_uint64,
+                    c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libstk.so")
@@ -76,6 +77,8 @@ _SIGNATURES = {
     "stk_adamw_step": (c_int, [c_int, _P, _P, _P, _P, c_int, c_float, c_float, c_float, c_float, c_float, c_float,
                                c_float, _P, c_float]),
     "stk_nsp_pool_bwd": (c_int, [c_int, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P]),
+    "stk_assemble_pairs": (c_int, [c_int, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "stk_mask_tokens": (c_int, [c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_uint64, c_uint32, c_int64]),
     "stk_cls_head_fwd": (c_int, [c_int, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "stk_cls_pool_bwd": (c_int, [c_int, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P]),
 }

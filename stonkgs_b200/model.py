@@ -68,6 +68,9 @@ def prepare_df(path: str):
     """Load the node2vec TSV (``name \\t 768 floats`` per line, reference node2vec.py:350-354) in file
     order.  Restates ``kg_baseline_model.py:270-280`` without the per-row pandas loop.
     Returns (names, float32 [N, 768])."""
+    if str(path).endswith(".npy"):      # binary table written by inputs.save_kg_table (SURVEY 8f.3)
+        from .inputs import load_kg_table
+        return load_kg_table(str(path))
     names, rows = [], []
     with open(path, "r") as f:
         for line in f:
