@@ -147,6 +147,27 @@ int stk_attn_bwd(int device, void* stream, const void* qkv_bf16, const float* ke
                  const void* out_bf16, const void* dout_bf16, const float* lse, float* workspace,
                  void* dqkv_bf16);
 
+/* Training-mode variants with dropout of the attention probabilities (HF:132).  keep(seed, site, row, key) is the
+ * counter-based decision of csrc/stk_rng.h with row = (b*12 + h)*S + query; thr = round(256 p) in [0, 255]
+ * (thr = 0: no dropout); survivors are scaled by 256 / (256 - thr).  lse stays that of the full softmax. */
+int stk_attn_fwd_dropout(int device, void* stream, const void* qkv_bf16, const float* key_bias, int B, int S,
+                         void* out_bf16, float* lse, uint32_t seed, uint32_t site, uint32_t thr);
+int stk_attn_bwd_dropout(int device, void* stream, const void* qkv_bf16, const float* key_bias, int B, int S,
+                         const void* out_bf16, const void* dout_bf16, const float* lse, float* workspace,
+                         void* dqkv_bf16, uint32_t seed, uint32_t site, uint32_t thr);
+
+/* ------------------------------------------------------------------------------------------------
+ * Hidden dropout (training mode; HF:110, 297, 355).  Same decision function, row = token row, column = hidden index.
+ * ---------------------------------------------------------------------------------------------- */
+/* y = drop(x) over bf16 [M,768] (in place allowed).  Also the backward of every hidden-dropout site. */
+int stk_dropout_fwd(int device, void* stream, const void* x_bf16, int M, uint32_t seed, uint32_t site, uint32_t thr,
+                    void* y_bf16);
+/* z = drop(x) + resid ; y = LayerNorm(z) * gamma + beta   (BertSelfOutput / BertOutput in train()).
+ * z_out (bf16, may be NULL) and mean / rstd (may be NULL) are what stk_layernorm_bwd needs. */
+int stk_dropout_resid_ln_fwd(int device, void* stream, const void* x_bf16, const void* resid_bf16, int M,
+                             const float* gamma, const float* beta, uint32_t seed, uint32_t site, uint32_t thr,
+                             void* z_out_bf16, void* y_bf16, float* mean, float* rstd);
+
 /* ------------------------------------------------------------------------------------------------
  * Small fused helpers
  * ---------------------------------------------------------------------------------------------- */

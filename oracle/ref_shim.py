@@ -39,9 +39,6 @@ def _import_reference():
         return _state["sm"]
     if not reference_available():
         raise RuntimeError("reference tree not present (dev container only)")
-    import transformers
-    from transformers import BertConfig, BertModel
-
     sys.dont_write_bytecode = True
     sys.modules.setdefault("mlflow", types.ModuleType("mlflow"))
     if "pytorch_lightning" not in sys.modules:
@@ -66,28 +63,54 @@ def _import_reference():
     if REFERENCE_SRC not in sys.path:
         sys.path.insert(0, REFERENCE_SRC)
 
-    def _cfg():
-        cfg = BertConfig(vocab_size=28996, num_hidden_layers=_state["num_layers"])
-        cfg._attn_implementation = "eager"  # the 2021 code path; canonical oracle
-        return cfg
-
-    def _bert_from_pretrained(cls, *a, **k):
-        m = BertModel(_cfg()).eval()
-        if _state["lm_sd"] is not None:
-            m.load_state_dict(_state["lm_sd"], strict=True)
-        return m
-
-    BertConfig.from_pretrained = classmethod(lambda cls, *a, **k: _cfg())
-    BertModel.from_pretrained = classmethod(_bert_from_pretrained)
-
-    class _Tok:
-        sep_token_id, mask_token_id, unk_token_id = 102, 103, 100
-
-    transformers.BertTokenizer.from_pretrained = classmethod(lambda cls, *a, **k: _Tok())
     import stonkgs.models.stonkgs_model as sm  # noqa: E402  (the reference's own module)
 
     _state["sm"] = sm
     return sm
+
+
+class _offline_hub:
+    """While active, the three hub-bound constructors the reference calls in ``__init__`` (stonkgs_model.py:96,107,
+    116-118) resolve to offline equivalents (BioBERT-v1.1 shape, weights from ``_state``); restored on exit so that
+    other code in the same process (e.g. a save_pretrained / from_pretrained round trip) sees the real ones."""
+
+    def __enter__(self):
+        import transformers
+        from transformers import BertConfig, BertModel
+        self._saved = (BertConfig.__dict__.get("from_pretrained"), BertModel.__dict__.get("from_pretrained"),
+                       transformers.BertTokenizer.__dict__.get("from_pretrained"))
+
+        def _cfg():
+            cfg = BertConfig(vocab_size=28996, num_hidden_layers=_state["num_layers"])
+            cfg._attn_implementation = "eager"  # the 2021 code path; canonical oracle (SURVEY 8c)
+            return cfg
+
+        def _bert_from_pretrained(cls, *a, **k):
+            m = BertModel(_cfg()).eval()
+            if _state["lm_sd"] is not None:
+                m.load_state_dict(_state["lm_sd"], strict=True)
+            return m
+
+        class _Tok:
+            sep_token_id, mask_token_id, unk_token_id = 102, 103, 100
+
+        BertConfig.from_pretrained = classmethod(lambda cls, *a, **k: _cfg())
+        BertModel.from_pretrained = classmethod(_bert_from_pretrained)
+        transformers.BertTokenizer.from_pretrained = classmethod(lambda cls, *a, **k: _Tok())
+        return self
+
+    def __exit__(self, *exc):
+        import transformers
+        from transformers import BertConfig, BertModel
+        for cls, saved in zip((BertConfig, BertModel, transformers.BertTokenizer), self._saved):
+            if saved is None:
+                try:
+                    delattr(cls, "from_pretrained")     # fall back to the inherited classmethod
+                except AttributeError:
+                    pass
+            else:
+                setattr(cls, "from_pretrained", saved)
+        return False
 
 
 def load_reference(state_dict, kg_table: np.ndarray, num_layers: int = 12):
@@ -104,7 +127,8 @@ def load_reference(state_dict, kg_table: np.ndarray, num_layers: int = 12):
     was_cuda = torch.cuda.is_available
     torch.cuda.is_available = lambda: False  # keep lm_backbone on CPU (stonkgs_model.py:109-110)
     try:
-        model = sm.STonKGsForPreTraining(config=None, kg_embedding_dict_path="unused")
+        with _offline_hub():
+            model = sm.STonKGsForPreTraining(config=None, kg_embedding_dict_path="unused")
     finally:
         torch.cuda.is_available = was_cuda
     missing, unexpected = model.load_state_dict(state_dict, strict=False)
@@ -128,7 +152,8 @@ def load_reference_classifier(state_dict, kg_table: np.ndarray, num_layers: int,
     was_cuda = torch.cuda.is_available
     torch.cuda.is_available = lambda: False
     try:
-        model = sf.STonKGsForSequenceClassification(cfg, kg_embedding_dict_path="unused")
+        with _offline_hub():
+            model = sf.STonKGsForSequenceClassification(cfg, kg_embedding_dict_path="unused")
     finally:
         torch.cuda.is_available = was_cuda
     missing, unexpected = model.load_state_dict(state_dict, strict=False)

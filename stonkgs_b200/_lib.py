@@ -64,6 +64,10 @@ _SIGNATURES = {
                          POINTER(GemmEpilogue), c_int]),
     "stk_attn_fwd": (c_int, [c_int, _P, _P, _P, c_int, c_int, _P, _P]),
     "stk_attn_bwd": (c_int, [c_int, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P]),
+    "stk_attn_fwd_dropout": (c_int, [c_int, _P, _P, _P, c_int, c_int, _P, _P, c_uint32, c_uint32, c_uint32]),
+    "stk_attn_bwd_dropout": (c_int, [c_int, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, c_uint32, c_uint32, c_uint32]),
+    "stk_dropout_fwd": (c_int, [c_int, _P, _P, c_int, c_uint32, c_uint32, c_uint32, _P]),
+    "stk_dropout_resid_ln_fwd": (c_int, [c_int, _P, _P, _P, c_int, _P, _P, c_uint32, c_uint32, c_uint32, _P, _P, _P, _P]),
     "stk_mask_to_bias": (c_int, [c_int, _P, _P, c_int64, _P]),
     "stk_cast_f32_to_bf16": (c_int, [c_int, _P, _P, _P, c_int64]),
     "stk_gather_rows": (c_int, [c_int, _P, _P, _P, c_int, _P]),

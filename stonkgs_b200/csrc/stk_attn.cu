@@ -26,6 +26,7 @@
 
 #include "stk_common.cuh"
 #include "stk_host.h"
+#include "stk_rng.cuh"
 
 namespace stk {
 
@@ -46,10 +47,14 @@ constexpr int ATT_SMEM = 16384 * 6 + 4096 + 2048 + 256;
 // DBG is a bring-up bit mask (env STK_ATTN_DEBUG; 0 in production) used to attribute time to hardware
 // units: 1 skip exp2 (MUFU), 2 skip the TMEM score loads, 4 skip the P stores, 8 skip fence.proxy.async,
 // 16 one mbarrier arrival per warp instead of per thread, 32 skip the block-max exchange barrier.
-template <int DBG>
+// DROP: training-mode dropout of the attention probabilities (HF:132): the normalised probabilities are masked and
+// rescaled before they multiply V, so the row sum (and the saved log-sum-exp) stay those of the full softmax; the
+// keep decisions are regenerated in the backward kernel from (seed, site, row, key) — see stk_rng.cuh.
+template <int DBG, bool DROP>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __restrict__ key_bias, int S, int num_items,
-                __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out) {
+                __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out, uint32_t drop_seed, uint32_t drop_site,
+                uint32_t drop_thr) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = smem + 16384;        // [3][128 keys][128 B]
@@ -252,6 +257,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
         blk_biased = __reduce_or_sync(0xffffffffu, blk_biased);
       }
       named_bar_sync(1, 128);
+      const uint32_t drop_key = DROP ? drop_row_key(drop_seed, drop_site, static_cast<uint32_t>((b * kHeads + h) * S + q0 + row)) : 0u;
       float m2 = -INFINITY;                // running (lazily advanced) row max, log2 domain
       float l0 = 0.f, l1 = 0.f;            // running sums of exp2(x2 - m2)
 
@@ -340,8 +346,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
             const float p3 = fast_exp2(fmaf(__uint_as_float(r[g][4 * c + 3]), k1, a3));
             l0 += p0 + p2;
             l1 += p1 + p3;
-            pk[2 * c] = pack_bf16x2(p0, p1);
-            pk[2 * c + 1] = pack_bf16x2(p2, p3);
+            if (DROP) {   // the sums above are those of the full softmax; only what multiplies V is masked
+              const uint32_t kb = drop_bytes(drop_key, static_cast<uint32_t>(j * 32 + g * 8 + c));
+              pk[2 * c] = pack_bf16x2(drop_keep(kb, 0, drop_thr) ? p0 : 0.f, drop_keep(kb, 1, drop_thr) ? p1 : 0.f);
+              pk[2 * c + 1] = pack_bf16x2(drop_keep(kb, 2, drop_thr) ? p2 : 0.f, drop_keep(kb, 3, drop_thr) ? p3 : 0.f);
+            } else {
+              pk[2 * c] = pack_bf16x2(p0, p1);
+              pk[2 * c + 1] = pack_bf16x2(p2, p3);
+            }
           }
           tmem_st_32x32b_x16(t_row + T_P + g * 16, pk);
         }
@@ -355,7 +367,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
       mbar_wait(bar_pv, (n_blk - 1) & 1);
       tc_fence_after();
       const float total = l0 + l1;
-      const float inv = 1.0f / total;
+      const float inv = (DROP ? drop_scale(drop_thr) : 1.0f) / total;
       uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(row_base + q0 + row)) * kHidden + h * 64);
 #pragma unroll
       for (int hh2 = 0; hh2 < 2; ++hh2) {
@@ -387,8 +399,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
 
 using namespace stk;
 
-extern "C" int stk_attn_fwd(int device, void* stream, const void* qkv, const float* key_bias, int B, int S, void* out,
-                            float* lse) {
+static int attn_fwd_impl(int device, void* stream, const void* qkv, const float* key_bias, int B, int S, void* out,
+                         float* lse, bool drop, uint32_t drop_seed, uint32_t drop_site, uint32_t drop_thr) {
   STK_REQUIRE(qkv && out && B > 0, "stk_attn_fwd: bad arguments");
   STK_REQUIRE(S == 128 || S == 256 || S == 384 || S == 512, "stk_attn_fwd: S must be 128, 256, 384 or 512 (got %d)", S);
   STK_CHECK_CUDA(cudaSetDevice(device));
@@ -406,15 +418,27 @@ extern "C" int stk_attn_fwd(int device, void* stream, const void* qkv, const flo
   auto go = [&](auto kern) -> int {
     STK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     kern<<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(
-        map, key_bias, S, num_items, static_cast<__nv_bfloat16*>(out), lse);
+        map, key_bias, S, num_items, static_cast<__nv_bfloat16*>(out), lse, drop_seed, drop_site, drop_thr);
     return STK_OK;
   };
   // 64 = record a clock64 timeline of CTA 0 (tools/attn_dbg.py); every other value runs the production kernel
-  rc = (dbg == 64) ? go(attn_fwd_kernel<64>) : go(attn_fwd_kernel<0>);
+  if (drop) rc = go(attn_fwd_kernel<0, true>);
+  else rc = (dbg == 64) ? go(attn_fwd_kernel<64, false>) : go(attn_fwd_kernel<0, false>);
   if (rc) return rc;
   STK_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return STK_OK;
+}
+
+extern "C" int stk_attn_fwd(int device, void* stream, const void* qkv, const float* key_bias, int B, int S, void* out,
+                            float* lse) {
+  return attn_fwd_impl(device, stream, qkv, key_bias, B, S, out, lse, false, 0, 0, 0);
+}
+
+extern "C" int stk_attn_fwd_dropout(int device, void* stream, const void* qkv, const float* key_bias, int B, int S,
+                                    void* out, float* lse, uint32_t seed, uint32_t site, uint32_t thr) {
+  STK_REQUIRE(thr < 256, "stk_attn_fwd_dropout: thr must be below 256");
+  return attn_fwd_impl(device, stream, qkv, key_bias, B, S, out, lse, thr > 0, seed, site, thr);
 }
 
 // (backward kernel: see stk_attn_bwd.cu)

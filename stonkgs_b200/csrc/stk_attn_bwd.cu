@@ -22,6 +22,7 @@
 
 #include "stk_common.cuh"
 #include "stk_host.h"
+#include "stk_rng.cuh"
 
 namespace stk {
 
@@ -69,12 +70,14 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_cast_kernel(const float* __re
       make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
 }
 
-template <int DBG>
+// DROP: the forward multiplied V with Pd = P o m / (1 - p_drop) (stk_attn.cu); then dV = Pd^T dO,
+// dS = P o (dP o m / (1 - p_drop) - D) / 8 with the same D = rowsum(dO o O), and the masks m are regenerated here.
+template <int DBG, bool DROP>
 __global__ void __launch_bounds__(ABW_THREADS)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
                 const __grid_constant__ CUtensorMap map_dq, const float* __restrict__ key_bias,
                 const float* __restrict__ lse, const float* __restrict__ Dws, int S,
-                __nv_bfloat16* __restrict__ dqkv) {
+                __nv_bfloat16* __restrict__ dqkv, uint32_t drop_seed, uint32_t drop_site, uint32_t drop_thr) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
@@ -242,6 +245,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       const float lse2 = row_lse * kL2e;
       const float k1 = scale * kL2e;
       const float nDs = -row_D * scale;
+      const uint32_t drop_key = DROP ? drop_row_key(drop_seed, drop_site, static_cast<uint32_t>(stat_base + i * 128 + row)) : 0u;
+      const float dscale = DROP ? drop_scale(drop_thr) : 1.0f;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {   // 32 key columns at a time: S and dP loaded together
         uint32_t rs[32], rd[32];
@@ -257,15 +262,31 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
           const float4 ba = bz[2 * g], bb = bz[2 * g + 1];
           const float bias8[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
           uint32_t wp[4], wd[4];
+          // keep decisions of the 8 keys j*128 + half*64 + hh*32 + g*8 .. +7 (two 4-key words)
+          uint32_t kb[2] = {0u, 0u};
+          if (DROP) {
+            const uint32_t c4 = static_cast<uint32_t>(j * 32 + half * 16 + hh * 8 + g * 2);
+            kb[0] = drop_bytes(drop_key, c4);
+            kb[1] = drop_bytes(drop_key, c4 + 1);
+          }
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const int e = g * 8 + t * 2;
             // p = exp(s/8 + bias - lse) in the log2 domain; dS = p * (dP - D) / 8
             const float p0 = fast_exp2(fmaf(__uint_as_float(rs[e]), k1, bias8[2 * t] - lse2));
             const float p1 = fast_exp2(fmaf(__uint_as_float(rs[e + 1]), k1, bias8[2 * t + 1] - lse2));
-            const float d0 = p0 * fmaf(__uint_as_float(rd[e]), scale, nDs);
-            const float d1 = p1 * fmaf(__uint_as_float(rd[e + 1]), scale, nDs);
-            wp[t] = pack_bf16x2(p0, p1);
+            float dp0 = __uint_as_float(rd[e]), dp1 = __uint_as_float(rd[e + 1]);
+            float pv0 = p0, pv1 = p1;   // what multiplied V in the forward
+            if (DROP) {
+              const bool k0 = drop_keep(kb[t >> 1], (t & 1) * 2, drop_thr), k1b = drop_keep(kb[t >> 1], (t & 1) * 2 + 1, drop_thr);
+              dp0 = k0 ? dp0 * dscale : 0.f;
+              dp1 = k1b ? dp1 * dscale : 0.f;
+              pv0 = k0 ? p0 * dscale : 0.f;
+              pv1 = k1b ? p1 * dscale : 0.f;
+            }
+            const float d0 = p0 * fmaf(dp0, scale, nDs);
+            const float d1 = p1 * fmaf(dp1, scale, nDs);
+            wp[t] = pack_bf16x2(pv0, pv1);
             wd[t] = pack_bf16x2(d0, d1);
           }
           const int off = ((hh * 4 + g) ^ (row & 7)) << 4;
@@ -339,8 +360,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
 
 using namespace stk;
 
-extern "C" int stk_attn_bwd(int device, void* stream_, const void* qkv, const float* key_bias, int B, int S,
-                            const void* out, const void* dout, const float* lse, float* workspace, void* dqkv) {
+static int attn_bwd_impl(int device, void* stream_, const void* qkv, const float* key_bias, int B, int S, const void* out,
+                         const void* dout, const float* lse, float* workspace, void* dqkv, bool drop, uint32_t drop_seed,
+                         uint32_t drop_site, uint32_t drop_thr) {
   STK_REQUIRE(qkv && out && dout && lse && workspace && dqkv && B > 0, "stk_attn_bwd: bad arguments");
   STK_REQUIRE(S == 128 || S == 256 || S == 384 || S == 512, "stk_attn_bwd: S must be 128, 256, 384 or 512 (got %d)", S);
   STK_CHECK_CUDA(cudaSetDevice(device));
@@ -367,10 +389,12 @@ extern "C" int stk_attn_bwd(int device, void* stream_, const void* qkv, const fl
   auto go = [&](auto kern) -> int {
     STK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ABW_SMEM));
     kern<<<dim3(S / 128, kHeads, B), ABW_THREADS, ABW_SMEM, stream>>>(map_qkv, map_do, map_dq, key_bias, lse, Dws, S,
-                                                                     static_cast<__nv_bfloat16*>(dqkv));
+                                                                     static_cast<__nv_bfloat16*>(dqkv), drop_seed, drop_site,
+                                                                     drop_thr);
     return STK_OK;
   };
-  rc = (dbg == 64) ? go(attn_bwd_kernel<64>) : go(attn_bwd_kernel<0>);
+  if (drop) rc = go(attn_bwd_kernel<0, true>);
+  else rc = (dbg == 64) ? go(attn_bwd_kernel<64, false>) : go(attn_bwd_kernel<0, false>);
   if (rc) return rc;
   STK_CHECK_CUDA(cudaGetLastError());
   attn_bwd_dq_cast_kernel<<<static_cast<unsigned>((rows * (kHidden / 8) + 255) / 256), 256, 0, stream>>>(
@@ -378,6 +402,18 @@ extern "C" int stk_attn_bwd(int device, void* stream_, const void* qkv, const fl
   STK_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(3, std::memory_order_relaxed);
   return STK_OK;
+}
+
+extern "C" int stk_attn_bwd(int device, void* stream, const void* qkv, const float* key_bias, int B, int S,
+                            const void* out, const void* dout, const float* lse, float* workspace, void* dqkv) {
+  return attn_bwd_impl(device, stream, qkv, key_bias, B, S, out, dout, lse, workspace, dqkv, false, 0, 0, 0);
+}
+
+extern "C" int stk_attn_bwd_dropout(int device, void* stream, const void* qkv, const float* key_bias, int B, int S,
+                                    const void* out, const void* dout, const float* lse, float* workspace, void* dqkv,
+                                    uint32_t seed, uint32_t site, uint32_t thr) {
+  STK_REQUIRE(thr < 256, "stk_attn_bwd_dropout: thr must be below 256");
+  return attn_bwd_impl(device, stream, qkv, key_bias, B, S, out, dout, lse, workspace, dqkv, thr > 0, seed, site, thr);
 }
 
 // bring-up only: clock64 timeline of CTA (0,0,0) of the last STK_ATTN_DEBUG=64 backward launch

@@ -86,13 +86,63 @@ class LayerCache:
 
 
 # --------------------------------------------------------------------------------------------------
+# training-mode dropout: site ids shared with oracle/dropout_oracle.py
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class DropCtx:
+    """Dropout state of one forward pass in train() mode: every site derives its mask from (seed, site id) through
+    the counter-based function of csrc/stk_rng.cuh, so the backward pass regenerates it instead of storing it.
+    Encoder 0 = frozen LM backbone, 1 = joint encoder (HF:110 embeddings, :132 attention probabilities, :297 / :355
+    dense outputs before the residual sums)."""
+    seed: int
+    p_hidden: float
+    p_attn: float
+
+    def embeddings(self, enc: int) -> ops.Drop:
+        return ops.Drop(self.seed, enc * 64 + 63, self.p_hidden)
+
+    def attention(self, enc: int, layer: int) -> ops.Drop:
+        return ops.Drop(self.seed, enc * 64 + layer * 4, self.p_attn)
+
+    def attn_out(self, enc: int, layer: int) -> ops.Drop:
+        return ops.Drop(self.seed, enc * 64 + layer * 4 + 1, self.p_hidden)
+
+    def ffn_out(self, enc: int, layer: int) -> ops.Drop:
+        return ops.Drop(self.seed, enc * 64 + layer * 4 + 2, self.p_hidden)
+
+
+# --------------------------------------------------------------------------------------------------
 # forward
 # --------------------------------------------------------------------------------------------------
-def encoder_layer_fwd(x, lw: LayerWeights, B: int, S: int, key_bias, cache: Optional[list] = None):
+def encoder_layer_fwd(x, lw: LayerWeights, B: int, S: int, key_bias, cache: Optional[list] = None,
+                      drop: Optional[DropCtx] = None, enc: int = 0, li: int = 0):
     """One BertLayer (post-LN). x: bf16 [B*S, 768]."""
     M = x.shape[0]
     train = cache is not None
     qkv = ops.linear(x, lw.wqkv, lw.bqkv)
+    if drop is not None:
+        # train() with dropout: the dense outputs are dropped BEFORE the residual sum, so the dense GEMMs use the plain
+        # bias epilogue and one row kernel does dropout + residual + LayerNorm (the fused epilogue is the eval path)
+        da = drop.attention(enc, li)
+        if train:
+            ctx, lse = ops.attention(qkv, key_bias, B, S, save_lse=True, drop=da)
+        else:
+            ctx, lse = ops.attention(qkv, key_bias, B, S, drop=da), None
+        d1 = ops.linear(ctx, lw.wo, lw.bo)
+        if train:
+            x1, z1, mean1, rstd1 = ops.dropout_resid_ln(d1, x, lw.ln1_g, lw.ln1_b, drop.attn_out(enc, li), save_for_backward=True)
+            u = torch.empty((M, I), dtype=torch.bfloat16, device=x.device)
+            h = ops.linear(x1, lw.w1, lw.b1, ops.EPI_BIAS_GELU_SAVE, c2=u)
+        else:
+            x1 = ops.dropout_resid_ln(d1, x, lw.ln1_g, lw.ln1_b, drop.attn_out(enc, li))
+            h = ops.linear(x1, lw.w1, lw.b1, ops.EPI_BIAS_GELU)
+        d2 = ops.linear(h, lw.w2, lw.b2)
+        if train:
+            x2, z2, mean2, rstd2 = ops.dropout_resid_ln(d2, x1, lw.ln2_g, lw.ln2_b, drop.ffn_out(enc, li), save_for_backward=True)
+            cache.append(LayerCache(x, qkv, lse, ctx, z1, mean1, rstd1, x1, u, h, z2, mean2, rstd2))
+        else:
+            x2 = ops.dropout_resid_ln(d2, x1, lw.ln2_g, lw.ln2_b, drop.ffn_out(enc, li))
+        return x2
     if train:
         ctx, lse = ops.attention(qkv, key_bias, B, S, save_lse=True)
     else:
@@ -126,17 +176,22 @@ def encoder_layer_fwd(x, lw: LayerWeights, B: int, S: int, key_bias, cache: Opti
     return x2
 
 
-def encoder_fwd(x, ew: EncoderWeights, B: int, S: int, key_bias, cache: Optional[list] = None):
-    for lw in ew.layers:
-        x = encoder_layer_fwd(x, lw, B, S, key_bias, cache)
+def encoder_fwd(x, ew: EncoderWeights, B: int, S: int, key_bias, cache: Optional[list] = None,
+                drop: Optional[DropCtx] = None, enc: int = 0):
+    for li, lw in enumerate(ew.layers):
+        x = encoder_layer_fwd(x, lw, B, S, key_bias, cache, drop, enc, li)
     return x
 
 
-def lm_backbone_fwd(ew: EncoderWeights, text_ids: torch.Tensor, key_bias=None, err_flag=None):
-    """``self.lm_backbone(input_ids[:, :256])[0]`` (stonkgs_model.py:178): ids only, no mask, types 0."""
+def lm_backbone_fwd(ew: EncoderWeights, text_ids: torch.Tensor, key_bias=None, err_flag=None,
+                    drop: Optional[DropCtx] = None):
+    """``self.lm_backbone(input_ids[:, :256])[0]`` (stonkgs_model.py:178): ids only, no mask, types 0.
+    In train() the frozen backbone is in training mode too (the reference never calls ``.eval()`` on it)."""
     B, S = text_ids.shape
     x = ops.embed_text_ln(text_ids, ew.word, ew.pos, ew.type_emb, ew.emb_g, ew.emb_b, err_flag=err_flag)
-    return encoder_fwd(x, ew, B, S, key_bias)
+    if drop is not None:
+        ops.dropout(x, drop.embeddings(0), out=x)
+    return encoder_fwd(x, ew, B, S, key_bias, None, drop, 0)
 
 
 def lm_special_rows(ew: EncoderWeights, token_ids) -> torch.Tensor:
@@ -155,18 +210,20 @@ def lm_special_rows(ew: EncoderWeights, token_ids) -> torch.Tensor:
 
 
 def joint_fwd(bert: EncoderWeights, input_ids, token_type_ids, attention_mask, lm_hidden, kg_table, *,
-              cache: Optional[dict] = None, want_inputs_embeds=False, err_flag=None):
+              cache: Optional[dict] = None, want_inputs_embeds=False, err_flag=None, drop: Optional[DropCtx] = None):
     """KG lookup + concat + joint embeddings + 12 layers + pooler (stonkgs_model.py:182-212)."""
     B = input_ids.shape[0]
     train = cache is not None
     x, mean, rstd, emb = ops.embed_joint_ln(input_ids, token_type_ids, lm_hidden, kg_table, bert.pos, bert.type_emb,
                                             bert.emb_g, bert.emb_b, save_stats=train,
                                             want_inputs_embeds=want_inputs_embeds, err_flag=err_flag)
+    if drop is not None:
+        ops.dropout(x, drop.embeddings(1), out=x)
     key_bias = ops.mask_to_bias(attention_mask) if attention_mask is not None else None
     layer_cache = [] if train else None
-    seq = encoder_fwd(x, bert, B, 512, key_bias, layer_cache)
+    seq = encoder_fwd(x, bert, B, 512, key_bias, layer_cache, drop, 1)
     # BertPooler: tanh(W h[:, 0] + b); rows b*512 are read in place through the A pitch
     pooled = ops.gemm(seq.view(B, 512, H)[:, 0], bert.wp, M=B, N=H, K=H, epilogue=ops.EPI_BIAS_TANH_F32, bias=bert.bp)
     if train:
-        cache.update(emb_mean=mean, emb_rstd=rstd, key_bias=key_bias, layers=layer_cache, lm_hidden=lm_hidden)
+        cache.update(emb_mean=mean, emb_rstd=rstd, key_bias=key_bias, layers=layer_cache, lm_hidden=lm_hidden, drop=drop)
     return seq, pooled, emb

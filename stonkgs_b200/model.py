@@ -187,6 +187,13 @@ class STonKGsForPreTraining(BertForPreTraining):
         self._special_rows_version = None
         self._dev_state = None
         self.return_prediction_logits = False   # dense [B,256,V] / [B,256,N] logits only on request
+        # train() mode dropout (HF:110,132,297,355): masks are a counter-based function of
+        # (stk_dropout_seed + step, site), so backward regenerates them; last_dropout_seed is what a test hands to
+        # oracle.dropout_oracle.DropSpec to reproduce the same step in fp32
+        self.stk_dropout = True
+        self.stk_dropout_seed = int(torch.initial_seed()) & 0xFFFFFFFF
+        self._dropout_step = 0
+        self.last_dropout_seed = None
 
     # ------------------------------------------------------------------------------------------
     @staticmethod
@@ -338,14 +345,27 @@ class STonKGsForPreTraining(BertForPreTraining):
             attention_mask = attention_mask.to(dev, torch.int64, non_blocking=True).contiguous()
         if token_type_ids is not None:
             token_type_ids = token_type_ids.to(dev, torch.int64, non_blocking=True).contiguous()
-        lm_hidden = engine.lm_backbone_fwd(st["lm"], input_ids[:, :256], None, err_flag=err)
+        drop = self._drop_ctx()
+        lm_hidden = engine.lm_backbone_fwd(st["lm"], input_ids[:, :256], None, err_flag=err, drop=drop)
         seq, pooled, emb = engine.joint_fwd(st["bert"], input_ids, token_type_ids, attention_mask, lm_hidden,
                                             self.kg_table, cache=cache, want_inputs_embeds=want_inputs_embeds,
-                                            err_flag=err)
+                                            err_flag=err, drop=drop)
         if cache is not None:
             cache.update(input_ids=input_ids, token_type_ids=token_type_ids, err=err)
         self._pending_err = err
         return seq, pooled, emb
+
+    def _drop_ctx(self):
+        """Dropout state of this forward pass: None in eval() (the reference's parity mode) or when disabled."""
+        p_h = float(getattr(self.config, "hidden_dropout_prob", 0.0) or 0.0)
+        p_a = float(getattr(self.config, "attention_probs_dropout_prob", 0.0) or 0.0)
+        if not (self.training and getattr(self, "stk_dropout", False) and (p_h > 0.0 or p_a > 0.0)):
+            self.last_dropout_seed = None
+            return None
+        seed = (self.stk_dropout_seed + 0x9E3779B9 * self._dropout_step) & 0xFFFFFFFF
+        self._dropout_step += 1
+        self.last_dropout_seed = seed
+        return engine.DropCtx(seed, p_h, p_a)
 
     def grad_buffer(self):
         """Flat fp32 gradient buffer of the live parameters (``param.grad`` are views of it)."""

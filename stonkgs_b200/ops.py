@@ -228,7 +228,45 @@ def linear(x, w, bias=None, epilogue=EPI_BIAS, **kw):
 # --------------------------------------------------------------------------------------------------
 # attention
 # --------------------------------------------------------------------------------------------------
-def attention(qkv: torch.Tensor, key_bias: Optional[torch.Tensor], B: int, S: int, save_lse=False, out=None):
+class Drop:
+    """One dropout site of a training step: (seed, site id, threshold = round(256 p)); see csrc/stk_rng.cuh."""
+    __slots__ = ("seed", "site", "thr")
+
+    def __init__(self, seed: int, site: int, p: float):
+        self.seed = seed & 0xFFFFFFFF
+        self.site = site & 0xFFFFFFFF
+        self.thr = min(255, int(round(256.0 * p)))
+
+
+def dropout(x: torch.Tensor, d: Drop, out=None) -> torch.Tensor:
+    """y = drop(x) over bf16 [M, 768]; the same call is the backward of the site."""
+    _req(x, torch.bfloat16, "x")
+    assert x.shape[1] == H and x.is_contiguous()
+    dev, stream = _ctx(x)
+    y = torch.empty_like(x) if out is None else out
+    check(_lib.load().stk_dropout_fwd(dev, stream, _ptr(x), x.shape[0], d.seed, d.site, d.thr, _ptr(y)), "stk_dropout_fwd")
+    return y
+
+
+def dropout_resid_ln(x, resid, gamma, beta, d: Drop, save_for_backward=False):
+    """y = LN(drop(x) + resid); returns y or (y, z, mean, rstd)."""
+    _req(x, torch.bfloat16, "x")
+    M = x.shape[0]
+    assert x.shape[1] == H and x.is_contiguous() and resid.is_contiguous()
+    dev, stream = _ctx(x)
+    y = torch.empty_like(x)
+    z = mean = rstd = None
+    if save_for_backward:
+        z = torch.empty_like(x)
+        mean = torch.empty(M, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+    check(_lib.load().stk_dropout_resid_ln_fwd(dev, stream, _ptr(x), _ptr(resid), M, _ptr(gamma), _ptr(beta), d.seed, d.site,
+                                               d.thr, _ptr(z), _ptr(y), _ptr(mean), _ptr(rstd)), "stk_dropout_resid_ln_fwd")
+    return (y, z, mean, rstd) if save_for_backward else y
+
+
+def attention(qkv: torch.Tensor, key_bias: Optional[torch.Tensor], B: int, S: int, save_lse=False, out=None,
+              drop: Optional["Drop"] = None):
     _req(qkv, torch.bfloat16, "qkv")
     assert qkv.shape == (B * S, 3 * H) and qkv.is_contiguous()
     dev, stream = _ctx(qkv)
@@ -238,14 +276,18 @@ def attention(qkv: torch.Tensor, key_bias: Optional[torch.Tensor], B: int, S: in
     if prof is not None:
         e0, e1 = prof.span("attn_fwd", 4.0 * B * HEADS * S * S * 64)
         e0.record()
-    check(_lib.load().stk_attn_fwd(dev, stream, _ptr(qkv), _ptr(key_bias), B, S, _ptr(ctx), _ptr(lse)),
-          "stk_attn_fwd")
+    if drop is not None and drop.thr > 0:
+        check(_lib.load().stk_attn_fwd_dropout(dev, stream, _ptr(qkv), _ptr(key_bias), B, S, _ptr(ctx), _ptr(lse), drop.seed,
+                                               drop.site, drop.thr), "stk_attn_fwd_dropout")
+    else:
+        check(_lib.load().stk_attn_fwd(dev, stream, _ptr(qkv), _ptr(key_bias), B, S, _ptr(ctx), _ptr(lse)),
+              "stk_attn_fwd")
     if prof is not None:
         e1.record()
     return (ctx, lse) if save_lse else ctx
 
 
-def attention_bwd(qkv, key_bias, B, S, out, dout, lse):
+def attention_bwd(qkv, key_bias, B, S, out, dout, lse, drop: Optional["Drop"] = None):
     dev, stream = _ctx(qkv)
     dqkv = torch.empty_like(qkv)
     ws = torch.empty(B * S * H + B * HEADS * S, dtype=torch.float32, device=qkv.device)
@@ -253,8 +295,12 @@ def attention_bwd(qkv, key_bias, B, S, out, dout, lse):
     if prof is not None:
         e0, e1 = prof.span("attn_bwd", 10.0 * B * HEADS * S * S * 64)
         e0.record()
-    check(_lib.load().stk_attn_bwd(dev, stream, _ptr(qkv), _ptr(key_bias), B, S, _ptr(out), _ptr(dout), _ptr(lse),
-                                   _ptr(ws), _ptr(dqkv)), "stk_attn_bwd")
+    if drop is not None and drop.thr > 0:
+        check(_lib.load().stk_attn_bwd_dropout(dev, stream, _ptr(qkv), _ptr(key_bias), B, S, _ptr(out), _ptr(dout), _ptr(lse),
+                                               _ptr(ws), _ptr(dqkv), drop.seed, drop.site, drop.thr), "stk_attn_bwd_dropout")
+    else:
+        check(_lib.load().stk_attn_bwd(dev, stream, _ptr(qkv), _ptr(key_bias), B, S, _ptr(out), _ptr(dout), _ptr(lse),
+                                       _ptr(ws), _ptr(dqkv)), "stk_attn_bwd")
     if prof is not None:
         e1.record()
     return dqkv

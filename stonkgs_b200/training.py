@@ -334,23 +334,29 @@ def backward_trunk(model, bert: engine.EncoderWeights, cache, dseq, gb: GradBuff
     M = dseq.shape[0]
     B = M // 512
     key_bias = cache["key_bias"]
+    drop: Optional[engine.DropCtx] = cache.get("drop")   # train() with dropout: masks are regenerated from (seed, site)
     dx = dseq
     for li in reversed(range(len(bert.layers))):
         lw = bert.layers[li]
         c: engine.LayerCache = cache["layers"][li]
         p = f"l{li}."
+        # dz = gradient w.r.t. the residual sum z; the dense branch sees it through the dropout mask, the residual
+        # branch (added back below through the dgrad epilogues) sees it as it is
         dz2 = ops.layernorm_bwd(dx, c.z2, lw.ln2_g, c.mean2, c.rstd2, gb[p + "ln2_g"], gb[p + "ln2_b"])
-        ops.colsum(dz2, gb[p + "b2"], accumulate=True)
-        _wgrad(dz2, c.h, gb[p + "w2"], M)
-        du = _dgrad(dz2, lw.w2, epilogue=ops.EPI_DGELU, resid=c.u)
+        dz2m = ops.dropout(dz2, drop.ffn_out(1, li)) if drop is not None else dz2
+        ops.colsum(dz2m, gb[p + "b2"], accumulate=True)
+        _wgrad(dz2m, c.h, gb[p + "w2"], M)
+        du = _dgrad(dz2m, lw.w2, epilogue=ops.EPI_DGELU, resid=c.u)
         ops.colsum(du, gb[p + "b1"], accumulate=True)
         _wgrad(du, c.x1, gb[p + "w1"], M)
         dx1 = _dgrad(du, lw.w1, epilogue=ops.EPI_BIAS_RESID, resid=dz2)
         dz1 = ops.layernorm_bwd(dx1, c.z1, lw.ln1_g, c.mean1, c.rstd1, gb[p + "ln1_g"], gb[p + "ln1_b"])
-        ops.colsum(dz1, gb[p + "bo"], accumulate=True)
-        _wgrad(dz1, c.ctx, gb[p + "wo"], M)
-        dctx = _dgrad(dz1, lw.wo)
-        dqkv = ops.attention_bwd(c.qkv, key_bias, B, 512, c.ctx, dctx, c.lse)
+        dz1m = ops.dropout(dz1, drop.attn_out(1, li)) if drop is not None else dz1
+        ops.colsum(dz1m, gb[p + "bo"], accumulate=True)
+        _wgrad(dz1m, c.ctx, gb[p + "wo"], M)
+        dctx = _dgrad(dz1m, lw.wo)
+        dqkv = ops.attention_bwd(c.qkv, key_bias, B, 512, c.ctx, dctx, c.lse,
+                                 drop=drop.attention(1, li) if drop is not None else None)
         # bias gradients of query and value; the key-bias gradient is analytically zero (softmax is
         # invariant to a per-query shift of the scores), so its segment stays exactly 0
         ops.colsum(dqkv[:, :H], gb[p + "bqkv"][:H], accumulate=True)
@@ -361,6 +367,8 @@ def backward_trunk(model, bert: engine.EncoderWeights, cache, dseq, gb: GradBuff
             ready(p + n)
 
     # ---- joint embedding stage (position / token-type tables and LayerNorm) ----------------------
+    if drop is not None:
+        dx = ops.dropout(dx, drop.embeddings(1))
     ops.embed_joint_ln_bwd(cache["input_ids"], cache["token_type_ids"], cache["lm_hidden"], model.kg_table, bert.pos,
                            bert.type_emb, bert.emb_g, cache["emb_mean"], cache["emb_rstd"], dx, gb["emb_pos"],
                            gb["emb_type"], gb["emb_g"], gb["emb_b"])

@@ -18,7 +18,7 @@ def _run(case):
     return reports
 
 
-@pytest.mark.parametrize("case", ["elementwise", "gemm_basic", "gemm_epilogues", "gemm_majors", "gemm_ln", "gemm_ce", "cls_head", "attn",
+@pytest.mark.parametrize("case", ["elementwise", "gemm_basic", "gemm_epilogues", "gemm_majors", "gemm_ln", "gemm_ce", "cls_head", "dropout", "attn",
                                   "attn_bwd"])
 def test_kernel_group(case):
     _run(case)

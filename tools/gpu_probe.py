@@ -273,6 +273,69 @@ def case_cls_head():
 
 
 
+def case_dropout():
+    """Training-mode dropout kernels vs torch fp32 with the SAME masks (numpy twin of csrc/stk_rng.cuh)."""
+    import numpy as np
+    import torch
+    from oracle import dropout_oracle as do
+    from stonkgs_b200 import ops
+    torch.manual_seed(5)
+    res = []
+    # --- row kernels
+    M = 1000
+    d = ops.Drop(seed=0xC0FFEE, site=77, p=0.1)
+    x = _mk(M, 768, "cuda")
+    r = _mk(M, 768, "cuda")
+    keep = torch.from_numpy(do.keep_mask(d.seed, d.site, M, 768, d.thr)).cuda()
+    scale = 256.0 / (256 - d.thr)
+    y = ops.dropout(x, d)
+    res.append({"case": "drop_fwd_exact", "ok": bool(torch.equal(y, torch.where(keep, x.float() * scale, torch.zeros(1, device="cuda")).bfloat16())),
+                "drop_rate": float(1 - keep.float().mean())})
+    res.append({"case": "drop_rate_26_256", "ok": abs(float(1 - keep.float().mean()) - 26 / 256) < 2e-3})
+    gamma = 1.0 + 0.2 * torch.randn(768, device="cuda")
+    beta = 0.3 * torch.randn(768, device="cuda")
+    yl, z, mean, rstd = ops.dropout_resid_ln(x, r, gamma, beta, d, save_for_backward=True)
+    zref = torch.where(keep, x.float() * scale, torch.zeros(1, device="cuda")) + r.float()
+    res.append(_err_report(z, zref, "drop_resid_z", 4e-2))
+    res.append(_err_report(yl, torch.nn.functional.layer_norm(zref, (768,), gamma, beta, 1e-12), "drop_resid_ln_y", 6e-2))
+    res.append(_err_report(mean, z.float().mean(1), "drop_resid_mean", 2e-3))
+    y_inf = ops.dropout_resid_ln(x, r, gamma, beta, d)
+    res.append(_err_report(y_inf, torch.nn.functional.layer_norm(zref, (768,), gamma, beta, 1e-12), "drop_resid_ln_y_nosave", 6e-2))
+    # --- attention forward / backward with injected masks
+    for (B, S, use_bias) in [(2, 256, False), (3, 512, True)]:
+        da = ops.Drop(seed=1234 + S, site=5, p=0.1)
+        qkv = (torch.randn(B * S, 2304, device="cuda") * 0.8).bfloat16()
+        bias = None
+        if use_bias:
+            mask = torch.ones(B, S, dtype=torch.int64, device="cuda")
+            mask[0, 100:256] = 0
+            mask[2, 40:256] = 0
+            bias = ops.mask_to_bias(mask)
+        keep = torch.from_numpy(do.keep_mask(da.seed, da.site, B * 12 * S, S, da.thr)).cuda().view(B, 12, S, S)
+        sc = 256.0 / (256 - da.thr)
+        xq = qkv.float().clone().requires_grad_(True)
+        q, k, v = xq.view(B, S, 3, 12, 64).permute(2, 0, 3, 1, 4)
+        s_ = q @ k.transpose(-1, -2) * 0.125
+        if bias is not None:
+            s_ = s_ + bias[:, None, None, :]
+        pr = torch.softmax(s_, -1)
+        prd = torch.where(keep, pr * sc, torch.zeros(1, device="cuda"))
+        oref = (prd @ v).permute(0, 2, 1, 3).reshape(B * S, 768)
+        out, lse = ops.attention(qkv, bias, B, S, save_lse=True, drop=da)
+        res.append(_err_report(out, oref, f"attn_drop_fwd_S{S}", 3e-2))
+        res.append(_err_report(lse, torch.logsumexp(s_, -1), f"attn_drop_lse_S{S}", 1e-3))
+        dout = (torch.randn(B * S, 768, device="cuda") * 0.5).bfloat16()
+        oref.backward(dout.float())
+        dqkv = ops.attention_bwd(qkv, bias, B, S, out, dout, lse, drop=da)
+        torch.cuda.synchronize()
+        for nm, sl in (("dq", slice(0, 768)), ("dk", slice(768, 1536)), ("dv", slice(1536, 2304))):
+            res.append(_err_report(dqkv[:, sl], xq.grad[:, sl], f"attn_drop_bwd_{nm}_S{S}", 4e-2))
+        out0 = ops.attention(qkv, bias, B, S)
+        res.append({"case": f"attn_drop_differs_S{S}", "ok": bool((out.float() - out0.float()).abs().max() > 1e-2)})
+    return res
+
+
+
 def case_gemm_majors():
     """dgrad (B MN-major) and wgrad (A and B MN-major, split-K reduce-add)."""
     import torch
@@ -448,6 +511,7 @@ CASES = {
     "gemm_epilogues": case_gemm_epilogues,
     "gemm_majors": case_gemm_majors,
     "cls_head": case_cls_head,
+    "dropout": case_dropout,
     "gemm_ln": case_gemm_ln,
     "gemm_ce": case_gemm_ce,
     "attn": case_attn,
