@@ -11,7 +11,8 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int
                     c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstk.so")
+# STK_LIB: bring-up override (A/B runs of two builds of the kernel library); the product path is the in-tree build
+LIB_PATH = os.environ.get("STK_LIB") or os.path.join(_HERE, "libstk.so")
 
 STK_VERSION = 101
 

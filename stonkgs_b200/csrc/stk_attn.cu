@@ -23,6 +23,7 @@
 // No S x S tensor ever goes to HBM.  Row log-sum-exp can be saved for the backward pass.
 #include <atomic>
 #include <stdlib.h>
+#include <type_traits>
 
 #include "stk_common.cuh"
 #include "stk_host.h"
@@ -32,14 +33,21 @@ namespace stk {
 
 extern std::atomic<long long> g_launches;
 
-constexpr int ATT_THREADS = 192;   // 4 softmax warps (one thread per query row) + TMA warp + MMA warp
+// Two warpgroups: warps 0-3 softmax (one thread per query row), warp 4 TMA, warp 5 MMA, warps 6-7 only complete the
+// second warpgroup so that setmaxnreg can move registers: the CTA is launched with 128 registers per thread (2 CTAs
+// per SM), warpgroup 1 drops to 56 and the softmax warpgroup rises to 200.  With a uniform budget (168) the softmax
+// path spilled ~20 loop variables; two CTAs' spill lines do not fit the 28 KB of L1 left beside 2 x 103 KB of shared
+// memory, so every item boundary paid a chain of L2 round trips (~5 k cycles per item, measured with the timeline).
+constexpr int ATT_THREADS = 256;
+constexpr int ATT_REGS_SOFTMAX = 200, ATT_REGS_OTHER = 56;
 __device__ long long g_attn_timeline[4096];   // bring-up only (DBG & 64): clock64 stamps of CTA 0
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 // sQ 16K | sK 3x16K | sV 2x16K | bias 2x2K | max/sum exchange 2K | barriers
 constexpr int ATT_KSTAGES = 3, ATT_VSTAGES = 2;
-constexpr int ATT_SMEM = 16384 * 6 + 4096 + 2048 + 256;
+// ... | output staging 4 x 2K (one 32-row x 64-byte tile per softmax warp)
+constexpr int ATT_SMEM = 16384 * 6 + 4096 + 2048 + 256 + 8192;
 
 // Persistent: grid = 2 CTAs per SM; every CTA walks work items (q-tile, head, batch) with the q-tile
 // index fastest, so CTAs that run together share K/V in L2, and the loads of the next item's
@@ -60,8 +68,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
   uint8_t* sK = smem + 16384;        // [3][128 keys][128 B]
   uint8_t* sV = smem + 65536;        // [2][128 keys][128 B]
   float* sBias = reinterpret_cast<float*>(smem + 98304);   // [2 item parity][512] key bias * log2e (clamped finite)
-  float* sXch = sBias + 1024;        // (unused scratch)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sXch + 512);
+  uint32_t* sMeta = reinterpret_cast<uint32_t*>(sBias + 1024);   // [2 item parity] bit j: key block j holds a biased key
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 1024 + 512);
   uint64_t* bar_q = bars;         // Q tile landed
   uint64_t* bar_k = bars + 1;     // [3] K block landed
   uint64_t* bar_v = bars + 4;     // [2] V block landed
@@ -74,7 +82,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
   uint64_t* bar_kfree = bars + 10;  // [3]
   uint64_t* bar_vfree = bars + 13;  // [2]
   uint64_t* bar_qfree = bars + 15;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* bar_bfull = bars + 16;  // [2] the prep warp has staged the key bias of an item
+  uint64_t* bar_bfree = bars + 18;  // [2] the softmax warps have finished reading it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint8_t* sOut = smem + 16384 * 6 + 4096 + 2048 + 256;   // [4 warps][32 rows][64 B]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = S >> 7;          // key blocks per item == q-tiles per (head, batch)
@@ -92,6 +103,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
       mbar_init(bar_sread, 128);
       mbar_init(bar_p, 128);
       mbar_init(bar_pv, 1);
+      for (int i = 0; i < 2; ++i) { mbar_init(bar_bfull + i, 1); mbar_init(bar_bfree + i, 128); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -107,6 +119,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
   const int total = my_items * nblk;
 
   if (warp == 4) {
+    setmaxnreg_dec<ATT_REGS_OTHER>();
     // ================================ TMA producer ================================
     // K_g -> ring slot g % 3, V_g -> ring slot g % 2, Q once per item; a slot is refilled as soon as the
     // MMA warp's tcgen05.commit reports that the MMAs reading it have completed.
@@ -157,17 +170,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
       if (g == 0) { load_q(item); ++n_item; }
       if (g >= ATT_KSTAGES) mbar_wait(bar_kfree + g % ATT_KSTAGES, ((g / ATT_KSTAGES) - 1) & 1);
       load_k();
-      if (g >= ATT_VSTAGES) mbar_wait(bar_vfree + g % ATT_VSTAGES, ((g / ATT_VSTAGES) - 1) & 1);
-      load_v();
-      if (j == 0 && g > 0) {   // first block of a later item: its K/V are already on their way, now Q
-        mbar_wait(bar_qfree, (n_item - 1) & 1);   // previous item's last score MMA has read Q
+      if (j == 0 && g > 0) {
+        // first block of a later item: Q goes out as soon as the previous item's last score MMA has read the tile,
+        // i.e. BEFORE the V slot wait (which follows a whole softmax pass later): a TMA load under load takes
+        // 2.5-3 k cycles, about one key-block period
+        mbar_wait(bar_qfree, (n_item - 1) & 1);
         load_q(item);
         ++n_item;
       }
+      if (g >= ATT_VSTAGES) mbar_wait(bar_vfree + g % ATT_VSTAGES, ((g / ATT_VSTAGES) - 1) & 1);
+      load_v();
       if (++j == nblk) { j = 0; item += gridDim.x; }
     }
     __syncwarp();
   } else if (warp == 5) {
+    setmaxnreg_dec<ATT_REGS_OTHER>();
     // ================================ MMA issuer ================================
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
@@ -205,11 +222,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
     };
     for (int g = 0; g < total; ++g) {
       stamp(g, 0);
-      if (g + 1 < total) {
+      // Inside an item the next scores are issued first (they run while softmax g is still busy).  For the last key
+      // block of an item the order is reversed: the next scores need the next item's Q tile, which may still be in
+      // flight, and the item's epilogue waits for this P V product.
+      // (when that Q tile has already landed, the normal order keeps the next item's first scores off the critical path)
+      bool scores_first = g + 1 < total;
+      if (scores_first && pj == nblk - 1) {   // whichever comes first: the next Q tile or P_g
+        while (true) {
+          if (__all_sync(0xffffffffu, mbar_test_wait(bar_q, n_q & 1))) break;
+          if (__all_sync(0xffffffffu, mbar_test_wait(bar_p, g & 1))) { scores_first = false; break; }
+        }
+      }
+      if (scores_first) {
         mbar_wait(bar_sread, g & 1);         // S_g sits in registers: the S columns are free
         tc_fence_after();
         stamp(g, 1);
-        issue_scores();                      // next scores run while softmax g is still busy
+        issue_scores();
       }
       stamp(g, 2);
       mbar_wait(bar_p, g & 1);               // P_g is in tensor memory, O rescaled if needed
@@ -227,36 +255,112 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
         umma_commit_warp(bar_vfree + vs);                    // V slot reusable
       }
       stamp(g, 5);
+      if (!scores_first && g + 1 < total) {
+        mbar_wait(bar_sread, g & 1);
+        tc_fence_after();
+        issue_scores();
+      }
       if (DBG & 64) { mbar_wait(bar_pv, g & 1); stamp(g, 6); }
       if (++vs == ATT_VSTAGES) { vs = 0; vph ^= 1; }
       if (++pj == nblk) pj = 0;
     }
+  } else if (warp == 6) {
+    setmaxnreg_dec<ATT_REGS_OTHER>();
+    // ================================ key-bias prep warp ================================
+    // Stages the additive key bias of the item after next's batch element (x log2e, clamped finite) and the mask of
+    // key blocks that hold a biased key, one item ahead of the softmax warps: the global-load latency of the bias
+    // never sits between two items.
+    if (key_bias) {
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int b = (item / nblk) / kHeads;
+        if (it >= 2) mbar_wait(bar_bfree + (it & 1), ((it >> 1) - 1) & 1);
+        float* bias_it = sBias + (it & 1) * 512;
+        const float4* src = reinterpret_cast<const float4*>(key_bias + static_cast<int64_t>(b) * S);
+        uint32_t biased = 0;
+        for (int i = lane; i < (S >> 2); i += 32) {     // S / 4 float4 words; word i covers keys 4i .. 4i+3
+          const float4 v = __ldg(src + i);
+          if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) biased |= 1u << (i >> 5);
+          float4 w;   // finfo.min * log2e overflows to -inf: keep it finite
+          w.x = fmaxf(v.x * kLog2e, -3.402823466e38f); w.y = fmaxf(v.y * kLog2e, -3.402823466e38f);
+          w.z = fmaxf(v.z * kLog2e, -3.402823466e38f); w.w = fmaxf(v.w * kLog2e, -3.402823466e38f);
+          reinterpret_cast<float4*>(bias_it)[i] = w;
+        }
+        biased = __reduce_or_sync(0xffffffffu, biased);
+        if (lane == 0) sMeta[it & 1] = biased;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_bfull + (it & 1));   // release: the stores above are visible to the waiters
+      }
+    }
+  } else if (warp == 7) {
+    setmaxnreg_dec<ATT_REGS_OTHER>();   // idle: completes warpgroup 1 for setmaxnreg
   } else {
+    setmaxnreg_inc<ATT_REGS_SOFTMAX>();
     // ================================ softmax warps ================================
     const int row = warp * 32 + lane;      // warp w may touch TMEM lanes 32w .. 32w+31
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     const float k1 = 0.125f * kLog2e;      // 1/sqrt(64) (HF:156) folded with log2(e)
     uint32_t n_blk = 0, it = 0;            // n_blk = flat key-block counter (mbarrier parities)
 
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-      const int qt = item % nblk, rest = item / nblk;
-      const int h = rest % kHeads, b = rest / kHeads;
-      const int row_base = b * S, q0 = qt * 128;
-      // key bias of this item's batch element (double-buffered by item parity)
-      float* bias_it = sBias + (it & 1) * 512;
-      for (int i = threadIdx.x; i < S; i += 128) {
-        const float bz = key_bias ? __ldg(key_bias + static_cast<int64_t>(b) * S + i) * kLog2e : 0.f;
-        bias_it[i] = fmaxf(bz, -3.402823466e38f);   // finfo.min * log2e overflows to -inf: keep it finite
+    // Item walk without per-item divisions: (q-tile, head, batch) of blockIdx.x, advanced by the decomposition of
+    // gridDim.x with carries.
+    int qt = static_cast<int>(blockIdx.x) % nblk, h, b;
+    {
+      const int rest = static_cast<int>(blockIdx.x) / nblk;
+      h = rest % kHeads;
+      b = rest / kHeads;
+    }
+    const int d_qt = static_cast<int>(gridDim.x) % nblk;
+    const int d_h = (static_cast<int>(gridDim.x) / nblk) % kHeads;
+    const int d_b = (static_cast<int>(gridDim.x) / nblk) / kHeads;
+
+    // The output of an item is written while the FIRST key block of the CTA's next item is in flight: its last P V
+    // product completes behind that block's score load / max / exponentials instead of stalling the softmax warps.
+    bool pending = false;
+    float pend_inv = 0.f, pend_lse = 0.f;
+    __nv_bfloat16* pend_dst = nullptr;     // warp-uniform: output row of the warp's first query row, head column 0
+    float* pend_lse_ptr = nullptr;
+    uint8_t* stage = sOut + warp * 2048;   // 32 rows x 64 B, 16-byte chunks XOR-swizzled with (row >> 1) & 3
+    auto flush_pending = [&]() {   // requires: the pending item's last P V product has completed
+      // A thread owns one output row (128 B); storing it directly would touch 32 different lines per warp instruction.
+      // Each 32-column half goes through the warp's staging tile instead, so that a store instruction covers 8 rows x
+      // 64 contiguous bytes.
+#pragma unroll
+      for (int hh2 = 0; hh2 < 2; ++hh2) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(t_row + T_O + hh2 * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            w[i] = pack_bf16x2(__uint_as_float(o[c * 8 + 2 * i]) * pend_inv, __uint_as_float(o[c * 8 + 2 * i + 1]) * pend_inv);
+          *reinterpret_cast<uint4*>(stage + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = i * 8 + (lane >> 2), c = lane & 3;
+          const uint4 v = *reinterpret_cast<const uint4*>(stage + rr * 64 + ((c ^ ((rr >> 1) & 3)) << 4));
+          *reinterpret_cast<uint4*>(pend_dst + static_cast<int64_t>(rr) * kHidden + hh2 * 32 + c * 8) = v;
+        }
+        __syncwarp();
       }
+      if (lse_out) *pend_lse_ptr = pend_lse;
+      pending = false;
+    };
+
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int row_base = b * S, q0 = qt * 128;
+      const float* bias_it = sBias + (it & 1) * 512;   // staged by the prep warp (double-buffered by item parity)
       // which 128-key blocks hold at least one biased (masked) key: blocks without any take the short
-      // instruction path below (no bias loads / adds)
+      // instruction stream below (no bias loads / adds)
       uint32_t blk_biased = 0;
       if (key_bias) {
-        for (int i = lane; i < S; i += 32)
-          if (__ldg(key_bias + static_cast<int64_t>(b) * S + i) != 0.f) blk_biased |= 1u << (i >> 7);
-        blk_biased = __reduce_or_sync(0xffffffffu, blk_biased);
+        mbar_wait(bar_bfull + (it & 1), (it >> 1) & 1);
+        blk_biased = sMeta[it & 1];
       }
-      named_bar_sync(1, 128);
       const uint32_t drop_key = DROP ? drop_row_key(drop_seed, drop_site, static_cast<uint32_t>((b * kHeads + h) * S + q0 + row)) : 0u;
       float m2 = -INFINITY;                // running (lazily advanced) row max, log2 domain
       float l0 = 0.f, l1 = 0.f;            // running sums of exp2(x2 - m2)
@@ -303,20 +407,66 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
           bm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * k1;
         }
         if (st) g_attn_timeline[n_blk * 16 + 10] = clock64();
+        // Lazy rescale.  The decision is per row, but tcgen05.ld / tcgen05.st are warp-collective
+        // (.sync.aligned): when ANY row of the warp must advance its max, the whole warp runs the O
+        // rescale with a per-lane factor (1.0 for rows that keep their max).
+        const bool advance = bm > m2 + kRescaleThreshold;   // always true for j == 0 (m2 = -inf)
+        const bool rescale = j > 0 && __any_sync(0xffffffffu, advance);
+        float alpha = 1.0f;
+        if (rescale) {
+          alpha = advance ? fast_exp2(m2 - bm) : 1.0f;
+          l0 *= alpha;
+          l1 *= alpha;
+        }
+        if (advance) m2 = bm;
+        const float nm2 = -m2;
+        // The exponentials only need registers, so they are formed BEFORE waiting for the previous P V product: its
+        // latency (P_{j-1} hand-over + 8 MMAs) hides behind this pass instead of stalling the softmax warps.
+        // Two separate instruction streams: blocks without biased keys run FFMA / MUFU / FADD (+ half a pack) per
+        // element; one predicated stream would carry the bias moves and adds through every block.
+        uint32_t pk[64];               // 128 keys -> 64 packed TMEM columns of the A operand
+        auto exp_pass = [&](auto biased_tag) {
+          constexpr bool kBiased = decltype(biased_tag)::value;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              float a0 = nm2, a1 = nm2, a2 = nm2, a3 = nm2;
+              if (kBiased) {
+                const float4 b0 = bz[g * 8 + c];
+                a0 += b0.x; a1 += b0.y; a2 += b0.z; a3 += b0.w;
+              }
+              const float p0 = fast_exp2(fmaf(__uint_as_float(r[g][4 * c]), k1, a0));
+              const float p1 = fast_exp2(fmaf(__uint_as_float(r[g][4 * c + 1]), k1, a1));
+              const float p2 = fast_exp2(fmaf(__uint_as_float(r[g][4 * c + 2]), k1, a2));
+              const float p3 = fast_exp2(fmaf(__uint_as_float(r[g][4 * c + 3]), k1, a3));
+              l0 += p0 + p2;
+              l1 += p1 + p3;
+              if (DROP) {   // the sums above are those of the full softmax; only what multiplies V is masked
+                const uint32_t kb = drop_bytes(drop_key, static_cast<uint32_t>(j * 32 + g * 8 + c));
+                pk[g * 16 + 2 * c] = pack_bf16x2(drop_keep(kb, 0, drop_thr) ? p0 : 0.f, drop_keep(kb, 1, drop_thr) ? p1 : 0.f);
+                pk[g * 16 + 2 * c + 1] = pack_bf16x2(drop_keep(kb, 2, drop_thr) ? p2 : 0.f, drop_keep(kb, 3, drop_thr) ? p3 : 0.f);
+              } else {
+                pk[g * 16 + 2 * c] = pack_bf16x2(p0, p1);
+                pk[g * 16 + 2 * c + 1] = pack_bf16x2(p2, p3);
+              }
+            }
+          }
+        };
+        if (biased) exp_pass(std::true_type{});
+        else exp_pass(std::false_type{});
         if (n_blk > 0) {
           // the previous P V product (possibly the previous item's last) must be complete before O is
           // touched and before the P columns are overwritten
           mbar_wait(bar_pv, (n_blk - 1) & 1);
           tc_fence_after();
         }
-        // Lazy rescale.  The decision is per row, but tcgen05.ld / tcgen05.st are warp-collective
-        // (.sync.aligned): when ANY row of the warp must advance its max, the whole warp runs the O
-        // rescale with a per-lane factor (1.0 for rows that keep their max).
-        const bool advance = bm > m2 + kRescaleThreshold;   // always true for j == 0 (m2 = -inf)
-        if (j > 0 && __any_sync(0xffffffffu, advance)) {
-          const float alpha = advance ? fast_exp2(m2 - bm) : 1.0f;
-          l0 *= alpha;
-          l1 *= alpha;
+        if (j == 0 && pending) {   // warp-uniform: the previous item's O leaves TMEM before this item's first P V
+          if (st) g_attn_timeline[n_blk * 16 + 12] = clock64();
+          flush_pending();
+          if (st) g_attn_timeline[n_blk * 16 + 13] = clock64();
+        }
+        if (rescale) {
 #pragma unroll 1
           for (int c0 = 0; c0 < 64; c0 += 8) {   // 8 columns at a time keeps the register peak low
             uint32_t o[8];
@@ -326,37 +476,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
             for (int c = 0; c < 8; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
             tmem_st_32x32b_x8(t_row + T_O + c0, o);
           }
-          tmem_st_wait();
         }
-        if (advance) m2 = bm;
-        const float nm2 = -m2;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {      // 32 keys -> 16 packed TMEM columns of the A operand
-          uint32_t pk[16];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float a0 = nm2, a1 = nm2, a2 = nm2, a3 = nm2;
-            if (biased) {
-              const float4 b0 = bz[g * 8 + c];
-              a0 += b0.x; a1 += b0.y; a2 += b0.z; a3 += b0.w;
-            }
-            const float p0 = fast_exp2(fmaf(__uint_as_float(r[g][4 * c]), k1, a0));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(r[g][4 * c + 1]), k1, a1));
-            const float p2 = fast_exp2(fmaf(__uint_as_float(r[g][4 * c + 2]), k1, a2));
-            const float p3 = fast_exp2(fmaf(__uint_as_float(r[g][4 * c + 3]), k1, a3));
-            l0 += p0 + p2;
-            l1 += p1 + p3;
-            if (DROP) {   // the sums above are those of the full softmax; only what multiplies V is masked
-              const uint32_t kb = drop_bytes(drop_key, static_cast<uint32_t>(j * 32 + g * 8 + c));
-              pk[2 * c] = pack_bf16x2(drop_keep(kb, 0, drop_thr) ? p0 : 0.f, drop_keep(kb, 1, drop_thr) ? p1 : 0.f);
-              pk[2 * c + 1] = pack_bf16x2(drop_keep(kb, 2, drop_thr) ? p2 : 0.f, drop_keep(kb, 3, drop_thr) ? p3 : 0.f);
-            } else {
-              pk[2 * c] = pack_bf16x2(p0, p1);
-              pk[2 * c + 1] = pack_bf16x2(p2, p3);
-            }
-          }
-          tmem_st_32x32b_x16(t_row + T_P + g * 16, pk);
-        }
+        for (int g = 0; g < 4; ++g) tmem_st_32x32b_x16(t_row + T_P + g * 16, *reinterpret_cast<const uint32_t(*)[16]>(pk + g * 16));
         tmem_st_wait();
         if (st) g_attn_timeline[n_blk * 16 + 11] = clock64();
         tc_fence_before();          // P store and O rescale are ordered before the next MMA
@@ -364,26 +486,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
         ++n_blk;
       }
 
+      if (key_bias) mbar_arrive(bar_bfree + (it & 1));   // the prep warp may restage this bias buffer
+      const float total = l0 + l1;
+      pend_inv = (DROP ? drop_scale(drop_thr) : 1.0f) / total;
+      pend_lse = (m2 + log2f(total)) * kLn2;
+      pend_dst = out + (static_cast<int64_t>(row_base + q0 + warp * 32)) * kHidden + h * 64;
+      pend_lse_ptr = lse_out + (static_cast<int64_t>(b) * kHeads + h) * S + q0 + row;
+      pending = true;
+      // next item of this CTA
+      qt += d_qt;
+      if (qt >= nblk) { qt -= nblk; ++h; }
+      h += d_h;
+      if (h >= kHeads) { h -= kHeads; ++b; }
+      b += d_b;
+    }
+    if (pending) {
       mbar_wait(bar_pv, (n_blk - 1) & 1);
       tc_fence_after();
-      const float total = l0 + l1;
-      const float inv = (DROP ? drop_scale(drop_thr) : 1.0f) / total;
-      uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(row_base + q0 + row)) * kHidden + h * 64);
-#pragma unroll
-      for (int hh2 = 0; hh2 < 2; ++hh2) {
-        uint32_t o[32];
-        tmem_ld_32x32b_x32(t_row + T_O + hh2 * 32, o);
-        tmem_ld_wait();
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t w[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            w[i] = pack_bf16x2(__uint_as_float(o[g * 8 + 2 * i]) * inv, __uint_as_float(o[g * 8 + 2 * i + 1]) * inv);
-          dst[hh2 * 4 + g] = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-      }
-      if (lse_out) lse_out[(static_cast<int64_t>(b) * kHeads + h) * S + q0 + row] = (m2 + log2f(total)) * kLn2;
+      flush_pending();
     }
   }
 

@@ -19,8 +19,8 @@ if int(os.environ.get("STK_ATTN_DEBUG", "0")) & 64:
     buf = (ctypes.c_longlong * 2048)()
     lib.stk_debug_attn_timeline(buf, 2048)
     t0 = buf[0]
-    names = ["m:loop", "m:sread", "m:S_issued", "m:p", "m:v", "m:PV_issued", "m:pv_done"] + [""] + ["s:start", "s:bar_s", "s:max_done", "s:p_done"]
+    names = ["m:loop", "m:sread", "m:S_issued", "m:p", "m:v", "m:PV_issued", "m:pv_done"] + [""] + ["s:start", "s:bar_s", "s:max_done", "s:p_done", "e:begin", "e:pv", "e:stored", "i:setup"]
     for g in range(12):
-        row = [buf[g * 16 + i] - t0 for i in range(12)]
+        row = [buf[g * 16 + i] - t0 for i in range(16)]
         print(g, " ".join(f"{n}={v}" for n, v in zip(names, row) if n))
     print("S issue start (after K ready):", [buf[1024 + i] - t0 for i in range(13)])
