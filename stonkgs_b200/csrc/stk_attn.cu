@@ -68,7 +68,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
   uint8_t* sK = smem + 16384;        // [3][128 keys][128 B]
   uint8_t* sV = smem + 65536;        // [2][128 keys][128 B]
   float* sBias = reinterpret_cast<float*>(smem + 98304);   // [2 item parity][512] key bias * log2e (clamped finite)
-  uint32_t* sMeta = reinterpret_cast<uint32_t*>(sBias + 1024);   // [2 item parity] bit j: key block j holds a biased key
+  uint32_t* sMeta = reinterpret_cast<uint32_t*>(sBias + 1024);   // [2 item parity] 2-bit state of every 32-key group
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 1024 + 512);
   uint64_t* bar_q = bars;         // Q tile landed
   uint64_t* bar_k = bars + 1;     // [3] K block landed
@@ -277,17 +277,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
         if (it >= 2) mbar_wait(bar_bfree + (it & 1), ((it >> 1) - 1) & 1);
         float* bias_it = sBias + (it & 1) * 512;
         const float4* src = reinterpret_cast<const float4*>(key_bias + static_cast<int64_t>(b) * S);
-        uint32_t biased = 0;
-        for (int i = lane; i < (S >> 2); i += 32) {     // S / 4 float4 words; word i covers keys 4i .. 4i+3
+        // 2 bits per 32-key group (16 groups at S = 512): 0 clean (no bias), 1 mixed, 2 masked (every key's bias is
+        // below -1e30, so its probability is exactly 0 in fp32 whatever the score).  A batch element whose keys are ALL
+        // masked keeps the exact path (the reference then attends uniformly).
+        uint32_t meta = 0;
+        bool all_masked = true;
+        for (int i0 = 0; i0 < (S >> 2); i0 += 32) {     // S / 4 float4 words; word i covers keys 4i .. 4i+3
+          const int i = i0 + lane;
           const float4 v = __ldg(src + i);
-          if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) biased |= 1u << (i >> 5);
+          const bool any_b = v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f;
+          const bool all_m = v.x < -1e30f && v.y < -1e30f && v.z < -1e30f && v.w < -1e30f;
           float4 w;   // finfo.min * log2e overflows to -inf: keep it finite
           w.x = fmaxf(v.x * kLog2e, -3.402823466e38f); w.y = fmaxf(v.y * kLog2e, -3.402823466e38f);
           w.z = fmaxf(v.z * kLog2e, -3.402823466e38f); w.w = fmaxf(v.w * kLog2e, -3.402823466e38f);
           reinterpret_cast<float4*>(bias_it)[i] = w;
+          const uint32_t ba = __ballot_sync(0xffffffffu, any_b), bm = __ballot_sync(0xffffffffu, all_m);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {                  // 8 words = one 32-key group
+            const uint32_t a8 = (ba >> (8 * q)) & 0xffu, m8 = (bm >> (8 * q)) & 0xffu;
+            const uint32_t state = (m8 == 0xffu) ? 2u : (a8 ? 1u : 0u);
+            all_masked = all_masked && (m8 == 0xffu);
+            meta |= state << (2 * ((i0 >> 3) + q));
+          }
         }
-        biased = __reduce_or_sync(0xffffffffu, biased);
-        if (lane == 0) sMeta[it & 1] = biased;
+        if (all_masked) meta = 0x55555555u;
+        if (lane == 0) sMeta[it & 1] = meta;
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_bfull + (it & 1));   // release: the stores above are visible to the waiters
       }
@@ -354,12 +368,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       const int row_base = b * S, q0 = qt * 128;
       const float* bias_it = sBias + (it & 1) * 512;   // staged by the prep warp (double-buffered by item parity)
-      // which 128-key blocks hold at least one biased (masked) key: blocks without any take the short
-      // instruction stream below (no bias loads / adds)
-      uint32_t blk_biased = 0;
+      // state of every 32-key group (0 clean, 1 mixed, 2 masked; warp-uniform): clean groups take the short instruction
+      // stream (no bias loads / adds), masked groups produce zeros without touching the special-function unit
+      uint32_t grp_state = 0;
       if (key_bias) {
         mbar_wait(bar_bfull + (it & 1), (it >> 1) & 1);
-        blk_biased = sMeta[it & 1];
+        grp_state = sMeta[it & 1];
       }
       const uint32_t drop_key = DROP ? drop_row_key(drop_seed, drop_site, static_cast<uint32_t>((b * kHeads + h) * S + q0 + row)) : 0u;
       float m2 = -INFINITY;                // running (lazily advanced) row max, log2 domain
@@ -379,12 +393,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
         tc_fence_before();
         mbar_arrive(bar_sread);
         const float4* bz = reinterpret_cast<const float4*>(bias_it + j * 128);
-        const bool biased = (blk_biased >> j) & 1u;   // warp-uniform
+        const uint32_t st4 = (grp_state >> (8 * j)) & 0xffu;   // states of this block's four groups
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
-        float bm;
-        if (biased) {
+        float mc[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // clean groups: max(s * k1) = k1 * max(s)
+        if (st4 == 0u) {   // whole block clean: one straight instruction stream
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
+          for (int g = 0; g < 4; g += 2)
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+              mc[0] = fmaxf(mc[0], fmaxf(__uint_as_float(r[g][c]), __uint_as_float(r[g + 1][c])));
+              mc[1] = fmaxf(mc[1], fmaxf(__uint_as_float(r[g][c + 1]), __uint_as_float(r[g + 1][c + 1])));
+              mc[2] = fmaxf(mc[2], fmaxf(__uint_as_float(r[g][c + 2]), __uint_as_float(r[g + 1][c + 2])));
+              mc[3] = fmaxf(mc[3], fmaxf(__uint_as_float(r[g][c + 3]), __uint_as_float(r[g + 1][c + 3])));
+            }
+        } else
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t gs = (st4 >> (2 * g)) & 3u;
+          if (gs == 0u) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 8) {
+              mc[0] = fmaxf(mc[0], fmaxf(__uint_as_float(r[g][c]), __uint_as_float(r[g][c + 4])));
+              mc[1] = fmaxf(mc[1], fmaxf(__uint_as_float(r[g][c + 1]), __uint_as_float(r[g][c + 5])));
+              mc[2] = fmaxf(mc[2], fmaxf(__uint_as_float(r[g][c + 2]), __uint_as_float(r[g][c + 6])));
+              mc[3] = fmaxf(mc[3], fmaxf(__uint_as_float(r[g][c + 3]), __uint_as_float(r[g][c + 7])));
+            }
+          } else if (gs == 1u) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
               const float4 b0 = bz[g * 8 + c];
@@ -393,19 +427,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
               mx[2] = fmaxf(mx[2], fmaf(__uint_as_float(r[g][4 * c + 2]), k1, b0.z));
               mx[3] = fmaxf(mx[3], fmaf(__uint_as_float(r[g][4 * c + 3]), k1, b0.w));
             }
-          bm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-        } else {   // max(s * k1) = k1 * max(s)
-#pragma unroll
-          for (int g = 0; g < 4; g += 2)
-#pragma unroll
-            for (int c = 0; c < 32; c += 4) {
-              mx[0] = fmaxf(mx[0], fmaxf(__uint_as_float(r[g][c]), __uint_as_float(r[g + 1][c])));
-              mx[1] = fmaxf(mx[1], fmaxf(__uint_as_float(r[g][c + 1]), __uint_as_float(r[g + 1][c + 1])));
-              mx[2] = fmaxf(mx[2], fmaxf(__uint_as_float(r[g][c + 2]), __uint_as_float(r[g + 1][c + 2])));
-              mx[3] = fmaxf(mx[3], fmaxf(__uint_as_float(r[g][c + 3]), __uint_as_float(r[g + 1][c + 3])));
-            }
-          bm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * k1;
+          }
         }
+        const float bm = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])),
+                               fmaxf(fmaxf(mc[0], mc[1]), fmaxf(mc[2], mc[3])) * k1);
         if (st) g_attn_timeline[n_blk * 16 + 10] = clock64();
         // Lazy rescale.  The decision is per row, but tcgen05.ld / tcgen05.st are warp-collective
         // (.sync.aligned): when ANY row of the warp must advance its max, the whole warp runs the O
@@ -422,39 +447,56 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
         const float nm2 = -m2;
         // The exponentials only need registers, so they are formed BEFORE waiting for the previous P V product: its
         // latency (P_{j-1} hand-over + 8 MMAs) hides behind this pass instead of stalling the softmax warps.
-        // Two separate instruction streams: blocks without biased keys run FFMA / MUFU / FADD (+ half a pack) per
-        // element; one predicated stream would carry the bias moves and adds through every block.
+        // Separate instruction streams per 32-key group: clean groups run FFMA / MUFU / FADD (+ half a pack) per
+        // element; one predicated stream would carry the bias moves and adds through every group.
         uint32_t pk[64];               // 128 keys -> 64 packed TMEM columns of the A operand
-        auto exp_pass = [&](auto biased_tag) {
+        auto exp_group = [&](auto g_tag, auto biased_tag) {
+          constexpr int g = decltype(g_tag)::value;
           constexpr bool kBiased = decltype(biased_tag)::value;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              float a0 = nm2, a1 = nm2, a2 = nm2, a3 = nm2;
-              if (kBiased) {
-                const float4 b0 = bz[g * 8 + c];
-                a0 += b0.x; a1 += b0.y; a2 += b0.z; a3 += b0.w;
-              }
-              const float p0 = fast_exp2(fmaf(__uint_as_float(r[g][4 * c]), k1, a0));
-              const float p1 = fast_exp2(fmaf(__uint_as_float(r[g][4 * c + 1]), k1, a1));
-              const float p2 = fast_exp2(fmaf(__uint_as_float(r[g][4 * c + 2]), k1, a2));
-              const float p3 = fast_exp2(fmaf(__uint_as_float(r[g][4 * c + 3]), k1, a3));
-              l0 += p0 + p2;
-              l1 += p1 + p3;
-              if (DROP) {   // the sums above are those of the full softmax; only what multiplies V is masked
-                const uint32_t kb = drop_bytes(drop_key, static_cast<uint32_t>(j * 32 + g * 8 + c));
-                pk[g * 16 + 2 * c] = pack_bf16x2(drop_keep(kb, 0, drop_thr) ? p0 : 0.f, drop_keep(kb, 1, drop_thr) ? p1 : 0.f);
-                pk[g * 16 + 2 * c + 1] = pack_bf16x2(drop_keep(kb, 2, drop_thr) ? p2 : 0.f, drop_keep(kb, 3, drop_thr) ? p3 : 0.f);
-              } else {
-                pk[g * 16 + 2 * c] = pack_bf16x2(p0, p1);
-                pk[g * 16 + 2 * c + 1] = pack_bf16x2(p2, p3);
-              }
+          for (int c = 0; c < 8; ++c) {
+            float a0 = nm2, a1 = nm2, a2 = nm2, a3 = nm2;
+            if (kBiased) {
+              const float4 b0 = bz[g * 8 + c];
+              a0 += b0.x; a1 += b0.y; a2 += b0.z; a3 += b0.w;
+            }
+            const float p0 = fast_exp2(fmaf(__uint_as_float(r[g][4 * c]), k1, a0));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(r[g][4 * c + 1]), k1, a1));
+            const float p2 = fast_exp2(fmaf(__uint_as_float(r[g][4 * c + 2]), k1, a2));
+            const float p3 = fast_exp2(fmaf(__uint_as_float(r[g][4 * c + 3]), k1, a3));
+            l0 += p0 + p2;
+            l1 += p1 + p3;
+            if (DROP) {   // the sums above are those of the full softmax; only what multiplies V is masked
+              const uint32_t kb = drop_bytes(drop_key, static_cast<uint32_t>(j * 32 + g * 8 + c));
+              pk[g * 16 + 2 * c] = pack_bf16x2(drop_keep(kb, 0, drop_thr) ? p0 : 0.f, drop_keep(kb, 1, drop_thr) ? p1 : 0.f);
+              pk[g * 16 + 2 * c + 1] = pack_bf16x2(drop_keep(kb, 2, drop_thr) ? p2 : 0.f, drop_keep(kb, 3, drop_thr) ? p3 : 0.f);
+            } else {
+              pk[g * 16 + 2 * c] = pack_bf16x2(p0, p1);
+              pk[g * 16 + 2 * c + 1] = pack_bf16x2(p2, p3);
             }
           }
         };
-        if (biased) exp_pass(std::true_type{});
-        else exp_pass(std::false_type{});
+        auto exp_dispatch = [&](auto g_tag) {
+          constexpr int g = decltype(g_tag)::value;
+          const uint32_t gs = (st4 >> (2 * g)) & 3u;
+          if (gs == 0u) exp_group(g_tag, std::false_type{});
+          else if (gs == 1u) exp_group(g_tag, std::true_type{});
+          else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) pk[g * 16 + c] = 0u;
+          }
+        };
+        if (st4 == 0u) {   // whole block clean: one straight stream (the groups' instructions interleave freely)
+          exp_group(std::integral_constant<int, 0>{}, std::false_type{});
+          exp_group(std::integral_constant<int, 1>{}, std::false_type{});
+          exp_group(std::integral_constant<int, 2>{}, std::false_type{});
+          exp_group(std::integral_constant<int, 3>{}, std::false_type{});
+        } else {
+          exp_dispatch(std::integral_constant<int, 0>{});
+          exp_dispatch(std::integral_constant<int, 1>{});
+          exp_dispatch(std::integral_constant<int, 2>{});
+          exp_dispatch(std::integral_constant<int, 3>{});
+        }
         if (n_blk > 0) {
           // the previous P V product (possibly the previous item's last) must be complete before O is
           // touched and before the P columns are overwritten

@@ -439,6 +439,21 @@ def case_attn():
         ref, lref = _attn_ref(qkv, bias, B, S)
         res.append(_err_report(out, ref, f"attn_fwd_S{S}_mask{int(masked)}", 2e-2))
         res.append(_err_report(lse, lref, f"attn_lse_S{S}", 2e-3))
+    # general additive key bias (not only the 0 / finfo.min padding mask): scattered finite values, a masked island in
+    # the middle of a key block, masked groups that start and end off the 32-key group boundaries
+    B, S = 3, 512
+    qkv = _mk(B * S, 2304, "cuda", 1.0)
+    bias = torch.zeros(B, S, device="cuda")
+    bias[0] = torch.randn(S, device="cuda") * 2.0
+    bias[1, 100:131] = -1.7
+    bias[1, 300:420] = torch.finfo(torch.float32).min
+    bias[2, 5:37] = torch.finfo(torch.float32).min
+    bias[2, 64:96] = torch.finfo(torch.float32).min
+    bias[2, 511] = torch.finfo(torch.float32).min
+    out, lse = ops.attention(qkv, bias, B, S, save_lse=True)
+    ref, lref = _attn_ref(qkv, bias, B, S)
+    res.append(_err_report(out, ref, "attn_fwd_general_bias", 2e-2))
+    res.append(_err_report(lse, lref, "attn_lse_general_bias", 2e-3))
     # large, growing scores: later key blocks dominate -> exercises the lazy O rescale in TMEM
     B, S = 2, 512
     qkv = _mk(B * S, 2304, "cuda", 1.0)
