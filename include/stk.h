@@ -73,6 +73,22 @@ int stk_embed_joint_ln_bwd(int device, void* stream, const int64_t* input_ids, c
                            const float* rstd, const void* dy_bf16, float* dpos, float* dtype, float* dgamma,
                            float* dbeta);
 
+/* Shape-generic forms of the two calls above for the TransE variant (transestonkgs_model.py:44,93: 256 text tokens +
+ * 4 KG tokens, max_position_embeddings = 260).  text_len = T, seq_len = S: input_ids / token_type_ids are [B, S],
+ * lm_hidden is [B, T, 768], pos is [S, 768].  Activations (out, mean, rstd, inputs_embeds_out, dy) use seq_pad >= S rows
+ * per pair; rows t >= S are written as zeros by the forward (the caller masks them out as attention keys) and ignored
+ * by the backward.  (256, 512, 512) is exactly stk_embed_joint_ln_fwd / _bwd. */
+int stk_embed_joint_ln_fwd_shape(int device, void* stream, const int64_t* input_ids, const int64_t* token_type_ids,
+                                 int B, int text_len, int seq_len, int seq_pad, const void* lm_hidden_bf16,
+                                 const float* kg_table, int64_t table_rows, const float* pos, const float* type_emb,
+                                 const float* gamma, const float* beta, void* out_bf16, float* mean, float* rstd,
+                                 float* inputs_embeds_out, int* err_flag);
+int stk_embed_joint_ln_bwd_shape(int device, void* stream, const int64_t* input_ids, const int64_t* token_type_ids,
+                                 int B, int text_len, int seq_len, int seq_pad, const void* lm_hidden_bf16,
+                                 const float* kg_table, int64_t table_rows, const float* pos, const float* type_emb,
+                                 const float* gamma, const float* mean, const float* rstd, const void* dy_bf16,
+                                 float* dpos, float* dtype, float* dgamma, float* dbeta);
+
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm over rows of 768 (HF:294-298, 352-356, 481-485; eps = 1e-12)
  * ---------------------------------------------------------------------------------------------- */

@@ -33,6 +33,11 @@ CASES = {
     "L2_B3_N3001_fullmask": (2, 3, 3001, 3, 5, True),
 }
 ROWS = [0, 1, 37, 255, 256, 300, 511]  # sequence positions kept in the sub-sampled fixtures
+# TransE variant (transestonkgs_model.py): 256 text + 4 KG tokens, 260 positions; same tuple layout
+TRANSE_CASES = {
+    "transe_L2_B3_N499": (2, 3, 499, 6, 8, False),
+}
+TRANSE_ROWS = [0, 1, 37, 255, 256, 257, 259]
 
 
 def sample_grad(g: torch.Tensor):
@@ -42,16 +47,20 @@ def sample_grad(g: torch.Tensor):
     return flat[idx].numpy().copy(), idx.numpy().copy()
 
 
-def run_case(name, num_layers, batch_size, n_kg, seed_w, seed_b, full_mask):
+def run_case(name, num_layers, batch_size, n_kg, seed_w, seed_b, full_mask, transe=False):
     torch.manual_seed(0)
-    sd = weights.make_state_dict(n_kg, num_layers, seed_w)
+    ROWS = TRANSE_ROWS if transe else globals()["ROWS"]  # noqa: N806
+    sd = weights.make_state_dict(n_kg, num_layers, seed_w, joint_max_pos=260 if transe else 512)
     rows = weights.make_kg_table(n_kg, seed_w)
-    batch = synthetic.make_batch(batch_size, n_kg, seed_b, full_mask=full_mask)
+    batch = synthetic.make_batch(batch_size, n_kg, seed_b, full_mask=full_mask, kg_len=4 if transe else 256)
     # put a few labels on padded text positions and on [CLS] (legal per the input contract)
     batch["masked_lm_labels"][0, 255] = 7
     batch["masked_lm_labels"][0, 0] = 11
+    if transe:   # one pair without any entity label, one with two
+        batch["ent_masked_lm_labels"][0, :] = -100
+        batch["ent_masked_lm_labels"][1, 2:] = torch.tensor([5, 17])
 
-    ref = ref_shim.load_reference(sd, rows, num_layers)
+    ref = (ref_shim.load_reference_transe if transe else ref_shim.load_reference)(sd, rows, num_layers)
     t0 = time.time()
     for p in ref.parameters():
         p.grad = None
@@ -101,7 +110,7 @@ def run_case(name, num_layers, batch_size, n_kg, seed_w, seed_b, full_mask):
 
     # ---- pin the restatement against the reference --------------------------------------------
     table = orc.build_kg_table(sd, rows)
-    o, grads = orc.forward_backward(sd, table, batch)
+    o, grads = orc.forward_backward(sd, table, batch, text_len=256)
     d_pool = (o["pooler_output"].detach() - out.pooler_output.detach()).abs().max().item()
     d_seq = (o["sequence_output"].detach() - out.hidden_states.detach()).abs().max().item()
     d_loss = abs(o["loss"].item() - out.loss.item())
@@ -184,6 +193,10 @@ def main():
         if only and name not in only:
             continue
         run_case(name, *cfg)
+    for name, cfg in TRANSE_CASES.items():
+        if only and name not in only:
+            continue
+        run_case(name, *cfg, transe=True)
     for name, cfg in CLS_CASES.items():
         if only and name not in only:
             continue

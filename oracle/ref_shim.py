@@ -136,6 +136,29 @@ def load_reference(state_dict, kg_table: np.ndarray, num_layers: int = 12):
     return model.eval()
 
 
+def load_reference_transe(state_dict, kg_table: np.ndarray, num_layers: int = 12):
+    """The reference's ``TransESTonKGsForPreTraining`` (transestonkgs_model.py:70-250) with a synthetic checkpoint
+    (``bert.embeddings.position_embeddings`` is [260, 768]) and synthetic TransE rows."""
+    _import_reference()
+    import stonkgs.models.transestonkgs_model as tm  # noqa: E402  (the reference's own module)
+    _state["num_layers"] = num_layers
+    _state["lm_sd"] = {
+        k[len("lm_backbone."):]: v for k, v in state_dict.items() if k.startswith("lm_backbone.")
+    }
+    tab64 = kg_table.astype(np.float64)
+    tm.prepare_df = lambda path: {f"n{i}": tab64[i] for i in range(tab64.shape[0])}
+    was_cuda = torch.cuda.is_available
+    torch.cuda.is_available = lambda: False
+    try:
+        with _offline_hub():
+            model = tm.TransESTonKGsForPreTraining(config=None, kg_embedding_dict_path="unused")
+    finally:
+        torch.cuda.is_available = was_cuda
+    missing, unexpected = model.load_state_dict(state_dict, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    return model.eval()
+
+
 def load_reference_classifier(state_dict, kg_table: np.ndarray, num_layers: int, num_labels: int):
     """The reference's ``STonKGsForSequenceClassification`` (stonkgs_finetuning.py:237-346) with the given
     synthetic checkpoint (pre-training keys + ``classifier.*``)."""

@@ -26,9 +26,10 @@ HEADS = 12
 LN_EPS = 1e-12
 
 
-def bert_keys(prefix: str, num_layers: int):
+def bert_keys(prefix: str, num_layers: int, max_pos: int = MAX_POS):
     """(key, shape, kind) for one HF BertModel (with pooler)."""
     H, I = HIDDEN, INTER
+    MAX_POS = max_pos  # noqa: N806
     out = [
         (f"{prefix}embeddings.word_embeddings.weight", (VOCAB, H), "w"),
         (f"{prefix}embeddings.position_embeddings.weight", (MAX_POS, H), "w"),
@@ -85,11 +86,13 @@ def cls_keys(n_kg: int):
     ]
 
 
-def all_keys(n_kg: int, num_layers: int = 12):
-    return bert_keys("bert.", num_layers) + bert_keys("lm_backbone.", num_layers) + cls_keys(n_kg)
+def all_keys(n_kg: int, num_layers: int = 12, joint_max_pos: int = MAX_POS):
+    """``joint_max_pos`` = 260 gives the TransE variant's checkpoint (transestonkgs_model.py:93): only
+    ``bert.embeddings.position_embeddings`` changes shape, the LM backbone keeps its 512 positions."""
+    return bert_keys("bert.", num_layers, joint_max_pos) + bert_keys("lm_backbone.", num_layers) + cls_keys(n_kg)
 
 
-def make_state_dict(n_kg: int, num_layers: int = 12, seed: int = 0, std: float = 0.02):
+def make_state_dict(n_kg: int, num_layers: int = 12, seed: int = 0, std: float = 0.02, joint_max_pos: int = MAX_POS):
     """Seeded synthetic checkpoint.
 
     Weights ~ N(0, std) (the BERT initialiser range), biases ~ N(0, std) (non-zero on purpose so
@@ -100,7 +103,7 @@ def make_state_dict(n_kg: int, num_layers: int = 12, seed: int = 0, std: float =
     of layers or ``n_kg`` never shifts the other tensors.
     """
     sd = OrderedDict()
-    for idx, (key, shape, kind) in enumerate(all_keys(n_kg, num_layers)):
+    for idx, (key, shape, kind) in enumerate(all_keys(n_kg, num_layers, joint_max_pos)):
         if kind in ("dead",):
             sd[key] = torch.zeros(shape, dtype=torch.float32)
             continue

@@ -59,6 +59,10 @@ _SIGNATURES = {
     "stk_embed_text_ln_fwd": (c_int, [c_int, _P, _P, c_int64, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, _P]),
     "stk_embed_joint_ln_fwd": (c_int, [c_int, _P, _P, _P, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "stk_embed_joint_ln_bwd": (c_int, [c_int, _P, _P, _P, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "stk_embed_joint_ln_fwd_shape": (c_int, [c_int, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P,
+                                             _P, _P, _P, _P]),
+    "stk_embed_joint_ln_bwd_shape": (c_int, [c_int, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P,
+                                             _P, _P, _P, _P, _P]),
     "stk_layernorm_fwd": (c_int, [c_int, _P, _P, c_int, _P, _P, _P, _P, _P]),
     "stk_layernorm_bwd": (c_int, [c_int, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P]),
     "stk_gemm": (c_int, [c_int, _P, c_int, c_int, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int64,

@@ -109,44 +109,60 @@ __global__ void __launch_bounds__(256) embed_text_ln_kernel(const int64_t* __res
 // ------------------------------------------------------------------------------------------------
 // A3+A4: joint stage. Gathered source row (LM hidden state or KG table row) + type + pos -> LN.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool joint_source_row(const int64_t* input_ids, const int64_t* token_type_ids, int64_t tok,
-                                                 const __nv_bfloat16* lm_hidden, const float* kg_table,
+// Shape of the joint sequence: T text tokens (LM-backbone rows) followed by S - T KG tokens; activations use SP >= S
+// rows per pair (SP = S for STonKGs: 256 + 256; the TransE variant, transestonkgs_model.py:44,93, has S = 260 = 256 + 4
+// and runs the encoder on SP = 384 rows so that the attention kernels see whole 128-key blocks; rows t >= S are zero
+// and masked out as keys).
+struct JointShape {
+  int T, S, SP;
+};
+
+__device__ __forceinline__ bool joint_source_row(const int64_t* input_ids, const int64_t* token_type_ids, int64_t b, int t,
+                                                 JointShape sh, const __nv_bfloat16* lm_hidden, const float* kg_table,
                                                  int64_t table_rows, int lane, float (&v)[kPerLane], int& tt) {
-  const int64_t b = tok >> 9;
-  const int t = static_cast<int>(tok & 511);
   bool ok = true;
-  if (t < 256) {
-    load_bf16_row(lm_hidden + (b * 256 + t) * kHidden, lane, v);
+  if (t < sh.T) {
+    load_bf16_row(lm_hidden + (b * sh.T + t) * kHidden, lane, v);
   } else {
-    int64_t id = __ldg(input_ids + tok);
+    int64_t id = __ldg(input_ids + b * sh.S + t);
     if (id < 0 || id >= table_rows) { ok = false; id = 0; }
     load_f32_row(kg_table + id * kHidden, lane, v);
   }
-  tt = token_type_ids ? static_cast<int>(__ldg(token_type_ids + tok)) : (t >= 256 ? 1 : 0);
+  tt = token_type_ids ? static_cast<int>(__ldg(token_type_ids + b * sh.S + t)) : (t >= sh.T ? 1 : 0);
   if (tt < 0 || tt > 1) { ok = false; tt = 0; }
   return ok;
 }
 
 __global__ void __launch_bounds__(256)
 embed_joint_ln_kernel(const int64_t* __restrict__ input_ids, const int64_t* __restrict__ token_type_ids, int B,
-                      const __nv_bfloat16* __restrict__ lm_hidden, const float* __restrict__ kg_table,
+                      JointShape sh, const __nv_bfloat16* __restrict__ lm_hidden, const float* __restrict__ kg_table,
                       int64_t table_rows, const float* __restrict__ pos, const float* __restrict__ type_emb,
                       const float* __restrict__ gamma, const float* __restrict__ beta,
                       __nv_bfloat16* __restrict__ out, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                       float* __restrict__ inputs_embeds_out, int* err_flag) {
   const int lane = threadIdx.x & 31;
-  const int64_t tok = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
-  if (tok >= static_cast<int64_t>(B) * 512) return;
+  const int64_t tok = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);   // row of the padded layout
+  if (tok >= static_cast<int64_t>(B) * sh.SP) return;
+  const int64_t b = tok / sh.SP;
+  const int t = static_cast<int>(tok - b * sh.SP);
   float v[kPerLane], a[kPerLane];
+  if (t >= sh.S) {   // padding row of the TransE layout: finite (zero) activations, never attended to
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) v[i] = 0.f;
+    if (inputs_embeds_out) store_f32_row(inputs_embeds_out + tok * kHidden, lane, v);
+    if (mean_out && lane == 0) { mean_out[tok] = 0.f; rstd_out[tok] = 0.f; }
+    store_bf16_row(out + tok * kHidden, lane, v);
+    return;
+  }
   int tt;
-  if (!joint_source_row(input_ids, token_type_ids, tok, lm_hidden, kg_table, table_rows, lane, v, tt)) {
+  if (!joint_source_row(input_ids, token_type_ids, b, t, sh, lm_hidden, kg_table, table_rows, lane, v, tt)) {
     if (lane == 0 && err_flag) atomicExch(err_flag, 1);
   }
   if (inputs_embeds_out) store_f32_row(inputs_embeds_out + tok * kHidden, lane, v);
   load_f32_row(type_emb + tt * kHidden, lane, a);
 #pragma unroll
   for (int i = 0; i < kPerLane; ++i) v[i] += a[i];
-  load_f32_row(pos + (tok & 511) * kHidden, lane, a);
+  load_f32_row(pos + static_cast<int64_t>(t) * kHidden, lane, a);
 #pragma unroll
   for (int i = 0; i < kPerLane; ++i) v[i] += a[i];
   float mean, rstd;
@@ -180,7 +196,7 @@ __device__ __forceinline__ void ln_row_bwd(float (&dy)[kPerLane], float (&xh)[kP
 // warps stride over the batch; per-block partial sums for dtype/dgamma/dbeta go out as atomics.
 __global__ void __launch_bounds__(128)
 embed_joint_ln_bwd_kernel(const int64_t* __restrict__ input_ids, const int64_t* __restrict__ token_type_ids, int B,
-                          const __nv_bfloat16* __restrict__ lm_hidden, const float* __restrict__ kg_table,
+                          JointShape sh, const __nv_bfloat16* __restrict__ lm_hidden, const float* __restrict__ kg_table,
                           int64_t table_rows, const float* __restrict__ pos, const float* __restrict__ type_emb,
                           const float* __restrict__ gamma, const float* __restrict__ mean_in,
                           const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ dy_in,
@@ -194,10 +210,10 @@ embed_joint_ln_bwd_kernel(const int64_t* __restrict__ input_ids, const int64_t* 
   load_f32_row(pos + static_cast<int64_t>(t) * kHidden, lane, pz);
   float dg[kPerLane] = {}, db[kPerLane] = {}, dp[kPerLane] = {}, dt0[kPerLane] = {}, dt1[kPerLane] = {};
   for (int b = warp; b < B; b += 4) {
-    const int64_t tok = static_cast<int64_t>(b) * 512 + t;
+    const int64_t tok = static_cast<int64_t>(b) * sh.SP + t;
     float x[kPerLane], a[kPerLane], dy[kPerLane];
     int tt;
-    joint_source_row(input_ids, token_type_ids, tok, lm_hidden, kg_table, table_rows, lane, x, tt);
+    joint_source_row(input_ids, token_type_ids, b, t, sh, lm_hidden, kg_table, table_rows, lane, x, tt);
     load_f32_row(type_emb + tt * kHidden, lane, a);
 #pragma unroll
     for (int i = 0; i < kPerLane; ++i) x[i] = (x[i] + a[i]) + pz[i];
@@ -310,20 +326,55 @@ extern "C" int stk_embed_text_ln_fwd(int device, void* stream, const int64_t* id
   STK_LAUNCHED();
 }
 
-extern "C" int stk_embed_joint_ln_fwd(int device, void* stream, const int64_t* input_ids, const int64_t* token_type_ids,
-                                      int B, const void* lm_hidden, const float* kg_table, int64_t table_rows,
-                                      const float* pos, const float* type_emb, const float* gamma, const float* beta,
-                                      void* out, float* mean, float* rstd, float* inputs_embeds_out, int* err_flag) {
-  STK_REQUIRE(B > 0, "stk_embed_joint_ln_fwd: bad batch %d", B);
+static int check_joint_shape(const char* who, int B, int T, int S, int SP) {
+  STK_REQUIRE(B > 0, "%s: bad batch %d", who, B);
+  STK_REQUIRE(T > 0 && S > T && SP >= S, "%s: bad joint shape (text %d, sequence %d, padded %d)", who, T, S, SP);
+  return STK_OK;
+}
+
+extern "C" int stk_embed_joint_ln_fwd_shape(int device, void* stream, const int64_t* input_ids,
+                                            const int64_t* token_type_ids, int B, int text_len, int seq_len, int seq_pad,
+                                            const void* lm_hidden, const float* kg_table, int64_t table_rows,
+                                            const float* pos, const float* type_emb, const float* gamma,
+                                            const float* beta, void* out, float* mean, float* rstd,
+                                            float* inputs_embeds_out, int* err_flag) {
+  if (int rc = check_joint_shape("stk_embed_joint_ln_fwd", B, text_len, seq_len, seq_pad)) return rc;
   STK_REQUIRE(input_ids && lm_hidden && kg_table && pos && type_emb && gamma && beta && out,
               "stk_embed_joint_ln_fwd: null pointer");
   STK_REQUIRE((mean == nullptr) == (rstd == nullptr), "stk_embed_joint_ln_fwd: mean/rstd must both be given or both NULL");
   STK_CHECK_CUDA(cudaSetDevice(device));
-  const int64_t rows = static_cast<int64_t>(B) * 512;
+  const int64_t rows = static_cast<int64_t>(B) * seq_pad;
   embed_joint_ln_kernel<<<static_cast<unsigned>((rows + kRowWarps - 1) / kRowWarps), 256, 0,
                           static_cast<cudaStream_t>(stream)>>>(
-      input_ids, token_type_ids, B, static_cast<const __nv_bfloat16*>(lm_hidden), kg_table, table_rows, pos, type_emb,
-      gamma, beta, static_cast<__nv_bfloat16*>(out), mean, rstd, inputs_embeds_out, err_flag);
+      input_ids, token_type_ids, B, JointShape{text_len, seq_len, seq_pad}, static_cast<const __nv_bfloat16*>(lm_hidden),
+      kg_table, table_rows, pos, type_emb, gamma, beta, static_cast<__nv_bfloat16*>(out), mean, rstd, inputs_embeds_out,
+      err_flag);
+  STK_LAUNCHED();
+}
+
+extern "C" int stk_embed_joint_ln_fwd(int device, void* stream, const int64_t* input_ids, const int64_t* token_type_ids,
+                                      int B, const void* lm_hidden, const float* kg_table, int64_t table_rows,
+                                      const float* pos, const float* type_emb, const float* gamma, const float* beta,
+                                      void* out, float* mean, float* rstd, float* inputs_embeds_out, int* err_flag) {
+  return stk_embed_joint_ln_fwd_shape(device, stream, input_ids, token_type_ids, B, 256, 512, 512, lm_hidden, kg_table,
+                                      table_rows, pos, type_emb, gamma, beta, out, mean, rstd, inputs_embeds_out, err_flag);
+}
+
+extern "C" int stk_embed_joint_ln_bwd_shape(int device, void* stream, const int64_t* input_ids,
+                                            const int64_t* token_type_ids, int B, int text_len, int seq_len, int seq_pad,
+                                            const void* lm_hidden, const float* kg_table, int64_t table_rows,
+                                            const float* pos, const float* type_emb, const float* gamma,
+                                            const float* mean, const float* rstd, const void* dy, float* dpos,
+                                            float* dtype, float* dgamma, float* dbeta) {
+  if (int rc = check_joint_shape("stk_embed_joint_ln_bwd", B, text_len, seq_len, seq_pad)) return rc;
+  STK_REQUIRE(input_ids && lm_hidden && kg_table && pos && type_emb && gamma && mean && rstd && dy && dpos && dtype &&
+                  dgamma && dbeta,
+              "stk_embed_joint_ln_bwd: null pointer");
+  STK_CHECK_CUDA(cudaSetDevice(device));
+  embed_joint_ln_bwd_kernel<<<seq_len, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      input_ids, token_type_ids, B, JointShape{text_len, seq_len, seq_pad}, static_cast<const __nv_bfloat16*>(lm_hidden),
+      kg_table, table_rows, pos, type_emb, gamma, mean, rstd, static_cast<const __nv_bfloat16*>(dy), dpos, dtype, dgamma,
+      dbeta);
   STK_LAUNCHED();
 }
 
@@ -332,15 +383,8 @@ extern "C" int stk_embed_joint_ln_bwd(int device, void* stream, const int64_t* i
                                       const float* pos, const float* type_emb, const float* gamma, const float* mean,
                                       const float* rstd, const void* dy, float* dpos, float* dtype, float* dgamma,
                                       float* dbeta) {
-  STK_REQUIRE(B > 0, "stk_embed_joint_ln_bwd: bad batch %d", B);
-  STK_REQUIRE(input_ids && lm_hidden && kg_table && pos && type_emb && gamma && mean && rstd && dy && dpos && dtype &&
-                  dgamma && dbeta,
-              "stk_embed_joint_ln_bwd: null pointer");
-  STK_CHECK_CUDA(cudaSetDevice(device));
-  embed_joint_ln_bwd_kernel<<<512, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      input_ids, token_type_ids, B, static_cast<const __nv_bfloat16*>(lm_hidden), kg_table, table_rows, pos, type_emb,
-      gamma, mean, rstd, static_cast<const __nv_bfloat16*>(dy), dpos, dtype, dgamma, dbeta);
-  STK_LAUNCHED();
+  return stk_embed_joint_ln_bwd_shape(device, stream, input_ids, token_type_ids, B, 256, 512, 512, lm_hidden, kg_table,
+                                      table_rows, pos, type_emb, gamma, mean, rstd, dy, dpos, dtype, dgamma, dbeta);
 }
 
 extern "C" int stk_layernorm_fwd(int device, void* stream, const void* x, int M, const float* gamma, const float* beta,

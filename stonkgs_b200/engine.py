@@ -210,20 +210,32 @@ def lm_special_rows(ew: EncoderWeights, token_ids) -> torch.Tensor:
 
 
 def joint_fwd(bert: EncoderWeights, input_ids, token_type_ids, attention_mask, lm_hidden, kg_table, *,
-              cache: Optional[dict] = None, want_inputs_embeds=False, err_flag=None, drop: Optional[DropCtx] = None):
-    """KG lookup + concat + joint embeddings + 12 layers + pooler (stonkgs_model.py:182-212)."""
+              cache: Optional[dict] = None, want_inputs_embeds=False, err_flag=None, drop: Optional[DropCtx] = None,
+              shape: ops.SeqShape = ops.STONKGS_SHAPE):
+    """KG lookup + concat + joint embeddings + 12 layers + pooler (stonkgs_model.py:182-212).
+    Activations hold ``shape.seq_pad`` rows per pair (== the sequence length for STonKGs; the 260-token TransE variant is
+    padded to 384 rows whose tail is masked out as attention keys)."""
     B = input_ids.shape[0]
+    S, SP = shape.seq_len, shape.seq_pad
     train = cache is not None
     x, mean, rstd, emb = ops.embed_joint_ln(input_ids, token_type_ids, lm_hidden, kg_table, bert.pos, bert.type_emb,
                                             bert.emb_g, bert.emb_b, save_stats=train,
-                                            want_inputs_embeds=want_inputs_embeds, err_flag=err_flag)
+                                            want_inputs_embeds=want_inputs_embeds, err_flag=err_flag, shape=shape)
     if drop is not None:
         ops.dropout(x, drop.embeddings(1), out=x)
+    if SP > S:   # the padding rows must never be attended to
+        am = torch.zeros((B, SP), dtype=torch.int64, device=input_ids.device)
+        if attention_mask is not None:
+            am[:, :S] = attention_mask
+        else:
+            am[:, :S] = 1
+        attention_mask = am
     key_bias = ops.mask_to_bias(attention_mask) if attention_mask is not None else None
     layer_cache = [] if train else None
-    seq = encoder_fwd(x, bert, B, 512, key_bias, layer_cache, drop, 1)
-    # BertPooler: tanh(W h[:, 0] + b); rows b*512 are read in place through the A pitch
-    pooled = ops.gemm(seq.view(B, 512, H)[:, 0], bert.wp, M=B, N=H, K=H, epilogue=ops.EPI_BIAS_TANH_F32, bias=bert.bp)
+    seq = encoder_fwd(x, bert, B, SP, key_bias, layer_cache, drop, 1)
+    # BertPooler: tanh(W h[:, 0] + b); rows b*SP are read in place through the A pitch
+    pooled = ops.gemm(seq.view(B, SP, H)[:, 0], bert.wp, M=B, N=H, K=H, epilogue=ops.EPI_BIAS_TANH_F32, bias=bert.bp)
     if train:
-        cache.update(emb_mean=mean, emb_rstd=rstd, key_bias=key_bias, layers=layer_cache, lm_hidden=lm_hidden, drop=drop)
+        cache.update(emb_mean=mean, emb_rstd=rstd, key_bias=key_bias, layers=layer_cache, lm_hidden=lm_hidden, drop=drop,
+                     shape=shape)
     return seq, pooled, emb

@@ -145,8 +145,9 @@ class STonKGsForPreTraining(BertForPreTraining):
                 config = BertConfig.from_dict(passed.to_dict())
                 lm_config = BertConfig.from_dict(passed.to_dict())
         config.update({"kg_vocab_size": n_kg})
+        self._adjust_config(config)
         super().__init__(config)
-        self.cls.predictions = STonKGsELMPredictionHead(config)
+        self.cls.predictions = self._head_class(config)
         # the head swap happens after HF's post_init(): register the two extra aliases now
         self._tied_weights_keys = {**(type(self)._tied_weights_keys or {}), **self._stk_alias_keys}
         if hasattr(self, "get_expanded_tied_weights_keys"):
@@ -157,7 +158,9 @@ class STonKGsForPreTraining(BertForPreTraining):
             try:
                 self.lm_backbone = BertModel.from_pretrained(nlp_model_type)
             except Exception:  # noqa: BLE001
-                self.lm_backbone = BertModel(config)       # weights then come from the checkpoint's lm_backbone.*
+                lm_fallback = BertConfig.from_dict(config.to_dict())   # weights then come from the checkpoint's lm_backbone.*
+                lm_fallback.max_position_embeddings = 512              # the LM keeps its own 512 positions in every variant
+                self.lm_backbone = BertModel(lm_fallback)
         else:
             self.lm_backbone = BertModel(lm_config)
         for p in self.lm_backbone.parameters():
@@ -196,12 +199,21 @@ class STonKGsForPreTraining(BertForPreTraining):
         self.last_dropout_seed = None
 
     # ------------------------------------------------------------------------------------------
+    _head_class = STonKGsELMPredictionHead
+
     @staticmethod
-    def _check_shape(config):
+    def _adjust_config(config):
+        """Variant hook (the TransE model changes max_position_embeddings here, transestonkgs_model.py:93)."""
+
+    #: joint sequence of one pair (text tokens, text + KG tokens, activation rows per pair); the TransE variant overrides it
+    seq_shape = ops.STONKGS_SHAPE
+
+    @classmethod
+    def _check_shape(cls, config):
         if (config.hidden_size, config.num_attention_heads, config.intermediate_size) != (768, 12, 3072) or \
-                config.max_position_embeddings != 512 or config.hidden_act != "gelu":
+                config.max_position_embeddings != cls.seq_shape.seq_len or config.hidden_act != "gelu":
             raise StkError("stonkgs_b200 kernels are specialised for the BERT-base shape of the reference "
-                           "(hidden 768, 12 heads, intermediate 3072, 512 positions, erf-GELU)")
+                           f"(hidden 768, 12 heads, intermediate 3072, {cls.seq_shape.seq_len} positions, erf-GELU)")
 
     @classmethod
     @lru_cache(maxsize=32)
@@ -326,18 +338,20 @@ class STonKGsForPreTraining(BertForPreTraining):
     def _check_ids(self, input_ids):
         """The reference raises KeyError for ids outside the KG dict (stonkgs_model.py:182-189)."""
         if not input_ids.is_cuda:
-            kg = input_ids[:, 256:]
+            kg = input_ids[:, self.seq_shape.text_len:]
             if kg.numel() and (int(kg.min()) < 0 or int(kg.max()) >= self.kg_table.shape[0]):
                 bad = kg[(kg < 0) | (kg >= self.kg_table.shape[0])][0]
                 raise KeyError(int(bad))
 
     def encode(self, input_ids, attention_mask=None, token_type_ids=None, *, cache=None, want_inputs_embeds=False,
                need_heads=False):
-        """LM backbone -> KG lookup -> joint encoder -> pooler.  Returns (seq bf16 [B*512,768], pooled fp32, emb)."""
+        """LM backbone -> KG lookup -> joint encoder -> pooler.  Returns (seq bf16 [B*seq_pad,768], pooled fp32, emb)."""
         st = self._device_state(need_heads)
         dev = self.kg_table.device
-        if input_ids.dim() != 2 or input_ids.shape[1] != 512:
-            raise StkError(f"input_ids must be [B, 512] (256 text + 256 KG tokens), got {tuple(input_ids.shape)}")
+        sh = self.seq_shape
+        if input_ids.dim() != 2 or input_ids.shape[1] != sh.seq_len:
+            raise StkError(f"input_ids must be [B, {sh.seq_len}] ({sh.text_len} text + {sh.kg_len} KG tokens), "
+                           f"got {tuple(input_ids.shape)}")
         self._check_ids(input_ids)
         err = torch.zeros(1, dtype=torch.int32, device=dev) if input_ids.is_cuda else None
         input_ids = input_ids.to(dev, torch.int64, non_blocking=True).contiguous()
@@ -346,10 +360,10 @@ class STonKGsForPreTraining(BertForPreTraining):
         if token_type_ids is not None:
             token_type_ids = token_type_ids.to(dev, torch.int64, non_blocking=True).contiguous()
         drop = self._drop_ctx()
-        lm_hidden = engine.lm_backbone_fwd(st["lm"], input_ids[:, :256], None, err_flag=err, drop=drop)
+        lm_hidden = engine.lm_backbone_fwd(st["lm"], input_ids[:, :sh.text_len], None, err_flag=err, drop=drop)
         seq, pooled, emb = engine.joint_fwd(st["bert"], input_ids, token_type_ids, attention_mask, lm_hidden,
                                             self.kg_table, cache=cache, want_inputs_embeds=want_inputs_embeds,
-                                            err_flag=err, drop=drop)
+                                            err_flag=err, drop=drop, shape=sh)
         if cache is not None:
             cache.update(input_ids=input_ids, token_type_ids=token_type_ids, err=err)
         self._pending_err = err
@@ -395,3 +409,35 @@ class STonKGsForPreTraining(BertForPreTraining):
         from . import training  # local import: keeps inference-only users free of the autograd glue
         return training.forward(self, input_ids, attention_mask, token_type_ids, masked_lm_labels,
                                 ent_masked_lm_labels, next_sentence_labels, return_dict)
+
+
+# --------------------------------------------------------------------------------------------------
+# TransE variant: same model on a 256 + 4 token sequence
+# --------------------------------------------------------------------------------------------------
+class TransESTonKGsELMPredictionHead(STonKGsELMPredictionHead):
+    """Parameter layout of the reference head (transestonkgs_model.py:29-52): the text part is
+    ``max_position_embeddings - 4`` positions long, the remaining four are entity positions."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        del self.half_length
+        self.text_part_length = config.max_position_embeddings - 4
+
+
+class TransESTonKGsForPreTraining(STonKGsForPreTraining):
+    """Drop-in for ``TransESTonKGsForPreTraining`` (transestonkgs_model.py:70-250): 256 text tokens through the frozen
+    LM backbone followed by 4 KG ids looked up in the TransE embedding table, ``max_position_embeddings`` = 260
+    (:93).  Same kernels as STonKGs: the joint encoder runs on 384 rows per pair (three 128-key attention blocks) whose
+    last 124 rows are zero and masked out as keys; outputs are sliced back to 260 positions."""
+
+    seq_shape = ops.SeqShape(256, 260, 384)
+    _head_class = TransESTonKGsELMPredictionHead
+
+    @staticmethod
+    def _adjust_config(config):
+        config.update({"max_position_embeddings": 260})
+
+    @classmethod
+    @lru_cache(maxsize=32)
+    def from_default_pretrained(cls, **kwargs):  # the reference publishes no TransE checkpoint
+        raise StkError("there is no default pre-trained TransESTonKGs checkpoint")

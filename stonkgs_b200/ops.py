@@ -89,40 +89,69 @@ def embed_text_ln(ids: torch.Tensor, word, pos, type_emb, gamma, beta, err_flag=
     return out
 
 
+class SeqShape:
+    """Joint sequence of one pair: ``text_len`` LM tokens + KG tokens = ``seq_len`` ids; activations hold ``seq_pad``
+    rows per pair (a multiple of 128 for the attention kernels; rows >= seq_len are zero and masked out as keys).
+    STonKGs: (256, 512, 512).  TransE variant (transestonkgs_model.py:44,93): (256, 260, 384)."""
+    __slots__ = ("text_len", "seq_len", "seq_pad")
+
+    def __init__(self, text_len: int = 256, seq_len: int = 512, seq_pad: Optional[int] = None):
+        self.text_len, self.seq_len = int(text_len), int(seq_len)
+        self.seq_pad = int(seq_pad) if seq_pad is not None else (self.seq_len + 127) // 128 * 128
+        if not (0 < self.text_len < self.seq_len <= self.seq_pad <= 512 and self.seq_pad % 128 == 0):
+            raise _lib.StkError(f"unsupported joint sequence shape {self.text_len}+{self.seq_len - self.text_len} "
+                           f"(padded {self.seq_pad}): at most 512 positions")
+
+    @property
+    def kg_len(self) -> int:
+        return self.seq_len - self.text_len
+
+    def __repr__(self):
+        return f"SeqShape({self.text_len}, {self.seq_len}, {self.seq_pad})"
+
+
+STONKGS_SHAPE = SeqShape(256, 512, 512)
+
+
 def embed_joint_ln(input_ids, token_type_ids, lm_hidden, kg_table, pos, type_emb, gamma, beta, *, save_stats=False,
-                   want_inputs_embeds=False, err_flag=None):
-    """Returns (out bf16 [B*512,768], mean, rstd, inputs_embeds fp32 or None)."""
+                   want_inputs_embeds=False, err_flag=None, shape: SeqShape = STONKGS_SHAPE):
+    """Returns (out bf16 [B*seq_pad,768], mean, rstd, inputs_embeds fp32 or None)."""
     _req(input_ids, torch.int64, "input_ids")
     B = input_ids.shape[0]
-    assert input_ids.shape[1] == 512 and input_ids.is_contiguous()
+    SP = shape.seq_pad
+    assert input_ids.shape[1] == shape.seq_len and input_ids.is_contiguous()
+    assert pos.shape[0] >= shape.seq_len and lm_hidden.shape[0] == B * shape.text_len
     if token_type_ids is not None:
         _req(token_type_ids, torch.int64, "token_type_ids")
         assert token_type_ids.is_contiguous() and token_type_ids.shape == input_ids.shape
     _req(lm_hidden, torch.bfloat16, "lm_hidden")
     _req(kg_table, torch.float32, "kg_table")
     dev, stream = _ctx(input_ids)
-    out = torch.empty((B * 512, H), dtype=torch.bfloat16, device=input_ids.device)
+    out = torch.empty((B * SP, H), dtype=torch.bfloat16, device=input_ids.device)
     mean = rstd = emb = None
     if save_stats:
-        mean = torch.empty(B * 512, dtype=torch.float32, device=input_ids.device)
+        mean = torch.empty(B * SP, dtype=torch.float32, device=input_ids.device)
         rstd = torch.empty_like(mean)
     if want_inputs_embeds:
-        emb = torch.empty((B * 512, H), dtype=torch.float32, device=input_ids.device)
-    check(_lib.load().stk_embed_joint_ln_fwd(dev, stream, _ptr(input_ids), _ptr(token_type_ids), B, _ptr(lm_hidden),
-                                             _ptr(kg_table), kg_table.shape[0], _ptr(pos), _ptr(type_emb),
-                                             _ptr(gamma), _ptr(beta), _ptr(out), _ptr(mean), _ptr(rstd), _ptr(emb),
-                                             _ptr(err_flag)), "stk_embed_joint_ln_fwd")
+        emb = torch.empty((B * SP, H), dtype=torch.float32, device=input_ids.device)
+    check(_lib.load().stk_embed_joint_ln_fwd_shape(dev, stream, _ptr(input_ids), _ptr(token_type_ids), B, shape.text_len,
+                                                   shape.seq_len, SP, _ptr(lm_hidden), _ptr(kg_table), kg_table.shape[0],
+                                                   _ptr(pos), _ptr(type_emb), _ptr(gamma), _ptr(beta), _ptr(out),
+                                                   _ptr(mean), _ptr(rstd), _ptr(emb), _ptr(err_flag)),
+          "stk_embed_joint_ln_fwd")
     return out, mean, rstd, emb
 
 
 def embed_joint_ln_bwd(input_ids, token_type_ids, lm_hidden, kg_table, pos, type_emb, gamma, mean, rstd, dy, dpos,
-                       dtype, dgamma, dbeta):
+                       dtype, dgamma, dbeta, shape: SeqShape = STONKGS_SHAPE):
     B = input_ids.shape[0]
     dev, stream = _ctx(input_ids)
-    check(_lib.load().stk_embed_joint_ln_bwd(dev, stream, _ptr(input_ids), _ptr(token_type_ids), B, _ptr(lm_hidden),
-                                             _ptr(kg_table), kg_table.shape[0], _ptr(pos), _ptr(type_emb),
-                                             _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dy), _ptr(dpos), _ptr(dtype),
-                                             _ptr(dgamma), _ptr(dbeta)), "stk_embed_joint_ln_bwd")
+    assert dy.shape[0] == B * shape.seq_pad and dpos.shape[0] >= shape.seq_len
+    check(_lib.load().stk_embed_joint_ln_bwd_shape(dev, stream, _ptr(input_ids), _ptr(token_type_ids), B, shape.text_len,
+                                                   shape.seq_len, shape.seq_pad, _ptr(lm_hidden), _ptr(kg_table),
+                                                   kg_table.shape[0], _ptr(pos), _ptr(type_emb), _ptr(gamma), _ptr(mean),
+                                                   _ptr(rstd), _ptr(dy), _ptr(dpos), _ptr(dtype), _ptr(dgamma),
+                                                   _ptr(dbeta)), "stk_embed_joint_ln_bwd")
 
 
 def layernorm(x: torch.Tensor, gamma, beta, save_stats=False, out=None):

@@ -137,16 +137,16 @@ class GradBuffer:
 # --------------------------------------------------------------------------------------------------
 # heads: forward
 # --------------------------------------------------------------------------------------------------
-def _label_rows(labels: torch.Tensor, col_offset: int, dev, vocab: int):
-    """Row indices (b*512 + col_offset + t) and int32 labels of the labelled positions."""
-    if labels.dim() != 2 or labels.shape[1] != HALF:
-        raise StkError(f"label tensors must be [B, 256], got {tuple(labels.shape)}")
+def _label_rows(labels: torch.Tensor, col_offset: int, width: int, row_pitch: int, dev, vocab: int):
+    """Row indices (b*row_pitch + col_offset + t) and int32 labels of the labelled positions."""
+    if labels.dim() != 2 or labels.shape[1] != width:
+        raise StkError(f"label tensors must be [B, {width}], got {tuple(labels.shape)}")
     sel = labels != IGNORE
     pos = torch.nonzero(sel, as_tuple=False)  # host-side when the batch is on the CPU; one sync otherwise
     lab = labels[sel]
     if lab.numel() and not labels.is_cuda and (int(lab.min()) < 0 or int(lab.max()) >= vocab):
         raise IndexError(f"label outside [0, {vocab})")
-    rows = (pos[:, 0] * 512 + pos[:, 1] + col_offset).to(torch.int32)
+    rows = (pos[:, 0] * row_pitch + pos[:, 1] + col_offset).to(torch.int32)
     return rows.to(dev, non_blocking=True), lab.to(torch.int32).to(dev, non_blocking=True)
 
 
@@ -165,8 +165,9 @@ def heads_fwd(model, hw: engine.HeadWeights, seq, pooled, mlm_labels, elm_labels
     dev = seq.device
     V = hw.w_text.shape[0]
     N = hw.w_ent.shape[0]
-    rows_t, lab_t = _label_rows(mlm_labels, 0, dev, V)
-    rows_e, lab_e = _label_rows(elm_labels, HALF, dev, N)
+    sh = model.seq_shape
+    rows_t, lab_t = _label_rows(mlm_labels, 0, sh.text_len, sh.seq_pad, dev, V)
+    rows_e, lab_e = _label_rows(elm_labels, sh.text_len, sh.kg_len, sh.seq_pad, dev, N)
     Rt, Re = rows_t.numel(), rows_e.numel()
     rows = torch.cat([rows_t, rows_e])
     R = Rt + Re
@@ -196,20 +197,21 @@ def heads_fwd(model, hw: engine.HeadWeights, seq, pooled, mlm_labels, elm_labels
     return loss, (mlm_loss, elm_loss, nsp_loss), nsp_logits, (lse_t, lse_e)
 
 
-def dense_prediction_logits(hw: engine.HeadWeights, seq, B):
+def dense_prediction_logits(hw: engine.HeadWeights, seq, B, shape: ops.SeqShape = ops.STONKGS_SHAPE):
     """API-parity mode: the full [B,256,V] and [B,256,N] fp32 logits of stonkgs_model.py:62-73."""
     dev = seq.device
-    ar = torch.arange(B, device=dev, dtype=torch.int32)[:, None] * 512 + torch.arange(HALF, device=dev, dtype=torch.int32)
     out = []
-    for off, w in ((0, hw.w_text), (HALF, hw.w_ent)):
+    for off, width, w in ((0, shape.text_len, hw.w_text), (shape.text_len, shape.kg_len, hw.w_ent)):
+        ar = (torch.arange(B, device=dev, dtype=torch.int32)[:, None] * shape.seq_pad +
+              torch.arange(width, device=dev, dtype=torch.int32))
         rows = (ar + off).reshape(-1).contiguous()
         h = ops.gather_rows(seq, rows)
         t = ops.layernorm(ops.linear(h, hw.wt, hw.bt, ops.EPI_BIAS_GELU), hw.ln_g, hw.ln_b)
         V = w.shape[0]
         pitch = (V + 3) // 4 * 4
-        buf = torch.empty((B * HALF, pitch), dtype=torch.float32, device=dev)
-        ops.gemm(t, w, M=B * HALF, N=V, K=H, epilogue=ops.EPI_F32, out=buf[:, :V])
-        out.append(buf[:, :V].view(B, HALF, V))
+        buf = torch.empty((B * width, pitch), dtype=torch.float32, device=dev)
+        ops.gemm(t, w, M=B * width, N=V, K=H, epilogue=ops.EPI_F32, out=buf[:, :V])
+        out.append(buf[:, :V].view(B, width, V))
     return tuple(out)
 
 
@@ -275,7 +277,7 @@ def backward(model, st, cache, dloss: torch.Tensor, gb: GradBuffer, on_ready=Non
     seq, pooled = cache["seq"], cache["pooled"]
     B = pooled.shape[0]
     dev = seq.device
-    M = B * 512
+    M = seq.shape[0]
     ready = on_ready or (lambda name: None)
     dloss = dloss.to(dev, torch.float32).reshape(())
 
@@ -319,11 +321,12 @@ def backward_pooler(bert: engine.EncoderWeights, seq, dpre, dseq, gb: GradBuffer
     """Backward of BertPooler's dense layer (HF:456-468) given the gradient w.r.t. its pre-activation;
     the [CLS] rows of ``dseq`` receive the result."""
     B = dpre.shape[0]
+    SP = seq.shape[0] // B
     ops.colsum(dpre, gb["pool_b"], accumulate=True)
-    seq0 = seq.view(B, 512, H)[:, 0]
+    seq0 = seq.view(B, SP, H)[:, 0]
     _wgrad(dpre, seq0, gb["pool_w"], B)
     dseq0 = _dgrad(dpre, bert.wp)
-    cls_rows = (torch.arange(B, device=seq.device, dtype=torch.int32) * 512).contiguous()
+    cls_rows = (torch.arange(B, device=seq.device, dtype=torch.int32) * SP).contiguous()
     ops.scatter_add_rows(dseq0, cls_rows, dseq)
     for n in ("pool_w", "pool_b"):
         ready(n)
@@ -332,7 +335,9 @@ def backward_pooler(bert: engine.EncoderWeights, seq, dpre, dseq, gb: GradBuffer
 def backward_trunk(model, bert: engine.EncoderWeights, cache, dseq, gb: GradBuffer, ready):
     """12 joint encoder layers (last to first) and the joint embedding stage, given d(loss)/d(sequence output)."""
     M = dseq.shape[0]
-    B = M // 512
+    shape: ops.SeqShape = cache.get("shape", ops.STONKGS_SHAPE)
+    SP = shape.seq_pad
+    B = M // SP
     key_bias = cache["key_bias"]
     drop: Optional[engine.DropCtx] = cache.get("drop")   # train() with dropout: masks are regenerated from (seed, site)
     dx = dseq
@@ -355,7 +360,7 @@ def backward_trunk(model, bert: engine.EncoderWeights, cache, dseq, gb: GradBuff
         ops.colsum(dz1m, gb[p + "bo"], accumulate=True)
         _wgrad(dz1m, c.ctx, gb[p + "wo"], M)
         dctx = _dgrad(dz1m, lw.wo)
-        dqkv = ops.attention_bwd(c.qkv, key_bias, B, 512, c.ctx, dctx, c.lse,
+        dqkv = ops.attention_bwd(c.qkv, key_bias, B, SP, c.ctx, dctx, c.lse,
                                  drop=drop.attention(1, li) if drop is not None else None)
         # bias gradients of query and value; the key-bias gradient is analytically zero (softmax is
         # invariant to a per-query shift of the scores), so its segment stays exactly 0
@@ -371,7 +376,7 @@ def backward_trunk(model, bert: engine.EncoderWeights, cache, dseq, gb: GradBuff
         dx = ops.dropout(dx, drop.embeddings(1))
     ops.embed_joint_ln_bwd(cache["input_ids"], cache["token_type_ids"], cache["lm_hidden"], model.kg_table, bert.pos,
                            bert.type_emb, bert.emb_g, cache["emb_mean"], cache["emb_rstd"], dx, gb["emb_pos"],
-                           gb["emb_type"], gb["emb_g"], gb["emb_b"])
+                           gb["emb_type"], gb["emb_g"], gb["emb_b"], shape=shape)
     for n in ("emb_pos", "emb_type", "emb_g", "emb_b"):
         ready(n)
 
@@ -383,7 +388,7 @@ def backward_classifier(model, st, cache, dloss: torch.Tensor, gb: GradBuffer, o
     B = pooled.shape[0]
     ready = on_ready or (lambda name: None)
     dloss = dloss.to(seq.device, torch.float32).reshape(())
-    dseq = torch.zeros((B * 512, H), dtype=torch.bfloat16, device=seq.device)
+    dseq = torch.zeros_like(seq)
     dpre = ops.cls_pool_bwd(pooled, cache["cls_logits"], cache["cls_labels"], (dloss / B).reshape(1),
                             model.classifier.weight.data, gb["cls_w"], gb["cls_b"])
     for n in ("cls_w", "cls_b"):
@@ -452,8 +457,11 @@ def forward(model, input_ids, attention_mask, token_type_ids, mlm, elm, nsp, ret
     prediction_scores = (None, None)
     if model.return_prediction_logits:
         with torch.no_grad():
-            prediction_scores = dense_prediction_logits(hw, seq, B)
-    sequence_output = seq.view(B, 512, H)
+            prediction_scores = dense_prediction_logits(hw, seq, B, model.seq_shape)
+    sh = model.seq_shape
+    sequence_output = seq.view(B, sh.seq_pad, H)
+    if sh.seq_pad != sh.seq_len:
+        sequence_output = sequence_output[:, :sh.seq_len]
     if return_dict:
         sequence_output = sequence_output.float()  # the reference returns fp32 hidden states
     if not return_dict:
