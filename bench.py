@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--layers", type=int, default=12)
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dropout", action="store_true", help="pretrain workload: switch the train()-mode dropout off")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -219,7 +220,10 @@ def main():
     model = build_model(dev, args.layers)
     opt = None
     if train:
-        model.train()  # the compute path has no dropout (reference parity is defined in eval)
+        # train() like the reference's Trainer loop: hidden / attention-probability dropout (p = 0.1) is ON, with
+        # counter-based masks regenerated in the backward pass; --no-dropout times the eval-numerics step
+        model.train()
+        model.stk_dropout = not args.no_dropout
         if world > 1:
             from stonkgs_b200.dp import DataParallel
             DataParallel(model, dist.group.WORLD)
@@ -337,7 +341,8 @@ def main():
         "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": ("STonKGs-150k-shape pretraining step (fwd + bwd + MLM/ELM/NSP losses + DP grad allreduce + clip + AdamW)"
+        "config": {"workload": ("STonKGs-150k-shape pretraining step (fwd + bwd + MLM/ELM/NSP losses + DP grad allreduce + clip + AdamW; "
+                                + ("dropout off" if args.no_dropout else "train() mode with dropout 0.1") + ")"
                                 if train else "get_stonkgs_embeddings-style extraction, STonKGs-150k shape"),
                    "batch_per_gpu": B, "global_batch": B * world, "seq_len": "256 text + 256 KG", "layers": f"{args.layers}+{args.layers}",
                    "kg_vocab": N_KG, "parallelism": f"dp{world}" if train else f"batch-sharded x{world}, no comms",

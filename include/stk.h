@@ -164,8 +164,8 @@ int stk_attn_bwd(int device, void* stream, const void* qkv_bf16, const float* ke
                  void* dqkv_bf16);
 
 /* Training-mode variants with dropout of the attention probabilities (HF:132).  keep(seed, site, row, key) is the
- * counter-based decision of csrc/stk_rng.h with row = (b*12 + h)*S + query; thr = round(256 p) in [0, 255]
- * (thr = 0: no dropout); survivors are scaled by 256 / (256 - thr).  lse stays that of the full softmax. */
+ * counter-based decision of csrc/stk_rng.cuh with row = (b*12 + h)*S + query; thr = round(128 p) in [0, 127]
+ * (thr = 0: no dropout); survivors are scaled by 128 / (128 - thr).  lse stays that of the full softmax. */
 int stk_attn_fwd_dropout(int device, void* stream, const void* qkv_bf16, const float* key_bias, int B, int S,
                          void* out_bf16, float* lse, uint32_t seed, uint32_t site, uint32_t thr);
 int stk_attn_bwd_dropout(int device, void* stream, const void* qkv_bf16, const float* key_bias, int B, int S,

@@ -376,6 +376,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
         grp_state = sMeta[it & 1];
       }
       const uint32_t drop_key = DROP ? drop_row_key(drop_seed, drop_site, static_cast<uint32_t>((b * kHeads + h) * S + q0 + row)) : 0u;
+      const uint32_t drop_thr4v = drop_thr4(drop_thr);
       float m2 = -INFINITY;                // running (lazily advanced) row max, log2 domain
       float l0 = 0.f, l1 = 0.f;            // running sums of exp2(x2 - m2)
 
@@ -453,6 +454,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
         auto exp_group = [&](auto g_tag, auto biased_tag) {
           constexpr int g = decltype(g_tag)::value;
           constexpr bool kBiased = decltype(biased_tag)::value;
+          uint32_t dw0 = 0u, dw1 = 0u;   // keep decisions of eight keys (two words), see stk_rng.cuh
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             float a0 = nm2, a1 = nm2, a2 = nm2, a3 = nm2;
@@ -467,9 +469,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
             l0 += p0 + p2;
             l1 += p1 + p3;
             if (DROP) {   // the sums above are those of the full softmax; only what multiplies V is masked
-              const uint32_t kb = drop_bytes(drop_key, static_cast<uint32_t>(j * 32 + g * 8 + c));
-              pk[g * 16 + 2 * c] = pack_bf16x2(drop_keep(kb, 0, drop_thr) ? p0 : 0.f, drop_keep(kb, 1, drop_thr) ? p1 : 0.f);
-              pk[g * 16 + 2 * c + 1] = pack_bf16x2(drop_keep(kb, 2, drop_thr) ? p2 : 0.f, drop_keep(kb, 3, drop_thr) ? p3 : 0.f);
+              if ((c & 1) == 0) drop_words(drop_key, static_cast<uint32_t>(j * 16 + g * 4 + (c >> 1)), dw0, dw1);
+              const uint32_t signs = drop_signs((c & 1) ? dw1 : dw0, drop_thr4v);
+              pk[g * 16 + 2 * c] = pack_bf16x2(p0, p1) & drop_mask16x2<0>(signs);
+              pk[g * 16 + 2 * c + 1] = pack_bf16x2(p2, p3) & drop_mask16x2<1>(signs);
             } else {
               pk[g * 16 + 2 * c] = pack_bf16x2(p0, p1);
               pk[g * 16 + 2 * c + 1] = pack_bf16x2(p2, p3);
@@ -599,7 +602,7 @@ extern "C" int stk_attn_fwd(int device, void* stream, const void* qkv, const flo
 
 extern "C" int stk_attn_fwd_dropout(int device, void* stream, const void* qkv, const float* key_bias, int B, int S,
                                     void* out, float* lse, uint32_t seed, uint32_t site, uint32_t thr) {
-  STK_REQUIRE(thr < 256, "stk_attn_fwd_dropout: thr must be below 256");
+  STK_REQUIRE(thr < 128, "stk_attn_fwd_dropout: thr must be below 128");
   return attn_fwd_impl(device, stream, qkv, key_bias, B, S, out, lse, thr > 0, seed, site, thr);
 }
 

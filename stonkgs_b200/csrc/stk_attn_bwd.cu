@@ -19,6 +19,7 @@
 // blocks in L2) and are converted to bf16 by a small tail kernel.
 #include <atomic>
 #include <stdlib.h>
+#include <type_traits>
 
 #include "stk_common.cuh"
 #include "stk_host.h"
@@ -246,7 +247,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       const float k1 = scale * kL2e;
       const float nDs = -row_D * scale;
       const uint32_t drop_key = DROP ? drop_row_key(drop_seed, drop_site, static_cast<uint32_t>(stat_base + i * 128 + row)) : 0u;
-      const float dscale = DROP ? drop_scale(drop_thr) : 1.0f;
+      const float dp_scale = DROP ? scale * drop_scale(drop_thr) : scale;   // dP / 8, times 1 / (1 - p_drop) with dropout
+      const uint32_t thr4 = drop_thr4(drop_thr);
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {   // 32 key columns at a time: S and dP loaded together
         uint32_t rs[32], rd[32];
@@ -262,33 +264,37 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
           const float4 ba = bz[2 * g], bb = bz[2 * g + 1];
           const float bias8[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
           uint32_t wp[4], wd[4];
-          // keep decisions of the 8 keys j*128 + half*64 + hh*32 + g*8 .. +7 (two 4-key words)
-          uint32_t kb[2] = {0u, 0u};
+          // keep decisions of the 8 keys j*128 + half*64 + hh*32 + g*8 .. +7 (two 4-key words); what multiplied V in
+          // the forward is P o m * dscale: the mask is applied to the packed P here, dscale to dV at the final readout
+          uint32_t sg[2] = {0u, 0u};
           if (DROP) {
-            const uint32_t c4 = static_cast<uint32_t>(j * 32 + half * 16 + hh * 8 + g * 2);
-            kb[0] = drop_bytes(drop_key, c4);
-            kb[1] = drop_bytes(drop_key, c4 + 1);
+            uint32_t w0, w1;
+            drop_words(drop_key, static_cast<uint32_t>(j * 16 + half * 8 + hh * 4 + g), w0, w1);
+            sg[0] = drop_signs(w0, thr4);
+            sg[1] = drop_signs(w1, thr4);
           }
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
+          auto pair = [&](auto t_tag) {
+            constexpr int t = decltype(t_tag)::value;
             const int e = g * 8 + t * 2;
             // p = exp(s/8 + bias - lse) in the log2 domain; dS = p * (dP - D) / 8
             const float p0 = fast_exp2(fmaf(__uint_as_float(rs[e]), k1, bias8[2 * t] - lse2));
             const float p1 = fast_exp2(fmaf(__uint_as_float(rs[e + 1]), k1, bias8[2 * t + 1] - lse2));
-            float dp0 = __uint_as_float(rd[e]), dp1 = __uint_as_float(rd[e + 1]);
-            float pv0 = p0, pv1 = p1;   // what multiplied V in the forward
-            if (DROP) {
-              const bool k0 = drop_keep(kb[t >> 1], (t & 1) * 2, drop_thr), k1b = drop_keep(kb[t >> 1], (t & 1) * 2 + 1, drop_thr);
-              dp0 = k0 ? dp0 * dscale : 0.f;
-              dp1 = k1b ? dp1 * dscale : 0.f;
-              pv0 = k0 ? p0 * dscale : 0.f;
-              pv1 = k1b ? p1 * dscale : 0.f;
+            uint32_t dp0 = rd[e], dp1 = rd[e + 1];
+            uint32_t pp = pack_bf16x2(p0, p1);
+            if (DROP) {   // dropped entries: dP -> 0 (their dS is -p D / 8) and P -> 0
+              dp0 &= drop_mask32<(t & 1) * 2>(sg[t >> 1]);
+              dp1 &= drop_mask32<(t & 1) * 2 + 1>(sg[t >> 1]);
+              pp &= drop_mask16x2<(t & 1)>(sg[t >> 1]);
             }
-            const float d0 = p0 * fmaf(dp0, scale, nDs);
-            const float d1 = p1 * fmaf(dp1, scale, nDs);
-            wp[t] = pack_bf16x2(pv0, pv1);
+            const float d0 = p0 * fmaf(__uint_as_float(dp0), dp_scale, nDs);
+            const float d1 = p1 * fmaf(__uint_as_float(dp1), dp_scale, nDs);
+            wp[t] = pp;
             wd[t] = pack_bf16x2(d0, d1);
-          }
+          };
+          pair(std::integral_constant<int, 0>{});
+          pair(std::integral_constant<int, 1>{});
+          pair(std::integral_constant<int, 2>{});
+          pair(std::integral_constant<int, 3>{});
           const int off = ((hh * 4 + g) ^ (row & 7)) << 4;
           *reinterpret_cast<uint4*>(prow + off) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
           *reinterpret_cast<uint4*>(dsrow + off) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
@@ -337,12 +343,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       tmem_ld_wait();
       uint4* dst = reinterpret_cast<uint4*>(dqkv + static_cast<int64_t>(row_base + j * 128 + row) * (3 * kHidden) +
                                             (which == 0 ? 2 * kHidden : kHidden) + h * 64 + half * 32);
+      const float osc = (DROP && which == 0) ? drop_scale(drop_thr) : 1.0f;   // dV = dscale * (P o m)^T dO
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         uint32_t w[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t)
-          w[t] = pack_bf16x2(__uint_as_float(r[g * 8 + 2 * t]), __uint_as_float(r[g * 8 + 2 * t + 1]));
+          w[t] = pack_bf16x2(__uint_as_float(r[g * 8 + 2 * t]) * osc, __uint_as_float(r[g * 8 + 2 * t + 1]) * osc);
         dst[g] = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
@@ -412,7 +419,7 @@ extern "C" int stk_attn_bwd(int device, void* stream, const void* qkv, const flo
 extern "C" int stk_attn_bwd_dropout(int device, void* stream, const void* qkv, const float* key_bias, int B, int S,
                                     const void* out, const void* dout, const float* lse, float* workspace, void* dqkv,
                                     uint32_t seed, uint32_t site, uint32_t thr) {
-  STK_REQUIRE(thr < 256, "stk_attn_bwd_dropout: thr must be below 256");
+  STK_REQUIRE(thr < 128, "stk_attn_bwd_dropout: thr must be below 128");
   return attn_bwd_impl(device, stream, qkv, key_bias, B, S, out, dout, lse, workspace, dqkv, thr > 0, seed, site, thr);
 }
 

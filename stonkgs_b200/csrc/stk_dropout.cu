@@ -4,7 +4,7 @@
 //                                                               hidden-dropout site (dropout is linear and self-adjoint)
 //   stk_dropout_resid_ln_fwd   z = drop(x) + r ; y = LN(z)      BertSelfOutput / BertOutput in train() (HF:296-298, 354-356)
 // One warp per 768-wide row, the lane layout of stk_embed.cu (chunk = lane + 32 i holds columns 4*chunk .. +3, i.e.
-// exactly one drop_bytes() word).  In eval() / extraction these sites are the fused GEMM epilogue
+// exactly one decision word of drop_words()).  In eval() / extraction these sites are the fused GEMM epilogue
 // (STK_EPI_BIAS_RESID_LN); with dropout the dense GEMM uses the plain bias epilogue and this kernel follows it.
 #include <atomic>
 
@@ -35,11 +35,15 @@ __device__ __forceinline__ void d_store_row(__nv_bfloat16* row, int lane, const 
     p[lane + 32 * i] = make_uint2(pack_bf16x2(v[4 * i], v[4 * i + 1]), pack_bf16x2(v[4 * i + 2], v[4 * i + 3]));
 }
 __device__ __forceinline__ void d_apply(float (&v)[kDPerLane], int lane, uint32_t row_key, uint32_t thr, float scale) {
+  const uint32_t thr4 = drop_thr4(thr);
 #pragma unroll
   for (int i = 0; i < kDChunks; ++i) {
-    const uint32_t bytes = drop_bytes(row_key, static_cast<uint32_t>(lane + 32 * i));
+    const uint32_t chunk = static_cast<uint32_t>(lane + 32 * i);   // columns 4*chunk .. 4*chunk + 3
+    uint32_t w0, w1;
+    drop_words(row_key, chunk >> 1, w0, w1);
+    const uint32_t signs = drop_signs((chunk & 1u) ? w1 : w0, thr4);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[4 * i + k] = drop_keep(bytes, k, thr) ? v[4 * i + k] * scale : 0.f;
+    for (int k = 0; k < 4; ++k) v[4 * i + k] = drop_keep(signs, k) ? v[4 * i + k] * scale : 0.f;
   }
 }
 
@@ -104,7 +108,7 @@ using namespace stk;
 
 extern "C" int stk_dropout_fwd(int device, void* stream, const void* x, int M, uint32_t seed, uint32_t site, uint32_t thr,
                                void* y) {
-  STK_REQUIRE(x && y && M > 0 && thr < 256, "stk_dropout_fwd: bad arguments");
+  STK_REQUIRE(x && y && M > 0 && thr < 128, "stk_dropout_fwd: bad arguments");
   STK_CHECK_CUDA(cudaSetDevice(device));
   dropout_fwd_kernel<<<(M + kDRowWarps - 1) / kDRowWarps, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), M, seed, site, thr, static_cast<__nv_bfloat16*>(y));
@@ -116,7 +120,7 @@ extern "C" int stk_dropout_fwd(int device, void* stream, const void* x, int M, u
 extern "C" int stk_dropout_resid_ln_fwd(int device, void* stream, const void* x, const void* resid, int M,
                                         const float* gamma, const float* beta, uint32_t seed, uint32_t site, uint32_t thr,
                                         void* z_out, void* y, float* mean, float* rstd) {
-  STK_REQUIRE(x && resid && y && gamma && beta && M > 0 && thr < 256, "stk_dropout_resid_ln_fwd: bad arguments");
+  STK_REQUIRE(x && resid && y && gamma && beta && M > 0 && thr < 128, "stk_dropout_resid_ln_fwd: bad arguments");
   STK_REQUIRE((mean == nullptr) == (rstd == nullptr), "stk_dropout_resid_ln_fwd: mean/rstd must both be given or both NULL");
   STK_CHECK_CUDA(cudaSetDevice(device));
   dropout_resid_ln_kernel<<<(M + kDRowWarps - 1) / kDRowWarps, 256, 0, static_cast<cudaStream_t>(stream)>>>(

@@ -258,13 +258,13 @@ def linear(x, w, bias=None, epilogue=EPI_BIAS, **kw):
 # attention
 # --------------------------------------------------------------------------------------------------
 class Drop:
-    """One dropout site of a training step: (seed, site id, threshold = round(256 p)); see csrc/stk_rng.cuh."""
+    """One dropout site of a training step: (seed, site id, threshold = round(128 p)); see csrc/stk_rng.cuh."""
     __slots__ = ("seed", "site", "thr")
 
     def __init__(self, seed: int, site: int, p: float):
         self.seed = seed & 0xFFFFFFFF
         self.site = site & 0xFFFFFFFF
-        self.thr = min(255, int(round(256.0 * p)))
+        self.thr = min(127, int(round(128.0 * p)))
 
 
 def dropout(x: torch.Tensor, d: Drop, out=None) -> torch.Tensor:

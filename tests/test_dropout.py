@@ -16,13 +16,27 @@ from oracle import ref_shim, stonkgs_oracle as orc
 
 
 def test_keep_mask_statistics_and_determinism():
-    m = do.keep_mask(123, 7, 4096, 768, 26)
-    assert abs((1 - m.mean()) - 26 / 256) < 1.5e-3
-    assert np.array_equal(m, do.keep_mask(123, 7, 4096, 768, 26))
-    assert (m != do.keep_mask(124, 7, 4096, 768, 26)).mean() > 0.1
-    assert (m != do.keep_mask(123, 8, 4096, 768, 26)).mean() > 0.1
+    m = do.keep_mask(123, 7, 4096, 768, 13)
+    assert abs((1 - m.mean()) - 13 / 128) < 1.5e-3
+    assert np.array_equal(m, do.keep_mask(123, 7, 4096, 768, 13))
+    assert (m != do.keep_mask(124, 7, 4096, 768, 13)).mean() > 0.1
+    assert (m != do.keep_mask(123, 8, 4096, 768, 13)).mean() > 0.1
     assert abs(m.mean(0).std()) < 0.01 and abs(m.mean(1).std()) < 0.02      # no row / column structure
     assert do.keep_mask(1, 1, 8, 16, 0).all()
+    # the eight decisions that share one hash (two words, four 7-bit fields each) are pairwise uncorrelated, and so are
+    # vertical neighbours (consecutive row keys)
+    d = (~m).astype(np.float64)
+    blk = d.reshape(4096, 96, 8)
+    p = d.mean()
+    for a in range(8):
+        for b in range(a + 1, 8):
+            joint = (blk[:, :, a] * blk[:, :, b]).mean()
+            assert abs(joint - p * p) < 1.2e-3, (a, b, joint, p * p)
+    assert abs((d[1:] * d[:-1]).mean() - p * p) < 1e-3
+    # known answers of the decision words (pin the bit layout shared with csrc/stk_rng.cuh)
+    w0, w1 = do.drop_words(np.uint32(0x12345678), np.uint32(5))
+    assert (int(w0), int(w1)) == (int(do.lowbias32(np.uint32((0x12345678 + 5 * 0x9E3779B9) & 0xFFFFFFFF))),
+                                  int(((int(w0) * 0x9E3779B1) >> 32) ^ ((int(w0) * 0x9E3779B1) & 0xFFFFFFFF)))
 
 
 @pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree only exists in the dev container")
