@@ -120,7 +120,7 @@ def embed_joint_ln(input_ids, token_type_ids, lm_hidden, kg_table, pos, type_emb
     B = input_ids.shape[0]
     SP = shape.seq_pad
     assert input_ids.shape[1] == shape.seq_len and input_ids.is_contiguous()
-    assert pos.shape[0] >= shape.seq_len and lm_hidden.shape[0] == B * shape.text_len
+    assert pos.shape[0] >= shape.seq_len and lm_hidden.numel() == B * shape.text_len * H and lm_hidden.is_contiguous()
     if token_type_ids is not None:
         _req(token_type_ids, torch.int64, "token_type_ids")
         assert token_type_ids.is_contiguous() and token_type_ids.shape == input_ids.shape
