@@ -101,6 +101,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const bool st0 = (DBG & 64) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
+  if (st0) g_abw_timeline[64] = clock64();   // CTA entry
   const int nq = S >> 7;
   const int row_base = b * S;
 
@@ -132,6 +134,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t T_S = 0, T_DP = 128, T_DV = 256, T_DK = 320, T_DQ = 384;
+  if (st0) g_abw_timeline[65] = clock64();   // prologue done
 
   if (warp == 8) {
     // ================================ TMA producer ================================
@@ -331,11 +334,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
         if (st) g_abw_timeline[i * 16 + 12] = clock64();
       }
     }
+    if (st0) g_abw_timeline[66] = clock64();   // query loop done
     if (issuer) tma_wait_group<0>();
     // dV_j, dK_j: accumulated over all query blocks; lane = key row.  Their last MMAs are issued after
     // the dQ MMAs, so wait for the dV / dK commit of the final pair before reading the accumulators.
     mbar_wait(bar_dvdk, (nq - 1) & 1);
     tc_fence_after();
+    if (st0) g_abw_timeline[67] = clock64();   // last dV / dK complete
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
       uint32_t r[32];
@@ -355,12 +360,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     }
   }
 
+  if (st0) g_abw_timeline[68] = clock64();     // dK / dV stored
   tc_fence_before();
   __syncthreads();
   if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  if (st0) g_abw_timeline[69] = clock64();     // CTA exit
 }
 
 }  // namespace stk

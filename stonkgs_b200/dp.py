@@ -22,6 +22,7 @@ exactly like the reference under DDP.
 from __future__ import annotations
 
 import contextlib
+import os
 from typing import List, Optional
 
 import torch
@@ -53,7 +54,8 @@ def plan_buckets(entries, offsets, bucket_elems: int) -> List[Bucket]:
 
 
 class DataParallel:
-    def __init__(self, model, process_group=None, bucket_mb: float = 64.0, wire_dtype=torch.bfloat16):
+    def __init__(self, model, process_group=None, bucket_mb: float = 64.0, wire_dtype=torch.bfloat16,
+                 overlap: Optional[bool] = None):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised (one process per GPU)")
         self.model = model
@@ -61,6 +63,9 @@ class DataParallel:
         self.world = dist.get_world_size(process_group)
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
         self.wire_dtype = wire_dtype
+        # overlap=False: the same buckets are reduced one after the other once backward has been enqueued (the
+        # persistent GEMMs then never share the SMs with a collective kernel); STK_DP_OVERLAP=0 selects it for A/B runs
+        self.overlap = (os.environ.get("STK_DP_OVERLAP", "1") != "0") if overlap is None else bool(overlap)
         self.buckets: Optional[List[Bucket]] = None
         self._name_to_bucket = {}
         self._sync = True
@@ -101,7 +106,7 @@ class DataParallel:
     def on_ready(self, name: str):
         b = self._name_to_bucket[name]
         b.pending -= 1
-        if b.pending == 0 and self._sync:
+        if b.pending == 0 and self._sync and self.overlap:
             self._reduce(b)
 
     def _reduce(self, b: Bucket):
@@ -133,5 +138,7 @@ class DataParallel:
         for b in self.buckets:
             if b.pending != 0:
                 raise RuntimeError(f"gradient bucket {b.names[0]}.. was never completed by backward")
+            if not self.overlap:
+                self._reduce(b)
             if b.event is not None:
                 torch.cuda.current_stream(gb.flat.device).wait_event(b.event)
