@@ -32,7 +32,7 @@ extern std::atomic<long long> g_launches;
 __device__ long long g_abw_timeline[2048];   // bring-up only (STK_ATTN_DEBUG=64): clock64 stamps of CTA 0
 constexpr int ABW_THREADS = 320;   // 8 compute warps + TMA warp + MMA warp
 constexpr float kL2e = 1.4426950408889634f;
-constexpr int ABW_SMEM = 1024 + 16384 * 2 + 32768 * 5 + 512 + 128;
+constexpr int ABW_SMEM = 1024 + 16384 * 2 + 32768 * 5 + 1024 + 128;
 
 // D[b,h,s] = sum_d dO * O : one warp per token row, 16-lane groups own one head
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o,
@@ -73,11 +73,21 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_cast_kernel(const float* __re
 
 // DROP: the forward multiplied V with Pd = P o m / (1 - p_drop) (stk_attn.cu); then dV = Pd^T dO,
 // dS = P o (dP o m / (1 - p_drop) - D) / 8 with the same D = rowsum(dO o O), and the masks m are regenerated here.
+//
+// Persistent: grid = one CTA per SM; CTA c walks the items c, c + gridDim.x, ... with item = (key block j fastest,
+// head, batch element), so the CTAs that run together share Q / dO tiles in L2.  All mbarrier parities follow flat
+// counters (g = query-block iteration across items, k = item), so the pipeline never drains between items:
+//   * Q / dO of the next item's first iteration are loaded into the ring during the current item's last iteration,
+//   * K / V of the next item are requested as soon as the current item's last dQ MMA has read K (bar_kvfree),
+//   * the dK / dV read-out and store of an item overlap those loads and the next item's first score MMAs.
+// A non-persistent grid (one CTA per item, first version) spent 39 % of every CTA's lifetime outside the query loop:
+// ~6.9 k cycles from entry to the first scores (TMEM allocation + the TMA round trip of four tiles, with all 148 CTAs
+// of a wave bursting at once), ~1.4 k for the last dV / dK MMAs and ~2.8 k for an uncoalesced dK / dV store.
 template <int DBG, bool DROP>
 __global__ void __launch_bounds__(ABW_THREADS)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
                 const __grid_constant__ CUtensorMap map_dq, const float* __restrict__ key_bias,
-                const float* __restrict__ lse, const float* __restrict__ Dws, int S,
+                const float* __restrict__ lse, const float* __restrict__ Dws, int S, int num_items,
                 __nv_bfloat16* __restrict__ dqkv, uint32_t drop_seed, uint32_t drop_site, uint32_t drop_thr) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -87,24 +97,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
   uint8_t* sdO = smem + 65536;   // [2][16 KB]
   uint8_t* sP = smem + 98304;    // [2 key chunks][128 q][128 B]
   uint8_t* sdS = smem + 131072;
-  uint8_t* sStage = smem + 163840;   // fp32 dQ staging: 2 x [128 rows][32 fp32] for the TMA reduce-add
-  float* sBias = reinterpret_cast<float*>(smem + 196608);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 128);
+  uint8_t* sStage = smem + 163840;   // fp32 dQ staging: 2 x [128 rows][32 fp32] for the TMA reduce-add; dK / dV staging
+  float* sBias = reinterpret_cast<float*>(smem + 196608);   // [2 item parity][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 256);
   uint64_t* bar_kv = bars;
   uint64_t* bar_q = bars + 1;  // [2]
   uint64_t* bar_s = bars + 3;
   uint64_t* bar_p = bars + 4;
   uint64_t* bar_dq = bars + 5;
-  uint64_t* bar_qfree = bars + 6;  // [2] Q_i / dO_i buffer released (only the TMA warp waits on these)
-  uint64_t* bar_dvdk = bars + 8;   // dV / dK MMAs of pair i have completed: the P / dS tiles may be rewritten
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* bar_qfree = bars + 6;  // [2] Q_g / dO_g buffer released (only the TMA warp waits on these)
+  uint64_t* bar_dvdk = bars + 8;   // dV / dK MMAs of iteration g have completed: the P / dS tiles may be rewritten
+  uint64_t* bar_kvfree = bars + 9; // the item's last dQ MMA has read K (V was last read by its last dP): K / V reusable
+  uint64_t* bar_accfree = bars + 10;  // the compute warps have read the item's dV / dK accumulators out of TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const bool st0 = (DBG & 64) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
+  const int nq = S >> 7;           // query blocks per item == key blocks per (head, batch)
+  const bool st0 = (DBG & 64) && blockIdx.x == 0 && threadIdx.x == 0;
   if (st0) g_abw_timeline[64] = clock64();   // CTA entry
-  const int nq = S >> 7;
-  const int row_base = b * S;
 
   if (warp == 8) {
     if (lane == 0) {
@@ -120,14 +130,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       mbar_init(bar_qfree, 1);
       mbar_init(bar_qfree + 1, 1);
       mbar_init(bar_dvdk, 1);
+      mbar_init(bar_kvfree, 1);
+      mbar_init(bar_accfree, 256);
       fence_barrier_init();
     }
     __syncwarp();
     tmem_alloc(tmem_slot, 512);
-  } else if (threadIdx.x < 128) {
-    // additive key bias in the log2 domain, clamped finite (finfo.min * log2e would overflow to -inf)
-    sBias[threadIdx.x] = key_bias ? fmaxf(__ldg(key_bias + static_cast<int64_t>(b) * S + j * 128 + threadIdx.x) * kL2e,
-                                          -3.402823466e38f) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -136,28 +144,42 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
   constexpr uint32_t T_S = 0, T_DP = 128, T_DV = 256, T_DK = 320, T_DQ = 384;
   if (st0) g_abw_timeline[65] = clock64();   // prologue done
 
+  const int my_items = (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  // item -> (key block j, head h, first token row of the batch element)
+  auto decode = [&](int item, int& j, int& h, int& b) {
+    j = item % nq;
+    const int rest = item / nq;
+    h = rest % kHeads;
+    b = rest / kHeads;
+  };
+
   if (warp == 8) {
     // ================================ TMA producer ================================
     const bool leader = elect_one();
-    if (leader) {
-      mbar_arrive_expect_tx(bar_kv, 32768);
-      tma_load_2d(&map_qkv, bar_kv, sK, 768 + h * 64, row_base + j * 128);
-      tma_load_2d(&map_qkv, bar_kv, sV, 1536 + h * 64, row_base + j * 128);
-      mbar_arrive_expect_tx(bar_q, 32768);
-      tma_load_2d(&map_qkv, bar_q, sQ, h * 64, row_base);
-      tma_load_2d(&map_do, bar_q, sdO, h * 64, row_base);
-    }
-    __syncwarp();
-    for (int i = 0; i + 1 < nq; ++i) {
-      // buffer (i+1)&1 was last read by the MMAs of iteration i-1 (its (i-1)/2-th use)
-      const int nb = (i + 1) & 1;
-      if (i > 0) mbar_wait(bar_qfree + nb, ((i - 1) >> 1) & 1);
-      if (leader) {
-        mbar_arrive_expect_tx(bar_q + nb, 32768);
-        tma_load_2d(&map_qkv, bar_q + nb, sQ + nb * 16384, h * 64, row_base + (i + 1) * 128);
-        tma_load_2d(&map_do, bar_q + nb, sdO + nb * 16384, h * 64, row_base + (i + 1) * 128);
+    int g = 0;
+    for (int k = 0; k < my_items; ++k) {
+      int j, h, b;
+      decode(static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x), j, h, b);
+      const int row_base = b * S;
+      for (int i = 0; i < nq; ++i, ++g) {
+        const int nb = g & 1;
+        // buffer g & 1 was last read by the dV / dK MMAs of iteration g - 2 (its ((g - 2) / 2)-th use)
+        if (g >= 2) mbar_wait(bar_qfree + nb, ((g - 2) >> 1) & 1);
+        if (leader) {
+          mbar_arrive_expect_tx(bar_q + nb, 32768);
+          tma_load_2d(&map_qkv, bar_q + nb, sQ + nb * 16384, h * 64, row_base + i * 128);
+          tma_load_2d(&map_do, bar_q + nb, sdO + nb * 16384, h * 64, row_base + i * 128);
+        }
+        if (i == 0) {   // after Q_0 / dO_0 (which can go out a whole iteration early): the item's K / V
+          if (k > 0) mbar_wait(bar_kvfree, (k - 1) & 1);
+          if (leader) {
+            mbar_arrive_expect_tx(bar_kv, 32768);
+            tma_load_2d(&map_qkv, bar_kv, sK, 768 + h * 64, row_base + j * 128);
+            tma_load_2d(&map_qkv, bar_kv, sV, 1536 + h * 64, row_base + j * 128);
+          }
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp == 9) {
     // ================================ MMA issuer ================================
@@ -178,10 +200,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     const uint64_t do_desc0 = umma_smem_desc(smem_u32(sdO), 16, 1024);
     const uint64_t qT_desc0 = umma_smem_desc(smem_u32(sQ), 8192, 1024);
     const uint64_t doT_desc0 = umma_smem_desc(smem_u32(sdO), 8192, 1024);
-    mbar_wait(bar_kv, 0);
-    auto issue_scores = [&](int i) {   // S_i = Q_i K_j^T and dP_i = dO_i V_j^T into their TMEM columns
-      const uint64_t boff = static_cast<uint64_t>((i & 1) * (16384 >> 4));
-      mbar_wait(bar_q + (i & 1), (i >> 1) & 1);
+    const int total = my_items * nq;
+    int sg = 0, si = 0, sk = 0;   // next scores to issue: flat iteration, iteration within its item, item
+    auto issue_scores = [&]() {   // S = Q K_j^T and dP = dO V_j^T of iteration sg into their TMEM columns
+      const uint64_t boff = static_cast<uint64_t>((sg & 1) * (16384 >> 4));
+      if (si == 0) mbar_wait(bar_kv, sk & 1);          // first iteration of an item: its K / V
+      mbar_wait(bar_q + (sg & 1), (sg >> 1) & 1);
       tc_fence_after();
       {
 #pragma unroll
@@ -190,43 +214,55 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
         for (int k = 0; k < 4; ++k) umma_bf16_warp(tmem_u + T_DP, do_desc0 + boff + 2 * k, v_desc + 2 * k, idesc_s, k > 0);
         umma_commit_warp(bar_s);
       }
+      ++sg;
+      if (++si == nq) { si = 0; ++sk; }
     };
-    auto stamp = [&](int i, int slot) {
-      if ((DBG & 64) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && leader) g_abw_timeline[i * 16 + slot] = clock64();
+    auto stamp = [&](int g, int slot) {
+      if ((DBG & 64) && blockIdx.x == 0 && leader && g < 4) g_abw_timeline[g * 16 + slot] = clock64();
     };
     stamp(0, 0);
-    issue_scores(0);
-    for (int i = 0; i < nq; ++i) {
-      const uint64_t boff = static_cast<uint64_t>((i & 1) * (16384 >> 4));
-      stamp(i, 1);
-      mbar_wait(bar_p, i & 1);           // P_i, dS_i are in smem; S_i / dP_i columns have been read
+    if (total > 0) issue_scores();
+    int i = 0, k = 0;
+    for (int g = 0; g < total; ++g) {
+      const uint64_t boff = static_cast<uint64_t>((g & 1) * (16384 >> 4));
+      const bool last = i == nq - 1;
+      stamp(g, 1);
+      mbar_wait(bar_p, g & 1);           // P_g, dS_g are in smem; S_g / dP_g columns have been read
       tc_fence_after();
-      stamp(i, 2);
+      stamp(g, 2);
       {
-        // dQ_i first: the compute warps are waiting for it (they drain it while dV / dK run)
+        // dQ_g first: the compute warps are waiting for it (they drain it while dV / dK run)
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_warp(tmem_u + T_DQ, ds_desc + kb * (16384 >> 4) + 2 * k, kT_desc + kb * (8192 >> 4) + k * 128, idesc_q,
-                      (kb | k) > 0);
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16_warp(tmem_u + T_DQ, ds_desc + kb * (16384 >> 4) + 2 * kk, kT_desc + kb * (8192 >> 4) + kk * 128, idesc_q,
+                      (kb | kk) > 0);
         umma_commit_warp(bar_dq);
+        if (last) umma_commit_warp(bar_kvfree);   // every MMA that reads this item's K / V has been issued above
       }
-      // the next pair's scores come next (the compute warps need them right after draining dQ_i) ...
-      if (i + 1 < nq) issue_scores(i + 1);
-      // ... and dV / dK of this pair last: nobody waits for them until the P / dS tiles are rewritten
+      // inside an item the next scores come next (the compute warps need them right after draining dQ_g) and
+      // dV / dK of this iteration last: nobody waits for them until the P / dS tiles are rewritten.  At the end of an
+      // item the order is reversed: the item's epilogue waits for dV / dK, and the next item's K / V are still in flight.
+      if (!last && g + 1 < total) issue_scores();
       {
+        if (i == 0 && k > 0) {   // the previous item's accumulators must have left TMEM before they are overwritten
+          mbar_wait(bar_accfree, (k - 1) & 1);
+          tc_fence_after();
+        }
         // MN-major operands: +2048 B (16 rows of the reduction dimension) per k step
         umma_bf16_warp(tmem_u + T_DV, pT_desc, doT_desc0 + boff, idesc_t, i > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 1; k < 8; ++k) umma_bf16_warp(tmem_u + T_DV, pT_desc + k * 128, doT_desc0 + boff + k * 128, idesc_t, 1u);
+        for (int kk = 1; kk < 8; ++kk) umma_bf16_warp(tmem_u + T_DV, pT_desc + kk * 128, doT_desc0 + boff + kk * 128, idesc_t, 1u);
         umma_bf16_warp(tmem_u + T_DK, dsT_desc, qT_desc0 + boff, idesc_t, i > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 1; k < 8; ++k) umma_bf16_warp(tmem_u + T_DK, dsT_desc + k * 128, qT_desc0 + boff + k * 128, idesc_t, 1u);
+        for (int kk = 1; kk < 8; ++kk) umma_bf16_warp(tmem_u + T_DK, dsT_desc + kk * 128, qT_desc0 + boff + kk * 128, idesc_t, 1u);
         umma_commit_warp(bar_dvdk);              // P / dS tiles reusable
-        umma_commit_warp(bar_qfree + (i & 1));   // Q_i / dO_i buffer reusable once everything above has completed
+        umma_commit_warp(bar_qfree + (g & 1));   // Q_g / dO_g buffer reusable once everything above has completed
       }
-      stamp(i, 3);
+      if (last && g + 1 < total) issue_scores();
+      stamp(g, 3);
+      if (++i == nq) { i = 0; ++k; }
     }
   } else {
     const int q = warp & 3, half = warp >> 2;
@@ -234,133 +270,173 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const bool issuer = threadIdx.x == 0;
     const float scale = 0.125f;
-    const int64_t stat_base = (static_cast<int64_t>(b) * kHeads + h) * S;
+    int g = 0;
 
-    for (int i = 0; i < nq; ++i) {
-      const float row_lse = __ldg(lse + stat_base + i * 128 + row);
-      const float row_D = __ldg(Dws + stat_base + i * 128 + row);
-      const bool st = (DBG & 64) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
-      if (st) g_abw_timeline[i * 16 + 8] = clock64();
-      mbar_wait(bar_s, i & 1);
-      tc_fence_after();
-      if (st) g_abw_timeline[i * 16 + 9] = clock64();
-      uint8_t* prow = sP + half * 16384 + row * 128;
-      uint8_t* dsrow = sdS + half * 16384 + row * 128;
-      const float lse2 = row_lse * kL2e;
-      const float k1 = scale * kL2e;
-      const float nDs = -row_D * scale;
-      const uint32_t drop_key = DROP ? drop_row_key(drop_seed, drop_site, static_cast<uint32_t>(stat_base + i * 128 + row)) : 0u;
-      const float dp_scale = DROP ? scale * drop_scale(drop_thr) : scale;   // dP / 8, times 1 / (1 - p_drop) with dropout
-      const uint32_t thr4 = drop_thr4(drop_thr);
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {   // 32 key columns at a time: S and dP loaded together
-        uint32_t rs[32], rd[32];
-        tmem_ld_32x32b_x32(t_row + T_S + half * 64 + hh * 32, rs);
-        tmem_ld_32x32b_x32(t_row + T_DP + half * 64 + hh * 32, rd);
-        tmem_ld_wait();
-        if (hh == 0 && i > 0) {   // dV / dK of the previous pair have finished reading the P / dS tiles
-          mbar_wait(bar_dvdk, (i - 1) & 1);
-        }
-        const float4* bz = reinterpret_cast<const float4*>(sBias + half * 64 + hh * 32);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const float4 ba = bz[2 * g], bb = bz[2 * g + 1];
-          const float bias8[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-          uint32_t wp[4], wd[4];
-          // keep decisions of the 8 keys j*128 + half*64 + hh*32 + g*8 .. +7 (two 4-key words); what multiplied V in
-          // the forward is P o m * dscale: the mask is applied to the packed P here, dscale to dV at the final readout
-          uint32_t sg[2] = {0u, 0u};
-          if (DROP) {
-            uint32_t w0, w1;
-            drop_words(drop_key, static_cast<uint32_t>(j * 16 + half * 8 + hh * 4 + g), w0, w1);
-            sg[0] = drop_signs(w0, thr4);
-            sg[1] = drop_signs(w1, thr4);
-          }
-          auto pair = [&](auto t_tag) {
-            constexpr int t = decltype(t_tag)::value;
-            const int e = g * 8 + t * 2;
-            // p = exp(s/8 + bias - lse) in the log2 domain; dS = p * (dP - D) / 8
-            const float p0 = fast_exp2(fmaf(__uint_as_float(rs[e]), k1, bias8[2 * t] - lse2));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(rs[e + 1]), k1, bias8[2 * t + 1] - lse2));
-            uint32_t dp0 = rd[e], dp1 = rd[e + 1];
-            uint32_t pp = pack_bf16x2(p0, p1);
-            if (DROP) {   // dropped entries: dP -> 0 (their dS is -p D / 8) and P -> 0
-              dp0 &= drop_mask32<(t & 1) * 2>(sg[t >> 1]);
-              dp1 &= drop_mask32<(t & 1) * 2 + 1>(sg[t >> 1]);
-              pp &= drop_mask16x2<(t & 1)>(sg[t >> 1]);
-            }
-            const float d0 = p0 * fmaf(__uint_as_float(dp0), dp_scale, nDs);
-            const float d1 = p1 * fmaf(__uint_as_float(dp1), dp_scale, nDs);
-            wp[t] = pp;
-            wd[t] = pack_bf16x2(d0, d1);
-          };
-          pair(std::integral_constant<int, 0>{});
-          pair(std::integral_constant<int, 1>{});
-          pair(std::integral_constant<int, 2>{});
-          pair(std::integral_constant<int, 3>{});
-          const int off = ((hh * 4 + g) ^ (row & 7)) << 4;
-          *reinterpret_cast<uint4*>(prow + off) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
-          *reinterpret_cast<uint4*>(dsrow + off) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
-        }
+    // additive key bias of an item's key block in the log2 domain, clamped finite (finfo.min * log2e would overflow
+    // to -inf); double-buffered by item parity: the next item's values are fetched while the current item runs
+    auto stage_bias = [&](int k) {
+      if (threadIdx.x < 128 && k < my_items) {
+        int j, h, b;
+        decode(static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x), j, h, b);
+        sBias[(k & 1) * 128 + threadIdx.x] =
+            key_bias ? fmaxf(__ldg(key_bias + static_cast<int64_t>(b) * S + j * 128 + threadIdx.x) * kL2e, -3.402823466e38f) : 0.f;
       }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      if (st) g_abw_timeline[i * 16 + 10] = clock64();
-      mbar_arrive(bar_p);
+    };
+    stage_bias(0);
+    named_bar_sync(1, 256);
 
-      mbar_wait(bar_dq, i & 1);
-      tc_fence_after();
-      if (st) g_abw_timeline[i * 16 + 11] = clock64();
-      {  // dQ_i partial: my 32 fp32 columns -> swizzled staging tile -> TMA reduce-add
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_row + T_DQ + half * 32, r);
-        tmem_ld_wait();
-        if (i > 0) {  // the reduce-add of the previous pair has finished reading the staging tiles
-          if (issuer) tma_wait_group_read<0>();
-          named_bar_sync(1, 256);
-        }
-        uint8_t* srow = sStage + half * 16384 + row * 128;
+    for (int k = 0; k < my_items; ++k) {
+      int j, h, b;
+      decode(static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x), j, h, b);
+      const int row_base = b * S;
+      const int64_t stat_base = (static_cast<int64_t>(b) * kHeads + h) * S;
+      const float* bias_k = sBias + (k & 1) * 128;
+      stage_bias(k + 1);   // consumed after this item's named barriers
+
+      for (int i = 0; i < nq; ++i, ++g) {
+        const float row_lse = __ldg(lse + stat_base + i * 128 + row);
+        const float row_D = __ldg(Dws + stat_base + i * 128 + row);
+        const bool st = (DBG & 64) && blockIdx.x == 0 && threadIdx.x == 0 && g < 4;
+        if (st) g_abw_timeline[g * 16 + 8] = clock64();
+        mbar_wait(bar_s, g & 1);
+        tc_fence_after();
+        if (st) g_abw_timeline[g * 16 + 9] = clock64();
+        uint8_t* prow = sP + half * 16384 + row * 128;
+        uint8_t* dsrow = sdS + half * 16384 + row * 128;
+        const float lse2 = row_lse * kL2e;
+        const float k1 = scale * kL2e;
+        const float nDs = -row_D * scale;
+        const uint32_t drop_key = DROP ? drop_row_key(drop_seed, drop_site, static_cast<uint32_t>(stat_base + i * 128 + row)) : 0u;
+        const float dp_scale = DROP ? scale * drop_scale(drop_thr) : scale;   // dP / 8, times 1 / (1 - p_drop) with dropout
+        const uint32_t thr4 = drop_thr4(drop_thr);
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<uint4*>(srow + ((c ^ (row & 7)) << 4)) = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+        for (int hh = 0; hh < 2; ++hh) {   // 32 key columns at a time: S and dP loaded together
+          uint32_t rs[32], rd[32];
+          tmem_ld_32x32b_x32(t_row + T_S + half * 64 + hh * 32, rs);
+          tmem_ld_32x32b_x32(t_row + T_DP + half * 64 + hh * 32, rd);
+          tmem_ld_wait();
+          if (hh == 0 && g > 0) {   // dV / dK of the previous iteration have finished reading the P / dS tiles
+            mbar_wait(bar_dvdk, (g - 1) & 1);
+          }
+          const float4* bz = reinterpret_cast<const float4*>(bias_k + half * 64 + hh * 32);
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            const float4 ba = bz[2 * gq], bb = bz[2 * gq + 1];
+            const float bias8[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+            uint32_t wp[4], wd[4];
+            // keep decisions of the 8 keys j*128 + half*64 + hh*32 + gq*8 .. +7 (two 4-key words); what multiplied V in
+            // the forward is P o m * dscale: the mask is applied to the packed P here, dscale to dV at the final readout
+            uint32_t sg2[2] = {0u, 0u};
+            if (DROP) {
+              uint32_t w0, w1;
+              drop_words(drop_key, static_cast<uint32_t>(j * 16 + half * 8 + hh * 4 + gq), w0, w1);
+              sg2[0] = drop_signs(w0, thr4);
+              sg2[1] = drop_signs(w1, thr4);
+            }
+            auto pair = [&](auto t_tag) {
+              constexpr int t = decltype(t_tag)::value;
+              const int e = gq * 8 + t * 2;
+              // p = exp(s/8 + bias - lse) in the log2 domain; dS = p * (dP - D) / 8
+              const float p0 = fast_exp2(fmaf(__uint_as_float(rs[e]), k1, bias8[2 * t] - lse2));
+              const float p1 = fast_exp2(fmaf(__uint_as_float(rs[e + 1]), k1, bias8[2 * t + 1] - lse2));
+              uint32_t dp0 = rd[e], dp1 = rd[e + 1];
+              uint32_t pp = pack_bf16x2(p0, p1);
+              if (DROP) {   // dropped entries: dP -> 0 (their dS is -p D / 8) and P -> 0
+                dp0 &= drop_mask32<(t & 1) * 2>(sg2[t >> 1]);
+                dp1 &= drop_mask32<(t & 1) * 2 + 1>(sg2[t >> 1]);
+                pp &= drop_mask16x2<(t & 1)>(sg2[t >> 1]);
+              }
+              const float d0 = p0 * fmaf(__uint_as_float(dp0), dp_scale, nDs);
+              const float d1 = p1 * fmaf(__uint_as_float(dp1), dp_scale, nDs);
+              wp[t] = pp;
+              wd[t] = pack_bf16x2(d0, d1);
+            };
+            pair(std::integral_constant<int, 0>{});
+            pair(std::integral_constant<int, 1>{});
+            pair(std::integral_constant<int, 2>{});
+            pair(std::integral_constant<int, 3>{});
+            const int off = ((hh * 4 + gq) ^ (row & 7)) << 4;
+            *reinterpret_cast<uint4*>(prow + off) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
+            *reinterpret_cast<uint4*>(dsrow + off) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+          }
+        }
         fence_proxy_async_smem();
         tc_fence_before();
-        named_bar_sync(1, 256);
-        if (issuer) {
-          tma_reduce_add_2d(&map_dq, sStage, h * 64, row_base + i * 128);
-          tma_reduce_add_2d(&map_dq, sStage + 16384, h * 64 + 32, row_base + i * 128);
-          tma_commit_group();
+        if (st) g_abw_timeline[g * 16 + 10] = clock64();
+        mbar_arrive(bar_p);
+
+        mbar_wait(bar_dq, g & 1);
+        tc_fence_after();
+        if (st) g_abw_timeline[g * 16 + 11] = clock64();
+        {  // dQ_g partial: my 32 fp32 columns -> swizzled staging tile -> TMA reduce-add
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + T_DQ + half * 32, r);
+          tmem_ld_wait();
+          if (g > 0) {  // the reduce-add of the previous iteration has finished reading the staging tiles
+            if (issuer) tma_wait_group_read<0>();
+            named_bar_sync(1, 256);
+          }
+          uint8_t* srow = sStage + half * 16384 + row * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(srow + ((c ^ (row & 7)) << 4)) = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+          fence_proxy_async_smem();
+          tc_fence_before();
+          named_bar_sync(1, 256);
+          if (issuer) {
+            tma_reduce_add_2d(&map_dq, sStage, h * 64, row_base + i * 128);
+            tma_reduce_add_2d(&map_dq, sStage + 16384, h * 64 + 32, row_base + i * 128);
+            tma_commit_group();
+          }
+          if (st) g_abw_timeline[g * 16 + 12] = clock64();
         }
-        if (st) g_abw_timeline[i * 16 + 12] = clock64();
       }
-    }
-    if (st0) g_abw_timeline[66] = clock64();   // query loop done
-    if (issuer) tma_wait_group<0>();
-    // dV_j, dK_j: accumulated over all query blocks; lane = key row.  Their last MMAs are issued after
-    // the dQ MMAs, so wait for the dV / dK commit of the final pair before reading the accumulators.
-    mbar_wait(bar_dvdk, (nq - 1) & 1);
-    tc_fence_after();
-    if (st0) g_abw_timeline[67] = clock64();   // last dV / dK complete
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(t_row + (which == 0 ? T_DV : T_DK) + half * 32, r);
+      if (st0 && k == 0) g_abw_timeline[66] = clock64();   // query loop of the first item done
+      // dV_j, dK_j: accumulated over all query blocks; lane = key row.  Their last MMAs are issued after
+      // the dQ MMAs, so wait for the dV / dK commit of the final iteration before reading the accumulators.
+      mbar_wait(bar_dvdk, (g - 1) & 1);
+      tc_fence_after();
+      if (st0 && k == 0) g_abw_timeline[67] = clock64();   // last dV / dK complete
+      uint32_t rv[32], rk[32];
+      tmem_ld_32x32b_x32(t_row + T_DV + half * 32, rv);
+      tmem_ld_32x32b_x32(t_row + T_DK + half * 32, rk);
       tmem_ld_wait();
-      uint4* dst = reinterpret_cast<uint4*>(dqkv + static_cast<int64_t>(row_base + j * 128 + row) * (3 * kHidden) +
-                                            (which == 0 ? 2 * kHidden : kHidden) + h * 64 + half * 32);
-      const float osc = (DROP && which == 0) ? drop_scale(drop_thr) : 1.0f;   // dV = dscale * (P o m)^T dO
+      tc_fence_before();
+      mbar_arrive(bar_accfree);   // the next item's first dV / dK MMAs may overwrite the accumulators
+      // bf16 through a staging tile so that one store instruction covers 8 rows x 64 contiguous bytes instead of
+      // 32 rows x 16 bytes.  The P tile is free here (its last reader, the final dV MMA, has completed), unlike the dQ
+      // staging tiles, which the last TMA reduce-add may still be reading.
+      uint8_t* stg = sP + warp * 4096;   // [dV | dK][32 rows][64 B], 16-byte chunks XOR-swizzled with (row >> 1) & 3
+      const float osc = DROP ? drop_scale(drop_thr) : 1.0f;   // dV = dscale * (P o m)^T dO
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint32_t w[4];
+      for (int c = 0; c < 4; ++c) {
+        uint32_t wv[4], wk[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t)
-          w[t] = pack_bf16x2(__uint_as_float(r[g * 8 + 2 * t]) * osc, __uint_as_float(r[g * 8 + 2 * t + 1]) * osc);
-        dst[g] = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int t = 0; t < 4; ++t) {
+          wv[t] = pack_bf16x2(__uint_as_float(rv[c * 8 + 2 * t]) * osc, __uint_as_float(rv[c * 8 + 2 * t + 1]) * osc);
+          wk[t] = pack_bf16x2(__uint_as_float(rk[c * 8 + 2 * t]), __uint_as_float(rk[c * 8 + 2 * t + 1]));
+        }
+        const int off = lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4);
+        *reinterpret_cast<uint4*>(stg + off) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        *reinterpret_cast<uint4*>(stg + 2048 + off) = make_uint4(wk[0], wk[1], wk[2], wk[3]);
       }
+      __syncwarp();
+      __nv_bfloat16* dst0 = dqkv + static_cast<int64_t>(row_base + j * 128 + q * 32) * (3 * kHidden) + h * 64 + half * 32;
+#pragma unroll
+      for (int which = 0; which < 2; ++which)
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+          const int rr = ii * 8 + (lane >> 2), c = lane & 3;
+          const uint4 v = *reinterpret_cast<const uint4*>(stg + which * 2048 + rr * 64 + ((c ^ ((rr >> 1) & 3)) << 4));
+          *reinterpret_cast<uint4*>(dst0 + static_cast<int64_t>(rr) * (3 * kHidden) + (which == 0 ? 2 * kHidden : kHidden) + c * 8) = v;
+        }
+      // the next item's first P / dS pass overwrites this tile: every warp must have finished reading its own part
+      named_bar_sync(1, 256);
+      if (st0 && k == 0) g_abw_timeline[68] = clock64();     // dK / dV stored
     }
+    if (issuer) tma_wait_group<0>();
   }
 
-  if (st0) g_abw_timeline[68] = clock64();     // dK / dV stored
   tc_fence_before();
   __syncthreads();
   if (warp == 8) {
@@ -402,9 +478,10 @@ static int attn_bwd_impl(int device, void* stream_, const void* qkv, const float
   }
   auto go = [&](auto kern) -> int {
     STK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ABW_SMEM));
-    kern<<<dim3(S / 128, kHeads, B), ABW_THREADS, ABW_SMEM, stream>>>(map_qkv, map_do, map_dq, key_bias, lse, Dws, S,
-                                                                     static_cast<__nv_bfloat16*>(dqkv), drop_seed, drop_site,
-                                                                     drop_thr);
+    const int num_items = (S / 128) * kHeads * B;
+    const int grid = num_items < num_sms(device) ? num_items : num_sms(device);
+    kern<<<grid, ABW_THREADS, ABW_SMEM, stream>>>(map_qkv, map_do, map_dq, key_bias, lse, Dws, S, num_items,
+                                                  static_cast<__nv_bfloat16*>(dqkv), drop_seed, drop_site, drop_thr);
     return STK_OK;
   };
   if (drop) rc = go(attn_bwd_kernel<0, true>);
