@@ -284,6 +284,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     };
     stage_bias(0);
     named_bar_sync(1, 256);
+    // row statistics (log-sum-exp, D) of the NEXT iteration are fetched one iteration ahead: their global-load latency
+    // would otherwise sit between the score load and the first exponential of every iteration
+    auto stat_index = [&](int k, int i) -> int64_t {
+      int j, h, b;
+      decode(static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x), j, h, b);
+      return (static_cast<int64_t>(b) * kHeads + h) * S + i * 128 + row;
+    };
+    float nxt_lse = 0.f, nxt_D = 0.f;
+    if (my_items > 0) {
+      const int64_t si0 = stat_index(0, 0);
+      nxt_lse = __ldg(lse + si0);
+      nxt_D = __ldg(Dws + si0);
+    }
 
     for (int k = 0; k < my_items; ++k) {
       int j, h, b;
@@ -294,8 +307,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       stage_bias(k + 1);   // consumed after this item's named barriers
 
       for (int i = 0; i < nq; ++i, ++g) {
-        const float row_lse = __ldg(lse + stat_base + i * 128 + row);
-        const float row_D = __ldg(Dws + stat_base + i * 128 + row);
+        const float row_lse = nxt_lse, row_D = nxt_D;
+        {
+          const bool more_i = i + 1 < nq;
+          if (more_i || k + 1 < my_items) {
+            const int64_t sn = more_i ? stat_base + (i + 1) * 128 + row : stat_index(k + 1, 0);
+            nxt_lse = __ldg(lse + sn);
+            nxt_D = __ldg(Dws + sn);
+          }
+        }
         const bool st = (DBG & 64) && blockIdx.x == 0 && threadIdx.x == 0 && g < 4;
         if (st) g_abw_timeline[g * 16 + 8] = clock64();
         mbar_wait(bar_s, g & 1);

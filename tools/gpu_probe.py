@@ -454,6 +454,26 @@ def case_attn():
     ref, lref = _attn_ref(qkv, bias, B, S)
     res.append(_err_report(out, ref, "attn_fwd_general_bias", 2e-2))
     res.append(_err_report(lse, lref, "attn_lse_general_bias", 2e-3))
+    # persistent paths: several items per CTA (forward: 296 CTAs, backward: 148), ragged padding masks, so that the
+    # item-boundary hand-overs (deferred output, prefetched Q / K / V / bias, flat barrier parities) are exercised
+    for (B, S) in [(17, 512), (41, 256), (30, 128), (11, 384)]:
+        qkv = _mk(B * S, 2304, "cuda", 1.0)
+        m = torch.ones(B, S, dtype=torch.long, device="cuda")
+        lens = torch.randint(3, S // 2 + 1, (B,), device="cuda")
+        m[:, : S // 2] = (torch.arange(S // 2, device="cuda")[None, :] < lens[:, None]).long()
+        m[0] = 1                                          # one element without any masked key
+        bias = ops.mask_to_bias(m)
+        out, lse = ops.attention(qkv, bias, B, S, save_lse=True)
+        ref, lref = _attn_ref(qkv, bias, B, S)
+        res.append(_err_report(out, ref, f"attn_fwd_multi_item_B{B}_S{S}", 2e-2))
+        res.append(_err_report(lse, lref, f"attn_lse_multi_item_B{B}_S{S}", 2e-3))
+        dout = _mk(B * S, 768, "cuda", 1.0)
+        dqkv = ops.attention_bwd(qkv, bias, B, S, out, dout, lse)
+        gref = _attn_bwd_ref(qkv, bias, B, S, dout)
+        res.append(_err_report(dqkv, gref, f"attn_bwd_multi_item_B{B}_S{S}", 0.03 * gref.abs().max().item()))
+        # determinism across launches (no race between items)
+        out2, lse2 = ops.attention(qkv, bias, B, S, save_lse=True)
+        res.append({"case": f"attn_fwd_deterministic_B{B}_S{S}", "ok": bool(torch.equal(out, out2) and torch.equal(lse, lse2))})
     # large, growing scores: later key blocks dominate -> exercises the lazy O rescale in TMEM
     B, S = 2, 512
     qkv = _mk(B * S, 2304, "cuda", 1.0)
