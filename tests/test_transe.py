@@ -160,6 +160,17 @@ def test_transe_forward_backward_on_gpu():
     nolab = dict(batch, ent_masked_lm_labels=torch.full((B, 4), -100))
     with torch.no_grad():
         assert torch.isnan(model(**nolab)[0]).item()
+    # train() mode (dropout on the padded 384-row layout): finite loss, gradients flow, eval numerics with dropout off
+    model.train()
+    model.zero_grad(set_to_none=True)
+    l1 = model(**batch)[0]
+    l1.backward()
+    torch.cuda.synchronize()
+    assert torch.isfinite(l1).item() and abs(l1.item() - loss.item()) > 1e-4
+    assert all(torch.isfinite(p.grad).all().item() for p in model.parameters() if p.grad is not None)
+    model.stk_dropout = False
+    np.testing.assert_allclose(model(**batch)[0].item(), float(fix["loss"]), rtol=2e-3)
+    model.eval()
     # wrong width is refused loudly
     from stonkgs_b200._lib import StkError
     with pytest.raises(StkError):
