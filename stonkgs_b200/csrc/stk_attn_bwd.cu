@@ -13,7 +13,7 @@
 //   warps 0-7  two threads per query row: read S and dP from TMEM, form P and dS in registers, write
 //              both as bf16 into 128B-swizzled shared tiles that serve BOTH as K-major A operand
 //              (dQ = dS K) and as MN-major A operand (dV = P^T dO, dK = dS^T Q) — no transposes.
-// TMEM columns: S [0,128) | dP [128,256) | dV [256,320) | dK [320,384) | dQ [384,448).
+// TMEM columns: S [0,128) | dP [128,256) | dV [256,320) | dK [320,384) | dQ (two accumulators) [384,512).
 // dK/dV accumulate in TMEM across the query loop and are written once as bf16 into dQKV;
 // dQ_i partial products go out as fp32 TMA reduce-adds into a workspace (summed over the key
 // blocks in L2) and are converted to bf16 by a small tail kernel.
@@ -109,7 +109,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
   uint64_t* bar_dvdk = bars + 8;   // dV / dK MMAs of iteration g have completed: the P / dS tiles may be rewritten
   uint64_t* bar_kvfree = bars + 9; // the item's last dQ MMA has read K (V was last read by its last dP): K / V reusable
   uint64_t* bar_accfree = bars + 10;  // the compute warps have read the item's dV / dK accumulators out of TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* bar_sread = bars + 11;    // every compute thread holds S_g / dP_g in registers: their TMEM columns are free
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nq = S >> 7;           // query blocks per item == key blocks per (head, batch)
@@ -132,6 +133,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       mbar_init(bar_dvdk, 1);
       mbar_init(bar_kvfree, 1);
       mbar_init(bar_accfree, 256);
+      mbar_init(bar_sread, 256);
       fence_barrier_init();
     }
     __syncwarp();
@@ -227,24 +229,29 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       const uint64_t boff = static_cast<uint64_t>((g & 1) * (16384 >> 4));
       const bool last = i == nq - 1;
       stamp(g, 1);
-      mbar_wait(bar_p, g & 1);           // P_g, dS_g are in smem; S_g / dP_g columns have been read
+      // Inside an item the next scores are issued as soon as the compute warps have S_g / dP_g in registers, i.e. in
+      // the middle of their P / dS pass: S_{g+1} / dP_{g+1} are then ready when that pass ends.  At the end of an item
+      // they follow dV / dK instead: the item's epilogue waits for those, and the next item's K / V are still in flight.
+      if (!last && g + 1 < total) {
+        mbar_wait(bar_sread, g & 1);
+        tc_fence_after();
+        issue_scores();
+      }
+      mbar_wait(bar_p, g & 1);           // P_g, dS_g are in smem
       tc_fence_after();
       stamp(g, 2);
       {
-        // dQ_g first: the compute warps are waiting for it (they drain it while dV / dK run)
+        // dQ_g first, into accumulator g & 1: the compute warps drain it one iteration later, behind their next P / dS
+        // pass (the other accumulator was drained before P_g was handed over, so no extra barrier is needed)
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_bf16_warp(tmem_u + T_DQ, ds_desc + kb * (16384 >> 4) + 2 * kk, kT_desc + kb * (8192 >> 4) + kk * 128, idesc_q,
-                      (kb | kk) > 0);
+            umma_bf16_warp(tmem_u + T_DQ + (g & 1) * 64, ds_desc + kb * (16384 >> 4) + 2 * kk, kT_desc + kb * (8192 >> 4) + kk * 128,
+                      idesc_q, (kb | kk) > 0);
         umma_commit_warp(bar_dq);
         if (last) umma_commit_warp(bar_kvfree);   // every MMA that reads this item's K / V has been issued above
       }
-      // inside an item the next scores come next (the compute warps need them right after draining dQ_g) and
-      // dV / dK of this iteration last: nobody waits for them until the P / dS tiles are rewritten.  At the end of an
-      // item the order is reversed: the item's epilogue waits for dV / dK, and the next item's K / V are still in flight.
-      if (!last && g + 1 < total) issue_scores();
       {
         if (i == 0 && k > 0) {   // the previous item's accumulators must have left TMEM before they are overwritten
           mbar_wait(bar_accfree, (k - 1) & 1);
@@ -291,6 +298,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       decode(static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x), j, h, b);
       return (static_cast<int64_t>(b) * kHeads + h) * S + i * 128 + row;
     };
+    // dQ partial of iteration gd (accumulator gd & 1): my 32 fp32 columns -> swizzled staging tile -> TMA reduce-add into
+    // the fp32 workspace at (row0, col0) of that iteration.  Requires bar_dq phase gd to have been waited for.
+    int pd_col = 0, pd_row = 0;
+    int n_drained = 0;
+    auto drain_dq = [&](int gd, int col0, int row0) {
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_row + T_DQ + (gd & 1) * 64 + half * 32, r);
+      tmem_ld_wait();
+      if (n_drained > 0) {  // the previous reduce-add has finished reading the staging tiles
+        if (issuer) tma_wait_group_read<0>();
+        named_bar_sync(1, 256);
+      }
+      uint8_t* srow = sStage + half * 16384 + row * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(srow + ((c ^ (row & 7)) << 4)) = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      named_bar_sync(1, 256);
+      if (issuer) {
+        tma_reduce_add_2d(&map_dq, sStage, col0, row0);
+        tma_reduce_add_2d(&map_dq, sStage + 16384, col0 + 32, row0);
+        tma_commit_group();
+      }
+      ++n_drained;
+    };
     float nxt_lse = 0.f, nxt_D = 0.f;
     if (my_items > 0) {
       const int64_t si0 = stat_index(0, 0);
@@ -335,6 +369,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
           tmem_ld_32x32b_x32(t_row + T_S + half * 64 + hh * 32, rs);
           tmem_ld_32x32b_x32(t_row + T_DP + half * 64 + hh * 32, rd);
           tmem_ld_wait();
+          if (hh == 1) {            // S_g / dP_g are in registers: the next scores may overwrite their TMEM columns
+            tc_fence_before();
+            mbar_arrive(bar_sread);
+          }
           if (hh == 0 && g > 0) {   // dV / dK of the previous iteration have finished reading the P / dS tiles
             mbar_wait(bar_dvdk, (g - 1) & 1);
           }
@@ -383,33 +421,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
         fence_proxy_async_smem();
         tc_fence_before();
         if (st) g_abw_timeline[g * 16 + 10] = clock64();
+        // dQ_{g-1} completed long ago; the wait must come BEFORE this thread hands over P_g: afterwards dQ_g could
+        // complete too and the barrier would be a whole phase ahead of a late waiter
+        if (g > 0) mbar_wait(bar_dq, (g - 1) & 1);
         mbar_arrive(bar_p);
-
-        mbar_wait(bar_dq, g & 1);
-        tc_fence_after();
-        if (st) g_abw_timeline[g * 16 + 11] = clock64();
-        {  // dQ_g partial: my 32 fp32 columns -> swizzled staging tile -> TMA reduce-add
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(t_row + T_DQ + half * 32, r);
-          tmem_ld_wait();
-          if (g > 0) {  // the reduce-add of the previous iteration has finished reading the staging tiles
-            if (issuer) tma_wait_group_read<0>();
-            named_bar_sync(1, 256);
-          }
-          uint8_t* srow = sStage + half * 16384 + row * 128;
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<uint4*>(srow + ((c ^ (row & 7)) << 4)) = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
-          fence_proxy_async_smem();
-          tc_fence_before();
-          named_bar_sync(1, 256);
-          if (issuer) {
-            tma_reduce_add_2d(&map_dq, sStage, h * 64, row_base + i * 128);
-            tma_reduce_add_2d(&map_dq, sStage + 16384, h * 64 + 32, row_base + i * 128);
-            tma_commit_group();
-          }
-          if (st) g_abw_timeline[g * 16 + 12] = clock64();
-        }
+        // the previous iteration's dQ partial leaves TMEM while the tensor core runs dQ_g and the next scores
+        if (g > 0) drain_dq(g - 1, pd_col, pd_row);
+        pd_col = h * 64;
+        pd_row = row_base + i * 128;
+        if (st) g_abw_timeline[g * 16 + 12] = clock64();
       }
       if (st0 && k == 0) g_abw_timeline[66] = clock64();   // query loop of the first item done
       // dV_j, dK_j: accumulated over all query blocks; lane = key row.  Their last MMAs are issued after
@@ -453,6 +473,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       // the next item's first P / dS pass overwrites this tile: every warp must have finished reading its own part
       named_bar_sync(1, 256);
       if (st0 && k == 0) g_abw_timeline[68] = clock64();     // dK / dV stored
+    }
+    if (g > 0) {   // the last iteration's dQ partial
+      mbar_wait(bar_dq, (g - 1) & 1);
+      drain_dq(g - 1, pd_col, pd_row);
     }
     if (issuer) tma_wait_group<0>();
   }
