@@ -303,13 +303,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     int pd_col = 0, pd_row = 0;
     int n_drained = 0;
     auto drain_dq = [&](int gd, int col0, int row0) {
+      // every warp stages and ships its own 32 x 32 slice (one 4 KB, 1024-aligned piece of the swizzled staging tile,
+      // TMA box of 32 rows): no CTA-wide barrier in the drain
       tc_fence_after();
       uint32_t r[32];
       tmem_ld_32x32b_x32(t_row + T_DQ + (gd & 1) * 64 + half * 32, r);
       tmem_ld_wait();
-      if (n_drained > 0) {  // the previous reduce-add has finished reading the staging tiles
-        if (issuer) tma_wait_group_read<0>();
-        named_bar_sync(1, 256);
+      if (n_drained > 0) {  // this warp's previous reduce-add has finished reading its staging slice
+        if (lane == 0) tma_wait_group_read<0>();
+        __syncwarp();
       }
       uint8_t* srow = sStage + half * 16384 + row * 128;
 #pragma unroll
@@ -317,10 +319,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
         *reinterpret_cast<uint4*>(srow + ((c ^ (row & 7)) << 4)) = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
       fence_proxy_async_smem();
       tc_fence_before();
-      named_bar_sync(1, 256);
-      if (issuer) {
-        tma_reduce_add_2d(&map_dq, sStage, col0, row0);
-        tma_reduce_add_2d(&map_dq, sStage + 16384, col0 + 32, row0);
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_2d(&map_dq, sStage + half * 16384 + q * 4096, col0 + half * 32, row0 + q * 32);
         tma_commit_group();
       }
       ++n_drained;
@@ -478,7 +479,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       mbar_wait(bar_dq, (g - 1) & 1);
       drain_dq(g - 1, pd_col, pd_row);
     }
-    if (issuer) tma_wait_group<0>();
+    if (lane == 0) tma_wait_group<0>();
   }
 
   tc_fence_before();
@@ -509,7 +510,7 @@ static int attn_bwd_impl(int device, void* stream_, const void* qkv, const float
   if (rc) return rc;
   rc = make_tmap_2d(&map_do, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dout, kHidden, rows, kHidden * 2, 64, 128);
   if (rc) return rc;
-  rc = make_tmap_2d(&map_dq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dq_acc, kHidden, rows, kHidden * 4, 32, 128);
+  rc = make_tmap_2d(&map_dq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dq_acc, kHidden, rows, kHidden * 4, 32, 32);
   if (rc) return rc;
   STK_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, sizeof(float) * rows * kHidden, stream));
   attn_bwd_prep_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
