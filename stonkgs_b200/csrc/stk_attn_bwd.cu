@@ -32,7 +32,8 @@ extern std::atomic<long long> g_launches;
 __device__ long long g_abw_timeline[2048];   // bring-up only (STK_ATTN_DEBUG=64): clock64 stamps of CTA 0
 constexpr int ABW_THREADS = 320;   // 8 compute warps + TMA warp + MMA warp
 constexpr float kL2e = 1.4426950408889634f;
-constexpr int ABW_SMEM = 1024 + 16384 * 2 + 32768 * 5 + 1024 + 128;
+constexpr int ABW_QSTAGES = 3;     // Q / dO ring depth
+constexpr int ABW_SMEM = 1024 + 16384 * 2 + 16384 * 2 * ABW_QSTAGES + 32768 * 3 + 1024 + 128;   // 231 552 B of the 232 448 available
 
 // D[b,h,s] = sum_d dO * O : one warp per token row, 16-lane groups own one head
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o,
@@ -93,24 +94,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
   uint8_t* sV = smem + 16384;
-  uint8_t* sQ = smem + 32768;    // [2][16 KB]
-  uint8_t* sdO = smem + 65536;   // [2][16 KB]
-  uint8_t* sP = smem + 98304;    // [2 key chunks][128 q][128 B]
-  uint8_t* sdS = smem + 131072;
-  uint8_t* sStage = smem + 163840;   // fp32 dQ staging: 2 x [128 rows][32 fp32] for the TMA reduce-add; dK / dV staging
-  float* sBias = reinterpret_cast<float*>(smem + 196608);   // [2 item parity][128]
+  uint8_t* sQ = smem + 32768;    // [3][16 KB]  Q / dO ring of three: a TMA load under load takes 2.5-3 k cycles, most of an
+  uint8_t* sdO = smem + 81920;   // [3][16 KB]  iteration, and the next scores are wanted in the middle of the current pass
+  uint8_t* sP = smem + 131072;   // [2 key chunks][128 q][128 B]
+  uint8_t* sdS = smem + 163840;
+  uint8_t* sStage = smem + 196608;   // fp32 dQ staging: 2 x [128 rows][32 fp32] for the TMA reduce-adds
+  float* sBias = reinterpret_cast<float*>(smem + 229376);   // [2 item parity][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 256);
   uint64_t* bar_kv = bars;
-  uint64_t* bar_q = bars + 1;  // [2]
-  uint64_t* bar_s = bars + 3;
-  uint64_t* bar_p = bars + 4;
-  uint64_t* bar_dq = bars + 5;
-  uint64_t* bar_qfree = bars + 6;  // [2] Q_g / dO_g buffer released (only the TMA warp waits on these)
-  uint64_t* bar_dvdk = bars + 8;   // dV / dK MMAs of iteration g have completed: the P / dS tiles may be rewritten
-  uint64_t* bar_kvfree = bars + 9; // the item's last dQ MMA has read K (V was last read by its last dP): K / V reusable
-  uint64_t* bar_accfree = bars + 10;  // the compute warps have read the item's dV / dK accumulators out of TMEM
-  uint64_t* bar_sread = bars + 11;    // every compute thread holds S_g / dP_g in registers: their TMEM columns are free
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* bar_q = bars + 1;  // [3]
+  uint64_t* bar_s = bars + 4;
+  uint64_t* bar_p = bars + 5;
+  uint64_t* bar_dq = bars + 6;
+  uint64_t* bar_qfree = bars + 7;  // [3] Q_g / dO_g buffer released (only the TMA warp waits on these)
+  uint64_t* bar_dvdk = bars + 10;  // dV / dK MMAs of iteration g have completed: the P / dS tiles may be rewritten
+  uint64_t* bar_kvfree = bars + 11; // the item's last dQ MMA has read K (V was last read by its last dP): K / V reusable
+  uint64_t* bar_accfree = bars + 12;  // the compute warps have read the item's dV / dK accumulators out of TMEM
+  uint64_t* bar_sread = bars + 13;    // every compute thread holds S_g / dP_g in registers: their TMEM columns are free
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nq = S >> 7;           // query blocks per item == key blocks per (head, batch)
@@ -123,13 +124,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       tma_prefetch_desc(&map_do);
       tma_prefetch_desc(&map_dq);
       mbar_init(bar_kv, 1);
-      mbar_init(bar_q, 1);
-      mbar_init(bar_q + 1, 1);
+      for (int r = 0; r < ABW_QSTAGES; ++r) { mbar_init(bar_q + r, 1); mbar_init(bar_qfree + r, 1); }
       mbar_init(bar_s, 1);
       mbar_init(bar_p, 256);
       mbar_init(bar_dq, 1);
-      mbar_init(bar_qfree, 1);
-      mbar_init(bar_qfree + 1, 1);
       mbar_init(bar_dvdk, 1);
       mbar_init(bar_kvfree, 1);
       mbar_init(bar_accfree, 256);
@@ -164,9 +162,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
       decode(static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x), j, h, b);
       const int row_base = b * S;
       for (int i = 0; i < nq; ++i, ++g) {
-        const int nb = g & 1;
-        // buffer g & 1 was last read by the dV / dK MMAs of iteration g - 2 (its ((g - 2) / 2)-th use)
-        if (g >= 2) mbar_wait(bar_qfree + nb, ((g - 2) >> 1) & 1);
+        const int nb = g % ABW_QSTAGES;
+        // the ring slot was last read by the dV / dK MMAs of iteration g - 3 (its (g / 3 - 1)-th use)
+        if (g >= ABW_QSTAGES) mbar_wait(bar_qfree + nb, ((g / ABW_QSTAGES) - 1) & 1);
         if (leader) {
           mbar_arrive_expect_tx(bar_q + nb, 32768);
           tma_load_2d(&map_qkv, bar_q + nb, sQ + nb * 16384, h * 64, row_base + i * 128);
@@ -205,9 +203,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     const int total = my_items * nq;
     int sg = 0, si = 0, sk = 0;   // next scores to issue: flat iteration, iteration within its item, item
     auto issue_scores = [&]() {   // S = Q K_j^T and dP = dO V_j^T of iteration sg into their TMEM columns
-      const uint64_t boff = static_cast<uint64_t>((sg & 1) * (16384 >> 4));
+      const uint64_t boff = static_cast<uint64_t>((sg % ABW_QSTAGES) * (16384 >> 4));
       if (si == 0) mbar_wait(bar_kv, sk & 1);          // first iteration of an item: its K / V
-      mbar_wait(bar_q + (sg & 1), (sg >> 1) & 1);
+      mbar_wait(bar_q + (sg % ABW_QSTAGES), (sg / ABW_QSTAGES) & 1);
       tc_fence_after();
       {
 #pragma unroll
@@ -226,7 +224,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     if (total > 0) issue_scores();
     int i = 0, k = 0;
     for (int g = 0; g < total; ++g) {
-      const uint64_t boff = static_cast<uint64_t>((g & 1) * (16384 >> 4));
+      const uint64_t boff = static_cast<uint64_t>((g % ABW_QSTAGES) * (16384 >> 4));
       const bool last = i == nq - 1;
       stamp(g, 1);
       // Inside an item the next scores are issued as soon as the compute warps have S_g / dP_g in registers, i.e. in
@@ -265,7 +263,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
 #pragma unroll
         for (int kk = 1; kk < 8; ++kk) umma_bf16_warp(tmem_u + T_DK, dsT_desc + kk * 128, qT_desc0 + boff + kk * 128, idesc_t, 1u);
         umma_commit_warp(bar_dvdk);              // P / dS tiles reusable
-        umma_commit_warp(bar_qfree + (g & 1));   // Q_g / dO_g buffer reusable once everything above has completed
+        umma_commit_warp(bar_qfree + (g % ABW_QSTAGES));   // Q_g / dO_g slot reusable once everything above has completed
       }
       if (last && g + 1 < total) issue_scores();
       stamp(g, 3);
@@ -364,19 +362,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
         const uint32_t drop_key = DROP ? drop_row_key(drop_seed, drop_site, static_cast<uint32_t>(stat_base + i * 128 + row)) : 0u;
         const float dp_scale = DROP ? scale * drop_scale(drop_thr) : scale;   // dP / 8, times 1 / (1 - p_drop) with dropout
         const uint32_t thr4 = drop_thr4(drop_thr);
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {   // 32 key columns at a time: S and dP loaded together
-          uint32_t rs[32], rd[32];
-          tmem_ld_32x32b_x32(t_row + T_S + half * 64 + hh * 32, rs);
-          tmem_ld_32x32b_x32(t_row + T_DP + half * 64 + hh * 32, rd);
-          tmem_ld_wait();
-          if (hh == 1) {            // S_g / dP_g are in registers: the next scores may overwrite their TMEM columns
-            tc_fence_before();
-            mbar_arrive(bar_sread);
-          }
-          if (hh == 0 && g > 0) {   // dV / dK of the previous iteration have finished reading the P / dS tiles
-            mbar_wait(bar_dvdk, (g - 1) & 1);
-          }
+        // The score / dP loads of the second 32-column half are in flight while the first half is processed (a thread
+        // has two warps per scheduler to hide the TMEM round trip behind, so it is software-pipelined instead).
+        uint32_t rs0[32], rd0[32], rs1[32], rd1[32];
+        tmem_ld_32x32b_x32(t_row + T_S + half * 64, rs0);
+        tmem_ld_32x32b_x32(t_row + T_DP + half * 64, rd0);
+        tmem_ld_wait();
+        tmem_ld_32x32b_x32(t_row + T_S + half * 64 + 32, rs1);
+        tmem_ld_32x32b_x32(t_row + T_DP + half * 64 + 32, rd1);
+        if (g > 0) {   // dV / dK of the previous iteration have finished reading the P / dS tiles
+          mbar_wait(bar_dvdk, (g - 1) & 1);
+        }
+        auto half_pass = [&](auto hh_tag, const uint32_t (&rs)[32], const uint32_t (&rd)[32]) {
+          constexpr int hh = decltype(hh_tag)::value;
           const float4* bz = reinterpret_cast<const float4*>(bias_k + half * 64 + hh * 32);
 #pragma unroll
           for (int gq = 0; gq < 4; ++gq) {
@@ -418,10 +416,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
             *reinterpret_cast<uint4*>(prow + off) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
             *reinterpret_cast<uint4*>(dsrow + off) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
           }
-        }
+        };
+        half_pass(std::integral_constant<int, 0>{}, rs0, rd0);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(bar_sread);   // S_g / dP_g are in registers: the next scores may overwrite their TMEM columns
+        half_pass(std::integral_constant<int, 1>{}, rs1, rd1);
         fence_proxy_async_smem();
         tc_fence_before();
         if (st) g_abw_timeline[g * 16 + 10] = clock64();
+        if ((DBG & 64) && blockIdx.x == 0 && g < 4 && lane == 0 && warp > 0) g_abw_timeline[128 + g * 8 + warp] = clock64();
         // dQ_{g-1} completed long ago; the wait must come BEFORE this thread hands over P_g: afterwards dQ_g could
         // complete too and the barrier would be a whole phase ahead of a late waiter
         if (g > 0) mbar_wait(bar_dq, (g - 1) & 1);

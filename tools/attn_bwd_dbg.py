@@ -23,3 +23,5 @@ if int(os.environ.get("STK_ATTN_DEBUG", "0")) & 64:
     for i in range(4):
         print(i, " ".join(f"{n}={buf[i * 16 + k] - t0}" for k, n in names.items()))
     print("cta: entry=%d prologue_done=%d loop_done=%d dvdk_done=%d stored=%d exit=%d" % tuple(buf[64 + k] - t0 for k in range(6)))
+    for g in range(4):
+        print("PdS_written per warp 1..7, iteration", g, [buf[128 + g * 8 + w] - t0 for w in range(1, 8)])
