@@ -97,6 +97,12 @@ int stk_layernorm_fwd(int device, void* stream, const void* x_bf16, int M, const
 /* dx: bf16 [M,768]; dgamma/dbeta: fp32 [768], accumulated (+=).  x is the forward INPUT. */
 int stk_layernorm_bwd(int device, void* stream, const void* dy_bf16, const void* x_bf16, int M, const float* gamma,
                       const float* mean, const float* rstd, void* dx_bf16, float* dgamma, float* dbeta);
+/* The same, fused with what follows it in the backward of BertSelfOutput / BertOutput (HF:294-298, 352-356): dxm (bf16,
+ * NULL when thr == 0) = dx through the dropout mask of the dense output (seed, site, thr as in stk_dropout_fwd) and
+ * dbias (fp32 [768], may be NULL) += column sums of dxm (of dx when thr == 0), i.e. the dense layer's bias gradient. */
+int stk_layernorm_bwd_fused(int device, void* stream, const void* dy_bf16, const void* x_bf16, int M, const float* gamma,
+                            const float* mean, const float* rstd, void* dx_bf16, float* dgamma, float* dbeta,
+                            void* dxm_bf16, float* dbias, uint32_t seed, uint32_t site, uint32_t thr);
 
 /* ------------------------------------------------------------------------------------------------
  * tcgen05 GEMM:  C[M,N] = epilogue( A[M,K] * B[N,K]^T )      (bf16 in, fp32 accumulate in TMEM)

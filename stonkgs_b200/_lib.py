@@ -65,6 +65,7 @@ _SIGNATURES = {
                                              _P, _P, _P, _P, _P]),
     "stk_layernorm_fwd": (c_int, [c_int, _P, _P, c_int, _P, _P, _P, _P, _P]),
     "stk_layernorm_bwd": (c_int, [c_int, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P]),
+    "stk_layernorm_bwd_fused": (c_int, [c_int, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_uint32, c_uint32, c_uint32]),
     "stk_gemm": (c_int, [c_int, _P, c_int, c_int, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int64,
                          POINTER(GemmEpilogue), c_int]),
     "stk_attn_fwd": (c_int, [c_int, _P, _P, _P, c_int, c_int, _P, _P]),

@@ -13,6 +13,7 @@
 
 #include "stk_common.cuh"
 #include "stk_host.h"
+#include "stk_rng.cuh"
 
 namespace stk {
 
@@ -266,16 +267,21 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16*
 }
 
 // grid-stride over rows; per-warp register accumulators for dgamma/dbeta, block reduce, atomics out
+template <bool FUSED>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_in, const __nv_bfloat16* __restrict__ x_in, int M,
                      const float* __restrict__ gamma, const float* __restrict__ mean_in,
                      const float* __restrict__ rstd_in, __nv_bfloat16* __restrict__ dx_out, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta) {
+                     float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dxm_out, float* __restrict__ dbias,
+                     uint32_t seed, uint32_t site, uint32_t thr) {
   __shared__ float red[kRowWarps][kHidden];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float g[kPerLane];
   load_f32_row(gamma, lane, g);
   float dg[kPerLane] = {}, db[kPerLane] = {};
+  float dbs[FUSED ? kPerLane : 1] = {};
+  const uint32_t thr4 = drop_thr4(thr);
+  const float dscale = drop_scale(thr);
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * kRowWarps + warp; row < M;
        row += static_cast<int64_t>(gridDim.x) * kRowWarps) {
     float dy[kPerLane], x[kPerLane];
@@ -283,6 +289,27 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_in, const __nv_bfloat1
     load_bf16_row(x_in + row * kHidden, lane, x);
     ln_row_bwd(dy, x, g, __ldg(mean_in + row), __ldg(rstd_in + row), dg, db);
     store_bf16_row(dx_out + row * kHidden, lane, dy);
+    if (FUSED) {
+      // what the dense layer before this LayerNorm sees: the gradient through its dropout mask (the residual branch
+      // takes dx as it is), plus that layer's bias gradient = column sum of the same rows
+      if (dxm_out) {
+        const uint32_t row_key = drop_row_key(seed, site, static_cast<uint32_t>(row));
+#pragma unroll
+        for (int i = 0; i < kChunks; ++i) {
+          const uint32_t chunk = static_cast<uint32_t>(lane + 32 * i);   // columns 4*chunk .. 4*chunk + 3
+          uint32_t w0, w1;
+          drop_words(row_key, chunk >> 1, w0, w1);
+          const uint32_t signs = drop_signs((chunk & 1u) ? w1 : w0, thr4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) dy[4 * i + k] = drop_keep(signs, k) ? dy[4 * i + k] * dscale : 0.f;
+        }
+        store_bf16_row(dxm_out + row * kHidden, lane, dy);
+      }
+      if (dbias) {
+#pragma unroll
+        for (int i = 0; i < kPerLane; ++i) dbs[i] += dy[i];
+      }
+    }
   }
   auto reduce_out = [&](float (&acc)[kPerLane], float* dst) {
     __syncthreads();
@@ -300,6 +327,9 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy_in, const __nv_bfloat1
   };
   reduce_out(dg, dgamma);
   reduce_out(db, dbeta);
+  if constexpr (FUSED) {
+    if (dbias) reduce_out(dbs, dbias);
+  }
 }
 
 }  // namespace stk
@@ -404,8 +434,24 @@ extern "C" int stk_layernorm_bwd(int device, void* stream, const void* dy, const
   int grid = (M + kRowWarps - 1) / kRowWarps;
   const int cap = num_sms(device) * 4;
   if (grid > cap) grid = cap;
-  layernorm_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  layernorm_bwd_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), M, gamma, mean, rstd,
-      static_cast<__nv_bfloat16*>(dx), dgamma, dbeta);
+      static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, nullptr, nullptr, 0u, 0u, 0u);
+  STK_LAUNCHED();
+}
+
+extern "C" int stk_layernorm_bwd_fused(int device, void* stream, const void* dy, const void* x, int M, const float* gamma,
+                                       const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
+                                       void* dxm, float* dbias, uint32_t seed, uint32_t site, uint32_t thr) {
+  STK_REQUIRE(M > 0 && dy && x && gamma && mean && rstd && dx && dgamma && dbeta, "stk_layernorm_bwd_fused: bad arguments");
+  STK_REQUIRE(thr < 128 && (dxm != nullptr || thr == 0), "stk_layernorm_bwd_fused: dropout needs the dxm output and thr < 128");
+  STK_CHECK_CUDA(cudaSetDevice(device));
+  int grid = (M + kRowWarps - 1) / kRowWarps;
+  const int cap = num_sms(device) * 4;
+  if (grid > cap) grid = cap;
+  layernorm_bwd_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), M, gamma, mean, rstd,
+      static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, thr > 0 ? static_cast<__nv_bfloat16*>(dxm) : nullptr, dbias, seed, site,
+      thr);
   STK_LAUNCHED();
 }

@@ -169,14 +169,23 @@ def layernorm(x: torch.Tensor, gamma, beta, save_stats=False, out=None):
     return (y, mean, rstd) if save_stats else y
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, out=None):
-    """dgamma/dbeta are accumulated into. Returns dx (bf16)."""
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, out=None, dbias=None, drop: Optional["Drop"] = None):
+    """dgamma/dbeta are accumulated into. Returns dx (bf16); with ``dbias`` / ``drop`` the fused form: the column sums
+    of the (masked) result are accumulated into ``dbias`` and, with dropout, ``(dx, dx through the mask)`` is returned."""
     M = x.shape[0]
     dev, stream = _ctx(x)
     dx = torch.empty_like(x) if out is None else out
-    check(_lib.load().stk_layernorm_bwd(dev, stream, _ptr(dy), _ptr(x), M, _ptr(gamma), _ptr(mean), _ptr(rstd),
-                                        _ptr(dx), _ptr(dgamma), _ptr(dbeta)), "stk_layernorm_bwd")
-    return dx
+    if dbias is None and drop is None:
+        check(_lib.load().stk_layernorm_bwd(dev, stream, _ptr(dy), _ptr(x), M, _ptr(gamma), _ptr(mean), _ptr(rstd),
+                                            _ptr(dx), _ptr(dgamma), _ptr(dbeta)), "stk_layernorm_bwd")
+        return dx
+    masked = drop is not None and drop.thr > 0
+    dxm = torch.empty_like(x) if masked else None
+    check(_lib.load().stk_layernorm_bwd_fused(dev, stream, _ptr(dy), _ptr(x), M, _ptr(gamma), _ptr(mean), _ptr(rstd),
+                                              _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(dxm), _ptr(dbias),
+                                              drop.seed if masked else 0, drop.site if masked else 0,
+                                              drop.thr if masked else 0), "stk_layernorm_bwd_fused")
+    return (dx, dxm if masked else dx) if drop is not None else dx
 
 
 # --------------------------------------------------------------------------------------------------

@@ -347,17 +347,24 @@ def backward_trunk(model, bert: engine.EncoderWeights, cache, dseq, gb: GradBuff
         p = f"l{li}."
         # dz = gradient w.r.t. the residual sum z; the dense branch sees it through the dropout mask, the residual
         # branch (added back below through the dgrad epilogues) sees it as it is
-        dz2 = ops.layernorm_bwd(dx, c.z2, lw.ln2_g, c.mean2, c.rstd2, gb[p + "ln2_g"], gb[p + "ln2_b"])
-        dz2m = ops.dropout(dz2, drop.ffn_out(1, li)) if drop is not None else dz2
-        ops.colsum(dz2m, gb[p + "b2"], accumulate=True)
+        # one row pass: LayerNorm backward, the dropout mask of the dense output and the dense bias gradient
+        if drop is not None:
+            dz2, dz2m = ops.layernorm_bwd(dx, c.z2, lw.ln2_g, c.mean2, c.rstd2, gb[p + "ln2_g"], gb[p + "ln2_b"],
+                                          dbias=gb[p + "b2"], drop=drop.ffn_out(1, li))
+        else:
+            dz2 = dz2m = ops.layernorm_bwd(dx, c.z2, lw.ln2_g, c.mean2, c.rstd2, gb[p + "ln2_g"], gb[p + "ln2_b"],
+                                           dbias=gb[p + "b2"])
         _wgrad(dz2m, c.h, gb[p + "w2"], M)
         du = _dgrad(dz2m, lw.w2, epilogue=ops.EPI_DGELU, resid=c.u)
         ops.colsum(du, gb[p + "b1"], accumulate=True)
         _wgrad(du, c.x1, gb[p + "w1"], M)
         dx1 = _dgrad(du, lw.w1, epilogue=ops.EPI_BIAS_RESID, resid=dz2)
-        dz1 = ops.layernorm_bwd(dx1, c.z1, lw.ln1_g, c.mean1, c.rstd1, gb[p + "ln1_g"], gb[p + "ln1_b"])
-        dz1m = ops.dropout(dz1, drop.attn_out(1, li)) if drop is not None else dz1
-        ops.colsum(dz1m, gb[p + "bo"], accumulate=True)
+        if drop is not None:
+            dz1, dz1m = ops.layernorm_bwd(dx1, c.z1, lw.ln1_g, c.mean1, c.rstd1, gb[p + "ln1_g"], gb[p + "ln1_b"],
+                                          dbias=gb[p + "bo"], drop=drop.attn_out(1, li))
+        else:
+            dz1 = dz1m = ops.layernorm_bwd(dx1, c.z1, lw.ln1_g, c.mean1, c.rstd1, gb[p + "ln1_g"], gb[p + "ln1_b"],
+                                           dbias=gb[p + "bo"])
         _wgrad(dz1m, c.ctx, gb[p + "wo"], M)
         dctx = _dgrad(dz1m, lw.wo)
         dqkv = ops.attention_bwd(c.qkv, key_bias, B, SP, c.ctx, dctx, c.lse,

@@ -301,6 +301,27 @@ def case_dropout():
     res.append(_err_report(mean, z.float().mean(1), "drop_resid_mean", 2e-3))
     y_inf = ops.dropout_resid_ln(x, r, gamma, beta, d)
     res.append(_err_report(y_inf, torch.nn.functional.layer_norm(zref, (768,), gamma, beta, 1e-12), "drop_resid_ln_y_nosave", 6e-2))
+    # --- fused LayerNorm backward + dropout mask + bias column sums
+    dy = _mk(M, 768, "cuda")
+    zz = _mk(M, 768, "cuda")
+    mu = zz.float().mean(1)
+    rs = torch.rsqrt(zz.float().var(1, unbiased=False) + 1e-12)
+    dg0, db0 = torch.zeros(768, device="cuda"), torch.zeros(768, device="cuda")
+    dx_plain = ops.layernorm_bwd(dy, zz, gamma, mu, rs, dg0, db0)
+    dg1, db1, dbias = torch.zeros(768, device="cuda"), torch.zeros(768, device="cuda"), torch.zeros(768, device="cuda")
+    dx_f, dxm_f = ops.layernorm_bwd(dy, zz, gamma, mu, rs, dg1, db1, dbias=dbias, drop=d)
+    res.append({"case": "ln_bwd_fused_dx_same", "ok": bool(torch.equal(dx_f, dx_plain))})
+    res.append(_err_report(dg1, dg0, "ln_bwd_fused_dgamma", 1e-3 * float(dg0.abs().max())))
+    res.append({"case": "ln_bwd_fused_mask_exact", "ok": bool(torch.equal(dxm_f != 0, keep & (dxm_f != 0)) and
+                                                                 bool((dxm_f[~keep] == 0).all()))})
+    # (dx_plain is the bf16-rounded dx; the fused kernel masks, scales and sums the fp32 values: one bf16 ulp / row apart)
+    ref_m = torch.where(keep, dx_plain.float() * scale, torch.zeros(1, device="cuda"))
+    res.append(_err_report(dxm_f, ref_m, "ln_bwd_fused_dxm", 8e-3 * float(ref_m.abs().max())))
+    res.append(_err_report(dbias, ref_m.sum(0), "ln_bwd_fused_dbias", 2e-2 * float(ref_m.sum(0).abs().max())))
+    dbias2 = torch.zeros(768, device="cuda")
+    dx_n = ops.layernorm_bwd(dy, zz, gamma, mu, rs, dg1, db1, dbias=dbias2)
+    res.append(_err_report(dbias2, dx_plain.float().sum(0), "ln_bwd_fused_dbias_nodrop", 2e-2 * float(dx_plain.float().sum(0).abs().max())))
+    res.append({"case": "ln_bwd_fused_nodrop_dx_same", "ok": bool(torch.equal(dx_n, dx_plain))})
     # --- attention forward / backward with injected masks
     for (B, S, use_bias) in [(2, 256, False), (3, 512, True)]:
         da = ops.Drop(seed=1234 + S, site=5, p=0.1)
