@@ -273,7 +273,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     const int q = warp & 3, half = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const bool issuer = threadIdx.x == 0;
     const float scale = 0.125f;
     int g = 0;
 

@@ -19,7 +19,7 @@ if int(os.environ.get("STK_ATTN_DEBUG", "0")) & 64:
     buf = (ctypes.c_longlong * 256)()
     lib.stk_debug_attn_bwd_timeline(buf, 256)
     t0 = buf[0]
-    names = {1: "m:loop", 2: "m:p_ready", 3: "m:issued", 8: "c:start", 9: "c:S_ready", 10: "c:PdS_written", 11: "c:dq_ready", 12: "c:dq_staged"}
+    names = {1: "m:loop", 2: "m:p_ready", 3: "m:issued", 8: "c:start", 9: "c:S_ready", 10: "c:PdS_written", 12: "c:prev_dq_drained"}
     for i in range(4):
         print(i, " ".join(f"{n}={buf[i * 16 + k] - t0}" for k, n in names.items()))
     print("cta: entry=%d prologue_done=%d loop_done=%d dvdk_done=%d stored=%d exit=%d" % tuple(buf[64 + k] - t0 for k in range(6)))
