@@ -314,7 +314,8 @@ def main():
             traffic = t["dram_bytes"] * (dom["work"] / dom["launches"]) / t["flops"]
     names = {"gemm_a0b0_epi0": "fused QKV projection", "gemm_a0b0_epi1": "FFN1 + erf-GELU epilogue",
              "gemm_a0b0_epi3": "Wo / FFN2 + residual epilogue", "gemm_a0b0_epi10": "Wo / FFN2 + bias + residual + LayerNorm epilogue (3-CTA cluster)", "gemm_a1b1_epi6": "wgrad (split-K reduce-add)",
-             "gemm_a0b1_epi3": "dgrad + residual", "gemm_a0b1_epi5": "dgrad * GELU'"}
+             "gemm_a0b1_epi3": "dgrad + residual", "gemm_a0b1_epi5": "dgrad * GELU'", "gemm_a0b1_epi12": "dgrad * saved GELU'",
+             "gemm_a0b0_epi11": "FFN1 + erf-GELU epilogue saving GELU'"}
     roofline = {
         "bound": "tensor",
         "kernel": f"stk::gemm_kernel<{dom_name}> ({names.get(dom_name, 'tcgen05 GEMM')})" if dom_name else None,

@@ -127,9 +127,12 @@ enum {
   STK_EPI_F32 = 7,           /* C(fp32) = acc                                                          */
   STK_EPI_CE_STATS = 8,      /* no C: per-row (max, sum exp) partials + target logit (A9+A10 fwd)     */
   STK_EPI_CE_DLOGIT = 9,     /* C(bf16) = (exp(acc - lse[m]) - [n+n_offset == label[m]]) * *scale_dev   */
-  STK_EPI_BIAS_RESID_LN = 10 /* z = acc + bias + R;  C(bf16) = LayerNorm_768(z) * gamma + beta  (HF:294-298,352-356);
+  STK_EPI_BIAS_RESID_LN = 10,/* z = acc + bias + R;  C(bf16) = LayerNorm_768(z) * gamma + beta  (HF:294-298,352-356);
                                 N must be 768 (rows are normalised across a 3-CTA cluster through distributed
                                 shared memory); optional C2(bf16) = z and ln_mean/ln_rstd[m] for the backward */
+  STK_EPI_BIAS_GELU_SAVE_GRAD = 11, /* C(bf16) = gelu_erf(u), C2(bf16) = gelu_erf'(u), u = acc + bias: the training forward of
+                                       BertIntermediate saves the derivative, so that the backward epilogue is one multiply */
+  STK_EPI_MUL = 12                  /* C(bf16) = acc * R[m,n]   (R = the saved derivative; backward of the GELU)              */
 };
 
 typedef struct StkGemmEpilogue {

@@ -19,6 +19,7 @@ STK_VERSION = 101
 # epilogue ids (include/stk.h)
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GELU_SAVE, EPI_BIAS_RESID, EPI_BIAS_TANH_F32 = 0, 1, 2, 3, 4
 EPI_DGELU, EPI_F32_ADD, EPI_F32, EPI_CE_STATS, EPI_CE_DLOGIT, EPI_BIAS_RESID_LN = 5, 6, 7, 8, 9, 10
+EPI_BIAS_GELU_SAVE_GRAD, EPI_MUL = 11, 12
 
 
 class StkError(RuntimeError):

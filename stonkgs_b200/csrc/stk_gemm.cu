@@ -565,7 +565,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     float ce_scale = 0.f;
     if (EPI == STK_EPI_CE_DLOGIT) ce_scale = __ldg(e.scale_dev);
     constexpr bool kHasBias = EPI == STK_EPI_BIAS || EPI == STK_EPI_BIAS_GELU || EPI == STK_EPI_BIAS_GELU_SAVE ||
-                              EPI == STK_EPI_BIAS_RESID || EPI == STK_EPI_BIAS_TANH_F32;
+                              EPI == STK_EPI_BIAS_GELU_SAVE_GRAD || EPI == STK_EPI_BIAS_RESID || EPI == STK_EPI_BIAS_TANH_F32;
+    constexpr bool kSaves2 = EPI == STK_EPI_BIAS_GELU_SAVE || EPI == STK_EPI_BIAS_GELU_SAVE_GRAD;   // second bf16 output
     const int gt = (ew & 3) * 32 + lane;   // thread index within the epilogue group
     float* s_bias = s_par + g * 128;       // bias of this group's 128 columns of the current tile (0 beyond N)
 
@@ -590,7 +591,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       }
       // Residual / saved pre-activation rows do not depend on the accumulator: fetch both 64-column
       // chunks of this thread's row now so the global-load latency hides behind the MMA of this tile.
-      constexpr bool kPrefetchExtra = EPI == STK_EPI_BIAS_RESID || EPI == STK_EPI_DGELU;
+      constexpr bool kPrefetchExtra = EPI == STK_EPI_BIAS_RESID || EPI == STK_EPI_DGELU || EPI == STK_EPI_MUL;
       // COALESCED: thread t of the 128-thread group fetches 16-byte piece (t + 128 i) of the
       // [128 rows x 128 B] residual tile (8 consecutive threads = one full 128-byte row segment); the
       // pieces are transposed to the thread-per-row accumulator layout through the staging tile later.
@@ -696,7 +697,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
 
         // bf16 outputs
-        constexpr bool kHasExtra = EPI == STK_EPI_BIAS_RESID || EPI == STK_EPI_DGELU;
+        constexpr bool kHasExtra = EPI == STK_EPI_BIAS_RESID || EPI == STK_EPI_DGELU || EPI == STK_EPI_MUL;
         if (kHasExtra) {
           // acquire the staging tile, drop the coalesced residual pieces into it (swizzled), then every
           // thread picks up its own row below; the result overwrites the same 16-byte slots
@@ -740,6 +741,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
               v0 = gelu_erf(v0);
               v1 = gelu_erf(v1);
             }
+            if (EPI == STK_EPI_BIAS_GELU_SAVE_GRAD) {
+              float d0, d1;
+              gelu_erf_with_grad(v0, v0, d0);
+              gelu_erf_with_grad(v1, v1, d1);
+              w2[i] = pack_bf16x2(d0, d1);
+            }
+            if (EPI == STK_EPI_MUL) {
+              v0 *= bf16_lo(ex[i]);
+              v1 *= bf16_hi(ex[i]);
+            }
             if (EPI == STK_EPI_BIAS_RESID) {
               v0 += bf16_lo(ex[i]);
               v1 += bf16_hi(ex[i]);
@@ -761,11 +772,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             w[i] = pack_bf16x2(v0, v1);
           }
           data[c] = make_uint4(w[0], w[1], w[2], w[3]);
-          if (EPI == STK_EPI_BIAS_GELU_SAVE) data2[c] = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+          if (kSaves2) data2[c] = make_uint4(w2[0], w2[1], w2[2], w2[3]);
         }
         STK_GEMM_STAMP(dbg_thr, dbg_t, 6 + chunk * 4);
         stage_and_store<false, kHasExtra>(&map_c, buf, row, data, nc, m0, store_thread, bar_id);
-        if (EPI == STK_EPI_BIAS_GELU_SAVE)
+        if (kSaves2)
           stage_and_store<false>(&map_c2, buf, row, data2, nc, m0, store_thread, bar_id);
         STK_GEMM_STAMP(dbg_thr, dbg_t, 7 + chunk * 4);
       }
@@ -889,10 +900,11 @@ extern "C" int stk_gemm(int device, void* stream_, int a_major, int b_major, con
 
   const bool f32_out = epilogue == STK_EPI_F32 || epilogue == STK_EPI_F32_ADD || epilogue == STK_EPI_BIAS_TANH_F32;
   const bool has_c = epilogue != STK_EPI_CE_STATS;
-  if (epilogue == STK_EPI_BIAS_RESID || epilogue == STK_EPI_DGELU) {
+  if (epilogue == STK_EPI_BIAS_RESID || epilogue == STK_EPI_DGELU || epilogue == STK_EPI_MUL) {
     STK_REQUIRE(epi && epi->resid && epi->ldr % 8 == 0 && N % 64 == 0, "stk_gemm: residual epilogue needs resid, ldr%%8==0, N%%64==0");
   }
-  if (epilogue == STK_EPI_BIAS_GELU_SAVE) STK_REQUIRE(epi && epi->c2 && epi->ldc2 % 8 == 0, "stk_gemm: GELU_SAVE needs c2");
+  if (epilogue == STK_EPI_BIAS_GELU_SAVE || epilogue == STK_EPI_BIAS_GELU_SAVE_GRAD)
+    STK_REQUIRE(epi && epi->c2 && epi->ldc2 % 8 == 0, "stk_gemm: GELU_SAVE needs c2");
   if (epilogue == STK_EPI_BIAS_RESID_LN) {
     STK_REQUIRE(N == kHidden && a_major == 0 && b_major == 0, "stk_gemm: the LayerNorm epilogue needs N == 768 and K-major operands");
     STK_REQUIRE(epi && epi->resid && epi->ldr % 8 == 0 && epi->ln_gamma && epi->ln_beta,
@@ -929,7 +941,8 @@ extern "C" int stk_gemm(int device, void* stream_, int a_major, int b_major, con
   }
   mc2 = mc;
   mr = mc;
-  if (epilogue == STK_EPI_BIAS_GELU_SAVE || (epilogue == STK_EPI_BIAS_RESID_LN && epi->c2)) {
+  if (epilogue == STK_EPI_BIAS_GELU_SAVE || epilogue == STK_EPI_BIAS_GELU_SAVE_GRAD ||
+      (epilogue == STK_EPI_BIAS_RESID_LN && epi->c2)) {
     rc = make_tmap_2d(&mc2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, epi->c2, N, M, epi->ldc2 * 2, 64, 128);
     if (rc) return rc;
   }
@@ -944,6 +957,7 @@ extern "C" int stk_gemm(int device, void* stream_, int a_major, int b_major, con
   STK_GEMM_CASE(0, 0, STK_EPI_BIAS)
   STK_GEMM_CASE(0, 0, STK_EPI_BIAS_GELU)
   STK_GEMM_CASE(0, 0, STK_EPI_BIAS_GELU_SAVE)
+  STK_GEMM_CASE(0, 0, STK_EPI_BIAS_GELU_SAVE_GRAD)
   STK_GEMM_CASE(0, 0, STK_EPI_BIAS_RESID)
   STK_GEMM_CASE(0, 0, STK_EPI_BIAS_RESID_LN)
   STK_GEMM_CASE(0, 0, STK_EPI_BIAS_TANH_F32)
@@ -953,6 +967,7 @@ extern "C" int stk_gemm(int device, void* stream_, int a_major, int b_major, con
   STK_GEMM_CASE(0, 1, STK_EPI_BIAS)
   STK_GEMM_CASE(0, 1, STK_EPI_BIAS_RESID)
   STK_GEMM_CASE(0, 1, STK_EPI_DGELU)
+  STK_GEMM_CASE(0, 1, STK_EPI_MUL)
   STK_GEMM_CASE(0, 1, STK_EPI_F32)
   STK_GEMM_CASE(0, 1, STK_EPI_F32_ADD)
   STK_GEMM_CASE(1, 1, STK_EPI_F32)

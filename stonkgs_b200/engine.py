@@ -132,7 +132,7 @@ def encoder_layer_fwd(x, lw: LayerWeights, B: int, S: int, key_bias, cache: Opti
         if train:
             x1, z1, mean1, rstd1 = ops.dropout_resid_ln(d1, x, lw.ln1_g, lw.ln1_b, drop.attn_out(enc, li), save_for_backward=True)
             u = torch.empty((M, I), dtype=torch.bfloat16, device=x.device)
-            h = ops.linear(x1, lw.w1, lw.b1, ops.EPI_BIAS_GELU_SAVE, c2=u)
+            h = ops.linear(x1, lw.w1, lw.b1, ops.EPI_BIAS_GELU_SAVE_GRAD, c2=u)   # u = gelu'(pre-activation)
         else:
             x1 = ops.dropout_resid_ln(d1, x, lw.ln1_g, lw.ln1_b, drop.attn_out(enc, li))
             h = ops.linear(x1, lw.w1, lw.b1, ops.EPI_BIAS_GELU)
@@ -151,7 +151,7 @@ def encoder_layer_fwd(x, lw: LayerWeights, B: int, S: int, key_bias, cache: Opti
         if train:
             x1, z1, mean1, rstd1 = ops.linear_resid_ln(ctx, lw.wo, lw.bo, x, lw.ln1_g, lw.ln1_b, save_for_backward=True)
             u = torch.empty((M, I), dtype=torch.bfloat16, device=x.device)
-            h = ops.linear(x1, lw.w1, lw.b1, ops.EPI_BIAS_GELU_SAVE, c2=u)
+            h = ops.linear(x1, lw.w1, lw.b1, ops.EPI_BIAS_GELU_SAVE_GRAD, c2=u)   # u = gelu'(pre-activation)
             x2, z2, mean2, rstd2 = ops.linear_resid_ln(h, lw.w2, lw.b2, x1, lw.ln2_g, lw.ln2_b, save_for_backward=True)
             cache.append(LayerCache(x, qkv, lse, ctx, z1, mean1, rstd1, x1, u, h, z2, mean2, rstd2))
         else:
@@ -163,7 +163,7 @@ def encoder_layer_fwd(x, lw: LayerWeights, B: int, S: int, key_bias, cache: Opti
     if train:
         x1, mean1, rstd1 = ops.layernorm(z1, lw.ln1_g, lw.ln1_b, save_stats=True)
         u = torch.empty((M, I), dtype=torch.bfloat16, device=x.device)
-        h = ops.linear(x1, lw.w1, lw.b1, ops.EPI_BIAS_GELU_SAVE, c2=u)
+        h = ops.linear(x1, lw.w1, lw.b1, ops.EPI_BIAS_GELU_SAVE_GRAD, c2=u)   # u = gelu'(pre-activation)
     else:
         x1 = ops.layernorm(z1, lw.ln1_g, lw.ln1_b, out=z1)
         h = ops.linear(x1, lw.w1, lw.b1, ops.EPI_BIAS_GELU)

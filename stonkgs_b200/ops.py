@@ -12,7 +12,8 @@ import torch
 
 from . import _lib
 from ._lib import (EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GELU_SAVE, EPI_BIAS_RESID, EPI_BIAS_RESID_LN, EPI_BIAS_TANH_F32,
-                   EPI_CE_DLOGIT, EPI_CE_STATS, EPI_DGELU, EPI_F32, EPI_F32_ADD, GemmEpilogue, check)
+                   EPI_BIAS_GELU_SAVE_GRAD, EPI_CE_DLOGIT, EPI_CE_STATS, EPI_DGELU, EPI_F32, EPI_F32_ADD, EPI_MUL, GemmEpilogue,
+                   check)
 
 H = 768
 HEADS = 12

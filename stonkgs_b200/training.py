@@ -355,7 +355,7 @@ def backward_trunk(model, bert: engine.EncoderWeights, cache, dseq, gb: GradBuff
             dz2 = dz2m = ops.layernorm_bwd(dx, c.z2, lw.ln2_g, c.mean2, c.rstd2, gb[p + "ln2_g"], gb[p + "ln2_b"],
                                            dbias=gb[p + "b2"])
         _wgrad(dz2m, c.h, gb[p + "w2"], M)
-        du = _dgrad(dz2m, lw.w2, epilogue=ops.EPI_DGELU, resid=c.u)
+        du = _dgrad(dz2m, lw.w2, epilogue=ops.EPI_MUL, resid=c.u)   # c.u holds gelu'(pre-activation), saved by the forward
         ops.colsum(du, gb[p + "b1"], accumulate=True)
         _wgrad(du, c.x1, gb[p + "w1"], M)
         dx1 = _dgrad(du, lw.w1, epilogue=ops.EPI_BIAS_RESID, resid=dz2)

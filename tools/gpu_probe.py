@@ -191,6 +191,27 @@ def case_gemm_epilogues():
     wT = w.T.contiguous()  # stored [K][N]: the dgrad layout
     res.append(_err_report(ops.gemm(a, wT, M=M, N=N, K=K, b_major=1, epilogue=ops.EPI_DGELU, resid=u), acc * uf.grad,
                            "epi_dgelu", tol))
+    # training forward of BertIntermediate: activation + SAVED DERIVATIVE, and the backward that multiplies by it
+    dsave = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+    act2 = ops.linear(a, w, bias, ops.EPI_BIAS_GELU_SAVE_GRAD, c2=dsave)
+    pre_f = (acc + bias).detach().requires_grad_(True)
+    torch.nn.functional.gelu(pre_f).sum().backward()
+    res.append(_err_report(act2, torch.nn.functional.gelu(acc + bias), "epi_gelu_save_grad_act", tol))
+    res.append(_err_report(dsave, pre_f.grad, "epi_gelu_save_grad_derivative", 1e-2))
+    res.append(_err_report(ops.gemm(a, wT, M=M, N=N, K=K, b_major=1, epilogue=ops.EPI_MUL, resid=u), acc * u.float(), "epi_mul", tol))
+    # activation and derivative over the whole useful range: acc[m, n] = x_m exactly (bf16 grid), bias 0
+    xs = torch.linspace(-9.0, 9.0, 4096, device="cuda").bfloat16()
+    a_x = torch.zeros(4096, 64, device="cuda").bfloat16()
+    a_x[:, 0] = xs
+    w_1 = torch.zeros(64, 64, device="cuda").bfloat16()
+    w_1[:, 0] = 1.0
+    dgrid = torch.empty((4096, 64), dtype=torch.bfloat16, device="cuda")
+    ygrid = ops.linear(a_x, w_1, torch.zeros(64, device="cuda"), ops.EPI_BIAS_GELU_SAVE_GRAD, c2=dgrid)
+    xg = xs.float().requires_grad_(True)
+    yref = torch.nn.functional.gelu(xg)
+    yref.sum().backward()
+    res.append(_err_report(ygrid[:, 5], yref.detach(), "gelu_grid_activation", 4e-2))
+    res.append(_err_report(dgrid[:, 5], xg.grad, "gelu_grid_derivative", 6e-3))
     # strided A (pooler reads row 0 of every sequence): lda = 512*768
     seq = _mk(4 * 512, 768, "cuda", 0.5)
     a0 = seq.view(4, 512, 768)[:, 0]
