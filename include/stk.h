@@ -137,7 +137,7 @@ enum {
 
 typedef struct StkGemmEpilogue {
   const float* bias;      /* [N] fp32 or NULL */
-  const void* resid;      /* bf16 [M, ldr]: residual (BIAS_RESID) or saved pre-activation (DGELU) */
+  const void* resid;      /* bf16 [M, ldr]: residual (BIAS_RESID), saved pre-activation (DGELU) or saved derivative (MUL) */
   int64_t ldr;
   void* c2;               /* second output (BIAS_GELU_SAVE): bf16 [M, ldc2] */
   int64_t ldc2;
