@@ -84,7 +84,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:  # noqa: BLE001
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
@@ -94,12 +94,20 @@ class ClockSampler:
                 mx.append(float(f[1]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[2]))
+            except ValueError:
+                pw.append(0.0)
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        busy = sorted(sm)[len(sm) // 2:] if sm else []   # upper half = samples under load
+        # "under load" = samples drawing at least 60 % of the highest power seen (an idle GPU sits at its maximum clock,
+        # a power-capped busy one well below it, so the clock value itself cannot tell the two apart)
+        top = max(pw) if pw else 0.0
+        busy = sorted(c for c, w in zip(sm, pw) if top <= 0.0 or w >= 0.6 * top)
         med = busy[len(busy) // 2] if busy else None
-        return {"sm_mhz": med, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": med, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm),
+                "samples_under_load": len(busy), "power_w_max": top or None}
 
 
 def dist_env():
