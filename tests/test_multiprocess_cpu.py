@@ -70,6 +70,15 @@ def _dp_worker(rank, world, port, out):
                 dp.on_ready(n)
             dp.finish(gb)
         assert torch.equal(gb.flat, local)
+        # overlap=False: the same buckets are reduced in finish(), after the whole backward has been enqueued
+        dp2 = DataParallel(model, bucket_mb=4096 * 4 / (1 << 20), wire_dtype=torch.float32, overlap=False)
+        gb.flat.copy_(local)
+        dp2.begin(gb)
+        for n, _ in sizes:
+            dp2.on_ready(n)
+        assert torch.equal(gb.flat, local)                     # nothing has moved yet
+        dp2.finish(gb)
+        torch.testing.assert_close(gb.flat, sum(both) / world)
         out[rank] = "ok"
     finally:
         dist.destroy_process_group()
