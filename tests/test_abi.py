@@ -36,3 +36,27 @@ def test_error_codes_and_text():
     rc = lib.stk_attn_fwd(0, None, ctypes.c_void_p(16), None, 1, 100, ctypes.c_void_p(16), None)
     assert rc == -1 and "S must be" in _lib.last_error()
     assert lib.stk_launch_count() == 0
+
+
+def test_epilogue_enum_matches_binding():
+    """The epilogue codes of include/stk.h and of the ctypes binding are the same numbers."""
+    src = open(os.path.join(ROOT, "include", "stk.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    header = {k: int(v) for k, v in re.findall(r"\bSTK_(EPI_\w+)\s*=\s*(\d+)", src)}
+    assert len(header) >= 13 and sorted(header.values()) == list(range(len(header)))
+    for name, code in header.items():
+        assert getattr(_lib, name) == code, name
+
+
+def test_new_entry_points_validate_arguments():
+    lib = _lib.load()
+    p16 = ctypes.c_void_p(16)
+    # joint embedding stage: text part must be shorter than the sequence, padding not below the sequence
+    rc = lib.stk_embed_joint_ln_fwd_shape(0, None, p16, None, 1, 256, 200, 384, p16, p16, 10, p16, p16, p16, p16, p16, None, None,
+                                          None, None)
+    assert rc == -1 and "bad joint shape" in _lib.last_error()
+    rc = lib.stk_dropout_fwd(0, None, p16, 8, 1, 2, 200, p16)          # threshold is round(128 p) < 128
+    assert rc == -1 and "stk_dropout_fwd" in _lib.last_error()
+    rc = lib.stk_layernorm_bwd_fused(0, None, p16, p16, 8, p16, p16, p16, p16, p16, p16, None, None, 1, 2, 13)
+    assert rc == -1 and "dxm" in _lib.last_error()                     # dropout needs the masked output
+    assert lib.stk_launch_count() == 0
