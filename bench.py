@@ -1,22 +1,31 @@
 """bench.py — headline benchmark of the STonKGs hot path on B200.
 
-    python bench.py --gpus N --steps K --warmup W [--workload extract|pretrain] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload all|extract|pretrain] [--impl reference]
 
-Default workload (BASELINE.json configs[1]): ``get_stonkgs_embeddings``-style extraction,
-STonKGs-150k shape (12+12 BERT-base layers, 256 text + 256 KG tokens, N_kg = 175 003), batch 256 per
-GPU, bf16 tensor-core compute; metric = text-triple pairs / second.  One "step" = one batch of 256
-pairs through LM backbone -> KG lookup -> joint encoder -> pooler.  N > 1 (torchrun): every rank
-embeds its own shard of the pairs, no data-path collective (weak scaling).
+One JSON line.  Top level = BASELINE.json configs[1]: ``get_stonkgs_embeddings``-style extraction, STonKGs-150k shape
+(12+12 BERT-base layers, 256 text + 256 KG tokens, N_kg = 175 003), batch 256 per GPU, bf16 tensor-core compute;
+metric = text-triple pairs / second.  One "step" = one batch of 256 pairs through LM backbone -> KG lookup -> joint
+encoder -> pooler.  N > 1 (torchrun): every rank embeds its own shard of the pairs, no data-path collective (weak).
 
-The JSON line carries
-  value     pairs/s with the step's inputs already resident in HBM (CUDA events, max over ranks)
-  e2e       the same through host buffers: pinned int64 ids -> H2D -> forward -> D2H pooled [256,768]
-  roofline  the dominant kernel's achieved TFLOP/s (algorithmic FLOPs / CUDA-event time inside a
-            profiled step) against the measured cuBLAS bf16 peak of MEASURED_PEAKS.json
-  cpu_baseline  the oracle port (fp32 torch CPU restatement of the reference) on the host cores,
-            bounded sample (N=1, rank 0 only)
-``--impl reference`` times the CPU oracle port alone (the reference is pure Python on HF BERT and
-cannot be pip-installed offline: its import needs pystow/indra/pybel + network).
+  value         pairs/s with the step's inputs already resident in HBM (CUDA events, max over ranks)
+  e2e           the same through host buffers: pinned int64 ids -> H2D -> forward -> D2H pooled [256,768]
+  roofline      dominant kernel's achieved TFLOP/s (algorithmic FLOPs / CUDA-event time, averaged over >= 5 profiled
+                steps, one entry per (epilogue, N, K) instantiation) against MEASURED_PEAKS.json
+  pretrain      the other half of BASELINE.json's metric (configs[2]): one pre-training step — train() with dropout,
+                forward + MLM/ELM/NSP losses + backward + bucketed bf16 gradient all-reduce overlapped with backward
+                (N > 1) + clip + AdamW — 64 pairs per GPU (global 512 at N = 8): value, e2e, roofline, and at N > 1
+                the exposed all-reduce time and the bytes on the wire
+  bulk          configs[4]: >= 1 M pairs per GPU streamed from host arrays through embeddings.embed_arrays
+                (double-buffered pinned staging, copy stream), pairs/s and the gap to `value`
+  library_baseline  the same extraction through HF BertModel x 2 in bf16 + SDPA (cuBLAS / flash kernels) on the same
+                GPU: the library path the reference would take on a B200 (N = 1 only)
+  elm_stress    configs[3]: fused GEMM + cross-entropy over 1 000 003 entities, 4 864 labelled rows (N = 1 only)
+  cpu_baseline  the reference module itself (baseline/_ref or /root/reference; else the oracle port) on the host cores,
+                bounded sample (N = 1, rank 0 only)
+``--impl reference`` times the reference's own extraction loop (stonkgs_for_embeddings.py:176-180: batch 1, label
+columns passed, autograd on) on the host cores: the UNMODIFIED reference package installed under baseline/_ref
+(`pip install --no-deps --target baseline/_ref`), imported through oracle/ref_shim.py (stubs for mlflow /
+pytorch_lightning / stonkgs.constants, offline from_pretrained); the oracle port only if that tree is absent.
 """
 from __future__ import annotations
 
@@ -32,12 +41,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("HF_HUB_OFFLINE", "1")
 os.environ.setdefault("TRANSFORMERS_OFFLINE", "1")
+# the DP all-reduce shares the GPU with persistent one-CTA-per-SM kernels: keep NCCL to a few CTAs
+os.environ.setdefault("NCCL_MAX_CTAS", "8")
 
 N_KG = 175003
 BATCH = 256            # pairs per GPU per step (extraction)
 TRAIN_BATCH = 64       # pairs per GPU per step (pre-training; global 512 at 8 GPUs)
+BULK_PAIRS = 1 << 20   # pairs per GPU streamed by the bulk leg
 GFLOP_PER_PAIR_EXTRACT = 142.54
 GFLOP_PER_PAIR_TRAIN = 371.8
+LIVE_PARAMS = 243306242           # SURVEY §8d (N_kg = 175 003)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -71,6 +84,7 @@ class ClockSampler:
             self.thread.start()
         except Exception:  # noqa: BLE001
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
@@ -135,28 +149,57 @@ def build_model(device, layers=12, n_kg=N_KG, seed=0):
     return model.eval().to(device)
 
 
-def cpu_port_throughput(n_pairs: int, seed=0):
-    """Oracle port (fp32 torch restatement of the reference forward) on all host cores."""
+# --------------------------------------------------------------------------------------------------
+# CPU arms: the reference module itself when its tree is present, else the oracle port
+# --------------------------------------------------------------------------------------------------
+def _reference_model(n_kg: int, layers: int = 12):
+    """(model, kind): the reference's own STonKGsForPreTraining on CPU (kind "reference"), or None."""
+    try:
+        from oracle import ref_shim, weights
+        if not ref_shim.reference_available():
+            return None
+        sd = weights.make_state_dict(n_kg, layers, 0)
+        return ref_shim.load_reference(sd, weights.make_kg_table(n_kg, 0), layers)
+    except Exception as e:  # noqa: BLE001
+        print(f"bench: reference module unavailable ({type(e).__name__}: {e}); using the oracle port", file=sys.stderr)
+        return None
+
+
+def cpu_reference_loop(n_rows: int, warm: int = 1, n_kg: int = N_KG):
+    """The reference's extraction loop (stonkgs_for_embeddings.py:176-180) on the host cores: one forward per row with
+    the label columns passed and autograd on, exactly as the reference runs it.  Returns (pairs/s, cores, kind, sample)."""
     import torch
-    from oracle import stonkgs_oracle as orc, weights
     from stonkgs_b200 import synthetic
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    n_kg = 3001  # the extraction forward never touches the decoders; a small table keeps set-up short
-    sd = weights.make_state_dict(n_kg, 12, seed)
-    table = torch.from_numpy(weights.make_kg_table(n_kg, seed))
-    table = torch.cat([table, torch.zeros(3, 768)])
+    ref = _reference_model(n_kg)
+    if ref is not None:
+        batch = synthetic.make_batch(max(n_rows, 1) + warm, n_kg, seed=1, with_labels=True)
+        rows = [{k: v[i:i + 1] for k, v in batch.items()} for i in range(n_rows + warm)]
+        for r in rows[:warm]:
+            ref(**r, return_dict=True).pooler_output[0].tolist()
+        t0 = time.perf_counter()
+        for r in rows[warm:]:
+            ref(**r, return_dict=True).pooler_output[0].tolist()
+        dt = time.perf_counter() - t0
+        return n_rows / dt, cores, "reference", (
+            f"{n_rows} rows through the reference's own loop (stonkgs_for_embeddings.py:176-180: batch 1, labels passed, "
+            f"autograd on, dense logits), unmodified reference module, N_kg {n_kg}, 12+12 layers, fp32")
+    from oracle import stonkgs_oracle as orc, weights
+    n_small = 3001  # the extraction forward never touches the decoders; a small table keeps set-up short
+    sd = weights.make_state_dict(n_small, 12, 0)
+    table = torch.cat([torch.from_numpy(weights.make_kg_table(n_small, 0)), torch.zeros(3, 768)])
     bs = 8
-    batch = synthetic.make_batch(bs, n_kg, seed=1, with_labels=False)
+    batch = synthetic.make_batch(bs, n_small, seed=1, with_labels=False)
     with torch.no_grad():
-        orc.forward(sd, table, **batch)  # warm-up
+        orc.forward(sd, table, **batch)
         t0 = time.perf_counter()
         done = 0
-        while done < n_pairs:
+        while done < n_rows:
             orc.forward(sd, table, **batch)
             done += bs
         dt = time.perf_counter() - t0
-    return done / dt, cores, f"{done} pairs as batches of {bs}, 12+12 layers, fp32, eval forward (extraction path)"
+    return done / dt, cores, "port", f"{done} pairs as batches of {bs}, 12+12 layers, fp32, eval forward (oracle port)"
 
 
 def run_reference(args):
@@ -164,35 +207,188 @@ def run_reference(args):
     if rank != 0:
         return
     t0 = time.perf_counter()
-    per_step = 8
-    import torch
-    from oracle import stonkgs_oracle as orc, weights
-    from stonkgs_b200 import synthetic
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    n_kg = 3001
-    sd = weights.make_state_dict(n_kg, 12, 0)
-    table = torch.cat([torch.from_numpy(weights.make_kg_table(n_kg, 0)), torch.zeros(3, 768)])
-    batch = synthetic.make_batch(per_step, n_kg, seed=1, with_labels=False)
-    with torch.no_grad():
-        for _ in range(max(args.warmup, 1)):
-            orc.forward(sd, table, **batch)
-        steps = min(args.steps, 6)   # bounded: a CPU step takes seconds
-        t1 = time.perf_counter()
-        for _ in range(steps):
-            orc.forward(sd, table, **batch)
-        dt = time.perf_counter() - t1
-    v = steps * per_step / dt
-    sample = f"{steps} steps x {per_step} pairs (bounded sample of the batch-256 workload), fp32 CPU"
+    per_step = 4                              # rows per "step": a bounded sample of the batch-256 workload
+    steps = max(1, min(args.steps, 8))        # a CPU row takes ~0.5 s
+    v, cores, kind, sample = cpu_reference_loop(steps * per_step, warm=min(max(args.warmup, 1), 2))
     print(json.dumps({
         "impl": "reference", "metric": "text-triple pairs/sec (embedding extraction)", "value": v, "unit": "pairs/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / steps,
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1000 * per_step / v,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "get_stonkgs_embeddings-style extraction, STonKGs-150k shape, CPU oracle port of the "
-                               "reference forward (the reference package itself is not importable offline)"},
-        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": "get_stonkgs_embeddings-style extraction, STonKGs-150k shape", "kg_vocab": N_KG,
+                   "layers": "12+12", "rows_per_step": per_step,
+                   "path": "reference get_stonkgs_embeddings loop on CPU" if kind == "reference" else "oracle port on CPU"},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0}))
+
+
+# --------------------------------------------------------------------------------------------------
+# roofline of the dominant kernel: CUDA events around every GEMM / attention launch of >= 5 profiled steps
+# --------------------------------------------------------------------------------------------------
+_EPI_NAMES = {0: "bias", 1: "bias + erf-GELU", 2: "bias + GELU (saving pre-activation)", 3: "bias + residual",
+              4: "bias + tanh (pooler)", 5: "dgrad * GELU'", 6: "fp32 reduce-add (wgrad / split-K)", 7: "fp32 store",
+              8: "cross-entropy statistics (no logits)", 9: "cross-entropy dlogit",
+              10: "bias + residual + LayerNorm (6-CTA cluster)", 11: "bias + erf-GELU saving GELU'", 12: "dgrad * saved GELU'",
+              13: "bias + dropout + residual + LayerNorm (6-CTA cluster)"}
+
+
+def _describe(name: str) -> str:
+    # gemm_a{A}b{B}_epi{E}_n{N}_k{K}
+    try:
+        parts = name.split("_")
+        epi = int(parts[2][3:])
+        n, k = int(parts[3][1:]), int(parts[4][1:])
+        kind = {("a0", "b0"): "fwd", ("a0", "b1"): "dgrad", ("a1", "b1"): "wgrad"}.get((parts[1][:2], parts[1][2:]), "")
+        return f"{kind} N={n} K={k}, {_EPI_NAMES.get(epi, 'epilogue ' + str(epi))}"
+    except Exception:  # noqa: BLE001
+        return name
+
+
+def profile_roofline(step_fn, n_steps: int, peaks, torch, ops):
+    prof = ops.LaunchProfiler()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+    ops.set_profiler(prof)
+    for i, (e0, e1) in enumerate(ev):
+        e0.record()
+        step_fn(i)
+        e1.record()
+    agg = prof.summary()
+    ops.set_profiler(None)
+    step_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    gemm = {k: v for k, v in agg.items() if k.startswith("gemm")}
+    if not gemm:
+        return None
+    dom_name = max(gemm, key=lambda k: gemm[k]["ms"])
+    dom = gemm[dom_name]
+    g_ms = sum(a["ms"] for a in gemm.values())
+    g_fl = sum(a["work"] for a in gemm.values())
+    achieved = dom["work"] / dom["ms"] / 1e9
+    traffic = None
+    for tname in ("r2_traffic.json", "r1_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            t = tj.get(dom_name) or tj.get("_".join(dom_name.split("_")[:3]))
+            if t:   # ncu-measured DRAM bytes of one captured launch, scaled to this run's launch by its FLOPs
+                traffic = t["dram_bytes"] * (dom["work"] / dom["launches"]) / t["flops"]
+                break
+    return {
+        "bound": "tensor",
+        "kernel": f"stk::gemm_kernel<{dom_name}> ({_describe(dom_name)})",
+        "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+        "frac": achieved / peaks["bf16_sustained"],
+        "peak_source": f"{peaks['source']} cuBLAS bf16 sustained (kernel timed inside a long step)",
+        "traffic": traffic,
+        "algorithmic_flops_per_launch": dom["work"] / dom["launches"],
+        "launches_per_step": dom["launches"] / n_steps, "ms_per_launch": dom["ms"] / dom["launches"],
+        "profiled_steps": n_steps,
+        "share_of_profiled_step": dom["ms"] / step_ms if step_ms else None,
+        "gemm_family": {"achieved": g_fl / g_ms / 1e9 if g_ms else None, "share_of_profiled_step": g_ms / step_ms if step_ms else None},
+        "per_kernel": {k: {"ms_per_step": round(v["ms"] / n_steps, 3), "tflops": round(v["work"] / v["ms"] / 1e9, 1),
+                           "launches_per_step": v["launches"] / n_steps, "what": _describe(k) if k.startswith("gemm") else k}
+                       for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])},
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+class TiledRows:
+    """n virtual rows that repeat a base [m, 512] array: lets the bulk leg stream >= 1 M pairs from host memory
+    without holding 3 x 4 GB of ids (embed_arrays only needs .shape[0] and a[lo:hi])."""
+
+    def __init__(self, base, n):
+        self.base, self.n = base, int(n)
+        self.shape = (self.n,) + tuple(base.shape[1:])
+
+    def __getitem__(self, s):
+        import numpy as np
+        lo, hi, _ = s.indices(self.n)
+        m = self.base.shape[0]
+        a, b = lo % m, lo % m + (hi - lo)
+        if b <= m:
+            return self.base[a:b]
+        return np.concatenate([self.base[a:], self.base[: b - m]], axis=0)
+
+
+def library_baseline(dev, torch, steps=5, warm=2):
+    """The extraction forward through the LIBRARY path on the same GPU: two HF BertModels (bf16 weights, SDPA
+    attention -> cuBLAS GEMMs + flash/efficient attention kernels), the KG lookup as a device-side gather from the dense
+    table.  Same shapes and batch as the headline (256 pairs, 12+12 layers, N_kg 175 003)."""
+    import numpy as np
+    from transformers import BertConfig, BertModel
+    from stonkgs_b200 import synthetic
+    torch.manual_seed(0)
+    cfg = BertConfig(vocab_size=28996)
+    cfg._attn_implementation = "sdpa"
+    lm = BertModel(cfg).eval().to(dev, torch.bfloat16)
+    joint = BertModel(cfg).eval().to(dev, torch.bfloat16)
+    table = torch.from_numpy(np.random.default_rng(0).standard_normal((N_KG + 3, 768)).astype(np.float32)).to(dev)
+    batches = [{k: v.to(dev) for k, v in synthetic.make_batch(BATCH, N_KG, seed=300 + i, with_labels=False).items()}
+               for i in range(2)]
+
+    @torch.no_grad()
+    def step(i):
+        b = batches[i % 2]
+        ids = b["input_ids"]
+        tok = lm(input_ids=ids[:, :256]).last_hidden_state                   # stonkgs_model.py:178 (ids only, no mask)
+        ent = table[ids[:, 256:]].to(torch.bfloat16)                         # :182-189 as one gather
+        out = joint(inputs_embeds=torch.cat([tok, ent], 1), attention_mask=b["attention_mask"],
+                    token_type_ids=b["token_type_ids"])                      # :204-210
+        return out.pooler_output.float()
+
+    for i in range(warm):
+        step(i)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    del lm, joint, table
+    torch.cuda.empty_cache()
+    return {"value": BATCH / (ms / 1000), "unit": "pairs/s", "ms_per_step": ms, "steps": steps,
+            "what": "HF BertModel x 2 (transformers, bf16 weights, attn_implementation=sdpa) + device-side table gather, "
+                    "batch 256, inputs resident, torch.no_grad()"}
+
+
+def elm_stress(dev, torch, steps=3):
+    """configs[3]: the entity-prediction head alone at ~1 M entities: 128 pairs x 38 labelled rows against
+    W_ent [1 000 003, 768]; fused GEMM + cross-entropy forward (no logits) and backward (dlogit recomputed per
+    L2-resident vocabulary chunk, dT and dW accumulated)."""
+    from stonkgs_b200 import training
+    N, R, H = 1_000_003, 128 * 38, 768
+    g = torch.Generator(device=dev).manual_seed(0)
+    W = (torch.randn(N, H, device=dev, generator=g) * 0.05).bfloat16()
+    t = torch.randn(R, H, device=dev, generator=g).bfloat16()
+    labels = torch.randint(0, N, (R,), device=dev, dtype=torch.int32, generator=g)
+    dT = torch.zeros(R, H, dtype=torch.float32, device=dev)
+    gW = torch.zeros(N, H, dtype=torch.float32, device=dev)
+    scale = torch.full((1,), 1.0 / R, device=dev)
+
+    def fwd():
+        return training._ce_forward(t, W, labels)
+
+    def fwd_bwd():
+        lse, _ = training._ce_forward(t, W, labels)
+        training._ce_backward(t, W, labels, lse, scale, dT, gW)
+
+    out = {}
+    for name, fn, mult in (("fwd", fwd, 1), ("fwd_bwd", fwd_bwd, 3)):
+        fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        out[name] = {"ms": ms, "tflops": mult * 2.0 * R * H * N / ms / 1e9}
+    del W, gW
+    torch.cuda.empty_cache()
+    return {"entities": N, "labelled_rows": R, "pairs_per_s_fwd_bwd": 128 / (out["fwd_bwd"]["ms"] / 1000), **out,
+            "what": "BASELINE configs[3]: ELM head, fused GEMM + cross-entropy, batch 128"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -202,16 +398,19 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="extract", choices=["extract", "pretrain"])
+    ap.add_argument("--workload", default="all", choices=["all", "extract", "pretrain"])
     ap.add_argument("--layers", type=int, default=12)
     ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--bulk-pairs", type=int, default=BULK_PAIRS, help="pairs per GPU streamed by the bulk leg (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip library_baseline / elm_stress / cpu_baseline")
     ap.add_argument("--no-dropout", action="store_true", help="pretrain workload: switch the train()-mode dropout off")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
 
+    import numpy as np
     import torch
     import torch.distributed as dist
     from stonkgs_b200 import ops, synthetic
@@ -222,51 +421,8 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-
-    train = args.workload == "pretrain"
-    B = args.batch or (TRAIN_BATCH if train else BATCH)
+    peaks = measured_peaks()
     model = build_model(dev, args.layers)
-    opt = None
-    if train:
-        # train() like the reference's Trainer loop: hidden / attention-probability dropout (p = 0.1) is ON, with
-        # counter-based masks regenerated in the backward pass (SURVEY 8f.4); --no-dropout times the eval-numerics step
-        model.train()
-        model.stk_dropout = not args.no_dropout
-        if world > 1:
-            from stonkgs_b200.dp import DataParallel
-            DataParallel(model, dist.group.WORLD)
-        from stonkgs_b200.optim import FusedAdamW
-        # HF Trainer defaults of the reference driver: AdamW lr 1e-4, wd 0, max_grad_norm 1.0
-        opt = FusedAdamW(model, lr=1e-4, weight_decay=0.0, max_grad_norm=1.0)
-    # distinct batches per step so that no step re-reads the previous step's inputs from L2
-    n_batches = 4
-    host = [synthetic.make_batch(B, N_KG, seed=100 + rank * 17 + i, with_labels=train) for i in range(n_batches)]
-    host = [{k: v.pin_memory() for k, v in b.items()} for b in host]
-    resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
-    pooled_host = torch.empty((B, 768), dtype=torch.float32).pin_memory()
-    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
-
-    def step_resident(i):
-        b = resident[i % n_batches]
-        if train:
-            opt.zero_grad()
-            loss = model(**b)[0]
-            loss.backward()
-            opt.step()
-            return loss
-        return model.embed(b["input_ids"], b["attention_mask"], b["token_type_ids"])
-
-    def step_e2e(i):
-        b = {k: v.to(dev, non_blocking=True) for k, v in host[i % n_batches].items()}
-        if train:
-            opt.zero_grad()
-            loss = model(**b)[0]
-            loss.backward()
-            opt.step()
-            loss_host.copy_(loss.detach(), non_blocking=True)
-        else:
-            pooled_host.copy_(model.embed(b["input_ids"], b["attention_mask"], b["token_type_ids"]), non_blocking=True)
-        torch.cuda.synchronize(dev)   # the caller reads the result every step
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -287,84 +443,186 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for i in range(args.warmup):
-        step_resident(i)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    launches0 = ops.launch_count()
-    ms = timed(step_resident, args.steps)
-    launches = ops.launch_count() - launches0
-    for i in range(2):
-        step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    n_batches = 4   # distinct batches per step so that no step re-reads the previous step's inputs from L2
+    l2_policy = "per-step working set (>1 GB activations) exceeds the 126 MB L2; 4 rotating input batches"
 
-    # ---- roofline of the dominant kernel: one profiled step, CUDA events around every GEMM/attention launch
-    prof = ops.LaunchProfiler()
-    ops.set_profiler(prof)
-    step_resident(0)
-    agg = prof.summary()
-    ops.set_profiler(None)
-    peaks = measured_peaks()
-    total_ms = sum(a["ms"] for a in agg.values())
-    gemm = {k: v for k, v in agg.items() if k.startswith("gemm")}
-    dom_name = max(gemm, key=lambda k: gemm[k]["ms"]) if gemm else None   # dominant kernel instantiation
-    dom = gemm[dom_name] if dom_name else None
-    g_ms = sum(a["ms"] for a in gemm.values())
-    g_fl = sum(a["work"] for a in gemm.values())
-    achieved = dom["work"] / dom["ms"] / 1e9 if dom else None
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if dom_name and os.path.exists(tpath):
-        t = json.load(open(tpath)).get(dom_name)
-        if t:   # ncu-measured DRAM bytes of one captured launch, scaled to this run's average launch
-            traffic = t["dram_bytes"] * (dom["work"] / dom["launches"]) / t["flops"]
-    names = {"gemm_a0b0_epi0": "fused QKV projection", "gemm_a0b0_epi1": "FFN1 + erf-GELU epilogue",
-             "gemm_a0b0_epi3": "Wo / FFN2 + residual epilogue", "gemm_a0b0_epi10": "Wo / FFN2 + bias + residual + LayerNorm epilogue (3-CTA cluster)", "gemm_a1b1_epi6": "wgrad (split-K reduce-add)",
-             "gemm_a0b1_epi3": "dgrad + residual", "gemm_a0b1_epi5": "dgrad * GELU'", "gemm_a0b1_epi12": "dgrad * saved GELU'",
-             "gemm_a0b0_epi11": "FFN1 + erf-GELU epilogue saving GELU'"}
-    roofline = {
-        "bound": "tensor",
-        "kernel": f"stk::gemm_kernel<{dom_name}> ({names.get(dom_name, 'tcgen05 GEMM')})" if dom_name else None,
-        "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-        "frac": (achieved / peaks["bf16_sustained"]) if achieved else None,
-        "peak_source": f"{peaks['source']} cuBLAS bf16 sustained (kernel timed inside a long step)",
-        "traffic": traffic,
-        "algorithmic_flops_per_launch": (dom["work"] / dom["launches"]) if dom else None,
-        "launches": dom["launches"] if dom else None, "ms_per_launch": (dom["ms"] / dom["launches"]) if dom else None,
-        "share_of_profiled_step": (dom["ms"] / total_ms) if dom and total_ms else None,
-        "gemm_family": {"achieved": g_fl / g_ms / 1e9 if g_ms else None, "share_of_profiled_step": g_ms / total_ms if total_ms else None},
-        "per_kernel": {k: {"ms": round(v["ms"], 3), "tflops": round(v["work"] / v["ms"] / 1e9, 1), "launches": v["launches"]}
-                       for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])},
-    }
+    # ---------------------------------------------------------------------------------- extraction (headline)
+    def bench_extract():
+        B = args.batch or BATCH
+        host = [synthetic.make_batch(B, N_KG, seed=100 + rank * 17 + i, with_labels=False) for i in range(n_batches)]
+        host = [{k: v.pin_memory() for k, v in b.items()} for b in host]
+        resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
+        pooled_host = torch.empty((B, 768), dtype=torch.float32).pin_memory()
 
-    pairs = world * B * args.steps
-    value = pairs / (ms / 1000)
-    e2e_value = pairs / (ms_e2e / 1000)
-    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
-    d2h = 4 if train else B * 768 * 4
-    gflop = GFLOP_PER_PAIR_TRAIN if train else GFLOP_PER_PAIR_EXTRACT
-    out = {
-        "metric": "text-triple pairs/sec (" + ("pretrain step" if train else "embedding extraction") + ")",
-        "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": ("STonKGs-150k-shape pretraining step (fwd + bwd + MLM/ELM/NSP losses + DP grad allreduce + clip + AdamW; "
-                                + ("dropout off" if args.no_dropout else "train() mode with dropout 0.1") + ")"
-                                if train else "get_stonkgs_embeddings-style extraction, STonKGs-150k shape"),
-                   "batch_per_gpu": B, "global_batch": B * world, "seq_len": "256 text + 256 KG", "layers": f"{args.layers}+{args.layers}",
-                   "kg_vocab": N_KG, "parallelism": f"dp{world}" if train else f"batch-sharded x{world}, no comms",
-                   "l2_policy": "per-step working set (>1 GB activations) exceeds the 126 MB L2; 4 rotating input batches"},
-        "model_tflops_per_gpu": value / world * gflop / 1000,
-        "frac_of_bf16_sustained_peak": value / world * gflop / 1000 / peaks["bf16_sustained"],
-        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-    }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, sample = cpu_port_throughput(24)
-        out["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample}
+        def step_resident(i):
+            b = resident[i % n_batches]
+            return model.embed(b["input_ids"], b["attention_mask"], b["token_type_ids"])
+
+        def step_e2e(i):
+            b = {k: v.to(dev, non_blocking=True) for k, v in host[i % n_batches].items()}
+            pooled_host.copy_(model.embed(b["input_ids"], b["attention_mask"], b["token_type_ids"]), non_blocking=True)
+            torch.cuda.synchronize(dev)   # the caller reads the result every step
+
+        for i in range(args.warmup):
+            step_resident(i)
+        sampler = ClockSampler(local).start() if rank == 0 else None
+        l0 = ops.launch_count()
+        ms = timed(step_resident, args.steps)
+        launches = ops.launch_count() - l0
+        for i in range(2):
+            step_e2e(i)
+        ms_e2e = timed(step_e2e, args.steps)
+        clocks = sampler.stop() if sampler else None
+        roof = profile_roofline(step_resident, 5, peaks, torch, ops)
+        pairs = world * B * args.steps
+        value = pairs / (ms / 1000)
+        return {
+            "metric": "text-triple pairs/sec (embedding extraction)",
+            "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "get_stonkgs_embeddings-style extraction, STonKGs-150k shape", "batch_per_gpu": B,
+                       "global_batch": B * world, "seq_len": "256 text + 256 KG", "layers": f"{args.layers}+{args.layers}",
+                       "kg_vocab": N_KG, "parallelism": f"batch-sharded x{world}, no comms", "l2_policy": l2_policy},
+            "model_tflops_per_gpu": value / world * GFLOP_PER_PAIR_EXTRACT / 1000,
+            "frac_of_bf16_sustained_peak": value / world * GFLOP_PER_PAIR_EXTRACT / 1000 / peaks["bf16_sustained"],
+            "e2e": {"value": pairs / (ms_e2e / 1000), "unit": "pairs/s",
+                    "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host[0].values()),
+                    "d2h_bytes_per_step": B * 768 * 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+        }
+
+    # ---------------------------------------------------------------------------------- bulk streaming extraction
+    def bench_bulk(resident_value):
+        from stonkgs_b200.embeddings import EmbeddingStreamer
+        n = int(args.bulk_pairs)
+        base = synthetic.make_batch(8192, N_KG, seed=500 + rank, with_labels=False)
+        cols = [TiledRows(base[k].numpy(), n) for k in ("input_ids", "attention_mask", "token_type_ids")]
+        st = EmbeddingStreamer(model, BATCH)
+        out = np.empty((n, 768), dtype=np.float32)
+        st.run(*[TiledRows(c.base, 4 * BATCH) for c in cols], out=out[: 4 * BATCH])   # warm-up
+        barrier()
+        st.h2d_bytes = st.d2h_bytes = 0
+        l0 = ops.launch_count()
+        t0 = time.perf_counter()
+        st.run(*cols, out=out)
+        torch.cuda.synchronize(dev)
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.item())
+        v = world * n / dt
+        # same rows -> same embeddings, whatever batch they travelled in (bit-exact): a checksum-free correctness check
+        same = bool(np.array_equal(out[:8192 if n >= 16384 else 0], out[8192:16384 if n >= 16384 else 0]))
+        return {"value": v, "unit": "pairs/s", "pairs_per_gpu": n, "seconds": dt, "gap_to_resident": 1.0 - v / resident_value,
+                "h2d_bytes": st.h2d_bytes, "d2h_bytes": st.d2h_bytes, "gpu_launches": ops.launch_count() - l0,
+                "repeat_rows_bit_identical": same, "finite": bool(np.isfinite(out[-BATCH:]).all()),
+                "what": "BASELINE configs[4] per-GPU share: host int64 id arrays -> embeddings.embed_arrays (2 pinned staging "
+                        "slots, copy stream: H2D of batch i+1 and D2H of batch i-1 under the kernels of batch i) -> "
+                        "float32 [n,768] NumPy array; wall clock, max over ranks; no collective"}
+
+    # ---------------------------------------------------------------------------------- pre-training step
+    def bench_pretrain():
+        from stonkgs_b200.optim import FusedAdamW
+        B = args.batch if (args.batch and args.workload == "pretrain") else TRAIN_BATCH
+        # train() like the reference's Trainer loop: hidden / attention-probability dropout (p = 0.1) is ON, with
+        # counter-based masks regenerated in the backward pass (SURVEY 8f.4); --no-dropout times the eval-numerics step
+        model.train()
+        model.stk_dropout = not args.no_dropout
+        dp = None
+        if world > 1:
+            from stonkgs_b200.dp import DataParallel
+            dp = DataParallel(model, dist.group.WORLD)
+        # HF Trainer defaults of the reference driver: AdamW lr 1e-4, wd 0, max_grad_norm 1.0
+        opt = FusedAdamW(model, lr=1e-4, weight_decay=0.0, max_grad_norm=1.0)
+        host = [synthetic.make_batch(B, N_KG, seed=200 + rank * 17 + i, with_labels=True) for i in range(n_batches)]
+        host = [{k: v.pin_memory() for k, v in b.items()} for b in host]
+        resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
+        loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+        def step_resident(i):
+            opt.zero_grad()
+            loss = model(**resident[i % n_batches])[0]
+            loss.backward()
+            opt.step()
+            return loss
+
+        def step_e2e(i):
+            b = {k: v.to(dev, non_blocking=True) for k, v in host[i % n_batches].items()}
+            opt.zero_grad()
+            loss = model(**b)[0]
+            loss.backward()
+            opt.step()
+            loss_host.copy_(loss.detach(), non_blocking=True)
+            torch.cuda.synchronize(dev)   # the caller reads the loss every step
+
+        for i in range(args.warmup):
+            step_resident(i)
+        sampler = ClockSampler(local).start() if rank == 0 else None
+        l0 = ops.launch_count()
+        ms = timed(step_resident, args.steps)
+        launches = ops.launch_count() - l0
+        for i in range(2):
+            step_e2e(i)
+        ms_e2e = timed(step_e2e, args.steps)
+        clocks = sampler.stop() if sampler else None
+        loss_val = float(loss_host.item())
+        extra = {}
+        if dp is not None:
+            k = max(3, min(args.steps, 10))
+            with dp.no_sync():                    # the same step without the collective: local math only
+                step_resident(0)
+                ms_local = timed(step_resident, k) / k
+            dp.overlap = False                    # buckets reduced after backward has been enqueued: nothing hidden
+            step_resident(0)
+            ms_serial = timed(step_resident, k) / k
+            dp.overlap = True
+            step_resident(0)
+            extra = {"allreduce_ms_exposed": ms / args.steps - ms_local, "ms_per_step_no_collective": ms_local,
+                     "ms_per_step_not_overlapped": ms_serial, "allreduce_ms_total": ms_serial - ms_local,
+                     "wire_bytes": int(2 * (world - 1) / world * 2 * LIVE_PARAMS), "wire_dtype": "bf16",
+                     "buckets": len(dp.buckets) if dp.buckets else None, "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS")}
+        roof = profile_roofline(step_resident, 5, peaks, torch, ops)
+        pairs = world * B * args.steps
+        value = pairs / (ms / 1000)
+        model.eval()
+        return {
+            "metric": "text-triple pairs/sec (pretrain step)", "value": value, "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "STonKGs-150k-shape pretraining step (fwd + bwd + MLM/ELM/NSP losses + DP grad allreduce + "
+                                   "clip + AdamW; " + ("dropout off" if args.no_dropout else "train() mode with dropout 0.1") + ")",
+                       "batch_per_gpu": B, "global_batch": B * world, "seq_len": "256 text + 256 KG",
+                       "layers": f"{args.layers}+{args.layers}", "kg_vocab": N_KG, "parallelism": f"dp{world}",
+                       "l2_policy": l2_policy},
+            "model_tflops_per_gpu": value / world * GFLOP_PER_PAIR_TRAIN / 1000,
+            "frac_of_bf16_sustained_peak": value / world * GFLOP_PER_PAIR_TRAIN / 1000 / peaks["bf16_sustained"],
+            "e2e": {"value": pairs / (ms_e2e / 1000), "unit": "pairs/s",
+                    "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host[0].values()),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "last_loss": loss_val, "clocks": clocks, "roofline": roof, **extra,
+        }
+
+    # ---------------------------------------------------------------------------------- assemble the line
+    if args.workload == "pretrain":
+        out = bench_pretrain()
+    else:
+        out = bench_extract()
+        if args.bulk_pairs > 0 and args.workload == "all":
+            out["bulk"] = bench_bulk(out["value"])
+        if args.workload == "all":
+            if rank == 0 and world == 1 and not args.no_extras:
+                out["library_baseline"] = library_baseline(dev, torch)
+                out["vs_library"] = out["value"] / out["library_baseline"]["value"]
+            out["pretrain"] = bench_pretrain()
+    if rank == 0 and world == 1 and not args.no_extras:
+        if args.workload == "all":
+            del model
+            torch.cuda.empty_cache()
+            out["elm_stress"] = elm_stress(dev, torch)
+        if not args.no_cpu_baseline:
+            v, cores, kind, sample = cpu_reference_loop(12)
+            out["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

@@ -1,7 +1,10 @@
-"""TEST INFRASTRUCTURE — side-effect-free import of the real reference module (dev container only).
+"""TEST INFRASTRUCTURE — side-effect-free import of the real reference module.
 
-Executes the reference's own ``stonkgs.models.stonkgs_model.STonKGsForPreTraining`` from
-``/root/reference/src`` on CPU, following the recipe that SURVEY.md Appendix A verified:
+Executes the reference's own ``stonkgs.models.stonkgs_model.STonKGsForPreTraining`` on CPU, from
+``/root/reference/src`` (dev container) or from ``baseline/_ref`` (the UNMODIFIED reference package installed with
+``pip install --no-index --no-deps --ignore-requires-python --target baseline/_ref <copy of /root/reference>``; git-ignored,
+it travels to the GPU box, where ``bench.py --impl reference`` and the ``cpu_baseline`` leg time it), following the
+recipe that SURVEY.md Appendix A verified:
 
 * stub ``mlflow`` / ``pytorch_lightning`` (imported by ``kg_baseline_model.py:16,19`` which
   ``stonkgs_model.py:23`` pulls in only for ``prepare_df``);
@@ -13,7 +16,8 @@ Executes the reference's own ``stonkgs.models.stonkgs_model.STonKGsForPreTrainin
 * ``prepare_df`` patched to return the synthetic node2vec rows as float64, the dtype the TSV
   parser yields (``kg_baseline_model.py:270-280``).
 
-``/root/reference`` does not exist on the GPU box: nothing that runs there may import this file.
+Only ``tests/`` (CPU, dev container), ``oracle/make_golden.py`` and the two CPU-baseline legs of ``bench.py`` import
+this file; the product never does.
 """
 from __future__ import annotations
 
@@ -24,11 +28,22 @@ import types
 import numpy as np
 import torch
 
-REFERENCE_SRC = "/root/reference/src"
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CANDIDATES = ("/root/reference/src", os.path.join(_REPO, "baseline", "_ref"))
+
+
+def _find_reference():
+    for c in _CANDIDATES:
+        if os.path.isfile(os.path.join(c, "stonkgs", "models", "stonkgs_model.py")):
+            return c
+    return None
+
+
+REFERENCE_SRC = _find_reference() or _CANDIDATES[0]
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_SRC, "stonkgs", "models", "stonkgs_model.py"))
+    return _find_reference() is not None
 
 
 _state = {"sm": None, "num_layers": 12, "lm_sd": None}

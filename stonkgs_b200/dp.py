@@ -79,6 +79,12 @@ class DataParallel:
         for t in list(self.model.parameters()) + list(self.model.buffers()):
             dist.broadcast(t.data, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
                            group=self.group)
+        # writes through .data do not bump Parameter._version, which is what the model's staleness check of its
+        # device-side state looks at: drop that state (bf16 GEMM copies, fused q|k|v bias, the three LM-backbone rows
+        # of the KG table) so that every rank rebuilds it from the weights it just received
+        if hasattr(self.model, "_dev_state"):
+            self.model._dev_state = None
+            self.model._special_rows_version = None
 
     @contextlib.contextmanager
     def no_sync(self):

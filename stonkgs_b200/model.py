@@ -189,7 +189,13 @@ class STonKGsForPreTraining(BertForPreTraining):
         self.kg_backbone = _KGBackboneView(self)
         self._special_rows_version = None
         self._dev_state = None
-        self.return_prediction_logits = False   # dense [B,256,V] / [B,256,N] logits only on request
+        # prediction_logits = the reference's dense pair (text [B,256,V], entity [B,256,N]; stonkgs_model.py:73,253).
+        # None (default): computed eagerly whenever no autograd step is being recorded (eval / no labels / no_grad) and
+        # the pair fits `dense_logits_max_bytes`; otherwise (the training step, whose loss never needs them) a lazy pair
+        # that runs the two decoder GEMMs the first time it is indexed / iterated.  True: always eager.  False: explicit
+        # opt-out, the field is (None, None).
+        self.return_prediction_logits = None
+        self.dense_logits_max_bytes = 16 << 30
         # train() mode dropout (HF:110,132,297,355): masks are a counter-based function of
         # (stk_dropout_seed + step, site), so backward regenerates them; last_dropout_seed is what a test hands to
         # oracle.dropout_oracle.DropSpec to reproduce the same step in fp32
@@ -344,7 +350,7 @@ class STonKGsForPreTraining(BertForPreTraining):
                 raise KeyError(int(bad))
 
     def encode(self, input_ids, attention_mask=None, token_type_ids=None, *, cache=None, want_inputs_embeds=False,
-               need_heads=False):
+               need_heads=False, err_flag=None, head_mask=None):
         """LM backbone -> KG lookup -> joint encoder -> pooler.  Returns (seq bf16 [B*seq_pad,768], pooled fp32, emb)."""
         st = self._device_state(need_heads)
         dev = self.kg_table.device
@@ -353,7 +359,9 @@ class STonKGsForPreTraining(BertForPreTraining):
             raise StkError(f"input_ids must be [B, {sh.seq_len}] ({sh.text_len} text + {sh.kg_len} KG tokens), "
                            f"got {tuple(input_ids.shape)}")
         self._check_ids(input_ids)
-        err = torch.zeros(1, dtype=torch.int32, device=dev) if input_ids.is_cuda else None
+        # ids already on the device are range-checked by the kernels (device flag, read later: _raise_on_bad_ids);
+        # a caller streaming many batches passes ONE flag for all of them (embeddings.EmbeddingStreamer)
+        err = err_flag if err_flag is not None else (torch.zeros(1, dtype=torch.int32, device=dev) if input_ids.is_cuda else None)
         input_ids = input_ids.to(dev, torch.int64, non_blocking=True).contiguous()
         if attention_mask is not None:
             attention_mask = attention_mask.to(dev, torch.int64, non_blocking=True).contiguous()
@@ -366,7 +374,8 @@ class STonKGsForPreTraining(BertForPreTraining):
                                             err_flag=err, drop=drop, shape=sh)
         if cache is not None:
             cache.update(input_ids=input_ids, token_type_ids=token_type_ids, err=err)
-        self._pending_err = err
+        if err_flag is None:
+            self._pending_err = err
         return seq, pooled, emb
 
     def _drop_ctx(self):
@@ -386,19 +395,29 @@ class STonKGsForPreTraining(BertForPreTraining):
         from .training import GradBuffer
         gb = getattr(self, "_grad_buffer", None)
         dev = self.bert.pooler.dense.weight.device
-        if gb is None or gb.flat.device != dev:
+        if gb is None or gb.flat.device != dev or gb.stale():
             gb = self._grad_buffer = GradBuffer(self)
         return gb
 
     def _raise_on_bad_ids(self):
+        """Read the device-side id / label range flag of the last forward (one host sync) and raise like the reference
+        (KeyError from ``kg_backbone[i]``, IndexError from the embedding / cross-entropy).  The training step calls this
+        from ``FusedAdamW.step`` (or the next forward), i.e. after backward has been enqueued, so that the read does not
+        drain the queue between forward and backward."""
         err = getattr(self, "_pending_err", None)
-        if err is not None and int(err.item()) != 0:
+        self._pending_err = None
+        if err is None:
+            return
+        code = int(err.item())
+        if code & 1:
             raise KeyError("input id outside the text vocabulary / KG table")
+        if code & 2:
+            raise IndexError("label outside the vocabulary of its head (text / entity / next-sentence)")
 
     @torch.no_grad()
-    def embed(self, input_ids, attention_mask=None, token_type_ids=None) -> torch.Tensor:
+    def embed(self, input_ids, attention_mask=None, token_type_ids=None, err_flag=None) -> torch.Tensor:
         """Extraction path: pooled 768-d output only (stonkgs_for_embeddings.py:180), heads skipped."""
-        _, pooled, _ = self.encode(input_ids, attention_mask, token_type_ids)
+        _, pooled, _ = self.encode(input_ids, attention_mask, token_type_ids, err_flag=err_flag)
         return pooled
 
     def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, masked_lm_labels=None,

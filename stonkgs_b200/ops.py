@@ -235,7 +235,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: int, N: int, K: int, a_major: i
         ldc = 0
     prof = _PROFILER
     if prof is not None:
-        e0, e1 = prof.span(f"gemm_a{a_major}b{b_major}_epi{epilogue}", 2.0 * M * N * K)
+        e0, e1 = prof.span(f"gemm_a{a_major}b{b_major}_epi{epilogue}_n{N}_k{K}", 2.0 * M * N * K)
         e0.record()
     check(_lib.load().stk_gemm(dev, stream, a_major, b_major, _ptr(a), a.stride(0), _ptr(b), b.stride(0), M, N, K,
                                epilogue, _ptr(out), ldc, ctypes.byref(epi), split_k), "stk_gemm")

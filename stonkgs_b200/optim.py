@@ -88,6 +88,7 @@ class FusedAdamW(torch.optim.Optimizer):
         self._chunk_seg = torch.tensor(chunk_seg, dtype=torch.int32, device=dev)
         self._chunk_off = torch.tensor(chunk_off, dtype=torch.int64, device=dev)
         self._n_chunks = len(chunk_seg)
+        self._runs = gb.trainable_runs()
         self._weights_state = self.model._dev_state   # tables point into these buffers
 
     # ------------------------------------------------------------------------------------------
@@ -95,6 +96,10 @@ class FusedAdamW(torch.optim.Optimizer):
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         gb = self._gb
+        if self.model.grad_buffer() is not gb:
+            raise StkError("the model's gradient buffer was rebuilt (moved to another device, or requires_grad of a "
+                           "parameter changed) after FusedAdamW was constructed: build a new optimizer")
+        self.model._raise_on_bad_ids()   # deferred id / label range check of this step's forward (backward is enqueued)
         if self.model._dev_state is not self._weights_state or self.model._dev_state is None:
             self._build_tables(gb.flat.device)   # the model was moved / its device state rebuilt
         if any(p.grad is None or p.grad.data_ptr() != v.data_ptr() for p, v in gb.param_views):
@@ -109,8 +114,9 @@ class FusedAdamW(torch.optim.Optimizer):
         clip = g["max_grad_norm"] is not None and g["max_grad_norm"] > 0
         if clip:
             self._sumsq.zero_()
-            check(lib.stk_sumsq(dev.index, stream, ctypes.c_void_p(gb.flat.data_ptr()), gb.flat.numel(),
-                                ctypes.c_void_p(self._sumsq.data_ptr())), "stk_sumsq")
+            for a, b in self._runs:   # one range unless some live parameters are frozen
+                check(lib.stk_sumsq(dev.index, stream, ctypes.c_void_p(gb.flat.data_ptr() + 4 * a), b - a,
+                                    ctypes.c_void_p(self._sumsq.data_ptr())), "stk_sumsq")
         check(lib.stk_adamw_step(dev.index, stream, ctypes.c_void_p(self._segs_dev.data_ptr()),
                                  ctypes.c_void_p(self._chunk_seg.data_ptr()), ctypes.c_void_p(self._chunk_off.data_ptr()),
                                  self._n_chunks, float(g["lr"]), float(b1), float(b2), float(g["eps"]),

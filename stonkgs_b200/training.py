@@ -90,18 +90,41 @@ class GradBuffer:
             total += (n + 3) // 4 * 4
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.views: Dict[str, torch.Tensor] = {}
-        self.param_views = []  # (param, view)
+        # (param, view) of the TRAINABLE live parameters only: a frozen tensor (requires_grad=False, e.g. frozen lower
+        # layers while fine-tuning) keeps its slot in the buffer — backward writes there unconditionally — but never
+        # gets a .grad, is not updated by FusedAdamW and does not count in the clipping norm (torch semantics)
+        self.param_views = []
         for name, shape, params in entries:
             off, n, _ = self.offsets[name]
             v = self.flat[off:off + n].view(shape)
             self.views[name] = v
             if len(params) == 1:
-                self.param_views.append((params[0], v))
+                pv = [(params[0], v)]
             else:  # fused q|k|v: consecutive row blocks
                 rows = shape[0] // len(params)
-                for j, p in enumerate(params):
-                    self.param_views.append((p, v[j * rows:(j + 1) * rows]))
+                pv = [(p, v[j * rows:(j + 1) * rows]) for j, p in enumerate(params)]
+            self.param_views += [(p, w) for p, w in pv if p.requires_grad]
         self.entries = [e[0] for e in entries]
+        self._trainable_key = tuple(p.requires_grad for _, _, ps in entries for p in ps)
+        self._all_params = [p for _, _, ps in entries for p in ps]
+
+    def stale(self) -> bool:
+        """True when requires_grad of a live parameter changed since the buffer was laid out."""
+        return tuple(p.requires_grad for p in self._all_params) != self._trainable_key
+
+    def trainable_runs(self):
+        """Maximal contiguous [start, end) element ranges of the flat buffer covered by trainable views (one range — the
+        whole buffer — when nothing is frozen): what the global-norm kernel sums over."""
+        base = self.flat.data_ptr()
+        spans = sorted(((v.data_ptr() - base) // 4, v.numel()) for _, v in self.param_views)
+        runs = []
+        for off, n in spans:
+            end = off + (n + 3) // 4 * 4          # segment padding is zero: harmless in a sum of squares
+            if runs and off <= runs[-1][1]:
+                runs[-1][1] = max(runs[-1][1], end)
+            else:
+                runs.append([off, end])
+        return [(a, min(b, self.flat.numel())) for a, b in runs]
 
     def __getitem__(self, name):
         return self.views[name]
@@ -213,6 +236,45 @@ def dense_prediction_logits(hw: engine.HeadWeights, seq, B, shape: ops.SeqShape 
         ops.gemm(t, w, M=B * width, N=V, K=H, epilogue=ops.EPI_F32, out=buf[:, :V])
         out.append(buf[:, :V].view(B, width, V))
     return tuple(out)
+
+
+class LazyPredictionLogits:
+    """``prediction_logits`` of a training step: the reference's dense pair ``(text [B,256,V], entity [B,256,N])``
+    (stonkgs_model.py:73,253), computed the first time it is indexed, iterated, unpacked or detached.  The training loss
+    comes from the fused GEMM + cross-entropy and never needs these 80 GFLOP / 1.4 GB per 8 pairs, so a step that does
+    not look at them does not pay for them; anything that does (``outputs[1][0]``, ``text, ent = ...``, HF
+    ``nested_detach``) gets real tensors."""
+
+    def __init__(self, hw, seq, B, shape):
+        self._args = (hw, seq, B, shape)
+        self._pair = None
+
+    def materialize(self):
+        if self._pair is None:
+            with torch.no_grad():
+                self._pair = dense_prediction_logits(*self._args)
+            self._args = None
+        return self._pair
+
+    def __getitem__(self, i):
+        return self.materialize()[i]
+
+    def __iter__(self):
+        return iter(self.materialize())
+
+    def __len__(self):
+        return 2
+
+    def detach(self):
+        return tuple(t.detach() for t in self.materialize())
+
+    def __repr__(self):
+        return "LazyPredictionLogits(materialized)" if self._pair is not None else "LazyPredictionLogits(pending)"
+
+
+def dense_logits_bytes(model, B: int) -> int:
+    sh = model.seq_shape
+    return 4 * B * (sh.text_len * model.config.vocab_size + sh.kg_len * model.config.kg_vocab_size)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -444,10 +506,11 @@ def forward(model, input_ids, attention_mask, token_type_ids, mlm, elm, nsp, ret
     from .model import BertForPreTrainingOutputWithPooling
     have_labels = mlm is not None and elm is not None and nsp is not None
     B = input_ids.shape[0]
-    grad = have_labels and torch.is_grad_enabled() and any(p.requires_grad for p in model.bert.parameters())
+    model._raise_on_bad_ids()   # a flag left by the previous step (deferred read, see model._raise_on_bad_ids)
+    anchor = next((p for p, _ in model.grad_buffer().param_views), None) if have_labels and torch.is_grad_enabled() else None
+    grad = anchor is not None   # a live, trainable parameter ties the Function into the autograd graph
     total_loss = None
     if grad:
-        anchor = model.bert.pooler.dense.bias  # any live parameter: ties the Function into the autograd graph
         total_loss, pooled, nsp_logits, seq = _PretrainStep.apply(
             model, (input_ids, attention_mask, token_type_ids, mlm, elm, nsp), anchor)
         hw = model._dev_state["heads"]
@@ -460,11 +523,16 @@ def forward(model, input_ids, attention_mask, token_type_ids, mlm, elm, nsp, ret
                 model._last_loss_parts = parts
             else:
                 nsp_logits, _ = ops.nsp_head(pooled, hw.w_nsp, hw.b_nsp, None)
-    model._raise_on_bad_ids()
-    prediction_scores = (None, None)
-    if model.return_prediction_logits:
+    if not grad:
+        model._raise_on_bad_ids()   # the training step reads the flag after backward has been enqueued
+    want = model.return_prediction_logits
+    if want is False:
+        prediction_scores = (None, None)                      # explicit opt-out
+    elif want or (not grad and dense_logits_bytes(model, B) <= model.dense_logits_max_bytes):
         with torch.no_grad():
             prediction_scores = dense_prediction_logits(hw, seq, B, model.seq_shape)
+    else:
+        prediction_scores = LazyPredictionLogits(hw, seq, B, model.seq_shape)
     sh = model.seq_shape
     sequence_output = seq.view(B, sh.seq_pad, H)
     if sh.seq_pad != sh.seq_len:

@@ -37,11 +37,37 @@ def test_config0_b8_full_model_vs_oracle():
         got = named[k].grad.detach().cpu().float()
         cos = torch.nn.functional.cosine_similarity(got.reshape(1, -1), g.reshape(1, -1)).item()
         worst_cos = min(worst_cos, cos)
-        assert cos > 0.99, (k, cos)
+        assert cos > 0.999, (k, cos)
     with torch.no_grad():
         pooled = model.embed(batch["input_ids"], batch["attention_mask"], batch["token_type_ids"]).cpu()
-    np.testing.assert_allclose(pooled.numpy(), ref["pooler_output"].detach().numpy(), atol=8e-2)
+    np.testing.assert_allclose(pooled.numpy(), ref["pooler_output"].detach().numpy(), atol=5e-2)
     print(f"config0: loss {loss.item():.4f} vs {ref['loss'].item():.4f}; worst grad cosine {worst_cos:.5f}")
+
+
+def test_config1_b256_extraction_vs_oracle():
+    """configs[1] at its full size: pooled [256, 768] of one batch of 256 pairs (12+12 layers, N_kg = 175 003)
+    against the fp32 CPU oracle on the same inputs.  Tolerance: atol 5e-2, mean-abs <= 1e-2 (SURVEY 8c guide)."""
+    from _util import build_model
+    from oracle import stonkgs_oracle as orc, weights
+    from stonkgs_b200 import synthetic
+    meta = dict(layers=12, n_kg=175003, seed_w=0)
+    sd = weights.make_state_dict(meta["n_kg"], 12, 0)
+    rows = weights.make_kg_table(meta["n_kg"], 0)
+    batch = synthetic.make_batch(256, meta["n_kg"], seed=21, with_labels=False)
+    model = build_model(meta, sd, rows, "cuda")
+    got = model.embed(**batch).cpu().numpy()
+    import os
+    torch.set_num_threads(max(torch.get_num_threads(), os.cpu_count() or 8))
+    table = orc.build_kg_table(sd, rows)
+    ref = []
+    with torch.no_grad():
+        for lo in range(0, 256, 32):   # the oracle in slices of 32 pairs (bounded host memory; rows are independent)
+            ref.append(orc.forward(sd, table, **{k: v[lo:lo + 32] for k, v in batch.items()})["pooler_output"].numpy())
+    ref = np.concatenate(ref)
+    assert got.shape == ref.shape == (256, 768)
+    np.testing.assert_allclose(got, ref, atol=5e-2)
+    assert np.abs(got - ref).mean() < 1e-2
+    print(f"config1 B=256: pooled max|d| {np.abs(got - ref).max():.4f}, mean|d| {np.abs(got - ref).mean():.5f}")
 
 
 def test_config3_million_entity_elm_head():

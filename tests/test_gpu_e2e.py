@@ -1,8 +1,8 @@
 """GPU: the drop-in model end to end against the reference-pinned oracle and the golden fixtures.
 
 Stated tolerances (bf16 tensor-core compute vs the fp32 CPU reference; SURVEY §8c guide):
-  pooled / hidden states  atol 8e-2, mean-abs <= 1.5e-2   loss rtol 2e-3   lse atol 2e-2
-  gradients               cosine >= 0.995 per tensor, max-rel <= 8 %
+  pooled atol 5e-2, hidden states atol 6e-2, mean-abs <= 1e-2   loss rtol 2e-3   lse atol 2e-2
+  gradients               cosine >= 0.999 per tensor, max-rel <= 3 %   (measured worst: pooler 0.028, cosine 0.9997)
   gathers / indices / label selection / KG table node rows: bit-exact
 """
 import numpy as np
@@ -29,18 +29,26 @@ def test_forward_matches_reference_golden(case):
     r = [int(v) for v in fix["rows"]]
     pooled = out.pooler_output.cpu().numpy()
     assert out.pooler_output.dtype == torch.float32 and out.hidden_states.shape == (meta["batch"], 512, 768)
-    np.testing.assert_allclose(pooled, fix["pooler_output"], atol=8e-2)
-    assert np.abs(pooled - fix["pooler_output"]).mean() < 1.5e-2
-    np.testing.assert_allclose(out.hidden_states[:, r].cpu().numpy(), fix["sequence_output_rows"], atol=1e-1)
+    np.testing.assert_allclose(pooled, fix["pooler_output"], atol=5e-2)
+    assert np.abs(pooled - fix["pooler_output"]).mean() < 1e-2
+    np.testing.assert_allclose(out.hidden_states[:, r].cpu().numpy(), fix["sequence_output_rows"], atol=6e-2)
     np.testing.assert_allclose(out.loss.item(), float(fix["loss"]), rtol=2e-3)
     mlm, elm, nsp = [float(v) for v in model._last_loss_parts]
     np.testing.assert_allclose(mlm, float(fix["mlm_loss"]), rtol=2e-3)
     np.testing.assert_allclose(elm, float(fix["elm_loss"]), rtol=2e-3)
     np.testing.assert_allclose(out.seq_relationship_logits.cpu().numpy(), fix["seq_relationship_logits"], atol=3e-2)
-    # tuple form of the reference (stonkgs_model.py:247-249)
+    # tuple form of the reference (stonkgs_model.py:247-249): (loss, (text_logits, entity_logits), nsp_logits)
     with torch.no_grad():
         tup = model(**batch)
-    assert len(tup) == 3 and tup[1] == (None, None) and torch.equal(tup[0], out.loss)
+    assert len(tup) == 3 and torch.equal(tup[0], out.loss)
+    assert tup[1][0].shape == (meta["batch"], 256, 28996) and tup[1][1].shape == (meta["batch"], 256, meta["n_kg"])
+    # explicit opt-out of the dense logits
+    model.return_prediction_logits = False
+    try:
+        with torch.no_grad():
+            assert model(**batch)[1] == (None, None)
+    finally:
+        model.return_prediction_logits = None
 
 
 def test_kg_gather_is_bit_exact(case):
@@ -62,15 +70,21 @@ def test_kg_gather_is_bit_exact(case):
     np.testing.assert_allclose(got[special], fix["kg_probe_rows"][special], atol=1e-1)   # LM-backbone rows (bf16 compute)
 
 
-def test_dense_logits_on_request(case):
+def test_dense_logits_are_the_default(case):
+    """prediction_logits is the reference's dense pair (stonkgs_model.py:73,253): eager without autograd, a lazy pair
+    that materialises on first use inside a training step."""
     fix, meta, batch, sd, rows, model = case
-    model.return_prediction_logits = True
-    try:
-        with torch.no_grad():
-            out = model(**batch, return_dict=True)
-    finally:
-        model.return_prediction_logits = False
+    from stonkgs_b200.training import LazyPredictionLogits
+    with torch.no_grad():
+        out = model(**batch, return_dict=True)
+    assert isinstance(out.prediction_logits, tuple)
     text, ent = out.prediction_logits
+    step = model(**batch, return_dict=True)          # autograd on + labels: the training step
+    assert isinstance(step.prediction_logits, LazyPredictionLogits) and len(step.prediction_logits) == 2
+    lt, le = step.prediction_logits                  # unpacking materialises
+    assert torch.equal(lt, text) and torch.equal(le, ent) and torch.equal(step.prediction_logits[0], text)
+    assert all(torch.equal(a, b) for a, b in zip(step.prediction_logits.detach(), (text, ent)))
+    del step, lt, le
     assert text.shape == (meta["batch"], 256, 28996) and ent.shape == (meta["batch"], 256, meta["n_kg"])
     sel = batch["masked_lm_labels"].reshape(-1) != -100
     got = text.reshape(-1, 28996)[sel.cuda()][:, :32].cpu().numpy()
@@ -95,7 +109,7 @@ def test_backward_matches_oracle(case):
             continue
         cos = torch.nn.functional.cosine_similarity(got.reshape(1, -1), g.reshape(1, -1)).item()
         rel = (got - g).abs().max().item() / (g.abs().max().item() + 1e-12)
-        assert cos > 0.995 and rel < 0.08, (k, cos, rel)
+        assert cos > 0.999 and rel < 0.03, (k, cos, rel)
     dead = sorted(k for k, p in named.items() if p.requires_grad and p.grad is None)
     assert dead == sorted(str(s) for s in fix["dead_names"])
     # second backward accumulates into the same flat buffer (grad views)
@@ -115,3 +129,9 @@ def test_out_of_table_id_raises(case):
     with pytest.raises(KeyError):                       # device-resident ids: flagged by the kernel
         with torch.no_grad():
             model(**{k: v.cuda() for k, v in bad.items()})
+    # training step: the flag is read after backward has been enqueued (FusedAdamW.step / the next forward)
+    loss = model(**{k: v.cuda() for k, v in bad.items()})[0]
+    loss.backward()
+    with pytest.raises(KeyError):
+        model._raise_on_bad_ids()
+    model.zero_grad(set_to_none=True)

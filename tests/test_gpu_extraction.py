@@ -51,9 +51,35 @@ def test_get_stonkgs_embeddings_dataframe_api(full_model):
     batch = synthetic.make_batch(37, n_kg, seed=5)   # label columns present, like the reference's rows
     df = pd.DataFrame({k: list(v.numpy()) for k, v in batch.items()}, index=[f"r{i}" for i in range(37)])
     out = get_stonkgs_embeddings(df, model=model, batch_size=16)
-    assert list(out.columns) == ["embedding"] and list(out.index) == list(df.index)
+    assert list(out.columns) == ["embedding"] and list(out.index) == list(range(37))   # fresh RangeIndex (reference :181-184)
     arr = np.asarray(out["embedding"].tolist(), dtype=np.float32)
     ref = model.embed(batch["input_ids"], batch["attention_mask"], batch["token_type_ids"]).cpu().numpy()
     assert np.array_equal(arr, ref)
-    some = get_stonkgs_embeddings(df, list_of_indices=["r3", "r20"], model=model)
+    some = get_stonkgs_embeddings(df, list_of_indices=[3, 20], model=model)   # positions (reference: df.iloc[idx])
     assert np.array_equal(np.asarray(some["embedding"].tolist(), dtype=np.float32), ref[[3, 20]])
+
+
+def test_streamed_embed_arrays(full_model):
+    """Bulk path (BASELINE configs[4]): host arrays -> double-buffered pinned staging on a copy stream -> NumPy.
+    Bit-identical to direct model.embed calls, for ragged tails, any integer dtype, reused streamers and virtual
+    (tiled) sources; an id outside the KG table raises KeyError like the reference's dict lookup."""
+    from stonkgs_b200 import synthetic
+    from stonkgs_b200.embeddings import EmbeddingStreamer, embed_arrays
+    model, n_kg = full_model
+    n = 2 * 64 + 23
+    batch = synthetic.make_batch(n, n_kg, seed=9, with_labels=False)
+    ref = model.embed(**batch).cpu().numpy()
+    ids, mask, types = (batch[k].numpy() for k in ("input_ids", "attention_mask", "token_type_ids"))
+    got = embed_arrays(model, ids, mask, types, batch_size=64)
+    assert got.dtype == np.float32 and got.shape == (n, 768) and np.array_equal(got, ref)
+    st = EmbeddingStreamer(model, batch_size=32, slots=3)
+    out = np.zeros((n, 768), dtype=np.float32)
+    assert st.run(ids.astype(np.int32), mask.astype(np.int32), types.astype(np.int32), out=out) is out
+    assert np.array_equal(out, ref)
+    assert np.array_equal(st.run(ids[:5], mask[:5], types[:5]), ref[:5])          # the streamer is reusable
+    assert st.h2d_bytes == (n + 5) * 512 * 8 * 3 and st.d2h_bytes == (n + 5) * 768 * 4
+    bad = ids.copy()
+    bad[70, 300] = n_kg + 3
+    with pytest.raises(KeyError):
+        embed_arrays(model, bad, mask, types, batch_size=64)
+    assert np.array_equal(embed_arrays(model, ids, mask, types, batch_size=64), ref)   # the flag does not stick

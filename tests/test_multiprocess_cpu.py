@@ -104,7 +104,10 @@ def _embed_worker(rank, world, port, out):
         lo, hi = (0, 6) if rank == 0 else (6, 11)
         assert list(mine) == list(range(lo, hi))                                   # contiguous shard per rank
         got = np.asarray(res["embedding"].tolist())
-        assert got.shape == (n, 768) and list(got[:, 0]) == list(range(n)) and list(res.index) == list(df.index)
+        assert got.shape == (n, 768) and list(got[:, 0]) == list(range(n)) and list(res.index) == list(range(n))   # fresh RangeIndex like the reference
+        # list_of_indices are POSITIONS (reference: preprocessed_df.iloc[idx]) whatever the frame's own index is
+        some = get_stonkgs_embeddings(df, list_of_indices=[7, 2, 9, 4], _embed_fn=fake_embed)
+        assert list(np.asarray(some["embedding"].tolist())[:, 0]) == [7, 2, 9, 4] and list(some.index) == [0, 1, 2, 3]
         out[rank] = "ok"
     finally:
         dist.destroy_process_group()
