@@ -29,7 +29,7 @@ extern "C" {
 #define STK_ERR_CUDA (-2)
 #define STK_ERR_UNSUPPORTED (-3)
 
-#define STK_VERSION 101
+#define STK_VERSION 102
 
 /* library version (STK_VERSION) */
 int stk_version(void);
@@ -47,7 +47,8 @@ long long stk_launch_count(void);
  * called with ids only, so token type is 0 and there is no mask).
  * ids: int64 [B, S] with row pitch ids_pitch (elements), so the text half of a [B,512] batch can be
  * passed in place.  word/pos/type tables and LayerNorm gain/bias are fp32.  out: bf16 [B*S, 768].
- * err_flag (device int, may be NULL) is set to 1 if an id is outside [0, vocab). */
+ * err_flag (device int, may be NULL): bit 0 (value 1) is set if an id is outside [0, vocab).  All err_flag arguments of
+ * this library are bit sets (atomic OR): 1 = input id out of range, 2 = label out of range, 4 = label capacity. */
 int stk_embed_text_ln_fwd(int device, void* stream, const int64_t* ids, int64_t ids_pitch, int B, int S,
                           const float* word, int vocab, const float* pos, const float* type_emb,
                           const float* gamma, const float* beta, void* out_bf16, int* err_flag);
@@ -132,7 +133,11 @@ enum {
                                 shared memory); optional C2(bf16) = z and ln_mean/ln_rstd[m] for the backward */
   STK_EPI_BIAS_GELU_SAVE_GRAD = 11, /* C(bf16) = gelu_erf(u), C2(bf16) = gelu_erf'(u), u = acc + bias: the training forward of
                                        BertIntermediate saves the derivative, so that the backward epilogue is one multiply */
-  STK_EPI_MUL = 12                  /* C(bf16) = acc * R[m,n]   (R = the saved derivative; backward of the GELU)              */
+  STK_EPI_MUL = 12,                 /* C(bf16) = acc * R[m,n]   (R = the saved derivative; backward of the GELU)              */
+  STK_EPI_BIAS_DROP_RESID_LN = 13   /* train() form of 10: z = drop(acc + bias) + R with the keep decisions of csrc/stk_rng.cuh for
+                                       (drop_seed, drop_site, row m, column n), survivors scaled by 128 / (128 - drop_thr)
+                                       (HF:296-298, 354-356: dropout of the dense output BEFORE the residual sum); the mask is
+                                       regenerated by stk_layernorm_bwd_fused, never stored */
 };
 
 typedef struct StkGemmEpilogue {
@@ -152,11 +157,52 @@ typedef struct StkGemmEpilogue {
   const float* ln_beta;   /* BIAS_RESID_LN: [768] LayerNorm bias */
   float* ln_mean;         /* BIAS_RESID_LN: optional [M] row mean of z (saved for the backward) */
   float* ln_rstd;         /* BIAS_RESID_LN: optional [M] 1/sqrt(var + 1e-12) */
+  uint32_t drop_seed;     /* BIAS_DROP_RESID_LN: dropout seed of this step */
+  uint32_t drop_site;     /* BIAS_DROP_RESID_LN: site id (encoder, layer, dense output) */
+  uint32_t drop_thr;      /* BIAS_DROP_RESID_LN: round(128 p) in [1, 127] */
 } StkGemmEpilogue;
 
+/* split_k: number of k-splits of an STK_EPI_F32_ADD GEMM (each split reduce-adds its partial tile); 0 = chosen by the
+ * library so that the persistent grid is full; ignored (1) for every other epilogue. */
 int stk_gemm(int device, void* stream, int a_major, int b_major, const void* A_bf16, int64_t lda,
              const void* B_bf16, int64_t ldb, int M, int N, int K, int epilogue, void* C, int64_t ldc,
              const StkGemmEpilogue* epi, int split_k);
+
+/* ------------------------------------------------------------------------------------------------
+ * MLM / ELM heads as single calls (stonkgs_model.py:62-73 decoders without bias, :229-245 mean cross-entropies)
+ * ---------------------------------------------------------------------------------------------- */
+/* Workspace bytes of the calls that take one; negative = STK_ERR_*.
+ *   STK_WS_ATTN_BWD       a = B, b = S            (stk_attn_bwd / stk_attn_bwd_dropout)
+ *   STK_WS_LINEAR_CE_FWD  a = rows, b = vocabulary (stk_linear_ce_fwd)
+ *   STK_WS_LINEAR_CE_BWD  a = rows, b = vocabulary (stk_linear_ce_bwd) */
+enum { STK_WS_ATTN_BWD = 0, STK_WS_LINEAR_CE_FWD = 1, STK_WS_LINEAR_CE_BWD = 2 };
+int64_t stk_query_workspace(int op, int64_t a, int64_t b);
+
+/* Label selection on the device (replaces `labels != -100` boolean indexing, stonkgs_model.py:229-245, and the host
+ * sync it costs): labels int64 [B, width] (-100 = ignore).  Writes, in row-major order of the labelled positions,
+ * rows_out[i] = b * row_pitch + col_offset + t (row of the [B * row_pitch, 768] sequence output) and labels_out[i];
+ * entries [count, capacity) are padding (row -1, label -1: gathered as zeros, no loss, zero gradient), so every
+ * consumer runs at the fixed size `capacity` and nothing is read back.  count_out[0] = number of labelled positions.
+ * err_flag (device int, may be NULL): bit 1 (value 2) = a label outside [0, vocab) (torch raises IndexError; the row
+ * is skipped), bit 2 (value 4) = more labelled positions than capacity (the surplus is dropped: caller must raise). */
+int stk_compact_labels(int device, void* stream, const int64_t* labels, int B, int width, int row_pitch, int col_offset,
+                       int vocab, int capacity, int32_t* rows_out, int32_t* labels_out, int32_t* count_out,
+                       int* err_flag);
+
+/* Fused decoder GEMM + cross-entropy forward over R rows: t bf16 [R, 768] (head-transform output of the labelled rows),
+ * w bf16 [V, 768] (text_decoder / entity_decoder weight, no bias), labels int32 [R] (target column, < 0 = padding row).
+ * Outputs: lse [R] (log-sum-exp of the full row of logits), row_loss [R] (lse - target logit; 0 for padding rows; may be
+ * NULL), loss_count [2] (may be NULL) = { mean of row_loss over the rows with label >= 0 — NaN if there are none, like
+ * torch — , that count as a float }.  The [R, V] logits are never materialised. */
+int stk_linear_ce_fwd(int device, void* stream, const void* t_bf16, const void* w_bf16, int R, int V,
+                      const int32_t* labels, void* workspace, int64_t workspace_bytes, float* lse, float* row_loss,
+                      float* loss_count);
+/* Its backward: dlogit = (softmax - onehot) * *scale_dev (scale_dev: device scalar = upstream gradient / labelled-row
+ * count; padding rows get 0), recomputed per vocabulary chunk into the workspace; dT fp32 [R, 768] and dW fp32 [V, 768]
+ * are accumulated (+=). */
+int stk_linear_ce_bwd(int device, void* stream, const void* t_bf16, const void* w_bf16, int R, int V,
+                      const int32_t* labels, const float* lse, const float* scale_dev, void* workspace,
+                      int64_t workspace_bytes, float* dT, float* dW);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused masked-softmax attention (HF:115-140 eager / 192-205 sdpa; additive key mask HF:666-672)
@@ -200,9 +246,10 @@ int stk_dropout_resid_ln_fwd(int device, void* stream, const void* x_bf16, const
 int stk_mask_to_bias(int device, void* stream, const int64_t* mask, int64_t n, float* bias);
 /* fp32 -> bf16 cast of n elements (weights after load / optimizer step) */
 int stk_cast_f32_to_bf16(int device, void* stream, const float* src, void* dst_bf16, int64_t n);
-/* gather rows: dst[i,:] = src[idx[i],:] for bf16 rows of 768 (labelled-row compaction for the heads) */
+/* gather rows: dst[i,:] = src[idx[i],:] for bf16 rows of 768 (labelled-row compaction for the heads); idx[i] < 0 = zeros */
 int stk_gather_rows(int device, void* stream, const void* src_bf16, const int32_t* idx, int n_rows, void* dst_bf16);
-/* scatter-add rows: dst[idx[i],:] += src[i,:]  (bf16 += bf16; idx unique) — head gradient back to the sequence */
+/* scatter-add rows: dst[idx[i],:] += src[i,:]  (bf16 += bf16; non-negative idx unique, idx[i] < 0 skipped) — head gradient
+ * back to the sequence */
 int stk_scatter_add_rows(int device, void* stream, const void* src_bf16, const int32_t* idx, int n_rows,
                          void* dst_bf16);
 /* column sums: out[n] (+)= sum_m x[m,n], x bf16 [M, ld]; bias gradients */
@@ -212,9 +259,14 @@ int stk_colsum(int device, void* stream, const void* x_bf16, int64_t ld, int M, 
 int stk_ce_finalize(int device, void* stream, const float* ce_partial, int64_t ce_pitch, const float* tgt_logit,
                     int M, float* lse, float* row_loss);
 /* A8+A11: pooled -> Linear(768->2) -> CE (HF:528-533); pooled fp32 [B,768]; logits fp32 [B,2];
- * row_loss fp32 [B] (may be NULL when labels is NULL) */
+ * row_loss fp32 [B] (may be NULL when labels is NULL); a label outside {0, 1} gives a NaN row loss and sets bit 1
+ * (value 2) of err_flag (may be NULL) — torch raises IndexError there */
 int stk_nsp_head_fwd(int device, void* stream, const float* pooled, int B, const float* w, const float* b,
-                     const int64_t* labels, float* logits, float* row_loss);
+                     const int64_t* labels, float* logits, float* row_loss, int* err_flag);
+/* head_mask of the reference forward (stonkgs_model.py:158,209 -> HF attention: probabilities * head_mask[layer, head]):
+ * a per-head scale of the attention probabilities is a per-head scale of the context columns.
+ * y[m, h*64 + d] = x[m, h*64 + d] * scales[h]  over bf16 [M, 768] (in place allowed); scales fp32 [12]. */
+int stk_scale_heads(int device, void* stream, const void* x_bf16, int M, const float* scales, void* y_bf16);
 
 /* dx = dy * gelu_erf'(pre), n bf16 elements (n % 8 == 0): backward of the head transform's GELU (HF:481-485) */
 int stk_gelu_bwd(int device, void* stream, const void* dy_bf16, const void* pre_bf16, int64_t n, void* dx_bf16);

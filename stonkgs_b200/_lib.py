@@ -14,12 +14,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # STK_LIB: bring-up override (A/B runs of two builds of the kernel library); the product path is the in-tree build
 LIB_PATH = os.environ.get("STK_LIB") or os.path.join(_HERE, "libstk.so")
 
-STK_VERSION = 101
+STK_VERSION = 102
 
 # epilogue ids (include/stk.h)
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GELU_SAVE, EPI_BIAS_RESID, EPI_BIAS_TANH_F32 = 0, 1, 2, 3, 4
 EPI_DGELU, EPI_F32_ADD, EPI_F32, EPI_CE_STATS, EPI_CE_DLOGIT, EPI_BIAS_RESID_LN = 5, 6, 7, 8, 9, 10
-EPI_BIAS_GELU_SAVE_GRAD, EPI_MUL = 11, 12
+EPI_BIAS_GELU_SAVE_GRAD, EPI_MUL, EPI_BIAS_DROP_RESID_LN = 11, 12, 13
+WS_ATTN_BWD, WS_LINEAR_CE_FWD, WS_LINEAR_CE_BWD = 0, 1, 2
+ERR_BAD_ID, ERR_BAD_LABEL, ERR_LABEL_CAPACITY = 1, 2, 4   # bits of the device-side err_flag
 
 
 class StkError(RuntimeError):
@@ -49,6 +51,9 @@ class GemmEpilogue(Structure):
         ("ln_beta", c_void_p),
         ("ln_mean", c_void_p),
         ("ln_rstd", c_void_p),
+        ("drop_seed", c_uint32),
+        ("drop_site", c_uint32),
+        ("drop_thr", c_uint32),
     ]
 
 
@@ -81,7 +86,12 @@ _SIGNATURES = {
     "stk_scatter_add_rows": (c_int, [c_int, _P, _P, _P, c_int, _P]),
     "stk_colsum": (c_int, [c_int, _P, _P, c_int64, c_int, c_int, _P, c_int]),
     "stk_ce_finalize": (c_int, [c_int, _P, _P, c_int64, _P, c_int, _P, _P]),
-    "stk_nsp_head_fwd": (c_int, [c_int, _P, _P, c_int, _P, _P, _P, _P, _P]),
+    "stk_nsp_head_fwd": (c_int, [c_int, _P, _P, c_int, _P, _P, _P, _P, _P, _P]),
+    "stk_scale_heads": (c_int, [c_int, _P, _P, c_int, _P, _P]),
+    "stk_query_workspace": (c_int64, [c_int, c_int64, c_int64]),
+    "stk_compact_labels": (c_int, [c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "stk_linear_ce_fwd": (c_int, [c_int, _P, _P, _P, c_int, c_int, _P, _P, c_int64, _P, _P, _P]),
+    "stk_linear_ce_bwd": (c_int, [c_int, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, c_int64, _P, _P]),
     "stk_gelu_bwd": (c_int, [c_int, _P, _P, _P, c_int64, _P]),
     "stk_unpack_scale": (c_int, [c_int, _P, _P, _P, c_int64, c_float]),
     "stk_sumsq": (c_int, [c_int, _P, _P, c_int64, _P]),

@@ -51,6 +51,11 @@ __device__ __forceinline__ f32x2_t pack_f32x2(float lo, float hi) {
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
   return r;
 }
+__device__ __forceinline__ f32x2_t pack_u32x2(uint32_t lo, uint32_t hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
 __device__ __forceinline__ void unpack_f32x2(f32x2_t v, float& lo, float& hi) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }

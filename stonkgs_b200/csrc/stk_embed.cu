@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) embed_text_ln_kernel(const int64_t* __res
   const int b = static_cast<int>(tok / S), t = static_cast<int>(tok % S);
   int64_t id = __ldg(ids + b * ids_pitch + t);
   if (id < 0 || id >= vocab) {
-    if (lane == 0 && err_flag) atomicExch(err_flag, 1);
+    if (lane == 0 && err_flag) atomicOr(err_flag, 1);
     id = 0;
   }
   float v[kPerLane], a[kPerLane];
@@ -157,7 +157,7 @@ embed_joint_ln_kernel(const int64_t* __restrict__ input_ids, const int64_t* __re
   }
   int tt;
   if (!joint_source_row(input_ids, token_type_ids, b, t, sh, lm_hidden, kg_table, table_rows, lane, v, tt)) {
-    if (lane == 0 && err_flag) atomicExch(err_flag, 1);
+    if (lane == 0 && err_flag) atomicOr(err_flag, 1);
   }
   if (inputs_embeds_out) store_f32_row(inputs_embeds_out + tok * kHidden, lane, v);
   load_f32_row(type_emb + tt * kHidden, lane, a);

@@ -22,6 +22,7 @@
 
 #include "stk_common.cuh"
 #include "stk_host.h"
+#include "stk_rng.cuh"
 
 #ifndef STK_GEMM_EPI_WARP0
 #define STK_GEMM_EPI_WARP0 0
@@ -43,7 +44,7 @@ constexpr int EPI_BUF_BYTES = 128 * 128;    // [128 rows][128 B] staging tile
 // residual in and the results out through FOUR staging tiles by TMA.
 template <int EPI, bool PAIR>
 struct GemmCfg {
-  static constexpr bool kLN = EPI == STK_EPI_BIAS_RESID_LN;
+  static constexpr bool kLN = EPI == STK_EPI_BIAS_RESID_LN || EPI == STK_EPI_BIAS_DROP_RESID_LN;
   static constexpr int kBRows = PAIR ? 128 : 256;                   // rows of B this CTA stages
   static constexpr int kBStageBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = A_STAGE_BYTES + kBStageBytes;
@@ -394,6 +395,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     named_bar_sync(3, 256);
     const bool save_z = e.c2 != nullptr;
     const uint32_t stats_bar_addr[2] = {smem_u32(stats_bar), smem_u32(stats_bar + 1)};
+    // train(): z = drop(acc + bias) + residual (HF:296-298, 354-356).  The keep decision is the pure function of
+    // (seed, site, token row, hidden column) of stk_rng.cuh — the same one the LayerNorm backward regenerates.
+    constexpr bool kDrop = EPI == STK_EPI_BIAS_DROP_RESID_LN;
+    const uint32_t drop_thr4 = kDrop ? drop_thr4_of(e.drop_thr) : 0u;
+    const f32x2_t drop_scale2 = kDrop ? pack_f32x2(drop_scale(e.drop_thr), drop_scale(e.drop_thr)) : 0ull;
 
     int as = 0;
     uint32_t as_phase = 0, it = 0;
@@ -410,6 +416,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
       uint4 zpk[2][8];
       float cmean[2], cm2[2];
+      const uint32_t drop_key = kDrop ? drop_row_key(e.drop_seed, e.drop_site, static_cast<uint32_t>(m)) : 0u;
 #pragma unroll
       for (int chunk = 0; chunk < 2; ++chunk) {
         uint32_t r[2][32];
@@ -439,11 +446,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           const float4 b0 = bias4[2 * c], b1 = bias4[2 * c + 1];
           const f32x2_t bv[4] = {pack_f32x2(b0.x, b0.y), pack_f32x2(b0.z, b0.w), pack_f32x2(b1.x, b1.y),
                                  pack_f32x2(b1.z, b1.w)};
+          f32x2_t keep[4];   // kDrop: all-ones / all-zeros per element of the four column pairs of this 8-column group
+          if (kDrop) {
+            uint32_t w0, w1;
+            drop_words(drop_key, static_cast<uint32_t>((static_cast<int>(rank) * BN + g * 128 + chunk * 64 + c * 8) >> 3), w0, w1);
+            const uint32_t sg0 = drop_signs(w0, drop_thr4), sg1 = drop_signs(w1, drop_thr4);
+            keep[0] = pack_u32x2(drop_mask32<0>(sg0), drop_mask32<1>(sg0));
+            keep[1] = pack_u32x2(drop_mask32<2>(sg0), drop_mask32<3>(sg0));
+            keep[2] = pack_u32x2(drop_mask32<0>(sg1), drop_mask32<1>(sg1));
+            keep[3] = pack_u32x2(drop_mask32<2>(sg1), drop_mask32<3>(sg1));
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int j = c * 8 + i * 2;
             const f32x2_t acc = pack_f32x2(__uint_as_float(r[j >> 5][j & 31]), __uint_as_float(r[(j + 1) >> 5][(j + 1) & 31]));
-            const f32x2_t z2 = add_f32x2(add_f32x2(acc, bv[i]), bf16x2_to_f32x2(ex[i]));
+            f32x2_t z2;
+            if (kDrop) z2 = fma_f32x2(add_f32x2(acc, bv[i]) & keep[i], drop_scale2, bf16x2_to_f32x2(ex[i]));
+            else z2 = add_f32x2(add_f32x2(acc, bv[i]), bf16x2_to_f32x2(ex[i]));
             v[c * 4 + i] = z2;
             s2 = add_f32x2(s2, z2);
           }
@@ -619,9 +638,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       // per-row CE state
       float ce_max = -INFINITY, ce_sum = 0.f;
       int label = -1;
+      bool row_on = m_ok;   // CE: rows with a negative label are padding of a fixed-capacity row list (stk_compact_labels)
       float row_lse = 0.f;
       if (EPI == STK_EPI_CE_STATS || EPI == STK_EPI_CE_DLOGIT) {
-        if (m_ok) label = __ldg(e.labels + m) - e.n_offset;  // column within this call's B block
+        if (m_ok) {
+          const int raw = __ldg(e.labels + m);
+          row_on = raw >= 0;
+          label = row_on ? raw - e.n_offset : -1;  // column within this call's B block
+        }
         if (EPI == STK_EPI_CE_DLOGIT && m_ok) row_lse = __ldg(e.lse + m);
       }
 
@@ -659,7 +683,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
               v = (n < p.N) ? v : -INFINITY;
               r[h][j] = __float_as_uint(v);
               cmax = fmaxf(cmax, v);
-              if (n == label) e.tgt_logit[m] = v;
+              if (n == label && row_on) e.tgt_logit[m] = v;
             }
           const float new_max = fmaxf(ce_max, cmax);
           if (new_max > -INFINITY) {
@@ -766,8 +790,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
               const int col = nc + j;  // column within this call's B block
               if (col == label) p0 -= 1.f;
               if (col + 1 == label) p1 -= 1.f;
-              v0 = m_ok ? p0 * ce_scale : 0.f;
-              v1 = m_ok ? p1 * ce_scale : 0.f;
+              v0 = row_on ? p0 * ce_scale : 0.f;
+              v1 = row_on ? p1 * ce_scale : 0.f;
             }
             w[i] = pack_bf16x2(v0, v1);
           }
@@ -858,6 +882,24 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
   return STK_OK;
 }
 
+// Split-K factor of a reduce-add GEMM (split_k = 0): fill the persistent grid (CTA pairs on 256 x 256 tiles when
+// there is more than one 128-row tile, else single CTAs on 128 x 256) with as few k-splits as possible — every
+// split re-reduces its tile through an fp32 TMA reduce-add, so more splits only for a clearly fuller grid.
+static int auto_splits(int M, int N, int K, int sms) {
+  const bool pair = M > BM;
+  const int tiles = ((M + (pair ? 2 * BM : BM) - 1) / (pair ? 2 * BM : BM)) * ((N + BN - 1) / BN);
+  const int units = pair ? sms / 2 : sms;
+  const int kb = (K + BK - 1) / BK;
+  int best = 1;
+  float best_eff = 0.f;
+  for (int s = 1; s <= (kb < 32 ? kb : 32); ++s) {
+    const int items = tiles * s;
+    const float eff = static_cast<float>(items) / static_cast<float>((items + units - 1) / units * units);
+    if (eff > best_eff + 0.05f) { best = s; best_eff = eff; }
+  }
+  return best;
+}
+
 }  // namespace stk
 
 using namespace stk;
@@ -872,7 +914,6 @@ extern "C" int stk_gemm(int device, void* stream_, int a_major, int b_major, con
   STK_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "stk_gemm: lda/ldb must be multiples of 8 elements (16 B)");
   STK_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
               "stk_gemm: operands must be 16-byte aligned");
-  STK_CHECK_CUDA(cudaSetDevice(device));
   // CTA pairs (256-row tiles, cta_group::2) whenever there is more than one 128-row tile of work
   static int pair_env = -1;
   if (pair_env < 0) {
@@ -885,9 +926,10 @@ extern "C" int stk_gemm(int device, void* stream_, int a_major, int b_major, con
   p.m_tiles = pair ? (M + 2 * BM - 1) / (2 * BM) : (M + BM - 1) / BM;
   p.n_tiles = (N + BN - 1) / BN;
   p.kb_total = (K + BK - 1) / BK;
-  int splits = split_k < 1 ? 1 : split_k;
-  if (splits > p.kb_total) splits = p.kb_total;
+  int splits = split_k < 0 ? 1 : split_k;
   if (epilogue != STK_EPI_F32_ADD) splits = 1;
+  else if (splits == 0) splits = auto_splits(M, N, K, num_sms(device));
+  if (splits > p.kb_total) splits = p.kb_total;
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   if (epi) p.epi = *epi;
@@ -905,7 +947,10 @@ extern "C" int stk_gemm(int device, void* stream_, int a_major, int b_major, con
   }
   if (epilogue == STK_EPI_BIAS_GELU_SAVE || epilogue == STK_EPI_BIAS_GELU_SAVE_GRAD)
     STK_REQUIRE(epi && epi->c2 && epi->ldc2 % 8 == 0, "stk_gemm: GELU_SAVE needs c2");
-  if (epilogue == STK_EPI_BIAS_RESID_LN) {
+  const bool ln_epi = epilogue == STK_EPI_BIAS_RESID_LN || epilogue == STK_EPI_BIAS_DROP_RESID_LN;
+  if (epilogue == STK_EPI_BIAS_DROP_RESID_LN)
+    STK_REQUIRE(epi && epi->drop_thr > 0 && epi->drop_thr < 128, "stk_gemm: the dropout LayerNorm epilogue needs 0 < drop_thr < 128");
+  if (ln_epi) {
     STK_REQUIRE(N == kHidden && a_major == 0 && b_major == 0, "stk_gemm: the LayerNorm epilogue needs N == 768 and K-major operands");
     STK_REQUIRE(epi && epi->resid && epi->ldr % 8 == 0 && epi->ln_gamma && epi->ln_beta,
                 "stk_gemm: the LayerNorm epilogue needs resid (ldr%%8==0), ln_gamma and ln_beta");
@@ -923,6 +968,7 @@ extern "C" int stk_gemm(int device, void* stream_, int a_major, int b_major, con
     STK_REQUIRE(ldc % (f32_out ? 4 : 8) == 0, "stk_gemm: ldc must be a multiple of 16 bytes");
   }
 
+  STK_CHECK_CUDA(cudaSetDevice(device));   // after argument validation: bad arguments are reported without a device
   CUtensorMap ma, mb, mc, mc2, mr;
   int rc;
   // A: K-major -> stored [M][K], box {64 k, 128 m};  MN-major -> stored [K][M], box {64 m, 64 k}
@@ -942,11 +988,11 @@ extern "C" int stk_gemm(int device, void* stream_, int a_major, int b_major, con
   mc2 = mc;
   mr = mc;
   if (epilogue == STK_EPI_BIAS_GELU_SAVE || epilogue == STK_EPI_BIAS_GELU_SAVE_GRAD ||
-      (epilogue == STK_EPI_BIAS_RESID_LN && epi->c2)) {
+      (ln_epi && epi->c2)) {
     rc = make_tmap_2d(&mc2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, epi->c2, N, M, epi->ldc2 * 2, 64, 128);
     if (rc) return rc;
   }
-  if (epilogue == STK_EPI_BIAS_RESID_LN) {
+  if (ln_epi) {
     rc = make_tmap_2d(&mr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, epi->resid, N, M, epi->ldr * 2, 64, 128);
     if (rc) return rc;
   }
@@ -960,6 +1006,7 @@ extern "C" int stk_gemm(int device, void* stream_, int a_major, int b_major, con
   STK_GEMM_CASE(0, 0, STK_EPI_BIAS_GELU_SAVE_GRAD)
   STK_GEMM_CASE(0, 0, STK_EPI_BIAS_RESID)
   STK_GEMM_CASE(0, 0, STK_EPI_BIAS_RESID_LN)
+  STK_GEMM_CASE(0, 0, STK_EPI_BIAS_DROP_RESID_LN)
   STK_GEMM_CASE(0, 0, STK_EPI_BIAS_TANH_F32)
   STK_GEMM_CASE(0, 0, STK_EPI_F32)
   STK_GEMM_CASE(0, 0, STK_EPI_CE_STATS)

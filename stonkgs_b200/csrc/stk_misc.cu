@@ -41,8 +41,14 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const __nv_bfloat16* _
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= n_rows) return;
-  const uint4* s = reinterpret_cast<const uint4*>(src + static_cast<int64_t>(__ldg(idx + row)) * kHidden);
+  const int32_t r = __ldg(idx + row);
   uint4* d = reinterpret_cast<uint4*>(dst + static_cast<int64_t>(row) * kHidden);
+  if (r < 0) {   // padding entry of a fixed-capacity row list: zeros
+#pragma unroll
+    for (int i = 0; i < 3; ++i) d[lane + 32 * i] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  const uint4* s = reinterpret_cast<const uint4*>(src + static_cast<int64_t>(r) * kHidden);
 #pragma unroll
   for (int i = 0; i < 3; ++i) d[lane + 32 * i] = __ldg(s + lane + 32 * i);
 }
@@ -53,8 +59,10 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const __nv_bfloat
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= n_rows) return;
+  const int32_t r = __ldg(idx + row);
+  if (r < 0) return;   // padding entry
   const uint4* s = reinterpret_cast<const uint4*>(src + static_cast<int64_t>(row) * kHidden);
-  uint4* d = reinterpret_cast<uint4*>(dst + static_cast<int64_t>(__ldg(idx + row)) * kHidden);
+  uint4* d = reinterpret_cast<uint4*>(dst + static_cast<int64_t>(r) * kHidden);
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const uint4 a = __ldg(s + lane + 32 * i);
@@ -132,7 +140,8 @@ __global__ void __launch_bounds__(256) ce_finalize_kernel(const float2* __restri
 __global__ void __launch_bounds__(256) nsp_head_fwd_kernel(const float* __restrict__ pooled, int B,
                                                            const float* __restrict__ w, const float* __restrict__ bias,
                                                            const int64_t* __restrict__ labels,
-                                                           float* __restrict__ logits, float* __restrict__ row_loss) {
+                                                           float* __restrict__ logits, float* __restrict__ row_loss,
+                                                           int* __restrict__ err_flag) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -151,7 +160,14 @@ __global__ void __launch_bounds__(256) nsp_head_fwd_kernel(const float* __restri
       const float m = fmaxf(s0, s1);
       const float lse = m + logf(expf(s0 - m) + expf(s1 - m));
       const int64_t l = __ldg(labels + b);
-      row_loss[b] = lse - (l == 0 ? s0 : s1);
+      // a target outside {0, 1} raises in torch's cross-entropy: flag it; NaN keeps the loss loud and the backward
+      // (which gives such a row no one-hot) consistent with what was reported
+      if (l != 0 && l != 1) {
+        row_loss[b] = __int_as_float(0x7fc00000);
+        if (err_flag) atomicOr(err_flag, 2);
+      } else {
+        row_loss[b] = lse - (l == 0 ? s0 : s1);
+      }
     }
   }
 }
@@ -210,6 +226,21 @@ __global__ void __launch_bounds__(256) nsp_pool_bwd_kernel(const float* __restri
 }
 
 
+// y[m, h*64 + d] = x[m, h*64 + d] * scales[h]: one thread per 8 columns (never crosses a head)
+__global__ void __launch_bounds__(256) scale_heads_kernel(const __nv_bfloat16* __restrict__ x, int64_t n8,
+                                                          const float* __restrict__ scales, __nv_bfloat16* __restrict__ y) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const float s = __ldg(scales + (i % (kHidden / 8)) / 8);
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(x) + i);
+  uint4 o;
+  o.x = pack_bf16x2(bf16_lo(v.x) * s, bf16_hi(v.x) * s);
+  o.y = pack_bf16x2(bf16_lo(v.y) * s, bf16_hi(v.y) * s);
+  o.z = pack_bf16x2(bf16_lo(v.z) * s, bf16_hi(v.z) * s);
+  o.w = pack_bf16x2(bf16_lo(v.w) * s, bf16_hi(v.w) * s);
+  reinterpret_cast<uint4*>(y)[i] = o;
+}
+
 // dst[i] = float(src[i]) * scale : gradient bucket coming back from the bf16 all-reduce (mean = sum / world)
 __global__ void unpack_scale_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int64_t n,
                                     float scale) {
@@ -259,7 +290,7 @@ __global__ void __launch_bounds__(256) cls_head_fwd_kernel(const float* __restri
     const float lse = m + logf(warp_sum(e));
     const int64_t lab = __ldg(labels + b);
     if (lab < 0 || lab >= L) {
-      if (lane == 0) { row_loss[b] = 0.f; if (err_flag) *err_flag = 1; }
+      if (lane == 0) { row_loss[b] = 0.f; if (err_flag) atomicOr(err_flag, 2); }
     } else {
       const float tgt = __shfl_sync(0xffffffffu, mine, static_cast<int>(lab));
       if (lane == 0) row_loss[b] = lse - tgt;
@@ -397,11 +428,11 @@ extern "C" int stk_ce_finalize(int device, void* stream, const float* ce_partial
 }
 
 extern "C" int stk_nsp_head_fwd(int device, void* stream, const float* pooled, int B, const float* w, const float* b,
-                                const int64_t* labels, float* logits, float* row_loss) {
+                                const int64_t* labels, float* logits, float* row_loss, int* err_flag) {
   STK_REQUIRE(pooled && w && b && logits && B > 0, "stk_nsp_head_fwd: bad arguments");
   STK_CHECK_CUDA(cudaSetDevice(device));
   nsp_head_fwd_kernel<<<(B + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(pooled, B, w, b, labels, logits,
-                                                                                   row_loss);
+                                                                                   row_loss, err_flag);
   STK_LAUNCHED();
 }
 
@@ -420,6 +451,15 @@ extern "C" int stk_nsp_pool_bwd(int device, void* stream, const float* pooled, c
   STK_CHECK_CUDA(cudaSetDevice(device));
   nsp_pool_bwd_kernel<<<3, 256, 0, static_cast<cudaStream_t>(stream)>>>(pooled, logits, labels, B, scale_dev, w, dw, db,
                                                                       static_cast<__nv_bfloat16*>(dpre));
+  STK_LAUNCHED();
+}
+
+extern "C" int stk_scale_heads(int device, void* stream, const void* x, int M, const float* scales, void* y) {
+  STK_REQUIRE(x && y && scales && M > 0, "stk_scale_heads: bad arguments");
+  STK_CHECK_CUDA(cudaSetDevice(device));
+  const int64_t n8 = static_cast<int64_t>(M) * (kHidden / 8);
+  scale_heads_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), n8, scales, static_cast<__nv_bfloat16*>(y));
   STK_LAUNCHED();
 }
 

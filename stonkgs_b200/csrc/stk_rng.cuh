@@ -37,6 +37,7 @@ __host__ __device__ __forceinline__ void drop_words(uint32_t row_key, uint32_t c
 }
 // thr replicated into the four bytes (thr < 128)
 __host__ __device__ __forceinline__ uint32_t drop_thr4(uint32_t thr) { return thr * 0x01010101u; }
+__host__ __device__ __forceinline__ uint32_t drop_thr4_of(uint32_t thr) { return drop_thr4(thr); }   // (a local may shadow drop_thr4)
 // bit 7 of byte k of the result is the keep decision of column k of the word: (byte & 0x7f) + 0x80 - thr has bit 7 set
 // iff (byte & 0x7f) >= thr, and no byte borrows from its neighbour
 __host__ __device__ __forceinline__ uint32_t drop_signs(uint32_t w, uint32_t thr4) {

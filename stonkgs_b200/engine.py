@@ -83,6 +83,7 @@ class LayerCache:
     z2: torch.Tensor
     mean2: torch.Tensor
     rstd2: torch.Tensor
+    ctx_used: Optional[torch.Tensor] = None   # ctx through head_mask (the Wo GEMM's operand); ctx itself when there is none
 
 
 # --------------------------------------------------------------------------------------------------
@@ -115,51 +116,56 @@ class DropCtx:
 # forward
 # --------------------------------------------------------------------------------------------------
 def encoder_layer_fwd(x, lw: LayerWeights, B: int, S: int, key_bias, cache: Optional[list] = None,
-                      drop: Optional[DropCtx] = None, enc: int = 0, li: int = 0):
-    """One BertLayer (post-LN). x: bf16 [B*S, 768]."""
+                      drop: Optional[DropCtx] = None, enc: int = 0, li: int = 0, head_scale=None):
+    """One BertLayer (post-LN). x: bf16 [B*S, 768].
+
+    eval() and train() take the same kernels: in train() the attention kernel drops probabilities (HF:132) and the
+    dense outputs are dropped inside the fused bias + residual + LayerNorm GEMM epilogue (HF:296-298, 354-356), masks
+    being a pure function of (seed, site, row, column).  ``head_scale`` (fp32 [12], optional) is this layer's row of the
+    reference's ``head_mask``: a per-head factor on the attention probabilities, i.e. on the context columns."""
     M = x.shape[0]
     train = cache is not None
     qkv = ops.linear(x, lw.wqkv, lw.bqkv)
-    if drop is not None:
-        # train() with dropout: the dense outputs are dropped BEFORE the residual sum, so the dense GEMMs use the plain
-        # bias epilogue and one row kernel does dropout + residual + LayerNorm (the fused epilogue is the eval path)
-        da = drop.attention(enc, li)
+    d_attn = drop.attention(enc, li) if drop is not None else None
+    d_o = drop.attn_out(enc, li) if drop is not None else None
+    d_f = drop.ffn_out(enc, li) if drop is not None else None
+    if train:
+        ctx, lse = ops.attention(qkv, key_bias, B, S, save_lse=True, drop=d_attn)
+    else:
+        ctx, lse = ops.attention(qkv, key_bias, B, S, drop=d_attn), None
+    ctx_used = ctx if head_scale is None else ops.scale_heads(ctx, head_scale)
+    if FUSED_LN:
         if train:
-            ctx, lse = ops.attention(qkv, key_bias, B, S, save_lse=True, drop=da)
-        else:
-            ctx, lse = ops.attention(qkv, key_bias, B, S, drop=da), None
-        d1 = ops.linear(ctx, lw.wo, lw.bo)
-        if train:
-            x1, z1, mean1, rstd1 = ops.dropout_resid_ln(d1, x, lw.ln1_g, lw.ln1_b, drop.attn_out(enc, li), save_for_backward=True)
+            x1, z1, mean1, rstd1 = ops.linear_resid_ln(ctx_used, lw.wo, lw.bo, x, lw.ln1_g, lw.ln1_b, save_for_backward=True,
+                                                       drop=d_o)
             u = torch.empty((M, I), dtype=torch.bfloat16, device=x.device)
             h = ops.linear(x1, lw.w1, lw.b1, ops.EPI_BIAS_GELU_SAVE_GRAD, c2=u)   # u = gelu'(pre-activation)
+            x2, z2, mean2, rstd2 = ops.linear_resid_ln(h, lw.w2, lw.b2, x1, lw.ln2_g, lw.ln2_b, save_for_backward=True,
+                                                       drop=d_f)
+            cache.append(LayerCache(x, qkv, lse, ctx, z1, mean1, rstd1, x1, u, h, z2, mean2, rstd2, ctx_used))
         else:
-            x1 = ops.dropout_resid_ln(d1, x, lw.ln1_g, lw.ln1_b, drop.attn_out(enc, li))
+            x1 = ops.linear_resid_ln(ctx_used, lw.wo, lw.bo, x, lw.ln1_g, lw.ln1_b, drop=d_o)
+            h = ops.linear(x1, lw.w1, lw.b1, ops.EPI_BIAS_GELU)
+            x2 = ops.linear_resid_ln(h, lw.w2, lw.b2, x1, lw.ln2_g, lw.ln2_b, drop=d_f)
+        return x2
+    # STK_FUSED_LN=0 (profiling tools only): dense GEMM, then a row kernel for (dropout +) residual + LayerNorm
+    if drop is not None:
+        d1 = ops.linear(ctx_used, lw.wo, lw.bo)
+        if train:
+            x1, z1, mean1, rstd1 = ops.dropout_resid_ln(d1, x, lw.ln1_g, lw.ln1_b, d_o, save_for_backward=True)
+            u = torch.empty((M, I), dtype=torch.bfloat16, device=x.device)
+            h = ops.linear(x1, lw.w1, lw.b1, ops.EPI_BIAS_GELU_SAVE_GRAD, c2=u)
+        else:
+            x1 = ops.dropout_resid_ln(d1, x, lw.ln1_g, lw.ln1_b, d_o)
             h = ops.linear(x1, lw.w1, lw.b1, ops.EPI_BIAS_GELU)
         d2 = ops.linear(h, lw.w2, lw.b2)
         if train:
-            x2, z2, mean2, rstd2 = ops.dropout_resid_ln(d2, x1, lw.ln2_g, lw.ln2_b, drop.ffn_out(enc, li), save_for_backward=True)
-            cache.append(LayerCache(x, qkv, lse, ctx, z1, mean1, rstd1, x1, u, h, z2, mean2, rstd2))
+            x2, z2, mean2, rstd2 = ops.dropout_resid_ln(d2, x1, lw.ln2_g, lw.ln2_b, d_f, save_for_backward=True)
+            cache.append(LayerCache(x, qkv, lse, ctx, z1, mean1, rstd1, x1, u, h, z2, mean2, rstd2, ctx_used))
         else:
-            x2 = ops.dropout_resid_ln(d2, x1, lw.ln2_g, lw.ln2_b, drop.ffn_out(enc, li))
+            x2 = ops.dropout_resid_ln(d2, x1, lw.ln2_g, lw.ln2_b, d_f)
         return x2
-    if train:
-        ctx, lse = ops.attention(qkv, key_bias, B, S, save_lse=True)
-    else:
-        ctx = ops.attention(qkv, key_bias, B, S)
-    if FUSED_LN:
-        if train:
-            x1, z1, mean1, rstd1 = ops.linear_resid_ln(ctx, lw.wo, lw.bo, x, lw.ln1_g, lw.ln1_b, save_for_backward=True)
-            u = torch.empty((M, I), dtype=torch.bfloat16, device=x.device)
-            h = ops.linear(x1, lw.w1, lw.b1, ops.EPI_BIAS_GELU_SAVE_GRAD, c2=u)   # u = gelu'(pre-activation)
-            x2, z2, mean2, rstd2 = ops.linear_resid_ln(h, lw.w2, lw.b2, x1, lw.ln2_g, lw.ln2_b, save_for_backward=True)
-            cache.append(LayerCache(x, qkv, lse, ctx, z1, mean1, rstd1, x1, u, h, z2, mean2, rstd2))
-        else:
-            x1 = ops.linear_resid_ln(ctx, lw.wo, lw.bo, x, lw.ln1_g, lw.ln1_b)
-            h = ops.linear(x1, lw.w1, lw.b1, ops.EPI_BIAS_GELU)
-            x2 = ops.linear_resid_ln(h, lw.w2, lw.b2, x1, lw.ln2_g, lw.ln2_b)
-        return x2
-    z1 = ops.linear(ctx, lw.wo, lw.bo, ops.EPI_BIAS_RESID, resid=x)
+    z1 = ops.linear(ctx_used, lw.wo, lw.bo, ops.EPI_BIAS_RESID, resid=x)
     if train:
         x1, mean1, rstd1 = ops.layernorm(z1, lw.ln1_g, lw.ln1_b, save_stats=True)
         u = torch.empty((M, I), dtype=torch.bfloat16, device=x.device)
@@ -170,16 +176,18 @@ def encoder_layer_fwd(x, lw: LayerWeights, B: int, S: int, key_bias, cache: Opti
     z2 = ops.linear(h, lw.w2, lw.b2, ops.EPI_BIAS_RESID, resid=x1)
     if train:
         x2, mean2, rstd2 = ops.layernorm(z2, lw.ln2_g, lw.ln2_b, save_stats=True)
-        cache.append(LayerCache(x, qkv, lse, ctx, z1, mean1, rstd1, x1, u, h, z2, mean2, rstd2))
+        cache.append(LayerCache(x, qkv, lse, ctx, z1, mean1, rstd1, x1, u, h, z2, mean2, rstd2, ctx_used))
     else:
         x2 = ops.layernorm(z2, lw.ln2_g, lw.ln2_b, out=z2)
     return x2
 
 
 def encoder_fwd(x, ew: EncoderWeights, B: int, S: int, key_bias, cache: Optional[list] = None,
-                drop: Optional[DropCtx] = None, enc: int = 0):
+                drop: Optional[DropCtx] = None, enc: int = 0, head_mask=None):
+    """``head_mask``: fp32 [layers, 12] on the device, or None."""
     for li, lw in enumerate(ew.layers):
-        x = encoder_layer_fwd(x, lw, B, S, key_bias, cache, drop, enc, li)
+        x = encoder_layer_fwd(x, lw, B, S, key_bias, cache, drop, enc, li,
+                              head_mask[li] if head_mask is not None else None)
     return x
 
 
@@ -211,7 +219,7 @@ def lm_special_rows(ew: EncoderWeights, token_ids) -> torch.Tensor:
 
 def joint_fwd(bert: EncoderWeights, input_ids, token_type_ids, attention_mask, lm_hidden, kg_table, *,
               cache: Optional[dict] = None, want_inputs_embeds=False, err_flag=None, drop: Optional[DropCtx] = None,
-              shape: ops.SeqShape = ops.STONKGS_SHAPE):
+              shape: ops.SeqShape = ops.STONKGS_SHAPE, head_mask=None):
     """KG lookup + concat + joint embeddings + 12 layers + pooler (stonkgs_model.py:182-212).
     Activations hold ``shape.seq_pad`` rows per pair (== the sequence length for STonKGs; the 260-token TransE variant is
     padded to 384 rows whose tail is masked out as attention keys)."""
@@ -232,10 +240,10 @@ def joint_fwd(bert: EncoderWeights, input_ids, token_type_ids, attention_mask, l
         attention_mask = am
     key_bias = ops.mask_to_bias(attention_mask) if attention_mask is not None else None
     layer_cache = [] if train else None
-    seq = encoder_fwd(x, bert, B, SP, key_bias, layer_cache, drop, 1)
+    seq = encoder_fwd(x, bert, B, SP, key_bias, layer_cache, drop, 1, head_mask)
     # BertPooler: tanh(W h[:, 0] + b); rows b*SP are read in place through the A pitch
     pooled = ops.gemm(seq.view(B, SP, H)[:, 0], bert.wp, M=B, N=H, K=H, epilogue=ops.EPI_BIAS_TANH_F32, bias=bert.bp)
     if train:
         cache.update(emb_mean=mean, emb_rstd=rstd, key_bias=key_bias, layers=layer_cache, lm_hidden=lm_hidden, drop=drop,
-                     shape=shape)
+                     shape=shape, head_mask=head_mask)
     return seq, pooled, emb

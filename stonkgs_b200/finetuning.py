@@ -46,9 +46,10 @@ class STonKGsForSequenceClassification(STonKGsForPreTraining):
     def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, position_ids=None, head_mask=None,
                 inputs_embeds=None, labels=None, output_attentions=None, output_hidden_states=None, return_dict=None):
         """Same contract as the reference forward (stonkgs_finetuning.py:257-337)."""
-        if head_mask is not None or position_ids is not None or inputs_embeds is not None:
-            raise StkError("head_mask / position_ids / inputs_embeds are not supported by the fused path "
-                           "(the reference ignores position_ids and inputs_embeds as well)")
+        if position_ids is not None or inputs_embeds is not None:
+            raise StkError("position_ids / inputs_embeds are not supported by the fused path "
+                           "(the reference ignores both as well)")
+        self._raise_on_bad_ids()   # a flag left by the previous training step
         if labels is not None:
             if self.config.problem_type is None:
                 if self.num_labels > 1 and labels.dtype in (torch.long, torch.int):
@@ -59,15 +60,17 @@ class STonKGsForSequenceClassification(STonKGsForPreTraining):
                     self.config.problem_type = "multi_label_classification"
             if self.config.problem_type != "single_label_classification":
                 raise StkError("only single_label_classification is implemented in the CUDA classification head")
-        grad = labels is not None and torch.is_grad_enabled() and self.classifier.weight.requires_grad
+        # any live, trainable parameter ties the Function into the autograd graph (frozen ones are skipped)
+        anchor = next((p for p, _ in self.grad_buffer().param_views), None) if labels is not None and torch.is_grad_enabled() else None
+        grad = anchor is not None
         if grad:
-            loss, logits = _FinetuneStep.apply(self, (input_ids, attention_mask, token_type_ids, labels),
-                                               self.classifier.bias)
+            loss, logits = _FinetuneStep.apply(self, (input_ids, attention_mask, token_type_ids, labels, head_mask), anchor)
+            self._stage_err_flag()     # checked by FusedAdamW.step / the next forward, after backward is enqueued
         else:
             with torch.no_grad():
-                _, pooled, _ = self.encode(input_ids, attention_mask, token_type_ids)
+                _, pooled, _ = self.encode(input_ids, attention_mask, token_type_ids, head_mask=head_mask)
                 loss, logits = _head_fwd(self, pooled, labels, None)
-        self._raise_on_bad_ids()
+            self._raise_on_bad_ids()
         if not return_dict:
             return ((loss, logits) if loss is not None else (logits,))
         return SequenceClassifierOutput(loss=loss, logits=logits, hidden_states=None, attentions=None)
@@ -82,7 +85,11 @@ class STonKGsForSequenceClassification(STonKGsForPreTraining):
 
 def _head_fwd(model, pooled, labels, cache: Optional[dict]):
     dev = pooled.device
-    err = torch.zeros(1, dtype=torch.int32, device=dev) if labels is not None else None
+    err = None
+    if labels is not None:
+        err = getattr(model, "_pending_err", None)
+        if err is None:
+            err = model._pending_err = torch.zeros(1, dtype=torch.int32, device=dev)
     lab = labels.to(dev, torch.int64, non_blocking=True).contiguous().view(-1) if labels is not None else None
     if lab is not None and not labels.is_cuda and lab.numel():
         lo, hi = int(labels.min()), int(labels.max())
@@ -101,8 +108,8 @@ class _FinetuneStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, batch, anchor):
         cache: dict = {}
-        input_ids, attention_mask, token_type_ids, labels = batch
-        seq, pooled, _ = model.encode(input_ids, attention_mask, token_type_ids, cache=cache)
+        input_ids, attention_mask, token_type_ids, labels, head_mask = batch
+        seq, pooled, _ = model.encode(input_ids, attention_mask, token_type_ids, cache=cache, head_mask=head_mask)
         cache["seq"] = seq
         loss, logits = _head_fwd(model, pooled, labels, cache)
         ctx.model, ctx.cache, ctx.st = model, cache, model._dev_state

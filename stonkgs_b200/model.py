@@ -199,6 +199,10 @@ class STonKGsForPreTraining(BertForPreTraining):
         # train() mode dropout (HF:110,132,297,355): masks are a counter-based function of
         # (stk_dropout_seed + step, site), so backward regenerates them; last_dropout_seed is what a test hands to
         # oracle.dropout_oracle.DropSpec to reproduce the same step in fp32
+        self.label_capacity = None    # labelled positions per pair and half the heads are sized for (None: 15 %)
+        self._pending_err = None
+        self._err_staged = None
+        self._err_stream = None
         self.stk_dropout = True
         self.stk_dropout_seed = int(torch.initial_seed()) & 0xFFFFFFFF
         self._dropout_step = 0
@@ -367,16 +371,31 @@ class STonKGsForPreTraining(BertForPreTraining):
             attention_mask = attention_mask.to(dev, torch.int64, non_blocking=True).contiguous()
         if token_type_ids is not None:
             token_type_ids = token_type_ids.to(dev, torch.int64, non_blocking=True).contiguous()
+        hm = self._head_mask_rows(head_mask, len(st["bert"].layers), dev)
         drop = self._drop_ctx()
         lm_hidden = engine.lm_backbone_fwd(st["lm"], input_ids[:, :sh.text_len], None, err_flag=err, drop=drop)
         seq, pooled, emb = engine.joint_fwd(st["bert"], input_ids, token_type_ids, attention_mask, lm_hidden,
                                             self.kg_table, cache=cache, want_inputs_embeds=want_inputs_embeds,
-                                            err_flag=err, drop=drop, shape=sh)
+                                            err_flag=err, drop=drop, shape=sh, head_mask=hm)
         if cache is not None:
             cache.update(input_ids=input_ids, token_type_ids=token_type_ids, err=err)
         if err_flag is None:
             self._pending_err = err
         return seq, pooled, emb
+
+    @staticmethod
+    def _head_mask_rows(head_mask, num_layers: int, dev):
+        """The reference hands ``head_mask`` to ``self.bert`` (stonkgs_model.py:158,209); HF's ``get_head_mask`` accepts
+        [heads] (same for every layer) or [layers, heads] and multiplies the attention probabilities of (layer, head) by
+        the entry.  Returns fp32 [layers, 12] on the device, or None."""
+        if head_mask is None:
+            return None
+        hm = torch.as_tensor(head_mask, dtype=torch.float32).to(dev)
+        if hm.dim() == 1:
+            hm = hm.unsqueeze(0).expand(num_layers, -1)
+        if hm.dim() != 2 or hm.shape != (num_layers, ops.HEADS):
+            raise StkError(f"head_mask must be [12] or [{num_layers}, 12], got {tuple(hm.shape)}")
+        return hm.contiguous()
 
     def _drop_ctx(self):
         """Dropout state of this forward pass: None in eval() (the reference's parity mode) or when disabled."""
@@ -399,20 +418,49 @@ class STonKGsForPreTraining(BertForPreTraining):
             gb = self._grad_buffer = GradBuffer(self)
         return gb
 
-    def _raise_on_bad_ids(self):
-        """Read the device-side id / label range flag of the last forward (one host sync) and raise like the reference
-        (KeyError from ``kg_backbone[i]``, IndexError from the embedding / cross-entropy).  The training step calls this
-        from ``FusedAdamW.step`` (or the next forward), i.e. after backward has been enqueued, so that the read does not
-        drain the queue between forward and backward."""
+    def _stage_err_flag(self):
+        """Training step: copy the id / label range flag of the forward just enqueued to pinned host memory on a side
+        stream.  By the time ``FusedAdamW.step`` (or the next forward) looks at it, the copy has long completed behind the
+        backward pass, so the check costs no device sync and never drains the launch queue."""
         err = getattr(self, "_pending_err", None)
-        self._pending_err = None
         if err is None:
             return
-        code = int(err.item())
+        if getattr(self, "_err_stream", None) is None or self._err_host.device != torch.device("cpu"):
+            self._err_stream = torch.cuda.Stream(device=err.device)
+            self._err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        fwd_done = torch.cuda.Event()
+        fwd_done.record(torch.cuda.current_stream(err.device))
+        with torch.cuda.stream(self._err_stream):
+            self._err_stream.wait_event(fwd_done)
+            self._err_host.copy_(err, non_blocking=True)
+            err.record_stream(self._err_stream)
+            self._err_staged = torch.cuda.Event()
+            self._err_staged.record(self._err_stream)
+
+    def _raise_on_bad_ids(self):
+        """Read the device-side id / label range flag of the last forward and raise like the reference (KeyError from
+        ``kg_backbone[i]``, IndexError from the embedding / cross-entropy).  Inference reads it right away (one sync);
+        the training step stages it (``_stage_err_flag``) and checks in ``FusedAdamW.step`` before the update is applied,
+        or at the next forward."""
+        err = getattr(self, "_pending_err", None)
+        staged = getattr(self, "_err_staged", None)
+        self._pending_err = None
+        self._err_staged = None
+        if err is None:
+            return
+        if staged is not None:
+            staged.synchronize()
+            code = int(self._err_host[0])
+        else:
+            code = int(err.item())
         if code & 1:
             raise KeyError("input id outside the text vocabulary / KG table")
         if code & 2:
             raise IndexError("label outside the vocabulary of its head (text / entity / next-sentence)")
+        if code & 4:
+            raise StkError("more labelled positions in the batch than the head kernels were sized for: set "
+                           "model.label_capacity (labelled positions per pair and half; default int(0.15 * 256) = 38 as "
+                           "produced by the reference's pre-processing) or pass the label tensors on the CPU")
 
     @torch.no_grad()
     def embed(self, input_ids, attention_mask=None, token_type_ids=None, err_flag=None) -> torch.Tensor:
@@ -423,11 +471,9 @@ class STonKGsForPreTraining(BertForPreTraining):
     def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, masked_lm_labels=None,
                 ent_masked_lm_labels=None, next_sentence_labels=None, return_dict=None, head_mask=None):
         """Same contract as the reference forward (stonkgs_model.py:149-258)."""
-        if head_mask is not None:
-            raise StkError("head_mask is not supported by the fused attention kernel")
         from . import training  # local import: keeps inference-only users free of the autograd glue
         return training.forward(self, input_ids, attention_mask, token_type_ids, masked_lm_labels,
-                                ent_masked_lm_labels, next_sentence_labels, return_dict)
+                                ent_masked_lm_labels, next_sentence_labels, return_dict, head_mask)
 
 
 # --------------------------------------------------------------------------------------------------

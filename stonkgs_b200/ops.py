@@ -11,9 +11,9 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GELU_SAVE, EPI_BIAS_RESID, EPI_BIAS_RESID_LN, EPI_BIAS_TANH_F32,
-                   EPI_BIAS_GELU_SAVE_GRAD, EPI_CE_DLOGIT, EPI_CE_STATS, EPI_DGELU, EPI_F32, EPI_F32_ADD, EPI_MUL, GemmEpilogue,
-                   check)
+from ._lib import (EPI_BIAS, EPI_BIAS_DROP_RESID_LN, EPI_BIAS_GELU, EPI_BIAS_GELU_SAVE, EPI_BIAS_RESID, EPI_BIAS_RESID_LN,
+                   EPI_BIAS_TANH_F32, EPI_BIAS_GELU_SAVE_GRAD, EPI_CE_DLOGIT, EPI_CE_STATS, EPI_DGELU, EPI_F32, EPI_F32_ADD,
+                   EPI_MUL, WS_ATTN_BWD, WS_LINEAR_CE_BWD, WS_LINEAR_CE_FWD, GemmEpilogue, check)
 
 H = 768
 HEADS = 12
@@ -195,7 +195,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, out=None, dbias=None,
 def gemm(a: torch.Tensor, b: torch.Tensor, *, M: int, N: int, K: int, a_major: int = 0, b_major: int = 0,
          epilogue: int = EPI_BIAS, out: Optional[torch.Tensor] = None, bias=None, resid=None, c2=None, labels=None,
          lse=None, scale_dev=None, ce_partial=None, tgt_logit=None, n_offset: int = 0, split_k: int = 1,
-         ln_gamma=None, ln_beta=None, ln_mean=None, ln_rstd=None):
+         ln_gamma=None, ln_beta=None, ln_mean=None, ln_rstd=None, drop: Optional["Drop"] = None):
     """C[M,N] = epilogue(A[M,K] B[N,K]^T); a/b are 2-D bf16 tensors in the stored layout
     (K-major: [M,K] / [N,K]; MN-major: [K,M] / [K,N]); row stride = leading dimension."""
     _req(a, torch.bfloat16, "A")
@@ -225,6 +225,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: int, N: int, K: int, a_major: i
     epi.ln_beta = ln_beta.data_ptr() if ln_beta is not None else None
     epi.ln_mean = ln_mean.data_ptr() if ln_mean is not None else None
     epi.ln_rstd = ln_rstd.data_ptr() if ln_rstd is not None else None
+    if drop is not None:
+        epi.drop_seed, epi.drop_site, epi.drop_thr = drop.seed, drop.site, drop.thr
     if epilogue != EPI_CE_STATS:
         if out is None:
             dt = torch.float32 if epilogue in _F32_EPIS else torch.bfloat16
@@ -244,8 +246,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, M: int, N: int, K: int, a_major: i
     return out
 
 
-def linear_resid_ln(x, w, bias, resid, gamma, beta, *, save_for_backward=False):
-    """y = LayerNorm(x @ w.T + bias + resid) * gamma + beta in ONE kernel (HF:294-298, 352-356).
+def linear_resid_ln(x, w, bias, resid, gamma, beta, *, save_for_backward=False, drop: Optional["Drop"] = None):
+    """y = LayerNorm(drop(x @ w.T + bias) + resid) * gamma + beta in ONE kernel (HF:294-298, 352-356; ``drop`` = the
+    train()-mode dropout of the dense output, masks generated inside the epilogue).
     Returns y, or (y, z, mean, rstd) with z the pre-LayerNorm sum when ``save_for_backward``."""
     M = x.shape[0]
     assert w.shape[0] == H
@@ -254,8 +257,9 @@ def linear_resid_ln(x, w, bias, resid, gamma, beta, *, save_for_backward=False):
         z = torch.empty((M, H), dtype=torch.bfloat16, device=x.device)
         mean = torch.empty(M, dtype=torch.float32, device=x.device)
         rstd = torch.empty_like(mean)
-    y = gemm(x, w, M=M, N=H, K=x.shape[1], bias=bias, epilogue=EPI_BIAS_RESID_LN, resid=resid, c2=z, ln_gamma=gamma,
-             ln_beta=beta, ln_mean=mean, ln_rstd=rstd)
+    dropping = drop is not None and drop.thr > 0
+    y = gemm(x, w, M=M, N=H, K=x.shape[1], bias=bias, epilogue=EPI_BIAS_DROP_RESID_LN if dropping else EPI_BIAS_RESID_LN,
+             resid=resid, c2=z, ln_gamma=gamma, ln_beta=beta, ln_mean=mean, ln_rstd=rstd, drop=drop if dropping else None)
     return (y, z, mean, rstd) if save_for_backward else y
 
 
@@ -329,7 +333,7 @@ def attention(qkv: torch.Tensor, key_bias: Optional[torch.Tensor], B: int, S: in
 def attention_bwd(qkv, key_bias, B, S, out, dout, lse, drop: Optional["Drop"] = None):
     dev, stream = _ctx(qkv)
     dqkv = torch.empty_like(qkv)
-    ws = torch.empty(B * S * H + B * HEADS * S, dtype=torch.float32, device=qkv.device)
+    ws = torch.empty(workspace_bytes(WS_ATTN_BWD, B, S) // 4, dtype=torch.float32, device=qkv.device)
     prof = _PROFILER
     if prof is not None:
         e0, e1 = prof.span("attn_bwd", 10.0 * B * HEADS * S * S * 64)
@@ -399,14 +403,88 @@ def ce_finalize(ce_partial, tgt_logit, M):
     return lse, row_loss
 
 
-def nsp_head(pooled, w, b, labels=None):
+def nsp_head(pooled, w, b, labels=None, err_flag=None):
     dev, stream = _ctx(pooled)
     B = pooled.shape[0]
     logits = torch.empty((B, 2), dtype=torch.float32, device=pooled.device)
     row_loss = torch.empty(B, dtype=torch.float32, device=pooled.device) if labels is not None else None
     check(_lib.load().stk_nsp_head_fwd(dev, stream, _ptr(pooled), B, _ptr(w), _ptr(b), _ptr(labels), _ptr(logits),
-                                       _ptr(row_loss)), "stk_nsp_head_fwd")
+                                       _ptr(row_loss), _ptr(err_flag)), "stk_nsp_head_fwd")
     return logits, row_loss
+
+
+def workspace_bytes(op: int, a: int, b: int) -> int:
+    n = int(_lib.load().stk_query_workspace(op, a, b))
+    if n < 0:
+        check(n, "stk_query_workspace")
+    return n
+
+
+def compact_labels(labels: torch.Tensor, row_pitch: int, col_offset: int, vocab: int, capacity: int, err_flag=None):
+    """Device-side label selection (``labels != -100``): returns (rows int32 [capacity], labels int32 [capacity],
+    count int32 [1]) with padding entries -1 beyond the count; nothing is read back to the host."""
+    _req(labels, torch.int64, "labels")
+    assert labels.dim() == 2 and labels.is_contiguous()
+    dev, stream = _ctx(labels)
+    B, width = labels.shape
+    rows = torch.empty(capacity, dtype=torch.int32, device=labels.device)
+    labs = torch.empty(capacity, dtype=torch.int32, device=labels.device)
+    count = torch.empty(1, dtype=torch.int32, device=labels.device)
+    check(_lib.load().stk_compact_labels(dev, stream, _ptr(labels), B, width, row_pitch, col_offset, vocab, capacity,
+                                         _ptr(rows), _ptr(labs), _ptr(count), _ptr(err_flag)), "stk_compact_labels")
+    return rows, labs, count
+
+
+def linear_ce_fwd(t_rows: torch.Tensor, w: torch.Tensor, labels_i32: torch.Tensor):
+    """Fused decoder GEMM + cross-entropy (no logits).  Returns (lse [R], row_loss [R], loss_count [2] = mean loss, count)."""
+    _req(t_rows, torch.bfloat16, "t")
+    _req(w, torch.bfloat16, "w")
+    _req(labels_i32, torch.int32, "labels")
+    assert t_rows.is_contiguous() and w.is_contiguous() and t_rows.shape[1] == H and w.shape[1] == H
+    dev, stream = _ctx(t_rows)
+    R, V = t_rows.shape[0], w.shape[0]
+    nbytes = workspace_bytes(WS_LINEAR_CE_FWD, R, V)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=t_rows.device)
+    lse = torch.empty(R, dtype=torch.float32, device=t_rows.device)
+    row_loss = torch.empty(R, dtype=torch.float32, device=t_rows.device)
+    loss_count = torch.empty(2, dtype=torch.float32, device=t_rows.device)
+    prof = _PROFILER
+    if prof is not None:
+        e0, e1 = prof.span(f"linear_ce_fwd_n{V}", 2.0 * R * V * H)
+        e0.record()
+    check(_lib.load().stk_linear_ce_fwd(dev, stream, _ptr(t_rows), _ptr(w), R, V, _ptr(labels_i32), _ptr(ws), nbytes,
+                                        _ptr(lse), _ptr(row_loss), _ptr(loss_count)), "stk_linear_ce_fwd")
+    if prof is not None:
+        e1.record()
+    return lse, row_loss, loss_count
+
+
+def linear_ce_bwd(t_rows, w, labels_i32, lse, scale_dev, dT, dW) -> None:
+    """dT += dlogit W, dW += dlogit^T t with dlogit = (softmax - onehot) * scale recomputed chunk by chunk."""
+    dev, stream = _ctx(t_rows)
+    R, V = t_rows.shape[0], w.shape[0]
+    assert dT.is_contiguous() and dW.is_contiguous() and dT.dtype == torch.float32 and dW.dtype == torch.float32
+    nbytes = workspace_bytes(WS_LINEAR_CE_BWD, R, V)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=t_rows.device)
+    prof = _PROFILER
+    if prof is not None:
+        e0, e1 = prof.span(f"linear_ce_bwd_n{V}", 6.0 * R * V * H)
+        e0.record()
+    check(_lib.load().stk_linear_ce_bwd(dev, stream, _ptr(t_rows), _ptr(w), R, V, _ptr(labels_i32), _ptr(lse),
+                                        _ptr(scale_dev), _ptr(ws), nbytes, _ptr(dT), _ptr(dW)), "stk_linear_ce_bwd")
+    if prof is not None:
+        e1.record()
+
+
+def scale_heads(x: torch.Tensor, scales: torch.Tensor, out=None) -> torch.Tensor:
+    """y[:, h*64:(h+1)*64] = x[:, h*64:(h+1)*64] * scales[h] (head_mask applied to the attention context)."""
+    _req(x, torch.bfloat16, "x")
+    _req(scales, torch.float32, "scales")
+    assert x.shape[1] == H and x.is_contiguous() and scales.numel() == HEADS
+    dev, stream = _ctx(x)
+    y = torch.empty_like(x) if out is None else out
+    check(_lib.load().stk_scale_heads(dev, stream, _ptr(x), x.shape[0], _ptr(scales), _ptr(y)), "stk_scale_heads")
+    return y
 
 
 def gelu_bwd(dy: torch.Tensor, pre: torch.Tensor) -> torch.Tensor:

@@ -160,63 +160,85 @@ class GradBuffer:
 # --------------------------------------------------------------------------------------------------
 # heads: forward
 # --------------------------------------------------------------------------------------------------
-def _label_rows(labels: torch.Tensor, col_offset: int, width: int, row_pitch: int, dev, vocab: int):
-    """Row indices (b*row_pitch + col_offset + t) and int32 labels of the labelled positions."""
+def label_capacity(model, labels: torch.Tensor, width: int) -> int:
+    """Rows the head kernels are sized for.  Labels still on the host are counted there (no device sync involved);
+    labels already on the device are NOT read back: the capacity is ``model.label_capacity`` per pair (default: the
+    ``int(0.15 * width)`` = 38 positions per half that the reference's pre-processing labels,
+    indra_for_pretraining.py:55-58; every position for the 4-token TransE entity part) times the batch size, and the
+    compaction kernel flags a batch that holds more (StkError at the deferred check)."""
+    B = labels.shape[0]
+    if not labels.is_cuda:
+        return int((labels != IGNORE).sum())
+    per_pair = getattr(model, "label_capacity", None)
+    if per_pair is None:
+        per_pair = int(width * 0.15) if width >= 64 else width
+    return max(1, min(int(per_pair), width) * B)
+
+
+def _compact(model, labels: torch.Tensor, col_offset: int, width: int, row_pitch: int, dev, vocab: int, err):
+    """(rows int32 [cap], labels int32 [cap], count int32 [1]) of the labelled positions, or None when cap == 0."""
     if labels.dim() != 2 or labels.shape[1] != width:
         raise StkError(f"label tensors must be [B, {width}], got {tuple(labels.shape)}")
-    sel = labels != IGNORE
-    pos = torch.nonzero(sel, as_tuple=False)  # host-side when the batch is on the CPU; one sync otherwise
-    lab = labels[sel]
-    if lab.numel() and not labels.is_cuda and (int(lab.min()) < 0 or int(lab.max()) >= vocab):
-        raise IndexError(f"label outside [0, {vocab})")
-    rows = (pos[:, 0] * row_pitch + pos[:, 1] + col_offset).to(torch.int32)
-    return rows.to(dev, non_blocking=True), lab.to(torch.int32).to(dev, non_blocking=True)
+    if not labels.is_cuda and labels.numel():
+        lab = labels[labels != IGNORE]
+        if lab.numel() and (int(lab.min()) < 0 or int(lab.max()) >= vocab):
+            raise IndexError(f"label outside [0, {vocab})")
+    cap = label_capacity(model, labels, width)
+    if cap == 0:
+        return None
+    labels_d = labels.to(dev, torch.int64, non_blocking=True).contiguous()
+    return ops.compact_labels(labels_d, row_pitch, col_offset, vocab, cap, err)
 
 
 def _ce_forward(t_rows, w, labels_i32):
     """Fused GEMM + cross-entropy statistics over the vocabulary; logits are never materialised."""
-    R = t_rows.shape[0]
-    V = w.shape[0]
-    pitch = 2 * ((V + 255) // 256)
-    part = torch.empty((R, pitch, 2), dtype=torch.float32, device=t_rows.device)
-    tgt = torch.empty(R, dtype=torch.float32, device=t_rows.device)
-    ops.gemm(t_rows, w, M=R, N=V, K=H, epilogue=ops.EPI_CE_STATS, labels=labels_i32, ce_partial=part, tgt_logit=tgt)
-    return ops.ce_finalize(part, tgt, R)  # lse, row_loss
+    lse, row_loss, _ = ops.linear_ce_fwd(t_rows, w, labels_i32)
+    return lse, row_loss
 
 
 def heads_fwd(model, hw: engine.HeadWeights, seq, pooled, mlm_labels, elm_labels, nsp_labels, cache: Optional[dict]):
+    """ELM head on the labelled rows + the three mean cross-entropies (stonkgs_model.py:62-73, 217-245).  No host sync:
+    label selection, row counts, means and range checks all stay on the device."""
     dev = seq.device
     V = hw.w_text.shape[0]
     N = hw.w_ent.shape[0]
     sh = model.seq_shape
-    rows_t, lab_t = _label_rows(mlm_labels, 0, sh.text_len, sh.seq_pad, dev, V)
-    rows_e, lab_e = _label_rows(elm_labels, sh.text_len, sh.kg_len, sh.seq_pad, dev, N)
-    Rt, Re = rows_t.numel(), rows_e.numel()
-    rows = torch.cat([rows_t, rows_e])
+    err = getattr(model, "_pending_err", None)
+    if err is None:
+        err = model._pending_err = torch.zeros(1, dtype=torch.int32, device=dev)
+    ct = _compact(model, mlm_labels, 0, sh.text_len, sh.seq_pad, dev, V, err)
+    ce = _compact(model, elm_labels, sh.text_len, sh.kg_len, sh.seq_pad, dev, N, err)
+    Rt = ct[0].numel() if ct is not None else 0
+    Re = ce[0].numel() if ce is not None else 0
     R = Rt + Re
     nan = torch.full((), float("nan"), dtype=torch.float32, device=dev)
     mlm_loss = elm_loss = nan
-    lse_t = lse_e = None
+    lse_t = lse_e = lc_t = lc_e = lab_t = lab_e = rows = None
     u = g = t = mean = rstd = hrows = None
     if R:
+        rows = torch.cat([c[0] for c in (ct, ce) if c is not None])
         hrows = ops.gather_rows(seq, rows)
         u = torch.empty((R, H), dtype=torch.bfloat16, device=dev)
         g = ops.linear(hrows, hw.wt, hw.bt, ops.EPI_BIAS_GELU_SAVE, c2=u)
         t, mean, rstd = ops.layernorm(g, hw.ln_g, hw.ln_b, save_stats=True)
         if Rt:
-            lse_t, rl = _ce_forward(t[:Rt], hw.w_text, lab_t)
-            mlm_loss = rl.mean()
+            lab_t = ct[1]
+            lse_t, _, lc_t = ops.linear_ce_fwd(t[:Rt], hw.w_text, lab_t)
+            mlm_loss = lc_t[0]
         if Re:
-            lse_e, rl = _ce_forward(t[Rt:], hw.w_ent, lab_e)
-            elm_loss = rl.mean()
+            lab_e = ce[1]
+            lse_e, _, lc_e = ops.linear_ce_fwd(t[Rt:], hw.w_ent, lab_e)
+            elm_loss = lc_e[0]
+    if not nsp_labels.is_cuda and nsp_labels.numel() and (int(nsp_labels.min()) < 0 or int(nsp_labels.max()) > 1):
+        raise IndexError("next_sentence_labels outside {0, 1}")
     nsp_labels_d = nsp_labels.to(dev, torch.int64, non_blocking=True).contiguous()
-    nsp_logits, nsp_rl = ops.nsp_head(pooled, hw.w_nsp, hw.b_nsp, nsp_labels_d)
+    nsp_logits, nsp_rl = ops.nsp_head(pooled, hw.w_nsp, hw.b_nsp, nsp_labels_d, err)
     nsp_loss = nsp_rl.mean()
     loss = mlm_loss + elm_loss + nsp_loss
     if cache is not None:
-        cache.update(rows=rows, Rt=Rt, Re=Re, lab_t=lab_t, lab_e=lab_e, lse_t=lse_t, lse_e=lse_e, hrows=hrows, u=u, g=g,
-                     t=t, t_mean=mean, t_rstd=rstd, nsp_logits=nsp_logits, nsp_labels=nsp_labels_d, pooled=pooled,
-                     seq=seq)
+        cache.update(rows=rows, Rt=Rt, Re=Re, lab_t=lab_t, lab_e=lab_e, lse_t=lse_t, lse_e=lse_e, lc_t=lc_t, lc_e=lc_e,
+                     hrows=hrows, u=u, g=g, t=t, t_mean=mean, t_rstd=rstd, nsp_logits=nsp_logits, nsp_labels=nsp_labels_d,
+                     pooled=pooled, seq=seq)
     return loss, (mlm_loss, elm_loss, nsp_loss), nsp_logits, (lse_t, lse_e)
 
 
@@ -280,27 +302,11 @@ def dense_logits_bytes(model, B: int) -> int:
 # --------------------------------------------------------------------------------------------------
 # backward
 # --------------------------------------------------------------------------------------------------
-def _splits(m_out: int, n_out: int, k: int, sms: int = 148) -> int:
-    """Split-K factor of a reduce-add GEMM: fill the persistent grid (CTA pairs on 256 x 256 tiles when there
-    is more than one 128-row tile, else single CTAs on 128 x 256) with as few k-splits as possible."""
-    pair = m_out > 128
-    tiles = ((m_out + (255 if pair else 127)) // (256 if pair else 128)) * ((n_out + 255) // 256)
-    units = sms // 2 if pair else sms
-    kb = (k + 63) // 64
-    best, best_eff = 1, 0.0
-    for s in range(1, min(kb, 32) + 1):
-        items = tiles * s
-        eff = items / (-(-items // units) * units)
-        if eff > best_eff + 0.05:   # more splits only for a clearly fuller grid (each split re-reduces the tile)
-            best, best_eff = s, eff
-    return best
-
-
 def _wgrad(dy, x, out, k_rows):
-    """out[Nout, Nin] += dy[k_rows, Nout]^T x[k_rows, Nin]  (both operands read in place, MN-major)."""
+    """out[Nout, Nin] += dy[k_rows, Nout]^T x[k_rows, Nin]  (both operands read in place, MN-major; split-K chosen by the
+    library so that the persistent grid is full)."""
     n_out, n_in = out.shape
-    ops.gemm(dy, x, M=n_out, N=n_in, K=k_rows, a_major=1, b_major=1, epilogue=ops.EPI_F32_ADD, out=out,
-             split_k=_splits(n_out, n_in, k_rows))
+    ops.gemm(dy, x, M=n_out, N=n_in, K=k_rows, a_major=1, b_major=1, epilogue=ops.EPI_F32_ADD, out=out, split_k=0)
 
 
 def _dgrad(dy, w, *, epilogue=ops.EPI_BIAS, resid=None):
@@ -311,24 +317,8 @@ def _dgrad(dy, w, *, epilogue=ops.EPI_BIAS, resid=None):
 
 
 def _ce_backward(t_rows, w, labels_i32, lse, scale_dev, dT, gW):
-    """Chunked fused linear + CE backward: per vocabulary chunk recompute the logits tile, form
-    dlogit = (softmax - onehot) * scale in the GEMM epilogue (bf16, chunk-sized workspace that stays
-    in L2), then dT += dlogit W_chunk and dW_chunk += dlogit^T t."""
-    R = t_rows.shape[0]
-    V = w.shape[0]
-    # chunk so that the dlogit workspace is ~<= 48 MB (L2-resident), multiple of 256
-    C = max(256, min(((48 << 20) // (2 * max(R, 1))) // 256 * 256, 32768))
-    C = min(C, (V + 255) // 256 * 256)
-    buf = torch.empty((R, C), dtype=torch.bfloat16, device=t_rows.device)
-    for c0 in range(0, V, C):
-        n = min(C, V - c0)
-        wc = w[c0:c0 + n]
-        dl = buf[:, :n]
-        ops.gemm(t_rows, wc, M=R, N=n, K=H, epilogue=ops.EPI_CE_DLOGIT, labels=labels_i32, lse=lse,
-                 scale_dev=scale_dev, n_offset=c0, out=dl)
-        ops.gemm(dl, wc, M=R, N=H, K=n, b_major=1, epilogue=ops.EPI_F32_ADD, out=dT, split_k=_splits(R, H, n))
-        ops.gemm(dl, t_rows, M=n, N=H, K=R, a_major=1, b_major=1, epilogue=ops.EPI_F32_ADD, out=gW[c0:c0 + n],
-                 split_k=_splits(n, H, R))
+    """Fused linear + cross-entropy backward (stk_linear_ce_bwd owns the vocabulary-chunk loop)."""
+    ops.linear_ce_bwd(t_rows, w, labels_i32, lse, scale_dev, dT, gW)
 
 
 def backward(model, st, cache, dloss: torch.Tensor, gb: GradBuffer, on_ready=None):
@@ -351,11 +341,14 @@ def backward(model, st, cache, dloss: torch.Tensor, gb: GradBuffer, on_ready=Non
     if R:
         t = cache["t"]
         dT = torch.zeros((R, H), dtype=torch.float32, device=dev)
+        # gradient scale = upstream / number of labelled rows (a device scalar: the count is never read back)
         if Re:
-            _ce_backward(t[Rt:], hw.w_ent, cache["lab_e"], cache["lse_e"], (dloss / Re).reshape(1), dT[Rt:], gb["w_ent"])
+            _ce_backward(t[Rt:], hw.w_ent, cache["lab_e"], cache["lse_e"], (dloss / cache["lc_e"][1]).reshape(1), dT[Rt:],
+                         gb["w_ent"])
         ready("w_ent")
         if Rt:
-            _ce_backward(t[:Rt], hw.w_text, cache["lab_t"], cache["lse_t"], (dloss / Rt).reshape(1), dT[:Rt], gb["w_text"])
+            _ce_backward(t[:Rt], hw.w_text, cache["lab_t"], cache["lse_t"], (dloss / cache["lc_t"][1]).reshape(1), dT[:Rt],
+                         gb["w_text"])
         ready("w_text")
         dT_bf = ops.cast_bf16(dT)
         dg = ops.layernorm_bwd(dT_bf, cache["g"], hw.ln_g, cache["t_mean"], cache["t_rstd"], gb["t_ln_g"], gb["t_ln_b"])
@@ -402,6 +395,7 @@ def backward_trunk(model, bert: engine.EncoderWeights, cache, dseq, gb: GradBuff
     B = M // SP
     key_bias = cache["key_bias"]
     drop: Optional[engine.DropCtx] = cache.get("drop")   # train() with dropout: masks are regenerated from (seed, site)
+    head_mask = cache.get("head_mask")
     dx = dseq
     for li in reversed(range(len(bert.layers))):
         lw = bert.layers[li]
@@ -427,8 +421,11 @@ def backward_trunk(model, bert: engine.EncoderWeights, cache, dseq, gb: GradBuff
         else:
             dz1 = dz1m = ops.layernorm_bwd(dx1, c.z1, lw.ln1_g, c.mean1, c.rstd1, gb[p + "ln1_g"], gb[p + "ln1_b"],
                                            dbias=gb[p + "bo"])
-        _wgrad(dz1m, c.ctx, gb[p + "wo"], M)
+        ctx_used = c.ctx_used if c.ctx_used is not None else c.ctx
+        _wgrad(dz1m, ctx_used, gb[p + "wo"], M)
         dctx = _dgrad(dz1m, lw.wo)
+        if head_mask is not None:   # ctx_used = ctx * head_mask[layer] per head: the same factor on the way back
+            ops.scale_heads(dctx, head_mask[li], out=dctx)
         dqkv = ops.attention_bwd(c.qkv, key_bias, B, SP, c.ctx, dctx, c.lse,
                                  drop=drop.attention(1, li) if drop is not None else None)
         # bias gradients of query and value; the key-bias gradient is analytically zero (softmax is
@@ -476,8 +473,9 @@ class _PretrainStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, batch, anchor):
         cache: dict = {}
-        input_ids, attention_mask, token_type_ids, mlm, elm, nsp = batch
-        seq, pooled, _ = model.encode(input_ids, attention_mask, token_type_ids, cache=cache, need_heads=True)
+        input_ids, attention_mask, token_type_ids, mlm, elm, nsp, head_mask = batch
+        seq, pooled, _ = model.encode(input_ids, attention_mask, token_type_ids, cache=cache, need_heads=True,
+                                      head_mask=head_mask)
         st = model._dev_state
         loss, parts, nsp_logits, _ = heads_fwd(model, st["heads"], seq, pooled, mlm, elm, nsp, cache)
         ctx.model, ctx.cache, ctx.st = model, cache, st
@@ -501,7 +499,7 @@ class _PretrainStep(torch.autograd.Function):
         return None, None, None
 
 
-def forward(model, input_ids, attention_mask, token_type_ids, mlm, elm, nsp, return_dict):
+def forward(model, input_ids, attention_mask, token_type_ids, mlm, elm, nsp, return_dict, head_mask=None):
     """Reference forward contract (stonkgs_model.py:149-258)."""
     from .model import BertForPreTrainingOutputWithPooling
     have_labels = mlm is not None and elm is not None and nsp is not None
@@ -512,11 +510,12 @@ def forward(model, input_ids, attention_mask, token_type_ids, mlm, elm, nsp, ret
     total_loss = None
     if grad:
         total_loss, pooled, nsp_logits, seq = _PretrainStep.apply(
-            model, (input_ids, attention_mask, token_type_ids, mlm, elm, nsp), anchor)
+            model, (input_ids, attention_mask, token_type_ids, mlm, elm, nsp, head_mask), anchor)
         hw = model._dev_state["heads"]
+        model._stage_err_flag()
     else:
         with torch.no_grad():
-            seq, pooled, _ = model.encode(input_ids, attention_mask, token_type_ids, need_heads=True)
+            seq, pooled, _ = model.encode(input_ids, attention_mask, token_type_ids, need_heads=True, head_mask=head_mask)
             hw = model._dev_state["heads"]
             if have_labels:
                 total_loss, parts, nsp_logits, _ = heads_fwd(model, hw, seq, pooled, mlm, elm, nsp, None)

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_in_header():
     src = open(os.path.join(ROOT, "include", "stk.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(?:int|long long)\s+(stk_\w+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(?:int|long long|int64_t)\s+(stk_\w+)\s*\(", src)))
 
 
 def test_header_and_binding_agree():
@@ -59,4 +59,32 @@ def test_new_entry_points_validate_arguments():
     assert rc == -1 and "stk_dropout_fwd" in _lib.last_error()
     rc = lib.stk_layernorm_bwd_fused(0, None, p16, p16, 8, p16, p16, p16, p16, p16, p16, None, None, 1, 2, 13)
     assert rc == -1 and "dxm" in _lib.last_error()                     # dropout needs the masked output
+    assert lib.stk_launch_count() == 0
+
+
+def test_workspace_query_and_head_entry_points():
+    """stk_query_workspace is host arithmetic (no GPU): sizes of the calls that take a workspace; the single-call heads
+    validate their arguments before anything is launched."""
+    lib = _lib.load()
+    B, S, R, V = 64, 512, 2432, 175003
+    assert lib.stk_query_workspace(_lib.WS_ATTN_BWD, B, S) == 4 * (B * S * 768 + B * 12 * S)
+    pitch = 2 * ((V + 255) // 256)
+    fwd = lib.stk_query_workspace(_lib.WS_LINEAR_CE_FWD, R, V)
+    assert fwd >= 4 * (R * pitch * 2 + R) and fwd % 256 == 0
+    bwd = lib.stk_query_workspace(_lib.WS_LINEAR_CE_BWD, R, V)
+    assert 0 < bwd <= (48 << 20) + 256 and bwd % (2 * R) % 1 == 0
+    assert lib.stk_query_workspace(_lib.WS_LINEAR_CE_BWD, 8, 1000) == 2 * 8 * 1024      # one chunk: vocabulary rounded to 256
+    assert lib.stk_query_workspace(99, 1, 1) == -1 and "unknown op" in _lib.last_error()
+    assert lib.stk_query_workspace(_lib.WS_ATTN_BWD, 0, 512) == -1
+    p16 = ctypes.c_void_p(16)
+    rc = lib.stk_linear_ce_fwd(0, None, p16, p16, R, V, p16, p16, 1024, p16, p16, None)
+    assert rc == -1 and "workspace too small" in _lib.last_error()
+    rc = lib.stk_linear_ce_bwd(0, None, p16, p16, R, V, p16, p16, p16, p16, 1024, p16, p16)
+    assert rc == -1 and "workspace too small" in _lib.last_error()
+    rc = lib.stk_compact_labels(0, None, p16, 4, 256, 512, 0, 28996, 0, p16, p16, p16, None)
+    assert rc == -1 and "stk_compact_labels" in _lib.last_error()
+    epi = _lib.GemmEpilogue()
+    epi.resid, epi.ldr, epi.ln_gamma, epi.ln_beta = 16, 768, 16, 16
+    rc = lib.stk_gemm(0, None, 0, 0, p16, 768, p16, 768, 256, 768, 768, _lib.EPI_BIAS_DROP_RESID_LN, p16, 768, ctypes.byref(epi), 1)
+    assert rc == -1 and "drop_thr" in _lib.last_error()
     assert lib.stk_launch_count() == 0

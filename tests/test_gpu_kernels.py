@@ -30,3 +30,36 @@ def test_product_never_touches_oracle():
     code = ("import sys, torch; from stonkgs_b200 import model, training, embeddings, engine, ops; "
             "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'")
     subprocess.run([sys.executable, "-c", code], check=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def test_dropout_inside_the_layernorm_epilogue():
+    """STK_EPI_BIAS_DROP_RESID_LN (train(): z = drop(x W^T + b) + r, y = LN(z)) against the unfused pair it replaces
+    (bias GEMM, then the dropout + residual + LayerNorm row kernel): the keep decisions are the same pure function of
+    (seed, site, row, column), so the dropped positions — where z is exactly the residual — must coincide bit for bit;
+    values agree to bf16 rounding (the fused form does not round the dense output to bf16 before the sum)."""
+    from stonkgs_b200 import ops
+    torch.manual_seed(0)
+    for M, K in ((1024, 768), (640, 3072)):
+        x = torch.randn(M, K, device="cuda").bfloat16()
+        w = (torch.randn(768, K, device="cuda") * K ** -0.5).bfloat16()
+        b = torch.randn(768, device="cuda") * 0.1
+        r = torch.randn(M, 768, device="cuda").bfloat16()
+        g = 1 + 0.1 * torch.randn(768, device="cuda")
+        beta = 0.1 * torch.randn(768, device="cuda")
+        d = ops.Drop(seed=1234567, site=69, p=0.1)
+        y0, z0, m0, s0 = ops.dropout_resid_ln(ops.linear(x, w, b), r, g, beta, d, save_for_backward=True)
+        y1, z1, m1, s1 = ops.linear_resid_ln(x, w, b, r, g, beta, save_for_backward=True, drop=d)
+        dropped0, dropped1 = z0 == r, z1 == r
+        frac = dropped1.float().mean().item()
+        assert abs(frac - 13 / 128) < 5e-3, frac
+        assert torch.equal(dropped0, dropped1)
+        torch.testing.assert_close(z1.float(), z0.float(), atol=3e-2, rtol=2e-2)
+        torch.testing.assert_close(y1.float(), y0.float(), atol=4e-2, rtol=2e-2)
+        torch.testing.assert_close(m1, m0, atol=2e-3, rtol=0)
+        torch.testing.assert_close(s1, s0, atol=0, rtol=5e-3)
+        # fp32 reference of the fused form
+        keep = (~dropped1).float() * (128.0 / 115.0)
+        zf = (x.float() @ w.float().T + b) * keep + r.float()
+        torch.testing.assert_close(z1.float(), zf, atol=2e-2, rtol=1e-2)
+        yf = torch.nn.functional.layer_norm(z1.float(), (768,), g, beta, 1e-12)
+        torch.testing.assert_close(y1.float(), yf, atol=3e-2, rtol=1e-2)
