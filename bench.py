@@ -512,9 +512,17 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         dt = float(dt.item())
         v = world * n / dt
+        # the resident loop again, right after the stream and for comparable duration (>= 5 s): the headline `value` is
+        # a 10-step burst on a cool chip, the stream runs for minutes at the sustained power-capped clock
+        rb = [{k: torch.from_numpy(c.base[i * BATCH:(i + 1) * BATCH]).to(dev) for k, c in
+               zip(("input_ids", "attention_mask", "token_type_ids"), cols)} for i in range(4)]
+        k_sus = max(20, min(n // BATCH, 160))
+        ms_sus = timed(lambda i: model.embed(**rb[i % 4]), k_sus)
+        sustained = world * BATCH * k_sus / (ms_sus / 1000)
         # same rows -> same embeddings, whatever batch they travelled in (bit-exact): a checksum-free correctness check
         same = bool(np.array_equal(out[:8192 if n >= 16384 else 0], out[8192:16384 if n >= 16384 else 0]))
-        return {"value": v, "unit": "pairs/s", "pairs_per_gpu": n, "seconds": dt, "gap_to_resident": 1.0 - v / resident_value,
+        return {"value": v, "unit": "pairs/s", "pairs_per_gpu": n, "seconds": dt, "resident_sustained": sustained,
+                "gap_to_resident": 1.0 - v / sustained, "gap_to_resident_burst": 1.0 - v / resident_value,
                 "h2d_bytes": st.h2d_bytes, "d2h_bytes": st.d2h_bytes, "gpu_launches": ops.launch_count() - l0,
                 "repeat_rows_bit_identical": same, "finite": bool(np.isfinite(out[-BATCH:]).all()),
                 "what": "BASELINE configs[4] per-GPU share: host int64 id arrays -> embeddings.embed_arrays (2 pinned staging "

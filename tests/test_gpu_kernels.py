@@ -4,6 +4,7 @@ import os
 import sys
 
 import pytest
+import torch
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
 
