@@ -319,6 +319,9 @@ int stk_unpack_scale(int device, void* stream, const void* src_bf16, float* dst,
  * ---------------------------------------------------------------------------------------------- */
 /* out[0] += sum(x^2): global gradient norm (caller zeroes out first) */
 int stk_sumsq(int device, void* stream, const float* x, int64_t n, float* out);
+/* out[0] += sum((scale * x)^2) over a bf16 buffer: the norm of the MEAN gradient taken straight from the all-reduced
+ * (summed) bf16 wire buffer of the data-parallel path, scale = 1 / world */
+int stk_sumsq_bf16(int device, void* stream, const void* x_bf16, int64_t n, float scale, float* out);
 
 typedef struct StkAdamSeg {
   void* p;        /* fp32 parameter [n] (updated in place) */
@@ -328,16 +331,19 @@ typedef struct StkAdamSeg {
   void* w16;      /* optional bf16 copy of the updated parameter [n] (GEMM operand), or NULL */
   void* p32_copy; /* optional second fp32 destination (fused q|k|v bias vector), or NULL */
   int64_t n;
+  const void* g16; /* optional bf16 gradient [n]: read INSTEAD of g (the all-reduced wire buffer, see grad_scale), or NULL */
 } StkAdamSeg;
 
 /* One multi-tensor AdamW step.  segs_dev: device array of segments; chunk_seg_dev / chunk_off_dev:
  * per 65 536-element chunk the segment index and the element offset inside it (n_chunks blocks).
  * sumsq_dev: device scalar with the squared global grad norm (NULL = no clipping);
- * clip coefficient = min(1, max_grad_norm / (sqrt(*sumsq_dev) + 1e-6)) like torch clip_grad_norm_. */
+ * clip coefficient = min(1, max_grad_norm / (sqrt(*sumsq_dev) + 1e-6)) like torch clip_grad_norm_.
+ * grad_scale multiplies every gradient first (1 for local gradients; 1 / world when the segments read the summed bf16
+ * wire buffer of the data-parallel all-reduce through g16, which fuses DDP's "unpack + mean" into this pass). */
 int stk_adamw_step(int device, void* stream, const StkAdamSeg* segs_dev, const int32_t* chunk_seg_dev,
                    const int64_t* chunk_off_dev, int n_chunks, float lr, float beta1, float beta2, float eps,
                    float weight_decay, float bias_correction1, float bias_correction2, const float* sumsq_dev,
-                   float max_grad_norm);
+                   float max_grad_norm, float grad_scale);
 
 #ifdef __cplusplus
 }

@@ -30,7 +30,7 @@ class StkError(RuntimeError):
 
 class AdamSeg(Structure):
     _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("w16", c_void_p), ("p32_copy", c_void_p),
-                ("n", c_int64)]
+                ("n", c_int64), ("g16", c_void_p)]
 
 
 class GemmEpilogue(Structure):
@@ -95,8 +95,9 @@ _SIGNATURES = {
     "stk_gelu_bwd": (c_int, [c_int, _P, _P, _P, c_int64, _P]),
     "stk_unpack_scale": (c_int, [c_int, _P, _P, _P, c_int64, c_float]),
     "stk_sumsq": (c_int, [c_int, _P, _P, c_int64, _P]),
+    "stk_sumsq_bf16": (c_int, [c_int, _P, _P, c_int64, c_float, _P]),
     "stk_adamw_step": (c_int, [c_int, _P, _P, _P, _P, c_int, c_float, c_float, c_float, c_float, c_float, c_float,
-                               c_float, _P, c_float]),
+                               c_float, _P, c_float, c_float]),
     "stk_nsp_pool_bwd": (c_int, [c_int, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P]),
     "stk_assemble_pairs": (c_int, [c_int, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "stk_mask_tokens": (c_int, [c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_uint64, c_uint32, c_int64]),

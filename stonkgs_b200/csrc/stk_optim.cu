@@ -45,27 +45,68 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x,
   }
 }
 
+// the same over a bf16 buffer scaled by `scale` (the all-reduced wire buffer of the data-parallel path: sum over ranks,
+// scale = 1 / world)
+__global__ void __launch_bounds__(256) sumsq_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t n, float scale,
+                                                         float* __restrict__ out) {
+  __shared__ float red[8];
+  float s = 0.f;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 8;
+  const bool vec = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  for (int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (vec && i + 8 <= n) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + i));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float a = bf16_lo(w[k]), b = bf16_hi(w[k]);
+        s = fmaf(a, a, s);
+        s = fmaf(b, b, s);
+      }
+    } else {
+      for (int64_t j = i; j < min(i + 8, n); ++j) { const float a = __bfloat162float(x[j]); s = fmaf(a, a, s); }
+    }
+  }
+  s = warp_sum(s) * scale * scale;
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = red[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffu, t, o);
+    if (threadIdx.x == 0) atomicAdd(out, t);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 adamw_kernel(const StkAdamSeg* __restrict__ segs, const int32_t* __restrict__ chunk_seg,
              const int64_t* __restrict__ chunk_off, float lr, float beta1, float beta2, float eps, float wd, float bc1,
-             float bc2, const float* __restrict__ sumsq, float max_norm) {
+             float bc2, const float* __restrict__ sumsq, float max_norm, float grad_scale) {
   const StkAdamSeg sg = segs[chunk_seg[blockIdx.x]];
   const int64_t off = chunk_off[blockIdx.x];
   const int64_t end = min(off + static_cast<int64_t>(kAdamChunk), sg.n);
   float clip = 1.f;
   if (sumsq != nullptr) clip = fminf(1.f, max_norm / (sqrtf(__ldg(sumsq)) + 1e-6f));
+  clip *= grad_scale;   // g16 gradients are a SUM over ranks: grad_scale = 1 / world turns it into the mean
   const float step = lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
   const float decay = 1.f - lr * wd;
   float* p = static_cast<float*>(sg.p);
   const float* g = static_cast<const float*>(sg.g);
+  const __nv_bfloat16* g16 = static_cast<const __nv_bfloat16*>(sg.g16);
   float* m = static_cast<float*>(sg.m);
   float* v = static_cast<float*>(sg.v);
   __nv_bfloat16* w16 = static_cast<__nv_bfloat16*>(sg.w16);
   float* pc = static_cast<float*>(sg.p32_copy);
   for (int64_t i = off + threadIdx.x * 4; i < end; i += 256 * 4) {
     if (i + 4 <= end) {
-      const float4 g4 = __ldg(reinterpret_cast<const float4*>(g + i));
+      float4 g4;
+      if (g16) {
+        const uint2 t = __ldg(reinterpret_cast<const uint2*>(g16 + i));
+        g4 = make_float4(bf16_lo(t.x), bf16_hi(t.x), bf16_lo(t.y), bf16_hi(t.y));
+      } else {
+        g4 = __ldg(reinterpret_cast<const float4*>(g + i));
+      }
       float4 p4 = *reinterpret_cast<float4*>(p + i);
       float4 m4 = *reinterpret_cast<float4*>(m + i);
       float4 v4 = *reinterpret_cast<float4*>(v + i);
@@ -86,7 +127,7 @@ adamw_kernel(const StkAdamSeg* __restrict__ segs, const int32_t* __restrict__ ch
       if (pc) *reinterpret_cast<float4*>(pc + i) = make_float4(pp[0], pp[1], pp[2], pp[3]);
     } else {
       for (int64_t j = i; j < end; ++j) {
-        const float gj = g[j] * clip;
+        const float gj = (g16 ? __bfloat162float(g16[j]) : g[j]) * clip;
         float pj = p[j] * decay;
         const float mj = beta1 * m[j] + (1.f - beta1) * gj;
         const float vj = beta2 * v[j] + (1.f - beta2) * gj * gj;
@@ -116,16 +157,30 @@ extern "C" int stk_sumsq(int device, void* stream, const float* x, int64_t n, fl
   return STK_OK;
 }
 
+extern "C" int stk_sumsq_bf16(int device, void* stream, const void* x_bf16, int64_t n, float scale, float* out) {
+  STK_REQUIRE(x_bf16 && out && n > 0, "stk_sumsq_bf16: bad arguments");
+  STK_CHECK_CUDA(cudaSetDevice(device));
+  int64_t blocks = (n / 8 + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(num_sms(device)) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  sumsq_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x_bf16), n, scale, out);
+  STK_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return STK_OK;
+}
+
 extern "C" int stk_adamw_step(int device, void* stream, const StkAdamSeg* segs_dev, const int32_t* chunk_seg_dev,
                               const int64_t* chunk_off_dev, int n_chunks, float lr, float beta1, float beta2, float eps,
                               float weight_decay, float bias_correction1, float bias_correction2,
-                              const float* sumsq_dev, float max_grad_norm) {
+                              const float* sumsq_dev, float max_grad_norm, float grad_scale) {
   STK_REQUIRE(segs_dev && chunk_seg_dev && chunk_off_dev && n_chunks > 0, "stk_adamw_step: bad arguments");
   STK_REQUIRE(bias_correction1 > 0.f && bias_correction2 > 0.f, "stk_adamw_step: bias corrections must be positive");
   STK_CHECK_CUDA(cudaSetDevice(device));
   adamw_kernel<<<n_chunks, 256, 0, static_cast<cudaStream_t>(stream)>>>(segs_dev, chunk_seg_dev, chunk_off_dev, lr, beta1,
                                                                       beta2, eps, weight_decay, bias_correction1,
-                                                                      bias_correction2, sumsq_dev, max_grad_norm);
+                                                                      bias_correction2, sumsq_dev, max_grad_norm, grad_scale);
   STK_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return STK_OK;

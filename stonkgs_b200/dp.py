@@ -15,6 +15,14 @@ in ``torch.nn.parallel.DistributedDataParallel`` (stonkgs_pretraining.py:147-168
   bytes) becomes ready first, so its transfer hides behind the whole trunk backward.
 * ``finish`` makes the compute stream wait for the last bucket; ``no_sync()`` skips the collective for
   gradient-accumulation micro-steps (the sum is reduced once, by the last micro-step).
+* With ``FusedAdamW`` attached (it attaches itself when it finds ``model._dp``) there is no unpack pass at all: the
+  optimizer reads the summed bf16 wire buffer directly, with 1 / world folded into its clip coefficient — DDP's
+  "copy back + divide" fused into the one pass that reads every gradient anyway (about 2 GB of HBM traffic per step
+  less at N_kg = 175 003).  ``param.grad`` then holds the rank-LOCAL fp32 gradient; ``materialize_grads()`` writes the
+  averaged one back for code that wants to look at it.
+* The collective shares the GPU with persistent one-CTA-per-SM GEMM / attention kernels that cannot co-reside with
+  an NCCL CTA (they use the whole shared memory): set ``NCCL_MAX_CTAS`` small (bench.py: 8) so that a bucket in
+  flight delays at most that many SMs' tiles.
 
 Gradients are averaged (DDP semantics).  Each cross-entropy is a mean over the *local* labelled rows,
 exactly like the reference under DDP.
@@ -71,6 +79,8 @@ class DataParallel:
         self._sync = True
         self._stream = None
         self._wire = None
+        self.defer_unpack = False     # FusedAdamW attached: it consumes the wire buffer, nothing is unpacked
+        self.wire_valid = False       # the wire buffer holds the all-reduced gradient of the last backward
         model._dp = self
         self.broadcast_parameters()
 
@@ -103,9 +113,12 @@ class DataParallel:
                     self._name_to_bucket[n] = b
             if gb.flat.is_cuda:
                 self._stream = torch.cuda.Stream(device=gb.flat.device)
-                biggest = max(b.end - b.start for b in self.buckets)
-                self._wire = torch.empty(biggest, dtype=self.wire_dtype, device=gb.flat.device)
+        if gb.flat.is_cuda and (self._wire is None or self._wire.numel() != gb.flat.numel()):
+            # one persistent wire buffer over the whole flat gradient: bucket k travels in its own slice, so buckets in
+            # flight never alias and the optimizer can read the reduced gradient in place
+            self._wire = torch.zeros(gb.flat.numel(), dtype=self.wire_dtype, device=gb.flat.device)
         self._gb = gb
+        self.wire_valid = False
         for b in self.buckets:
             b.pending, b.work, b.event = len(b.names), None, None
 
@@ -128,10 +141,11 @@ class DataParallel:
         with torch.cuda.stream(self._stream):
             self._stream.wait_event(ready)
             if self.wire_dtype == torch.bfloat16:
-                wire = self._wire[: b.end - b.start]
+                wire = self._wire[b.start:b.end]
                 ops.cast_bf16(flat, out=wire)                    # pack: fp32 -> bf16 on the wire
                 dist.all_reduce(wire, op=dist.ReduceOp.SUM, group=self.group)
-                ops.unpack_scale(wire, flat, 1.0 / self.world)   # unpack: mean, back to fp32
+                if not self.defer_unpack:
+                    ops.unpack_scale(wire, flat, 1.0 / self.world)   # unpack: mean, back to fp32
             else:
                 dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
                 flat.mul_(1.0 / self.world)
@@ -148,3 +162,25 @@ class DataParallel:
                 self._reduce(b)
             if b.event is not None:
                 torch.cuda.current_stream(gb.flat.device).wait_event(b.event)
+        self.wire_valid = bool(self.defer_unpack and gb.flat.is_cuda and self.wire_dtype == torch.bfloat16)
+
+    def attach_optimizer(self, opt) -> bool:
+        """Called by FusedAdamW: from now on the optimizer reads the reduced bf16 wire buffer itself (scaled by 1 / world)
+        and no unpack pass runs.  Returns False (nothing changes) for an fp32 wire."""
+        if self.wire_dtype != torch.bfloat16:
+            return False
+        self.defer_unpack = True
+        return True
+
+    def wire_buffer(self, gb):
+        if self._wire is None or self._wire.numel() != gb.flat.numel():
+            self._wire = torch.zeros(gb.flat.numel(), dtype=self.wire_dtype, device=gb.flat.device)
+        return self._wire
+
+    def materialize_grads(self):
+        """Write the averaged gradient of the last synchronised backward into ``param.grad`` (the flat fp32 buffer).
+        Only needed with an attached FusedAdamW, and only by code that inspects gradients."""
+        if self.wire_valid:
+            from . import ops
+            ops.unpack_scale(self._wire, self._gb.flat, 1.0 / self.world)
+            self.wire_valid = False   # the fp32 buffer is authoritative again (the optimizer falls back to it)

@@ -34,6 +34,9 @@ class FusedAdamW(torch.optim.Optimizer):
         self.exp_avg_sq = torch.zeros_like(gb.flat)
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self._step = 0
+        # data parallel: consume the all-reduced bf16 wire buffer directly (no unpack pass), see dp.DataParallel
+        self._dp = getattr(model, "_dp", None)
+        self._use_wire = bool(self._dp is not None and gb.flat.is_cuda and self._dp.attach_optimizer(self))
         self._build_tables(dev)
 
     # ------------------------------------------------------------------------------------------
@@ -56,6 +59,7 @@ class FusedAdamW(torch.optim.Optimizer):
             view_to_seg[v.data_ptr()] = name
         segs, chunk_seg, chunk_off = [], [], []
         base = gb.flat.data_ptr()
+        wire = self._dp.wire_buffer(gb) if self._use_wire else None
         keep = []
         # one AdamSeg per parameter; the fused q|k|v gradient block maps onto three parameters
         for p, gv in gb.param_views:
@@ -77,6 +81,7 @@ class FusedAdamW(torch.optim.Optimizer):
             s.w16 = (w16[seg_name].data_ptr() + inner * 2) if seg_name in w16 else None
             s.p32_copy = (p32[seg_name].data_ptr() + inner * 4) if seg_name in p32 else None
             s.n = n
+            s.g16 = None
             idx = len(segs)
             segs.append(s)
             for c in range(0, n, CHUNK):
@@ -85,6 +90,13 @@ class FusedAdamW(torch.optim.Optimizer):
         arr = (AdamSeg * len(segs))(*segs)
         host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
         self._segs_dev = host.to(dev)
+        self._segs_wire_dev = None
+        if wire is not None:   # the same segments reading the bf16 wire buffer instead of the fp32 gradient
+            for sg in segs:
+                sg.g16 = wire.data_ptr() + ((sg.g - base) // 4) * 2
+            arr = (AdamSeg * len(segs))(*segs)
+            self._segs_wire_dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+            self._wire = wire
         self._chunk_seg = torch.tensor(chunk_seg, dtype=torch.int32, device=dev)
         self._chunk_off = torch.tensor(chunk_off, dtype=torch.int64, device=dev)
         self._n_chunks = len(chunk_seg)
@@ -112,17 +124,25 @@ class FusedAdamW(torch.optim.Optimizer):
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         lib = _lib.load()
         clip = g["max_grad_norm"] is not None and g["max_grad_norm"] > 0
+        # data parallel with the collective done for this backward: gradients = wire buffer (sum over ranks) / world
+        from_wire = self._segs_wire_dev is not None and self._dp.wire_valid and self._dp._wire is self._wire
+        gscale = 1.0 / self._dp.world if from_wire else 1.0
         if clip:
             self._sumsq.zero_()
             for a, b in self._runs:   # one range unless some live parameters are frozen
-                check(lib.stk_sumsq(dev.index, stream, ctypes.c_void_p(gb.flat.data_ptr() + 4 * a), b - a,
-                                    ctypes.c_void_p(self._sumsq.data_ptr())), "stk_sumsq")
-        check(lib.stk_adamw_step(dev.index, stream, ctypes.c_void_p(self._segs_dev.data_ptr()),
+                if from_wire:
+                    check(lib.stk_sumsq_bf16(dev.index, stream, ctypes.c_void_p(self._wire.data_ptr() + 2 * a), b - a,
+                                             gscale, ctypes.c_void_p(self._sumsq.data_ptr())), "stk_sumsq_bf16")
+                else:
+                    check(lib.stk_sumsq(dev.index, stream, ctypes.c_void_p(gb.flat.data_ptr() + 4 * a), b - a,
+                                        ctypes.c_void_p(self._sumsq.data_ptr())), "stk_sumsq")
+        segs_dev = self._segs_wire_dev if from_wire else self._segs_dev
+        check(lib.stk_adamw_step(dev.index, stream, ctypes.c_void_p(segs_dev.data_ptr()),
                                  ctypes.c_void_p(self._chunk_seg.data_ptr()), ctypes.c_void_p(self._chunk_off.data_ptr()),
                                  self._n_chunks, float(g["lr"]), float(b1), float(b2), float(g["eps"]),
                                  float(g["weight_decay"]), 1.0 - b1 ** self._step, 1.0 - b2 ** self._step,
                                  ctypes.c_void_p(self._sumsq.data_ptr()) if clip else None,
-                                 float(g["max_grad_norm"] or 0.0)), "stk_adamw_step")
+                                 float(g["max_grad_norm"] or 0.0), gscale), "stk_adamw_step")
         return loss
 
     def grad_norm(self) -> torch.Tensor:

@@ -48,6 +48,47 @@ def main():
     print(f"rank {rank}: dp vs full-batch worst rel grad diff = {worst:.4f}; identical across ranks = {same}; "
           f"buckets = {len(model._dp.buckets)}", flush=True)
     assert worst < 3e-2 and same
+
+    # ---- with FusedAdamW attached: no unpack pass, the optimizer consumes the summed bf16 wire buffer ----------------
+    from stonkgs_b200.optim import FusedAdamW
+    opt = FusedAdamW(model, lr=1e-3, weight_decay=0.0, max_grad_norm=1.0)
+    assert model._dp.defer_unpack
+    opt.zero_grad()
+    model(**mine)[0].backward()
+    assert model._dp.wire_valid
+    local = model.grad_buffer().flat.clone()          # param.grad now holds the rank-LOCAL gradient
+    wire = model._dp._wire.float() / world
+    torch.cuda.synchronize()
+    worst2 = 0.0
+    for n, p in model.named_parameters():
+        if p.grad is None or "key.bias" in n:
+            continue
+        off = (p.grad.data_ptr() - model.grad_buffer().flat.data_ptr()) // 4
+        got = wire[off:off + p.numel()].view_as(p)
+        worst2 = max(worst2, (got - ref[n]).abs().max().item() / (ref[n].abs().max().item() + 1e-12))
+    # clip norm from the wire buffer == norm of the averaged gradient
+    opt.step()
+    torch.cuda.synchronize()
+    norm_wire = float(opt.grad_norm())
+    norm_ref = float(torch.sqrt(sum((g.float() ** 2).sum() for g in ref.values())))
+    flatp = torch.cat([p.data.reshape(-1) for p, _ in model.grad_buffer().param_views])
+    other = flatp.clone()
+    dist.broadcast(other, src=0)
+    same_p = bool(torch.equal(other, flatp))
+    losses = []
+    for _ in range(4):
+        opt.zero_grad()
+        loss = model(**mine)[0]
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    print(f"rank {rank}: fused-optimizer path: wire vs full-batch worst rel = {worst2:.4f}; grad norm {norm_wire:.4f} vs "
+          f"{norm_ref:.4f}; params identical across ranks after step = {same_p}; losses {[round(x, 3) for x in losses]}",
+          flush=True)
+    assert worst2 < 3e-2 and same_p and abs(norm_wire - norm_ref) < 2e-2 * norm_ref and losses[-1] < losses[0]
+    assert not torch.equal(local, wire)               # (sanity: local and averaged gradients differ)
+    model._dp.materialize_grads()
+    torch.cuda.synchronize()
     dist.destroy_process_group()
 
 
