@@ -22,7 +22,42 @@ extern std::atomic<long long> g_launches;
 
 constexpr int kAdamChunk = 65536;  // elements per block-chunk
 
-__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+// Deterministic global sum of squares: block b writes its partial into slot b of a per-launch scratch row, the block
+// that arrives last adds the partials in index order and accumulates into *out.  (atomicAdd of the partials would make
+// the clip coefficient — and with it every updated weight — depend on arrival order: data-parallel ranks holding
+// bit-identical gradients must stay bit-identical after the step.)
+constexpr int kSumsqMaxBlocks = 2048;
+constexpr int kSumsqSlots = 8;
+__device__ float g_sumsq_part[kSumsqSlots][kSumsqMaxBlocks];
+__device__ unsigned int g_sumsq_done[kSumsqSlots];
+
+__device__ __forceinline__ void sumsq_finish(float block_sum, int slot, float* __restrict__ out) {
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) {
+    g_sumsq_part[slot][blockIdx.x] = block_sum;
+    __threadfence();
+    s_last = atomicAdd(&g_sumsq_done[slot], 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  __shared__ float red[8];
+  float t = 0.f;   // thread i sums slots i, i + 256, ... in order; then a fixed tree
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += 256) t += __ldcg(&g_sumsq_part[slot][i]);
+  t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float total = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) total += red[w];
+    out[0] += total;
+    g_sumsq_done[slot] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out,
+                                                    int slot) {
   __shared__ float red[8];
   float s = 0.f;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 4;
@@ -37,18 +72,18 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x,
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
-  if (threadIdx.x < 8) {
-    float t = red[threadIdx.x];
+  float t = 0.f;
+  if (threadIdx.x == 0) {
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffu, t, o);
-    if (threadIdx.x == 0) atomicAdd(out, t);
+    for (int w = 0; w < 8; ++w) t += red[w];
   }
+  sumsq_finish(t, slot, out);
 }
 
 // the same over a bf16 buffer scaled by `scale` (the all-reduced wire buffer of the data-parallel path: sum over ranks,
 // scale = 1 / world)
 __global__ void __launch_bounds__(256) sumsq_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t n, float scale,
-                                                         float* __restrict__ out) {
+                                                         float* __restrict__ out, int slot) {
   __shared__ float red[8];
   float s = 0.f;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x * 8;
@@ -70,12 +105,12 @@ __global__ void __launch_bounds__(256) sumsq_bf16_kernel(const __nv_bfloat16* __
   s = warp_sum(s) * scale * scale;
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
-  if (threadIdx.x < 8) {
-    float t = red[threadIdx.x];
+  float t = 0.f;
+  if (threadIdx.x == 0) {
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffu, t, o);
-    if (threadIdx.x == 0) atomicAdd(out, t);
+    for (int w = 0; w < 8; ++w) t += red[w];
   }
+  sumsq_finish(t, slot, out);
 }
 
 __global__ void __launch_bounds__(256)
@@ -144,6 +179,11 @@ adamw_kernel(const StkAdamSeg* __restrict__ segs, const int32_t* __restrict__ ch
 
 using namespace stk;
 
+static int next_sumsq_slot() {
+  static std::atomic<unsigned> n{0};
+  return static_cast<int>(n.fetch_add(1, std::memory_order_relaxed) % kSumsqSlots);
+}
+
 extern "C" int stk_sumsq(int device, void* stream, const float* x, int64_t n, float* out) {
   STK_REQUIRE(x && out && n > 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "stk_sumsq: bad arguments");
   STK_CHECK_CUDA(cudaSetDevice(device));
@@ -151,7 +191,7 @@ extern "C" int stk_sumsq(int device, void* stream, const float* x, int64_t n, fl
   const int64_t cap = static_cast<int64_t>(num_sms(device)) * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  sumsq_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, out);
+  sumsq_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, out, next_sumsq_slot());
   STK_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return STK_OK;
@@ -165,7 +205,7 @@ extern "C" int stk_sumsq_bf16(int device, void* stream, const void* x_bf16, int6
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   sumsq_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x_bf16), n, scale, out);
+      static_cast<const __nv_bfloat16*>(x_bf16), n, scale, out, next_sumsq_slot());
   STK_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return STK_OK;

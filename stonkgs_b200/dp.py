@@ -52,7 +52,7 @@ def plan_buckets(entries, offsets, bucket_elems: int) -> List[Bucket]:
     cur: Optional[Bucket] = None
     for name in entries:
         off, n, _ = offsets[name]
-        padded = (n + 3) // 4 * 4
+        padded = (n + 7) // 8 * 8   # training.GradBuffer.PAD
         if cur is None or (cur.end - cur.start) + padded > bucket_elems and cur.names:
             cur = Bucket(off)
             buckets.append(cur)

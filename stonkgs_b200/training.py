@@ -29,7 +29,10 @@ class GradBuffer:
     """One flat fp32 buffer holding the gradients of all live parameters.
 
     Order = order in which backward produces them, so that bucket k is complete (and can be
-    all-reduced) long before backward ends.  Segments are padded to 16 B for TMA."""
+    all-reduced) long before backward ends.  Segments are padded to 8 elements: 32 B here (TMA needs 16) and 16 B in
+    the bf16 wire buffer of the data-parallel path, whose bucket slices start at segment boundaries."""
+
+    PAD = 8
 
     def __init__(self, model):
         self.model = model
@@ -87,7 +90,7 @@ class GradBuffer:
             for s in shape:
                 n *= s
             self.offsets[name] = (total, n, shape)
-            total += (n + 3) // 4 * 4
+            total += (n + self.PAD - 1) // self.PAD * self.PAD
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.views: Dict[str, torch.Tensor] = {}
         # (param, view) of the TRAINABLE live parameters only: a frozen tensor (requires_grad=False, e.g. frozen lower
@@ -119,7 +122,7 @@ class GradBuffer:
         spans = sorted(((v.data_ptr() - base) // 4, v.numel()) for _, v in self.param_views)
         runs = []
         for off, n in spans:
-            end = off + (n + 3) // 4 * 4          # segment padding is zero: harmless in a sum of squares
+            end = off + (n + self.PAD - 1) // self.PAD * self.PAD   # segment padding is zero: harmless in a sum of squares
             if runs and off <= runs[-1][1]:
                 runs[-1][1] = max(runs[-1][1], end)
             else:

@@ -48,12 +48,16 @@ def test_dropout_inside_the_layernorm_epilogue():
         g = 1 + 0.1 * torch.randn(768, device="cuda")
         beta = 0.1 * torch.randn(768, device="cuda")
         d = ops.Drop(seed=1234567, site=69, p=0.1)
-        y0, z0, m0, s0 = ops.dropout_resid_ln(ops.linear(x, w, b), r, g, beta, d, save_for_backward=True)
+        dense = ops.linear(x, w, b)
+        y0, z0, m0, s0 = ops.dropout_resid_ln(dense, r, g, beta, d, save_for_backward=True)
         y1, z1, m1, s1 = ops.linear_resid_ln(x, w, b, r, g, beta, save_for_backward=True, drop=d)
         dropped0, dropped1 = z0 == r, z1 == r
         frac = dropped1.float().mean().item()
         assert abs(frac - 13 / 128) < 5e-3, frac
-        assert torch.equal(dropped0, dropped1)
+        # (a tiny dense value can also leave z == r after rounding: compare the decisions where it cannot)
+        big = dense.float().abs() > 0.25
+        assert torch.equal(dropped0[big], dropped1[big])
+        assert (dropped0 != dropped1).float().mean().item() < 2e-3
         torch.testing.assert_close(z1.float(), z0.float(), atol=3e-2, rtol=2e-2)
         torch.testing.assert_close(y1.float(), y0.float(), atol=4e-2, rtol=2e-2)
         torch.testing.assert_close(m1, m0, atol=2e-3, rtol=0)

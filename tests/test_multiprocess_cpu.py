@@ -27,7 +27,7 @@ class _FakeGradBuffer:
         self.offsets, total = {}, 0
         for n, k in sizes:
             self.offsets[n] = (total, k, (k,))
-            total += (k + 3) // 4 * 4
+            total += (k + 7) // 8 * 8
         self.flat = torch.zeros(total)
 
 
