@@ -20,9 +20,9 @@ in ``torch.nn.parallel.DistributedDataParallel`` (stonkgs_pretraining.py:147-168
   "copy back + divide" fused into the one pass that reads every gradient anyway (about 2 GB of HBM traffic per step
   less at N_kg = 175 003).  ``param.grad`` then holds the rank-LOCAL fp32 gradient; ``materialize_grads()`` writes the
   averaged one back for code that wants to look at it.
-* The collective shares the GPU with persistent one-CTA-per-SM GEMM / attention kernels that cannot co-reside with
-  an NCCL CTA (they use the whole shared memory): set ``NCCL_MAX_CTAS`` small (bench.py: 8) so that a bucket in
-  flight delays at most that many SMs' tiles.
+* The collective shares the GPU with persistent one-CTA-per-SM GEMM / attention kernels.  Measured on 2 x B200
+  (r2c_pretrain_x2*.json): what matters is how long a bucket is in flight, not how many SMs it borrows — with
+  ``NCCL_MAX_CTAS`` = 2 / 8 / 32 the exposed all-reduce time is 4.7 / 1.9 / 0.8 ms per step, so NCCL keeps its default.
 
 Gradients are averaged (DDP semantics).  Each cross-entropy is a mean over the *local* labelled rows,
 exactly like the reference under DDP.
@@ -62,13 +62,15 @@ def plan_buckets(entries, offsets, bucket_elems: int) -> List[Bucket]:
 
 
 class DataParallel:
-    def __init__(self, model, process_group=None, bucket_mb: float = 64.0, wire_dtype=torch.bfloat16,
+    def __init__(self, model, process_group=None, bucket_mb: Optional[float] = None, wire_dtype=torch.bfloat16,
                  overlap: Optional[bool] = None):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised (one process per GPU)")
         self.model = model
         self.group = process_group
         self.world = dist.get_world_size(process_group)
+        if bucket_mb is None:   # fp32 megabytes of gradient per bucket (STK_DP_BUCKET_MB: A/B runs)
+            bucket_mb = float(os.environ.get("STK_DP_BUCKET_MB", "64"))
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
         self.wire_dtype = wire_dtype
         # overlap=False: the same buckets are reduced one after the other once backward has been enqueued (the
