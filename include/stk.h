@@ -37,6 +37,10 @@ int stk_version(void);
 int stk_last_error(char* buf, size_t n);
 /* number of kernel launches issued by this library in the calling process so far */
 long long stk_launch_count(void);
+/* Leave n SMs of `device` free in every persistent kernel launched from now on (tcgen05 GEMM, attention): room for the
+ * CTAs of a concurrent collective (the data-parallel gradient all-reduce, stonkgs_pretraining.py:147-168).  Returns the
+ * previous value (>= 0) or STK_ERR_BAD_ARG.  0 = use every SM (default). */
+int stk_set_sm_reserve(int device, int n);
 
 /* ------------------------------------------------------------------------------------------------
  * Embedding stages

@@ -579,7 +579,7 @@ static int attn_fwd_impl(int device, void* stream, const void* qkv, const float*
     dbg = e ? atoi(e) : 0;
   }
   const int num_items = (S / 128) * kHeads * B;
-  const int grid = num_items < 2 * num_sms(device) ? num_items : 2 * num_sms(device);
+  const int grid = num_items < 2 * persistent_sms(device) ? num_items : 2 * persistent_sms(device);
   auto go = [&](auto kern) -> int {
     STK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     kern<<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(

@@ -527,7 +527,7 @@ static int attn_bwd_impl(int device, void* stream_, const void* qkv, const float
   auto go = [&](auto kern) -> int {
     STK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ABW_SMEM));
     const int num_items = (S / 128) * kHeads * B;
-    const int grid = num_items < num_sms(device) ? num_items : num_sms(device);
+    const int grid = num_items < persistent_sms(device) ? num_items : persistent_sms(device);
     kern<<<grid, ABW_THREADS, ABW_SMEM, stream>>>(map_qkv, map_do, map_dq, key_bias, lse, Dws, S, num_items,
                                                   static_cast<__nv_bfloat16*>(dqkv), drop_seed, drop_site, drop_thr);
     return STK_OK;

@@ -845,7 +845,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
   }
   const int items = p.m_tiles * p.n_tiles * p.splits;
   if (Cfg::kCluster == 1) {
-    const int sms = num_sms(dev);
+    const int sms = persistent_sms(dev);
     kern<<<items < sms ? items : sms, Cfg::kThreads, Cfg::kSmem, stream>>>(ma, mb, mc, mc2, mr, p);
   } else {
     // clusters: CTA pairs (cta_group::2 MMAs), three column slabs of a LayerNorm row, or three pairs;
@@ -873,7 +873,10 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
     }
     // work per cluster: a LayerNorm cluster takes whole row tiles (its slabs are the n-tiles), a pair one item
     const int work = Cfg::kLN ? p.m_tiles : items;
-    const int clusters = work < max_clusters[dev & 63] ? work : max_clusters[dev & 63];
+    const int reserved = num_sms(dev) - persistent_sms(dev);   // SMs left free for a concurrent collective
+    int fit = max_clusters[dev & 63] - (reserved + Cfg::kCluster - 1) / Cfg::kCluster;
+    if (fit < 1) fit = 1;
+    const int clusters = work < fit ? work : fit;
     cfg.gridDim = dim3(Cfg::kCluster * clusters);
     STK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, mc2, mr, p));
   }
@@ -928,7 +931,7 @@ extern "C" int stk_gemm(int device, void* stream_, int a_major, int b_major, con
   p.kb_total = (K + BK - 1) / BK;
   int splits = split_k < 0 ? 1 : split_k;
   if (epilogue != STK_EPI_F32_ADD) splits = 1;
-  else if (splits == 0) splits = auto_splits(M, N, K, num_sms(device));
+  else if (splits == 0) splits = auto_splits(M, N, K, persistent_sms(device));
   if (splits > p.kb_total) splits = p.kb_total;
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;

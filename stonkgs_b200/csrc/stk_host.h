@@ -14,6 +14,7 @@ namespace stk {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 int num_sms(int device);
+int persistent_sms(int device);   // num_sms minus the SMs reserved for a concurrent collective (stk_set_sm_reserve)
 
 #define STK_CHECK_CUDA(expr)                                   \
   do {                                                         \

@@ -45,15 +45,31 @@ class Bucket:
         self.pending, self.work, self.event = 0, None, None
 
 
-def plan_buckets(entries, offsets, bucket_elems: int) -> List[Bucket]:
+def plan_buckets(entries, offsets, bucket_elems: int, tail_elems: int = 0) -> List[Bucket]:
     """Greedy contiguous buckets over the flat buffer in production order.  A segment larger than the
-    target gets a bucket of its own (so the entity-decoder gradient ships as soon as it is complete)."""
+    target gets a bucket of its own (so the entity-decoder gradient ships as soon as it is complete).
+    ``tail_elems`` > 0: the LAST bucket — the only one whose all-reduce cannot hide behind backward — is cut short: it
+    takes the trailing segments that fit into ``tail_elems`` (at least one segment)."""
+    n_tail = 0
+    if tail_elems > 0 and len(entries) > 1:
+        acc = 0
+        for name in reversed(entries):
+            padded = (offsets[name][1] + 7) // 8 * 8
+            if n_tail > 0 and acc + padded > tail_elems:
+                break
+            acc += padded
+            n_tail += 1
+        n_tail = min(n_tail, len(entries) - 1)
+    head = entries[: len(entries) - n_tail]
     buckets: List[Bucket] = []
     cur: Optional[Bucket] = None
-    for name in entries:
+    for i, name in enumerate(entries):
+        if n_tail and i == len(head):
+            cur = None   # the tail bucket starts here
         off, n, _ = offsets[name]
         padded = (n + 7) // 8 * 8   # training.GradBuffer.PAD
-        if cur is None or (cur.end - cur.start) + padded > bucket_elems and cur.names:
+        in_tail = bool(n_tail) and i >= len(head)
+        if cur is None or (not in_tail and (cur.end - cur.start) + padded > bucket_elems and cur.names):
             cur = Bucket(off)
             buckets.append(cur)
         cur.names.append(name)
@@ -72,6 +88,8 @@ class DataParallel:
         if bucket_mb is None:   # fp32 megabytes of gradient per bucket (STK_DP_BUCKET_MB: A/B runs)
             bucket_mb = float(os.environ.get("STK_DP_BUCKET_MB", "64"))
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
+        # the last bucket's all-reduce is exposed by construction: keep it to the first encoder layer + embeddings
+        self.tail_elems = int(float(os.environ.get("STK_DP_TAIL_MB", "32")) * (1 << 20) / 4)
         self.wire_dtype = wire_dtype
         # overlap=False: the same buckets are reduced one after the other once backward has been enqueued (the
         # persistent GEMMs then never share the SMs with a collective kernel); STK_DP_OVERLAP=0 selects it for A/B runs
@@ -81,6 +99,9 @@ class DataParallel:
         self._sync = True
         self._stream = None
         self._wire = None
+        # SMs the persistent GEMM / attention kernels leave free while buckets are in flight (0 = none); pair it with
+        # NCCL_MAX_CTAS = the same number so that the collective's CTAs always find room
+        self.sm_reserve = int(os.environ.get("STK_DP_SM_RESERVE", "0"))
         self.defer_unpack = False     # FusedAdamW attached: it consumes the wire buffer, nothing is unpacked
         self.wire_valid = False       # the wire buffer holds the all-reduced gradient of the last backward
         model._dp = self
@@ -109,7 +130,7 @@ class DataParallel:
     # ---- hooks called by training._PretrainStep.backward ------------------------------------------
     def begin(self, gb):
         if self.buckets is None:
-            self.buckets = plan_buckets(gb.entries, gb.offsets, self.bucket_elems)
+            self.buckets = plan_buckets(gb.entries, gb.offsets, self.bucket_elems, self.tail_elems)
             for b in self.buckets:
                 for n in b.names:
                     self._name_to_bucket[n] = b
@@ -121,6 +142,9 @@ class DataParallel:
             self._wire = torch.zeros(gb.flat.numel(), dtype=self.wire_dtype, device=gb.flat.device)
         self._gb = gb
         self.wire_valid = False
+        if self.sm_reserve and gb.flat.is_cuda and self._sync and self.overlap:
+            from . import _lib
+            _lib.load().stk_set_sm_reserve(gb.flat.device.index, self.sm_reserve)
         for b in self.buckets:
             b.pending, b.work, b.event = len(b.names), None, None
 
@@ -155,6 +179,9 @@ class DataParallel:
             b.event.record(self._stream)
 
     def finish(self, gb):
+        if self.sm_reserve and gb.flat.is_cuda:
+            from . import _lib
+            _lib.load().stk_set_sm_reserve(gb.flat.device.index, 0)
         if not self._sync:
             return
         for b in self.buckets:
