@@ -42,6 +42,10 @@ sys.path.insert(0, ROOT)
 os.environ.setdefault("HF_HUB_OFFLINE", "1")
 os.environ.setdefault("TRANSFORMERS_OFFLINE", "1")
 
+# Data-parallel pre-training: NCCL is held to 4 CTAs and the persistent GEMM / attention kernels leave 4 SMs free while
+# gradient buckets are in flight (dp.DataParallel.sm_reserve follows this variable; measurements in DESIGN.md §6)
+os.environ.setdefault("NCCL_MAX_CTAS", "4")
+
 N_KG = 175003
 BATCH = 256            # pairs per GPU per step (extraction)
 TRAIN_BATCH = 64       # pairs per GPU per step (pre-training; global 512 at 8 GPUs)
@@ -588,7 +592,7 @@ def main():
                      "ms_per_step_not_overlapped": ms_serial, "allreduce_ms_total": ms_serial - ms_local,
                      "wire_bytes": int(2 * (world - 1) / world * 2 * LIVE_PARAMS), "wire_dtype": "bf16",
                      "buckets": len(dp.buckets) if dp.buckets else None,
-                     "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS", "default")}
+                     "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS", "default"), "sm_reserve": dp.sm_reserve}
         roof = profile_roofline(step_resident, 5, peaks, torch, ops)
         pairs = world * B * args.steps
         value = pairs / (ms / 1000)

@@ -20,9 +20,14 @@ in ``torch.nn.parallel.DistributedDataParallel`` (stonkgs_pretraining.py:147-168
   "copy back + divide" fused into the one pass that reads every gradient anyway (about 2 GB of HBM traffic per step
   less at N_kg = 175 003).  ``param.grad`` then holds the rank-LOCAL fp32 gradient; ``materialize_grads()`` writes the
   averaged one back for code that wants to look at it.
-* The collective shares the GPU with persistent one-CTA-per-SM GEMM / attention kernels.  Measured on 2 x B200
-  (r2c_pretrain_x2*.json): what matters is how long a bucket is in flight, not how many SMs it borrows — with
-  ``NCCL_MAX_CTAS`` = 2 / 8 / 32 the exposed all-reduce time is 4.7 / 1.9 / 0.8 ms per step, so NCCL keeps its default.
+* The collective shares the GPU with persistent one-CTA-per-SM GEMM / attention kernels whose CTAs are scheduled
+  statically.  When an NCCL CTA holds an SM at such a kernel's launch, the CTA meant for that SM starts only when the
+  others finish, and the kernel takes about twice as long: on 2 x B200 the exposed all-reduce time was 0.41-0.47 x the
+  collective's own duration whatever ``NCCL_MAX_CTAS`` was (2 / 8 / 32 CTAs: 4.7 / 1.9 / 0.8 ms exposed of 11.4 / 4.1 /
+  1.9 ms).  So the persistent kernels leave ``sm_reserve`` SMs free while buckets are in flight (``stk_set_sm_reserve``)
+  and NCCL is held to the same number of CTAs: with 4 (bench.py's setting) the collective takes longer (6.6 ms on two
+  GPUs) but hides completely behind backward; what remains is the 4 / 148 of the backward GEMMs' throughput and the
+  tail bucket (0.6 ms exposed instead of 0.9 with NCCL's default, 8 or 16 reserved SMs cost more than they save).
 
 Gradients are averaged (DDP semantics).  Each cross-entropy is a mean over the *local* labelled rows,
 exactly like the reference under DDP.
@@ -99,9 +104,12 @@ class DataParallel:
         self._sync = True
         self._stream = None
         self._wire = None
-        # SMs the persistent GEMM / attention kernels leave free while buckets are in flight (0 = none); pair it with
-        # NCCL_MAX_CTAS = the same number so that the collective's CTAs always find room
-        self.sm_reserve = int(os.environ.get("STK_DP_SM_RESERVE", "0"))
+        # SMs the persistent GEMM / attention kernels leave free while buckets are in flight, so that the collective's
+        # CTAs always find room.  Only meaningful together with NCCL_MAX_CTAS (read by NCCL when the communicator is
+        # created): by default it follows that variable when it is set to a small number, else nothing is reserved.
+        ncc = os.environ.get("NCCL_MAX_CTAS", "")
+        follow = int(ncc) if ncc.isdigit() and 0 < int(ncc) <= 16 else 0
+        self.sm_reserve = int(os.environ.get("STK_DP_SM_RESERVE", follow))
         self.defer_unpack = False     # FusedAdamW attached: it consumes the wire buffer, nothing is unpacked
         self.wire_valid = False       # the wire buffer holds the all-reduced gradient of the last backward
         model._dp = self
