@@ -445,6 +445,17 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    def timed_wall(fn):
+        """Wall clock around one host call that ends with its results on the host (max over ranks), in ms."""
+        barrier()
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize(dev)
+        dt = torch.tensor([(time.perf_counter() - t0) * 1000.0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return float(dt.item())
+
     n_batches = 4   # distinct batches per step so that no step re-reads the previous step's inputs from L2
     l2_policy = "per-step working set (>1 GB activations) exceeds the 126 MB L2; 4 rotating input batches"
 
@@ -454,16 +465,21 @@ def main():
         host = [synthetic.make_batch(B, N_KG, seed=100 + rank * 17 + i, with_labels=False) for i in range(n_batches)]
         host = [{k: v.pin_memory() for k, v in b.items()} for b in host]
         resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
-        pooled_host = torch.empty((B, 768), dtype=torch.float32).pin_memory()
-
         def step_resident(i):
             b = resident[i % n_batches]
             return model.embed(b["input_ids"], b["attention_mask"], b["token_type_ids"])
 
-        def step_e2e(i):
-            b = {k: v.to(dev, non_blocking=True) for k, v in host[i % n_batches].items()}
-            pooled_host.copy_(model.embed(b["input_ids"], b["attention_mask"], b["token_type_ids"]), non_blocking=True)
-            torch.cuda.synchronize(dev)   # the caller reads the result every step
+        # e2e = the public bulk call (embeddings.embed_arrays): host id arrays in, float32 [n, 768] NumPy array out; every
+        # step's ids go host -> pinned staging -> device and its pooled rows device -> pinned -> result array inside the
+        # timed region (copies of step i+1 / i-1 run under the kernels of step i on a copy stream)
+        from stonkgs_b200.embeddings import EmbeddingStreamer
+        streamer = EmbeddingStreamer(model, B)
+        e2e_cols = [np.concatenate([host[i % n_batches][k].numpy() for i in range(args.steps)])
+                    for k in ("input_ids", "attention_mask", "token_type_ids")]
+        e2e_out = np.empty((args.steps * B, 768), dtype=np.float32)
+
+        def run_e2e():
+            streamer.run(*e2e_cols, out=e2e_out)
 
         for i in range(args.warmup):
             step_resident(i)
@@ -471,9 +487,8 @@ def main():
         l0 = ops.launch_count()
         ms = timed(step_resident, args.steps)
         launches = ops.launch_count() - l0
-        for i in range(2):
-            step_e2e(i)
-        ms_e2e = timed(step_e2e, args.steps)
+        run_e2e()
+        ms_e2e = timed_wall(run_e2e)
         clocks = sampler.stop() if sampler else None
         roof = profile_roofline(step_resident, 5, peaks, torch, ops)
         pairs = world * B * args.steps
@@ -548,7 +563,9 @@ def main():
         host = [synthetic.make_batch(B, N_KG, seed=200 + rank * 17 + i, with_labels=True) for i in range(n_batches)]
         host = [{k: v.pin_memory() for k, v in b.items()} for b in host]
         resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
-        loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+        loss_ring = torch.zeros(2, dtype=torch.float32).pin_memory()
+        loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        loss_log = []
 
         def step_resident(i):
             opt.zero_grad()
@@ -558,13 +575,18 @@ def main():
             return loss
 
         def step_e2e(i):
+            # the batch comes from pinned host memory every step; the loss goes back to the host every step and is READ
+            # there one step later (when its copy has completed), the way a training loop logs it — no per-step drain
             b = {k: v.to(dev, non_blocking=True) for k, v in host[i % n_batches].items()}
             opt.zero_grad()
             loss = model(**b)[0]
             loss.backward()
             opt.step()
-            loss_host.copy_(loss.detach(), non_blocking=True)
-            torch.cuda.synchronize(dev)   # the caller reads the loss every step
+            if i >= 2:
+                loss_ev[i % 2].synchronize()
+                loss_log.append(float(loss_ring[i % 2]))
+            loss_ring[i % 2].copy_(loss.detach(), non_blocking=True)
+            loss_ev[i % 2].record()
 
         for i in range(args.warmup):
             step_resident(i)
@@ -576,7 +598,8 @@ def main():
             step_e2e(i)
         ms_e2e = timed(step_e2e, args.steps)
         clocks = sampler.stop() if sampler else None
-        loss_val = float(loss_host.item())
+        torch.cuda.synchronize(dev)
+        loss_val = float(loss_ring[(args.steps - 1) % 2])
         extra = {}
         if dp is not None:
             k = max(3, min(args.steps, 10))

@@ -1,6 +1,6 @@
 """Build libstk.so (the sm_100a kernel library) in-tree with nvcc.
 
-    python -m stonkgs_b200.build [--force]
+    python -m stonkgs_b200.build [--force] [--debug]
 
 nvcc cross-compiles for sm_100a without a GPU.  Objects go to ``stonkgs_b200/csrc/_build`` and the
 shared library to ``stonkgs_b200/libstk.so`` (git-ignored, but shipped to the GPU box by gpurun).
@@ -45,8 +45,12 @@ def _digest(paths) -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, debug: bool = False) -> str:
+    """``debug``: compile the bring-up instrumentation of the GEMM in (STK_GEMM_DEBUG timelines for tools/gemm_dbg.py);
+    the default build carries none of it."""
     os.makedirs(BUILD, exist_ok=True)
+    if debug and "-DSTK_GEMM_DEBUG_BUILD=1" not in NVCC_FLAGS:
+        NVCC_FLAGS.append("-DSTK_GEMM_DEBUG_BUILD=1")
     sources = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(INCLUDE, "stk.h"))
@@ -90,4 +94,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv))

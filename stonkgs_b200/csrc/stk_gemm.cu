@@ -6,14 +6,19 @@
 // stonkgs_model.py:62-73,204-217; arithmetic in HF modeling_bert.py:158-160,179-181,287-298,
 // 330-356,456-468,471-485).
 //
-// Design (one CTA per SM, 320 threads):
-//   warp 0      TMA producer: A/B tiles -> 4-stage shared-memory ring (128B-swizzled boxes)
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128x256x16, cta_group::1)
-//   warps 2-9   epilogue: tcgen05.ld the 128x256 fp32 accumulator (two column halves x four lane
-//               quarters), fused epilogue math, swizzled staging tile, TMA store / reduce-add
-// Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers over TWO
-// accumulator stages (2 x 256 columns = all 512 TMEM columns) so the epilogue of tile i overlaps the
-// MMAs of tile i+1, and a static persistent tile scheduler (grid = #SMs).
+// Design (persistent; one CTA per SM, CTA pairs on 256 x 256 tiles whenever M > 128):
+//   warps 0-7   epilogue: tcgen05.ld of this CTA's 128 x 256 fp32 accumulator (warp w: TMEM lane quarter w % 4, column
+//               half w / 4), fused epilogue math, swizzled staging tile, TMA store / reduce-add
+//   warp 8      TMA producer: A / B tiles -> shared-memory ring of 128B-swizzled boxes (PAIR: 6 stages of 32 KB, each CTA
+//               stages its 128 rows of A and 128 of the 256 rows of B; both CTAs' loads complete on the even CTA's
+//               mbarrier)
+//   warp 9      TMEM allocator + MMA issuer: the whole converged warp executes one statement per k-block (elect.sync
+//               inside it, four UMMA 128x256x16 / cta_group::2 256x256x16 + a probe of the next slot + the slot-free
+//               commit), see umma_kblock_warp
+//   warps 10-11 (LayerNorm epilogues only) I/O warps: residual in, pre-LN sum / normalised rows out, by TMA
+// Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers over TWO accumulator stages
+// (2 x 256 columns = all 512 TMEM columns) so the epilogue of tile i overlaps the MMAs of tile i+1, and a static
+// persistent tile scheduler (grid = the SMs stk_set_sm_reserve leaves to persistent kernels).
 // Operand layouts: K-major or MN-major for A and B independently (UMMA descriptor major bits), so
 // forward, dgrad and wgrad read the tensors where they lie — no transposed copies.
 // Tails in M, N and K are handled by TMA (zero fill on load, clipping on store).
@@ -65,6 +70,14 @@ constexpr int kEpiWarp0 = STK_GEMM_EPI_WARP0;
 constexpr int kProducerWarp = kEpiWarp0 == 0 ? 8 : 0;
 constexpr int kMmaWarp = kEpiWarp0 == 0 ? 9 : 1;
 
+// Bring-up instrumentation (clock64 timelines, "skip the loads / MMAs / epilogue math" switches driven by the env
+// variable STK_GEMM_DEBUG) is compiled in only with -DSTK_GEMM_DEBUG_BUILD=1 (python -m stonkgs_b200.build --debug);
+// the production instantiations carry none of it.
+#ifndef STK_GEMM_DEBUG_BUILD
+#define STK_GEMM_DEBUG_BUILD 0
+#endif
+#define STK_DBG(expr) (STK_GEMM_DEBUG_BUILD && (expr))
+
 struct GemmParams {
   int M, N, K;
   int m_tiles, n_tiles, splits, kb_total, kb_per_split;
@@ -74,7 +87,7 @@ struct GemmParams {
 
 __device__ long long g_gemm_timeline[4096];   // bring-up only: [tile][16] clock64 stamps of CTA 0
 #define STK_GEMM_STAMP(cond, t, slot) \
-  do { if (p.dbg && blockIdx.x < 3 && (cond) && (t) < 64) g_gemm_timeline[blockIdx.x * 1024 + (t) * 16 + (slot)] = clock64(); } while (0)
+  do { if (STK_DBG(p.dbg) && blockIdx.x < 3 && (cond) && (t) < 64) g_gemm_timeline[blockIdx.x * 1024 + (t) * 16 + (slot)] = clock64(); } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // epilogue helpers
@@ -194,7 +207,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(empty_bar + stage, phase ^ 1);
         if (kb == kb0 && !kLN) STK_GEMM_STAMP(leader, (item - unit) / units, 12);
-        if ((p.dbg & 4) && n_loaded >= STAGES) {   // bring-up: no loads after the ring's first fill (pure MMA rate)
+        if (STK_DBG(p.dbg & 4) && n_loaded >= STAGES) {   // bring-up: no loads after the ring's first fill (pure MMA rate)
           if (leader && (!PAIR || pr == 0)) mbar_arrive(full_bar + stage);
         } else if (leader) {
           // PAIR: both CTAs' loads complete on the even CTA's barrier, which expects the bytes of both
@@ -261,7 +274,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       for (int kb = kb0; kb < kb1; ++kb) {
         // `ready` = the look-ahead probe issued between the previous k-block's MMAs already saw this slot full
         if (!ready) {
-          if (p.dbg) {
+          if (STK_DBG(p.dbg)) {
             const long long t0 = clock64();
             mbar_wait(full_bar + stage, phase);
             waited += clock64() - t0;
@@ -270,7 +283,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           }
         }
         tc_fence_after();
-        const long long kb_t0 = p.dbg ? clock64() : 0;
+        const long long kb_t0 = STK_DBG(p.dbg) ? clock64() : 0;
         if (kb == kb0) STK_GEMM_STAMP(leader, (item - unit) / units, 13);
         if (kb == kb1 - 1) STK_GEMM_STAMP(leader, (item - unit) / units, 1);
         {
@@ -291,7 +304,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           const int nstage = stage + 1 == STAGES ? 0 : stage + 1;
           const uint32_t nphase = stage + 1 == STAGES ? phase ^ 1 : phase;
           static_assert(BK / 16 == 4, "k-steps per stage");
-          if (!(p.dbg & 8)) {   // bring-up bit 8: no MMAs (pure TMA fill rate)
+          if (!STK_DBG(p.dbg & 8)) {   // bring-up bit 8: no MMAs (pure TMA fill rate)
             ready = umma_kblock_warp<PAIR>(d_tmem, a_desc, b_desc, a_desc + a_kstep, b_desc + b_kstep,
                                            a_desc + 2 * a_kstep, b_desc + 2 * b_kstep, a_desc + 3 * a_kstep,
                                            b_desc + 3 * b_kstep, idesc, kb != kb0 ? 1u : 0u, empty_bar + stage, pair_mask,
@@ -301,14 +314,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             commit(empty_bar + stage);
           }
           if (kb == kb1 - 1) commit(tfull_bar + as);
-          if (p.dbg && blockIdx.x == 0 && leader && (item - unit) / units == 2 && kb - kb0 < 64) {
+          if (STK_DBG(p.dbg) && blockIdx.x == 0 && leader && (item - unit) / units == 2 && kb - kb0 < 64) {
             g_gemm_timeline[3072 + (kb - kb0) * 2] = kb_t0;          // k-block operands ready
             g_gemm_timeline[3072 + (kb - kb0) * 2 + 1] = clock64();  // its MMAs + commits issued
           }
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      if (p.dbg && blockIdx.x < 3 && leader && (item - unit) / units < 64)
+      if (STK_DBG(p.dbg) && blockIdx.x < 3 && leader && (item - unit) / units < 64)
         g_gemm_timeline[blockIdx.x * 1024 + ((item - unit) / units) * 16 + 14] = waited;   // cycles starved for operands
       if (++as == 2) { as = 0; as_phase ^= 1; }
     }
@@ -665,8 +678,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           }
         }
         const int nc = n0 + g * 128 + chunk * 64;  // first global column of this chunk
-        if (p.dbg & 16) continue;   // bring-up: accumulator read only (isolates the epilogue's effect on the MMA rate)
-        if ((p.dbg & 32) && q == 1 && EPI == STK_EPI_BIAS_GELU) {   // bring-up: no epilogue math on the MMA warp's scheduler
+        if (STK_DBG(p.dbg & 16)) continue;   // bring-up: accumulator read only (isolates the epilogue's effect on the MMA rate)
+        if (STK_DBG(p.dbg & 32) && q == 1 && EPI == STK_EPI_BIAS_GELU) {   // bring-up: no epilogue math on the MMA warp's scheduler
           uint4 data[8] = {};
           stage_and_store<false, false>(&map_c, buf, row, data, nc, m0, store_thread, bar_id);
           continue;
