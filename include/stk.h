@@ -267,6 +267,12 @@ int stk_ce_finalize(int device, void* stream, const float* ce_partial, int64_t c
  * (value 2) of err_flag (may be NULL) — torch raises IndexError there */
 int stk_nsp_head_fwd(int device, void* stream, const float* pooled, int B, const float* w, const float* b,
                      const int64_t* labels, float* logits, float* row_loss, int* err_flag);
+/* Mean-pooled extraction output (BASELINE north_star "mean-pooled embedding extraction path"; an EXTRA beside the
+ * reference's pooler_output, stonkgs_for_embeddings.py:180, never a replacement): out[b, :] = mean over the attended
+ * tokens (attention_mask[b, t] != 0, t < seq_len; NULL = all) of the last hidden state x bf16 [B*seq_pad, 768]; out fp32
+ * [B, 768]. */
+int stk_masked_mean_pool(int device, void* stream, const void* x_bf16, const int64_t* attention_mask, int B, int seq_len,
+                         int seq_pad, float* out);
 /* head_mask of the reference forward (stonkgs_model.py:158,209 -> HF attention: probabilities * head_mask[layer, head]):
  * a per-head scale of the attention probabilities is a per-head scale of the context columns.
  * y[m, h*64 + d] = x[m, h*64 + d] * scales[h]  over bf16 [M, 768] (in place allowed); scales fp32 [12]. */

@@ -89,6 +89,7 @@ _SIGNATURES = {
     "stk_ce_finalize": (c_int, [c_int, _P, _P, c_int64, _P, c_int, _P, _P]),
     "stk_nsp_head_fwd": (c_int, [c_int, _P, _P, c_int, _P, _P, _P, _P, _P, _P]),
     "stk_scale_heads": (c_int, [c_int, _P, _P, c_int, _P, _P]),
+    "stk_masked_mean_pool": (c_int, [c_int, _P, _P, _P, c_int, c_int, c_int, _P]),
     "stk_query_workspace": (c_int64, [c_int, c_int64, c_int64]),
     "stk_compact_labels": (c_int, [c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
     "stk_linear_ce_fwd": (c_int, [c_int, _P, _P, _P, c_int, c_int, _P, _P, c_int64, _P, _P, _P]),

@@ -241,6 +241,35 @@ __global__ void __launch_bounds__(256) scale_heads_kernel(const __nv_bfloat16* _
   reinterpret_cast<uint4*>(y)[i] = o;
 }
 
+// Masked mean over the sequence: out[b, c] = sum_t mask[b, t] * x[b * seq_pad + t, c] / sum_t mask[b, t]  (t < seq_len).
+// grid = (B, 3): block (b, k) owns 256 columns, its 8 warps stride over the tokens, a lane holds 8 columns (16 B loads).
+__global__ void __launch_bounds__(256) masked_mean_pool_kernel(const __nv_bfloat16* __restrict__ x,
+                                                               const int64_t* __restrict__ mask, int seq_len, int seq_pad,
+                                                               float* __restrict__ out) {
+  __shared__ float red[8][256];
+  __shared__ int cnt[8];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.y * 256 + lane * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int n = 0;
+  for (int t = warp; t < seq_len; t += 8) {
+    if (mask != nullptr && __ldg(mask + static_cast<int64_t>(b) * seq_len + t) == 0) continue;   // warp-uniform
+    ++n;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (static_cast<int64_t>(b) * seq_pad + t) * kHidden + c0));
+    acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+    acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = acc[i];
+  if (lane == 0) cnt[warp] = n;
+  __syncthreads();
+  float s = 0.f;
+  int total = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { s += red[w][threadIdx.x]; total += cnt[w]; }
+  out[static_cast<int64_t>(b) * kHidden + blockIdx.y * 256 + threadIdx.x] = s / static_cast<float>(total);   // 0 / 0 = NaN like torch
+}
+
 // dst[i] = float(src[i]) * scale : gradient bucket coming back from the bf16 all-reduce (mean = sum / world)
 __global__ void unpack_scale_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int64_t n,
                                     float scale) {
@@ -451,6 +480,15 @@ extern "C" int stk_nsp_pool_bwd(int device, void* stream, const float* pooled, c
   STK_CHECK_CUDA(cudaSetDevice(device));
   nsp_pool_bwd_kernel<<<3, 256, 0, static_cast<cudaStream_t>(stream)>>>(pooled, logits, labels, B, scale_dev, w, dw, db,
                                                                       static_cast<__nv_bfloat16*>(dpre));
+  STK_LAUNCHED();
+}
+
+extern "C" int stk_masked_mean_pool(int device, void* stream, const void* x, const int64_t* mask, int B, int seq_len,
+                                    int seq_pad, float* out) {
+  STK_REQUIRE(x && out && B > 0 && seq_len > 0 && seq_pad >= seq_len, "stk_masked_mean_pool: bad arguments");
+  STK_CHECK_CUDA(cudaSetDevice(device));
+  masked_mean_pool_kernel<<<dim3(B, kHidden / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), mask, seq_len, seq_pad, out);
   STK_LAUNCHED();
 }
 

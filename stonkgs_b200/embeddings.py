@@ -52,8 +52,10 @@ class EmbeddingStreamer:
     """Reusable streaming state of :func:`embed_arrays` (staging ring + copy stream); ``h2d_bytes`` / ``d2h_bytes`` count
     what crossed the bus."""
 
-    def __init__(self, model: STonKGsForPreTraining, batch_size: int = 256, slots: int = 2, columns: int = 3):
+    def __init__(self, model: STonKGsForPreTraining, batch_size: int = 256, slots: int = 2, columns: int = 3,
+                 pooling: str = "pooler"):
         self.model = model
+        self.pooling = pooling
         self.dev = model.bert.pooler.dense.weight.device
         if self.dev.type != "cuda":
             raise StkError("embedding extraction runs on CUDA only: move the model with .to('cuda')")
@@ -104,7 +106,7 @@ class EmbeddingStreamer:
                     self.h2d_bytes += m * self.seq_len * 8
                 slot.h2d.record(self.copy_stream)
             compute.wait_event(slot.h2d)
-            pooled = model.embed(*dcols, err_flag=self.err)
+            pooled = model.embed(*dcols, err_flag=self.err, pooling=self.pooling)
             ready = torch.cuda.Event()
             ready.record(compute)
             with torch.cuda.stream(self.copy_stream):
@@ -124,10 +126,11 @@ class EmbeddingStreamer:
 
 def embed_arrays(model: STonKGsForPreTraining, input_ids, attention_mask=None, token_type_ids=None,
                  batch_size: int = 256, out: Optional[np.ndarray] = None,
-                 streamer: Optional[EmbeddingStreamer] = None) -> np.ndarray:
-    """Pooled 768-d embeddings (``pooler_output``, stonkgs_for_embeddings.py:180) for host id arrays ``[n, 512]``.
-    Returns float32 ``[n, 768]``; see :class:`EmbeddingStreamer` for the staging scheme."""
-    st = streamer if streamer is not None else EmbeddingStreamer(model, batch_size)
+                 streamer: Optional[EmbeddingStreamer] = None, pooling: str = "pooler") -> np.ndarray:
+    """Pooled 768-d embeddings (``pooler_output``, stonkgs_for_embeddings.py:180; ``pooling="mean"``: masked mean of the
+    last hidden state) for host id arrays ``[n, 512]``.  Returns float32 ``[n, 768]``; see :class:`EmbeddingStreamer`
+    for the staging scheme."""
+    st = streamer if streamer is not None else EmbeddingStreamer(model, batch_size, pooling=pooling)
     return st.run(input_ids, attention_mask, token_type_ids, out=out)
 
 

@@ -463,10 +463,19 @@ class STonKGsForPreTraining(BertForPreTraining):
                            "produced by the reference's pre-processing) or pass the label tensors on the CPU")
 
     @torch.no_grad()
-    def embed(self, input_ids, attention_mask=None, token_type_ids=None, err_flag=None) -> torch.Tensor:
-        """Extraction path: pooled 768-d output only (stonkgs_for_embeddings.py:180), heads skipped."""
-        _, pooled, _ = self.encode(input_ids, attention_mask, token_type_ids, err_flag=err_flag)
-        return pooled
+    def embed(self, input_ids, attention_mask=None, token_type_ids=None, err_flag=None, pooling: str = "pooler") -> torch.Tensor:
+        """Extraction path, heads skipped.  ``pooling="pooler"`` (default) is the reference's output: the BERT pooler
+        ``tanh(W h[:, 0] + b)`` (stonkgs_for_embeddings.py:180).  ``pooling="mean"`` is an extra: the mean of the last
+        hidden state over the attended tokens (``attention_mask != 0``) of each pair."""
+        if pooling not in ("pooler", "mean"):
+            raise StkError(f"pooling must be 'pooler' or 'mean', got {pooling!r}")
+        seq, pooled, _ = self.encode(input_ids, attention_mask, token_type_ids, err_flag=err_flag)
+        if pooling == "pooler":
+            return pooled
+        am = attention_mask
+        if am is not None:
+            am = am.to(seq.device, torch.int64, non_blocking=True).contiguous()
+        return ops.masked_mean_pool(seq, am, input_ids.shape[0], self.seq_shape)
 
     def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, masked_lm_labels=None,
                 ent_masked_lm_labels=None, next_sentence_labels=None, return_dict=None, head_mask=None):

@@ -476,6 +476,20 @@ def linear_ce_bwd(t_rows, w, labels_i32, lse, scale_dev, dT, dW) -> None:
         e1.record()
 
 
+def masked_mean_pool(seq: torch.Tensor, attention_mask: Optional[torch.Tensor], B: int, shape: "SeqShape") -> torch.Tensor:
+    """fp32 [B, 768]: mean of the last hidden state over the attended tokens of each pair."""
+    _req(seq, torch.bfloat16, "seq")
+    assert seq.shape == (B * shape.seq_pad, H) and seq.is_contiguous()
+    if attention_mask is not None:
+        _req(attention_mask, torch.int64, "attention_mask")
+        assert attention_mask.shape == (B, shape.seq_len) and attention_mask.is_contiguous()
+    dev, stream = _ctx(seq)
+    out = torch.empty((B, H), dtype=torch.float32, device=seq.device)
+    check(_lib.load().stk_masked_mean_pool(dev, stream, _ptr(seq), _ptr(attention_mask), B, shape.seq_len, shape.seq_pad,
+                                           _ptr(out)), "stk_masked_mean_pool")
+    return out
+
+
 def scale_heads(x: torch.Tensor, scales: torch.Tensor, out=None) -> torch.Tensor:
     """y[:, h*64:(h+1)*64] = x[:, h*64:(h+1)*64] * scales[h] (head_mask applied to the attention context)."""
     _req(x, torch.bfloat16, "x")

@@ -83,3 +83,31 @@ def test_streamed_embed_arrays(full_model):
     with pytest.raises(KeyError):
         embed_arrays(model, bad, mask, types, batch_size=64)
     assert np.array_equal(embed_arrays(model, ids, mask, types, batch_size=64), ref)   # the flag does not stick
+
+
+def test_mean_pooled_extraction_vs_oracle():
+    """pooling="mean" (an extra beside the reference's pooler_output): masked mean of the last hidden state, against the
+    fp32 oracle's sequence_output on a golden case; stated tolerance atol 3e-2 (a mean over >= 288 rows of bf16 states)."""
+    from _util import build_model, load_fixture, seeded_weights
+    from oracle import stonkgs_oracle as orc
+    from stonkgs_b200.embeddings import embed_arrays
+    fix, meta, batch = load_fixture("L2_B2_N997")
+    sd, rows = seeded_weights(meta)
+    model = build_model(meta, sd, rows, "cuda")
+    ids, mask, types = batch["input_ids"], batch["attention_mask"], batch["token_type_ids"]
+    got = model.embed(ids, mask, types, pooling="mean").cpu()
+    with torch.no_grad():
+        seq = orc.forward(sd, orc.build_kg_table(sd, rows), ids, mask, types)["sequence_output"]
+    m = mask.float()[:, :, None]
+    want = (seq * m).sum(1) / m.sum(1)
+    assert got.shape == (meta["batch"], 768) and got.dtype == torch.float32
+    torch.testing.assert_close(got, want, atol=3e-2, rtol=0)
+    # no mask = plain mean over all 512 positions; the streamed path returns the same rows
+    got_all = model.embed(ids, None, types, pooling="mean").cpu()
+    with torch.no_grad():
+        seq_all = orc.forward(sd, orc.build_kg_table(sd, rows), ids, None, types)["sequence_output"]
+    torch.testing.assert_close(got_all, seq_all.mean(1), atol=3e-2, rtol=0)
+    arr = embed_arrays(model, ids.numpy(), mask.numpy(), types.numpy(), batch_size=1, pooling="mean")
+    assert np.array_equal(arr, got.numpy())
+    with pytest.raises(Exception):
+        model.embed(ids, mask, types, pooling="max")
