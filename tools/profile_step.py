@@ -26,14 +26,23 @@ def main():
     dev = torch.device("cuda", 0)
     model = bench.build_model(dev, a.layers)
     b = {k: v.to(dev) for k, v in synthetic.make_batch(a.batch, bench.N_KG, seed=3, with_labels=a.train).items()}
+    opt = None
+    if a.train:   # the bench's pre-training step: train() with dropout, clip + AdamW
+        from stonkgs_b200.optim import FusedAdamW
+        model.train()
+        opt = FusedAdamW(model, lr=1e-4, weight_decay=0.0, max_grad_norm=1.0)
+    from stonkgs_b200 import ops
     for i in range(a.warmup + a.steps):
+        l0 = ops.launch_count()
         if a.train:
-            model.zero_grad(set_to_none=True)
+            opt.zero_grad()
             model(**b)[0].backward()
+            opt.step()
         else:
             model.embed(b["input_ids"], b["attention_mask"], b["token_type_ids"])
+        per_step = ops.launch_count() - l0
     torch.cuda.synchronize()
-    print("profile_step done")
+    print(f"profile_step done: {per_step} libstk launches per step")
 
 
 if __name__ == "__main__":
