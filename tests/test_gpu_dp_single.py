@@ -32,6 +32,7 @@ def test_world_of_one_matches_plain_step():
 
     def one_step(dp: bool):
         model = build_model(meta, sd, rows, "cuda")
+        model.label_capacity = 64            # this fixture labels more than the default 38 positions per half
         d = DataParallel(model, bucket_mb=8.0) if dp else None
         opt = FusedAdamW(model, lr=1e-3, weight_decay=0.01, max_grad_norm=1.0)
         opt.zero_grad()
