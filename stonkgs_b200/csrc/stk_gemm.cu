@@ -898,20 +898,30 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
   return STK_OK;
 }
 
-// Split-K factor of a reduce-add GEMM (split_k = 0): fill the persistent grid (CTA pairs on 256 x 256 tiles when
-// there is more than one 128-row tile, else single CTAs on 128 x 256) with as few k-splits as possible — every
-// split re-reduces its tile through an fp32 TMA reduce-add, so more splits only for a clearly fuller grid.
+// Split-K factor of a reduce-add GEMM (split_k = 0).  Cost model in tensor-pipe cycles: the persistent grid runs
+// ceil(tiles * s / units) waves (units = CTA pairs on 256 x 256 tiles when there is more than one 128-row tile, else
+// single CTAs on 128 x 256), a wave costs the split's k-blocks (512 cycles each: four 128-cycle MMAs) plus a fixed
+// per-item overhead (ring fill + the fp32 TMA reduce-add of the tile, ~8 k cycles).  The first version maximised grid
+// occupancy alone and cut the cross-entropy backward's GEMMs into 23-k-block splits whose reduce-adds cost as much as
+// their MMAs (dT at 525 TFLOP/s).
 static int auto_splits(int M, int N, int K, int sms) {
+  static int overhead = -1;
+  if (overhead < 0) {
+    const char* e = getenv("STK_SPLITK_OVERHEAD");
+    overhead = e ? atoi(e) : 8000;
+  }
   const bool pair = M > BM;
   const int tiles = ((M + (pair ? 2 * BM : BM) - 1) / (pair ? 2 * BM : BM)) * ((N + BN - 1) / BN);
   const int units = pair ? sms / 2 : sms;
   const int kb = (K + BK - 1) / BK;
   int best = 1;
-  float best_eff = 0.f;
+  long long best_cost = -1;
   for (int s = 1; s <= (kb < 32 ? kb : 32); ++s) {
-    const int items = tiles * s;
-    const float eff = static_cast<float>(items) / static_cast<float>((items + units - 1) / units * units);
-    if (eff > best_eff + 0.05f) { best = s; best_eff = eff; }
+    const int per = (kb + s - 1) / s;
+    const int real = (kb + per - 1) / per;   // splits that actually get k-blocks
+    const long long waves = (static_cast<long long>(tiles) * real + units - 1) / units;
+    const long long cost = waves * (static_cast<long long>(per) * 512 + overhead);
+    if (best_cost < 0 || cost < best_cost) { best = s; best_cost = cost; }
   }
   return best;
 }
