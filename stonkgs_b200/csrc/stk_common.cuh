@@ -123,45 +123,33 @@ __device__ __forceinline__ float phi_neg_abs(float a, float& e) {  // Phi(-a) fo
   e = fast_exp2((-0.5f * 1.4426950408889634f) * a * a);
   return p * e;
 }
-// Forward only needs Phi, not the Gaussian factor: Abramowitz & Stegun 7.1.28
-//   erfc(z) = 1 / (1 + a1 z + ... + a6 z^6)^16,  |err| <= 3e-7   (coefficients below are a_k / sqrt2^k, z = a / sqrt2)
-// costs ONE MUFU.RCP (and no MUFU.EX2) per element — the FFN1 epilogue is bound by the 16-per-clock
-// special-function unit.  gelu(x) = max(x, 0) - |x| * 0.5 erfc(|x| / sqrt2): absolute error < 1e-6, relative
-// error < 3e-4 wherever |gelu| > 1e-3 (bf16 rounding of the stored activation: 4e-3).
-// The factor 0.5 is folded into the polynomial: every coefficient is scaled by 2^(1/16), so that (1 / p)^16 is already
-// 0.5 erfc (one multiply per element less in an issue-bound epilogue; max abs error 7e-7 in fp32).
+// Forward: Phi(-a) = exp2(q(a)) with q the degree-5 minimax fit of log2(0.5 erfc(a / sqrt2)) on [0, 5] (a = min(|x|, 5);
+// beyond 5, |x| Phi(-|x|) < 1.5e-6).  Relative error of Phi(-a) <= 1.6e-4 over the whole range, i.e. of gelu(x) =
+// max(x, 0) - a Phi(-a) everywhere: a twelfth of the bf16 half-ulp (1.95e-3) of the activation it is stored as; absolute
+// error <= 2.3e-5.  ONE MUFU.EX2 + 5 FFMA + 2 FMNMX + 1 FFMA per element.  (Round 1 used Abramowitz & Stegun 7.1.28,
+// erfc = 1 / (1 + a1 z + ... + a6 z^6)^16: 6 FFMA + MUFU.RCP + 4 FMUL — five more instructions per element in an epilogue
+// that is issue-bound (≈21 SASS instructions per element made FFN1 the slowest encoder GEMM), for an absolute error of
+// 7e-7 that the bf16 store cannot show; its relative error on small outputs was 3e-4 as well.)
+__device__ __forceinline__ float phi_neg_exp2(float a) {   // a in [0, 5]
+  float q = fmaf(-0.0002699168981052935f, a, 0.0052973381243646145f);
+  q = fmaf(q, a, -0.04631929472088814f);
+  q = fmaf(q, a, -0.4669075310230255f);
+  q = fmaf(q, a, -1.1477888822555542f);
+  q = fmaf(q, a, -1.0002284049987793f);
+  return fast_exp2(q);
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float a = fabsf(x);
-  float p = fmaf(5.62129980608006e-06f, a, 5.105520904180594e-05f);
-  p = fmaf(p, a, 3.9686136005911976e-05f);
-  p = fmaf(p, a, 3.422739217057824e-03f);
-  p = fmaf(p, a, 2.207699790596962e-02f);
-  p = fmaf(p, a, 5.2075162529945374e-02f);
-  p = fmaf(p, a, 1.0442737340927124f);
-  float q = fast_rcp(p);
-  q *= q;
-  q *= q;
-  q *= q;
-  q *= q;
-  return fmaf(-a, q, fmaxf(x, 0.0f));
+  const float a = fminf(fabsf(x), 5.0f);
+  return fmaf(-a, phi_neg_exp2(a), fmaxf(x, 0.0f));
 }
 // gelu(x) and d/dx gelu(x) together (training forward of BertIntermediate: the derivative is stored instead of the
-// pre-activation): the rcp^16 form gives Phi(-|x|) for both, the derivative adds one exponential for the Gaussian factor.
+// pre-activation): Phi(-|x|) serves both, the derivative adds one exponential for the Gaussian factor.
 __device__ __forceinline__ void gelu_erf_with_grad(float x, float& y, float& dy) {
-  const float a = fabsf(x);
-  float p = fmaf(5.62129980608006e-06f, a, 5.105520904180594e-05f);
-  p = fmaf(p, a, 3.9686136005911976e-05f);
-  p = fmaf(p, a, 3.422739217057824e-03f);
-  p = fmaf(p, a, 2.207699790596962e-02f);
-  p = fmaf(p, a, 5.2075162529945374e-02f);
-  p = fmaf(p, a, 1.0442737340927124f);
-  float q = fast_rcp(p);
-  q *= q;
-  q *= q;
-  q *= q;
-  q *= q;                                   // Phi(-|x|)
+  const float ax = fabsf(x);
+  const float a = fminf(ax, 5.0f);
+  const float q = phi_neg_exp2(a);              // Phi(-|x|)
   y = fmaf(-a, q, fmaxf(x, 0.0f));
-  const float e = fast_exp2((-0.5f * 1.4426950408889634f) * a * a);
+  const float e = fast_exp2((-0.5f * 1.4426950408889634f) * ax * ax);
   const float cdf = x >= 0.0f ? 1.0f - q : q;
   dy = fmaf(x * 0.3989422804014327f, e, cdf);
 }
