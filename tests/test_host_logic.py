@@ -119,3 +119,71 @@ def test_checkpoint_round_trip_hf_layout(tmp_path, small):
     fresh = build_model(meta, weights.make_state_dict(meta["n_kg"], meta["layers"], seed=5), rows)
     missing, unexpected = fresh.load_state_dict(torch.load(tmp_path / "pytorch_model.bin"), strict=True)
     assert not missing and not unexpected
+
+
+def test_frozen_live_parameters_are_left_alone(small):
+    """requires_grad=False on a live parameter (frozen lower layers while fine-tuning): it keeps its slot in the flat
+    buffer but gets no .grad, is not handed to the optimizer and is not part of the clipping norm (torch semantics)."""
+    _, meta, _, _, _, model = small
+    model._grad_buffer = None
+    full = model.grad_buffer()
+    n_views = len(full.param_views)
+    assert full.trainable_runs() == [(0, full.flat.numel())] and not full.stale()
+    layer0 = list(model.bert.encoder.layer[0].parameters())
+    try:
+        for p in layer0:
+            p.requires_grad_(False)
+        assert full.stale()
+        gb = model.grad_buffer()                                   # rebuilt: the layout is unchanged, the views are filtered
+        assert gb is not full and gb.offsets == full.offsets
+        assert len(gb.param_views) == n_views - len(layer0)
+        frozen = {id(p) for p in layer0}
+        assert not any(id(p) in frozen for p, _ in gb.param_views)
+        runs = gb.trainable_runs()
+        assert len(runs) == 2 and runs[0][0] == 0 and runs[-1][1] == gb.flat.numel()       # layer 0 sits before the embeddings
+        assert runs[1][0] - runs[0][1] >= sum(p.numel() for p in layer0)                   # the frozen layer's segments
+        gb.publish("fresh")
+        assert all(p.grad is None for p in layer0) and model.bert.pooler.dense.weight.grad is not None
+    finally:
+        for p in layer0:
+            p.requires_grad_(True)
+        model.zero_grad(set_to_none=True)
+        model._grad_buffer = None
+
+
+def test_bucket_plan_with_a_short_tail():
+    """dp.plan_buckets: contiguous cover in production order, a segment above the target ships alone, and the last
+    bucket — the only one whose all-reduce cannot hide behind backward — is cut to the trailing segments that fit."""
+    from stonkgs_b200.dp import plan_buckets
+    entries, offsets, tot = [], {}, 0
+    for name, k in [("w_ent", 1000), ("w_text", 300), ("a", 90), ("b", 3), ("c", 120), ("d", 50), ("e", 50), ("f", 7)]:
+        entries.append(name)
+        offsets[name] = (tot, k, (k,))
+        tot += (k + 7) // 8 * 8
+    for tail in (0, 70, 10 ** 6):
+        bs = plan_buckets(entries, offsets, 200, tail)
+        assert bs[0].names == ["w_ent"] and bs[0].start == 0 and bs[-1].end == tot
+        assert all(x.end == y.start for x, y in zip(bs, bs[1:]))
+        assert [n for b in bs for n in b.names] == entries
+        assert all(b.start % 8 == 0 for b in bs)                    # bf16 wire slices stay 16-byte aligned
+    assert plan_buckets(entries, offsets, 200, 70)[-1].names == ["e", "f"]           # 56 + 8 <= 70, + 56 would not fit
+    assert plan_buckets(entries, offsets, 200, 1)[-1].names == ["f"]                 # at least one segment
+    assert len(plan_buckets(entries, offsets, 200, 10 ** 6)) == 2                    # a tail never swallows the first segment
+
+
+def test_label_capacity_rules(small):
+    from stonkgs_b200.training import label_capacity
+    _, _, batch, _, _, model = small
+    mlm = batch["masked_lm_labels"]
+    assert label_capacity(model, mlm, 256) == int((mlm != -100).sum())              # host labels: counted exactly
+
+    class _OnDevice:                                                                 # stands in for a CUDA tensor
+        is_cuda, shape = True, (8, 256)
+
+    assert label_capacity(model, _OnDevice(), 256) == 38 * 8                         # int(0.15 * 256) per pair (reference)
+    assert label_capacity(model, _OnDevice(), 4) == 4 * 8                            # TransE entity part: every position
+    model.label_capacity = 50
+    try:
+        assert label_capacity(model, _OnDevice(), 256) == 50 * 8 and label_capacity(model, _OnDevice(), 4) == 4 * 8
+    finally:
+        model.label_capacity = None
