@@ -45,8 +45,13 @@ def _dp_worker(rank, world, port, out):
         model = _FakeModel()
         with torch.no_grad():
             model.w.fill_(float(rank + 1))
+        # device-side state derived from the weights BEFORE the broadcast (an optimizer or a forward built it): it must
+        # be dropped, because the broadcast writes through .data and does not bump Parameter._version
+        model._dev_state = {"bf16 copies of rank-local weights": rank}
+        model._special_rows_version = 7
         dp = DataParallel(model, bucket_mb=4096 * 4 / (1 << 20), wire_dtype=torch.float32)   # 4096-element buckets
         assert torch.equal(model.w.data, torch.ones(5))                                     # rank 0's weights everywhere
+        assert model._dev_state is None and model._special_rows_version is None
         sizes = [("w_ent", 10000), ("w_text", 3000), ("t_w", 700), ("t_b", 2), ("l1.w2", 2500), ("l1.b2", 3),
                  ("l0.w2", 2500), ("emb_b", 7)]
         gb = _FakeGradBuffer(sizes)

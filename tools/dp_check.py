@@ -28,6 +28,13 @@ def main():
     model(**full)[0].backward()
     ref = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
     model.zero_grad(set_to_none=True)
+    # ranks start from DIFFERENT weights with their device-side copies already built (the forward above built them):
+    # the broadcast must reach the bf16 GEMM copies too, not only the fp32 masters
+    if rank != 0:
+        with torch.no_grad():
+            for p in model.bert.parameters():
+                p.add_(0.01 * rank)
+        model(**mine)   # rebuilds the bf16 copies from the perturbed weights
     DataParallel(model, dist.group.WORLD)
     loss = model(**mine)[0]
     loss.backward()
