@@ -268,7 +268,8 @@ class LazyPredictionLogits:
     (stonkgs_model.py:73,253), computed the first time it is indexed, iterated, unpacked or detached.  The training loss
     comes from the fused GEMM + cross-entropy and never needs these 80 GFLOP / 1.4 GB per 8 pairs, so a step that does
     not look at them does not pay for them; anything that does (``outputs[1][0]``, ``text, ent = ...``, HF
-    ``nested_detach``) gets real tensors."""
+    ``nested_detach``) gets real tensors.  Materialise before ``optimizer.step()``: afterwards the decoder weights are
+    the updated ones (the sequence output is the step's own)."""
 
     def __init__(self, hw, seq, B, shape):
         self._args = (hw, seq, B, shape)
