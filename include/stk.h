@@ -41,6 +41,11 @@ long long stk_launch_count(void);
  * CTAs of a concurrent collective (the data-parallel gradient all-reduce, stonkgs_pretraining.py:147-168).  Returns the
  * previous value (>= 0) or STK_ERR_BAD_ARG.  0 = use every SM (default). */
 int stk_set_sm_reserve(int device, int n);
+/* Tile scheduling of stk_gemm (all epilogues except the LayerNorm-fused ones): 0 = static stride over a persistent grid,
+ * 1 = dynamic through cluster launch control (one CTA pair per tile is launched; running pairs cancel pending ones and
+ * take over their tiles), which keeps a GEMM at full speed on the SMs it gets when a concurrent kernel holds some of
+ * them.  Returns the previous setting.  Default: env STK_GEMM_DYNAMIC, else 0. */
+int stk_set_gemm_dynamic(int on);
 
 /* ------------------------------------------------------------------------------------------------
  * Embedding stages

@@ -63,6 +63,7 @@ _SIGNATURES = {
     "stk_last_error": (c_int, [c_char_p, c_size_t]),
     "stk_launch_count": (c_longlong, []),
     "stk_set_sm_reserve": (c_int, [c_int, c_int]),
+    "stk_set_gemm_dynamic": (c_int, [c_int]),
     "stk_embed_text_ln_fwd": (c_int, [c_int, _P, _P, c_int64, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P, _P]),
     "stk_embed_joint_ln_fwd": (c_int, [c_int, _P, _P, _P, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "stk_embed_joint_ln_bwd": (c_int, [c_int, _P, _P, _P, c_int, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

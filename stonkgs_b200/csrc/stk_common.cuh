@@ -607,6 +607,37 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
 
 // One lane of a fully converged warp (warp-uniform control flow keeps descriptor math on the
 // uniform datapath; only the issuing instruction is predicated).
+// ---------------------------------------------------------------------------------------------
+// Cluster launch control (sm_100): a running CTA / cluster cancels one that has not been launched yet and takes over
+// its block index — hardware work stealing for persistent kernels launched with grid = number of work items.
+// The 16-byte response lands in shared memory and completes 16 transaction bytes on the mbarrier.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void clc_try_cancel(uint32_t resp_smem, uint32_t bar_smem) {
+  asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];"
+               ::"r"(resp_smem), "r"(bar_smem) : "memory");
+}
+// the response and the mbarrier signal go to the same offsets in EVERY CTA of the cluster (issue from one CTA only)
+__device__ __forceinline__ void clc_try_cancel_multicast(uint32_t resp_smem, uint32_t bar_smem) {
+  asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];"
+               ::"r"(resp_smem), "r"(bar_smem) : "memory");
+}
+// returns the x block index of the first CTA of the cancelled cluster, or -1 when nothing was left to cancel
+__device__ __forceinline__ int clc_decode(const uint4& r) {
+  const unsigned long long lo = (static_cast<unsigned long long>(r.y) << 32) | r.x;
+  const unsigned long long hi = (static_cast<unsigned long long>(r.w) << 32) | r.z;
+  uint32_t ok, x;
+  asm volatile(
+      "{\n\t.reg .b128 R;\n\t.reg .pred p;\n\t"
+      "mov.b128 R, {%2, %3};\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p, R;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "mov.u32 %1, 0;\n\t"
+      "@p clusterlaunchcontrol.query_cancel.get_first_ctaid::x.b32.b128 %1, R;\n\t}"
+      : "=r"(ok), "=r"(x)
+      : "l"(lo), "l"(hi));
+  return ok ? static_cast<int>(x) : -1;
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(

@@ -115,7 +115,16 @@ __device__ __forceinline__ void stage_and_store(const CUtensorMap* map, uint8_t*
   }
 }
 
-template <int A_MN, int B_MN, int EPI, bool PAIR>
+// DYN: dynamic tile scheduling through cluster launch control.  The kernel is then launched with one CTA (pair) per work
+// item; the CTAs that get an SM behave like persistent ones, but instead of walking a static stride they CANCEL a
+// not-yet-launched CTA (pair) of the same grid and take over its item.  A CTA that cannot get an SM — because a
+// collective's CTA sits there — therefore costs nothing: its item is simply stolen by the others (with the static
+// schedule the kernel takes ~2 x as long).  Response ring of four 16-byte slots: the producer warp of the
+// issuing CTA requests item k+1 when it starts item k; every role that walks the item sequence (producer, MMA issuer,
+// eight epilogue warps) waits for the slot, decodes it and releases it.  Not used by the LayerNorm variants.
+constexpr int kClcDepth = 4;
+
+template <int A_MN, int B_MN, int EPI, bool PAIR, bool DYN>
 __global__ void __launch_bounds__(GemmCfg<EPI, PAIR>::kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_c2,
@@ -144,7 +153,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   uint64_t* zdone_bar = bars + 32;           // [4] ... and read out by its TMA store
   uint64_t* stats_bar = bars + 36;           // [2] row statistics of all three slabs have arrived (cluster scope)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 38);
+  // DYN only:
+  uint64_t* clc_full = bars + 40;            // [4] response k has landed in slot k % 4
+  uint64_t* clc_empty = bars + 44;           // [4] every reader has released the slot (PAIR: the even CTA's are used)
+  uint4* clc_resp = reinterpret_cast<uint4*>(bars + 48);   // [4] 16-byte try_cancel responses
   static_assert(STAGES <= 8, "barrier layout");
+  static_assert(!(DYN && kLN), "the LayerNorm variants keep the static schedule");
+  // readers of every response: producer warp + eight epilogue warps of each CTA, MMA warp of the issuing CTA
+  constexpr int kClcReaders = PAIR ? 19 : 10;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -166,6 +182,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar + i, 1);
       mbar_init(tempty_bar + i, PAIR ? 16 : 8);  // one arrive per epilogue warp (of both CTAs of a pair)
+    }
+    if (DYN) {
+      for (int i = 0; i < kClcDepth; ++i) {
+        mbar_init(clc_full + i, 1);
+        mbar_init(clc_empty + i, kClcReaders);
+      }
     }
     if (kLN) {
       for (int i = 0; i < 4; ++i) {
@@ -189,6 +211,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_items = p.m_tiles * p.n_tiles * p.splits;
+  // item walk: static stride over the persistent grid, or (DYN) this CTA's own block index first and then whatever
+  // try_cancel hands over.  clc_next(k): the item after the k-th one (-1 = nothing left); called by whole warps.
+  const int first_item = DYN ? static_cast<int>(blockIdx.x) / Cfg::kCluster : unit;
+  auto clc_next = [&](int k) -> int {
+    const int sl = k % kClcDepth;
+    mbar_wait(clc_full + sl, (k / kClcDepth) & 1);
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_u32(clc_resp + sl)) : "memory");
+    const int bx = clc_decode(r);
+    __syncwarp();
+    if (lane == 0) {
+      if (PAIR) mbar_arrive_remote(map_to_cta(smem_u32(clc_empty + sl), pair_leader));
+      else mbar_arrive(clc_empty + sl);
+    }
+    return bx < 0 ? -1 : bx / Cfg::kCluster;
+  };
+  auto next_item = [&](int item, int k) -> int {
+    if (DYN) return clc_next(k);
+    return item + units < num_items ? item + units : -1;
+  };
 
   if (warp == kProducerWarp) {
     // ============================== TMA producer ==============================
@@ -197,7 +240,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const bool leader = elect_one();
     int stage = 0, n_loaded = 0;
     uint32_t phase = 0;
-    for (int item = unit; item < num_items; item += units) {
+    int it_k = 0;
+    for (int item = first_item; item >= 0 && item < num_items; item = next_item(item, it_k), ++it_k) {
+      if (DYN) {
+        // request the item that follows this one: the slot's previous response (k - 4) must have been released by all
+        // of its readers; every CTA arms its own barrier, the even CTA of a pair issues for both (multicast)
+        const int sl = it_k % kClcDepth;
+        if (it_k >= kClcDepth && (!PAIR || pr == 0)) mbar_wait(clc_empty + sl, ((it_k / kClcDepth) - 1) & 1);
+        if (leader) {
+          mbar_arrive_expect_tx(clc_full + sl, 16);
+          if (!PAIR) clc_try_cancel(smem_u32(clc_resp + sl), smem_u32(clc_full + sl));
+          else if (pr == 0) clc_try_cancel_multicast(smem_u32(clc_resp + sl), smem_u32(clc_full + sl));
+        }
+        __syncwarp();
+      }
       const int split = item % p.splits;
       const int tile = item / p.splits;
       const int n0 = (tile % p.n_tiles) * BN;
@@ -206,7 +262,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(empty_bar + stage, phase ^ 1);
-        if (kb == kb0 && !kLN) STK_GEMM_STAMP(leader, (item - unit) / units, 12);
+        if (kb == kb0 && !kLN) STK_GEMM_STAMP(leader, it_k, 12);
         if (STK_DBG(p.dbg & 4) && n_loaded >= STAGES) {   // bring-up: no loads after the ring's first fill (pure MMA rate)
           if (leader && (!PAIR || pr == 0)) mbar_arrive(full_bar + stage);
         } else if (leader) {
@@ -260,7 +316,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     int as = 0;
     uint32_t as_phase = 0;
     bool ready = false;
-    for (int item = unit; item < num_items; item += units) {
+    int it_k = 0;
+    for (int item = first_item; item >= 0 && item < num_items; item = next_item(item, it_k), ++it_k) {
       const int split = item % p.splits;
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
@@ -269,7 +326,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       // warp-uniform by construction (redux result): a per-lane register here makes the compiler wrap every
       // tcgen05.mma in an elect / R2UR.BROADCAST / branch "waterfall" (~180 cycles per MMA instead of 128)
       const uint32_t d_tmem = tmem_base_u + as * BN;
-      STK_GEMM_STAMP(leader, (item - unit) / units, 0);
+      STK_GEMM_STAMP(leader, it_k, 0);
       long long waited = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         // `ready` = the look-ahead probe issued between the previous k-block's MMAs already saw this slot full
@@ -284,8 +341,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
         tc_fence_after();
         const long long kb_t0 = STK_DBG(p.dbg) ? clock64() : 0;
-        if (kb == kb0) STK_GEMM_STAMP(leader, (item - unit) / units, 13);
-        if (kb == kb1 - 1) STK_GEMM_STAMP(leader, (item - unit) / units, 1);
+        if (kb == kb0) STK_GEMM_STAMP(leader, it_k, 13);
+        if (kb == kb1 - 1) STK_GEMM_STAMP(leader, it_k, 1);
         {
           // The whole (converged) warp executes every tcgen05 statement; elect.sync inside the statement picks
           // the issuing lane, all operands are warp-uniform: ptxas emits ELECT + @P UTCHMMA back to back and
@@ -314,15 +371,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             commit(empty_bar + stage);
           }
           if (kb == kb1 - 1) commit(tfull_bar + as);
-          if (STK_DBG(p.dbg) && blockIdx.x == 0 && leader && (item - unit) / units == 2 && kb - kb0 < 64) {
+          if (STK_DBG(p.dbg) && blockIdx.x == 0 && leader && it_k == 2 && kb - kb0 < 64) {
             g_gemm_timeline[3072 + (kb - kb0) * 2] = kb_t0;          // k-block operands ready
             g_gemm_timeline[3072 + (kb - kb0) * 2 + 1] = clock64();  // its MMAs + commits issued
           }
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      if (STK_DBG(p.dbg) && blockIdx.x < 3 && leader && (item - unit) / units < 64)
-        g_gemm_timeline[blockIdx.x * 1024 + ((item - unit) / units) * 16 + 14] = waited;   // cycles starved for operands
+      if (STK_DBG(p.dbg) && blockIdx.x < 3 && leader && it_k < 64)
+        g_gemm_timeline[blockIdx.x * 1024 + it_k * 16 + 14] = waited;   // cycles starved for operands
       if (++as == 2) { as = 0; as_phase ^= 1; }
     }
     }
@@ -604,14 +661,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
     int as = 0;
     uint32_t as_phase = 0;
-    for (int item = unit; item < num_items; item += units) {
+    int it_k = 0;
+    for (int item = first_item; item >= 0 && item < num_items; item = next_item(item, it_k), ++it_k) {
       const int tile = item / p.splits;
       const int n_blk = tile % p.n_tiles;
       const int n0 = n_blk * BN;
       const int m0 = (tile / p.n_tiles) * TM + static_cast<int>(pr) * 128;
       const int m = m0 + row;
       const bool m_ok = m < p.M;
-      const int dbg_t = (item - unit) / units;
+      const int dbg_t = it_k;
       const bool dbg_thr = threadIdx.x == kEpiWarp0 * 32;
       STK_GEMM_STAMP(dbg_thr, dbg_t, 2);
       if (kHasBias) {
@@ -843,11 +901,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 // ------------------------------------------------------------------------------------------------
 extern std::atomic<long long> g_launches;
 
-template <int A_MN, int B_MN, int EPI, bool PAIR>
+// 0 = static persistent schedule, 1 = dynamic (cluster launch control); stk_set_gemm_dynamic / env STK_GEMM_DYNAMIC
+static std::atomic<int> g_gemm_dynamic{-1};
+
+static bool gemm_dynamic() {
+  int v = g_gemm_dynamic.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("STK_GEMM_DYNAMIC");
+    v = e ? (atoi(e) != 0) : 0;
+    g_gemm_dynamic.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
+
+template <int A_MN, int B_MN, int EPI, bool PAIR, bool DYN>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mc2,
                   const CUtensorMap& mr, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<EPI, PAIR>;
-  auto kern = gemm_kernel<A_MN, B_MN, EPI, PAIR>;
+  auto kern = gemm_kernel<A_MN, B_MN, EPI, PAIR, DYN>;
   static bool configured[64] = {};
   static int max_clusters[64] = {};
   int dev = 0;
@@ -859,7 +930,8 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
   const int items = p.m_tiles * p.n_tiles * p.splits;
   if (Cfg::kCluster == 1) {
     const int sms = persistent_sms(dev);
-    kern<<<items < sms ? items : sms, Cfg::kThreads, Cfg::kSmem, stream>>>(ma, mb, mc, mc2, mr, p);
+    // DYN: one CTA per item; the ones that get an SM steal the rest
+    kern<<<DYN ? items : (items < sms ? items : sms), Cfg::kThreads, Cfg::kSmem, stream>>>(ma, mb, mc, mc2, mr, p);
   } else {
     // clusters: CTA pairs (cta_group::2 MMAs), three column slabs of a LayerNorm row, or three pairs;
     // persistent over the tiles, as many clusters as the device can keep resident
@@ -889,7 +961,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
     const int reserved = num_sms(dev) - persistent_sms(dev);   // SMs left free for a concurrent collective
     int fit = max_clusters[dev & 63] - (reserved + Cfg::kCluster - 1) / Cfg::kCluster;
     if (fit < 1) fit = 1;
-    const int clusters = work < fit ? work : fit;
+    const int clusters = DYN ? work : (work < fit ? work : fit);
     cfg.gridDim = dim3(Cfg::kCluster * clusters);
     STK_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, mc2, mr, p));
   }
@@ -1022,10 +1094,16 @@ extern "C" int stk_gemm(int device, void* stream_, int a_major, int b_major, con
     rc = make_tmap_2d(&mr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, epi->resid, N, M, epi->ldr * 2, 64, 128);
     if (rc) return rc;
   }
-#define STK_GEMM_CASE(AM, BMJ, E)                                            \
-  if (a_major == AM && b_major == BMJ && epilogue == E)                      \
-    return pair ? launch<AM, BMJ, E, true>(ma, mb, mc, mc2, mr, p, stream)   \
-                : launch<AM, BMJ, E, false>(ma, mb, mc, mc2, mr, p, stream);
+  const bool dyn = gemm_dynamic() && !ln_epi;
+#define STK_GEMM_CASE(AM, BMJ, E)                                                                                    \
+  if (a_major == AM && b_major == BMJ && epilogue == E) {                                                            \
+    constexpr bool kCanDyn = E != STK_EPI_BIAS_RESID_LN && E != STK_EPI_BIAS_DROP_RESID_LN;                           \
+    if (kCanDyn && dyn)                                                                                               \
+      return pair ? launch<AM, BMJ, E, true, kCanDyn>(ma, mb, mc, mc2, mr, p, stream)                                 \
+                  : launch<AM, BMJ, E, false, kCanDyn>(ma, mb, mc, mc2, mr, p, stream);                               \
+    return pair ? launch<AM, BMJ, E, true, false>(ma, mb, mc, mc2, mr, p, stream)                                     \
+                : launch<AM, BMJ, E, false, false>(ma, mb, mc, mc2, mr, p, stream);                                   \
+  }
   STK_GEMM_CASE(0, 0, STK_EPI_BIAS)
   STK_GEMM_CASE(0, 0, STK_EPI_BIAS_GELU)
   STK_GEMM_CASE(0, 0, STK_EPI_BIAS_GELU_SAVE)
@@ -1048,6 +1126,12 @@ extern "C" int stk_gemm(int device, void* stream_, int a_major, int b_major, con
 #undef STK_GEMM_CASE
   set_error("stk_gemm: unsupported combination a_major=%d b_major=%d epilogue=%d", a_major, b_major, epilogue);
   return STK_ERR_UNSUPPORTED;
+}
+
+extern "C" int stk_set_gemm_dynamic(int on) {
+  const int prev = gemm_dynamic() ? 1 : 0;
+  g_gemm_dynamic.store(on != 0 ? 1 : 0, std::memory_order_relaxed);
+  return prev;
 }
 
 // bring-up only: copy the clock64 timeline recorded by CTA 0 of the last STK_GEMM_DEBUG launch
