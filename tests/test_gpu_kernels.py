@@ -25,6 +25,19 @@ def test_kernel_group(case):
     _run(case)
 
 
+@pytest.mark.parametrize("case", ["gemm_basic", "gemm_epilogues", "gemm_majors", "gemm_ce"])
+def test_gemm_with_dynamic_tile_scheduling(case):
+    """The same GEMM cases with the cluster-launch-control scheduler (stk_set_gemm_dynamic): one CTA pair per tile is
+    launched, running pairs cancel pending ones and take over their tiles; results must not depend on the schedule."""
+    from stonkgs_b200 import _lib
+    lib = _lib.load()
+    prev = lib.stk_set_gemm_dynamic(1)
+    try:
+        _run(case)
+    finally:
+        lib.stk_set_gemm_dynamic(prev)
+
+
 def test_product_never_touches_oracle():
     """The product path must not import anything from oracle/ (only tests / bench may)."""
     import subprocess
