@@ -42,6 +42,12 @@ import torch
 import torch.distributed as dist
 
 
+# bring-up only (STK_DP_DEBUG_SKIP_AR=1): run the bucket walk and the pack kernels but not the collective, to separate the
+# cost of the orchestration from the cost of the all-reduce itself (gradients are then NOT averaged)
+_SKIP_COLLECTIVE = os.environ.get("STK_DP_DEBUG_SKIP_AR", "0") == "1"
+_SKIP_PACK = os.environ.get("STK_DP_DEBUG_SKIP_PACK", "0") == "1"
+
+
 class Bucket:
     __slots__ = ("start", "end", "names", "pending", "work", "event")
 
@@ -176,8 +182,10 @@ class DataParallel:
             self._stream.wait_event(ready)
             if self.wire_dtype == torch.bfloat16:
                 wire = self._wire[b.start:b.end]
-                ops.cast_bf16(flat, out=wire)                    # pack: fp32 -> bf16 on the wire
-                dist.all_reduce(wire, op=dist.ReduceOp.SUM, group=self.group)
+                if not _SKIP_PACK:
+                    ops.cast_bf16(flat, out=wire)                # pack: fp32 -> bf16 on the wire
+                if not _SKIP_COLLECTIVE:
+                    dist.all_reduce(wire, op=dist.ReduceOp.SUM, group=self.group)
                 if not self.defer_unpack:
                     ops.unpack_scale(wire, flat, 1.0 / self.world)   # unpack: mean, back to fp32
             else:
