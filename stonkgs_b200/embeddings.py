@@ -37,11 +37,11 @@ def shard_bounds(n: int, rank: int, world: int):
 class _Slot:
     """One staging slot: pinned host ids -> device ids (copy stream), pooled -> pinned host (copy stream)."""
 
-    def __init__(self, batch: int, seq_len: int, n_cols: int, dev):
+    def __init__(self, batch: int, seq_len: int, n_cols: int, dev, out_width: int = 768):
         self.h_in = torch.empty((n_cols, batch, seq_len), dtype=torch.int64).pin_memory()
         self.h_in_np = self.h_in.numpy()
         self.d_in = torch.empty((n_cols, batch, seq_len), dtype=torch.int64, device=dev)
-        self.h_out = torch.empty((batch, 768), dtype=torch.float32).pin_memory()
+        self.h_out = torch.empty((batch, out_width), dtype=torch.float32).pin_memory()
         self.h_out_np = self.h_out.numpy()
         self.h2d = torch.cuda.Event()     # ids are on the device
         self.done = torch.cuda.Event()    # pooled rows are in h_out
@@ -53,16 +53,20 @@ class EmbeddingStreamer:
     what crossed the bus."""
 
     def __init__(self, model: STonKGsForPreTraining, batch_size: int = 256, slots: int = 2, columns: int = 3,
-                 pooling: str = "pooler"):
+                 pooling: str = "pooler", fn=None, out_width: int = 768):
+        """``fn(input_ids, attention_mask, token_type_ids, err_flag=...)`` -> fp32 [m, out_width] on the device replaces
+        ``model.embed`` (the fine-tuning model streams class probabilities through the same staging ring)."""
         self.model = model
         self.pooling = pooling
+        self.fn = fn
+        self.out_width = int(out_width)
         self.dev = model.bert.pooler.dense.weight.device
         if self.dev.type != "cuda":
             raise StkError("embedding extraction runs on CUDA only: move the model with .to('cuda')")
         self.batch_size = int(batch_size)
         self.seq_len = model.seq_shape.seq_len
         self.columns = columns
-        self.slots = [_Slot(self.batch_size, self.seq_len, columns, self.dev) for _ in range(max(2, slots))]
+        self.slots = [_Slot(self.batch_size, self.seq_len, columns, self.dev, self.out_width) for _ in range(max(2, slots))]
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.err = torch.zeros(1, dtype=torch.int32, device=self.dev)   # one id-range flag for the whole stream
         self.h2d_bytes = 0
@@ -82,7 +86,7 @@ class EmbeddingStreamer:
         sources stream without being materialised.  ``out`` may be a caller-provided float32 [n, 768] array / memmap."""
         n = int(input_ids.shape[0])
         if out is None:
-            out = np.empty((n, 768), dtype=np.float32)
+            out = np.empty((n, self.out_width), dtype=np.float32)
         cols = [input_ids, attention_mask, token_type_ids][: self.columns]
         compute = torch.cuda.current_stream(self.dev)
         model, bs = self.model, self.batch_size
@@ -106,7 +110,10 @@ class EmbeddingStreamer:
                     self.h2d_bytes += m * self.seq_len * 8
                 slot.h2d.record(self.copy_stream)
             compute.wait_event(slot.h2d)
-            pooled = model.embed(*dcols, err_flag=self.err, pooling=self.pooling)
+            if self.fn is not None:
+                pooled = self.fn(*dcols, err_flag=self.err)
+            else:
+                pooled = model.embed(*dcols, err_flag=self.err, pooling=self.pooling)
             ready = torch.cuda.Event()
             ready.record(compute)
             with torch.cuda.stream(self.copy_stream):
@@ -114,7 +121,7 @@ class EmbeddingStreamer:
                 pooled.record_stream(self.copy_stream)
                 slot.h_out[:m].copy_(pooled, non_blocking=True)
                 slot.done.record(self.copy_stream)
-            self.d2h_bytes += m * 768 * 4
+            self.d2h_bytes += m * self.out_width * 4
             slot.span = (lo, hi)
         for slot in self.slots:                           # drain
             self._retire(slot, out)

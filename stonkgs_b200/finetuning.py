@@ -76,9 +76,9 @@ class STonKGsForSequenceClassification(STonKGsForPreTraining):
         return SequenceClassifierOutput(loss=loss, logits=logits, hidden_states=None, attentions=None)
 
     @torch.no_grad()
-    def predict_proba(self, input_ids, attention_mask=None, token_type_ids=None) -> torch.Tensor:
+    def predict_proba(self, input_ids, attention_mask=None, token_type_ids=None, err_flag=None) -> torch.Tensor:
         """softmax(logits) for a batch: what ``infer_iter`` of the reference yields row by row."""
-        _, pooled, _ = self.encode(input_ids, attention_mask, token_type_ids)
+        _, pooled, _ = self.encode(input_ids, attention_mask, token_type_ids, err_flag=err_flag)
         logits, _ = ops.cls_head(pooled, self.classifier.weight.data, self.classifier.bias.data)
         return torch.softmax(logits, dim=1)
 
@@ -136,24 +136,11 @@ class _FinetuneStep(torch.autograd.Function):
 def infer_arrays(model: STonKGsForSequenceClassification, input_ids: np.ndarray,
                  attention_mask: Optional[np.ndarray] = None, token_type_ids: Optional[np.ndarray] = None,
                  batch_size: int = 256) -> np.ndarray:
-    """Class probabilities [n, num_labels] for int64 host arrays [n, 512] (batched ``infer_iter``)."""
-    n = input_ids.shape[0]
-    dev = model.classifier.weight.device
-    out = torch.empty((n, model.num_labels), dtype=torch.float32, pin_memory=True)
-
-    def stage(a, lo, hi):
-        if a is None:
-            return None
-        return torch.from_numpy(np.ascontiguousarray(a[lo:hi], dtype=np.int64)).pin_memory().to(dev, non_blocking=True)
-
-    for lo in range(0, n, batch_size):
-        hi = min(lo + batch_size, n)
-        model._check_ids(torch.from_numpy(np.ascontiguousarray(input_ids[lo:hi], dtype=np.int64)))
-        out[lo:hi].copy_(model.predict_proba(stage(input_ids, lo, hi), stage(attention_mask, lo, hi),
-                                             stage(token_type_ids, lo, hi)), non_blocking=True)
-    torch.cuda.synchronize(dev)
-    model._raise_on_bad_ids()
-    return out.numpy()
+    """Class probabilities [n, num_labels] for host id arrays [n, 512] (batched ``infer_iter``), streamed through the
+    same reusable pinned staging ring as the embedding extraction (embeddings.EmbeddingStreamer)."""
+    from .embeddings import EmbeddingStreamer
+    st = EmbeddingStreamer(model, batch_size, fn=model.predict_proba, out_width=model.num_labels)
+    return st.run(input_ids, attention_mask, token_type_ids)
 
 
 def infer_iter(model: STonKGsForSequenceClassification, rows: Iterable[dict],
