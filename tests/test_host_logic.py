@@ -187,3 +187,24 @@ def test_label_capacity_rules(small):
         assert label_capacity(model, _OnDevice(), 256) == 50 * 8 and label_capacity(model, _OnDevice(), 4) == 4 * 8
     finally:
         model.label_capacity = None
+
+
+def test_lazy_prediction_logits_behave_like_the_pair(monkeypatch):
+    """prediction_logits of a training step (training.LazyPredictionLogits): nothing is computed until the pair is
+    looked at; indexing, unpacking, len() and HF Trainer's nested_detach all see the reference's (text, entity) pair."""
+    from transformers.trainer_pt_utils import nested_detach
+    from stonkgs_b200 import training
+    calls = []
+
+    def fake_dense(hw, seq, B, shape):
+        calls.append(B)
+        return torch.ones(B, 256, 7), torch.zeros(B, 256, 5)
+
+    monkeypatch.setattr(training, "dense_prediction_logits", fake_dense)
+    lazy = training.LazyPredictionLogits("hw", "seq", 3, "shape")
+    assert not calls and len(lazy) == 2 and "pending" in repr(lazy)
+    text, ent = lazy                                           # unpacking materialises, once
+    assert calls == [3] and text.shape == (3, 256, 7) and ent.shape == (3, 256, 5)
+    assert lazy[0] is text and lazy[1] is ent and calls == [3]
+    out = nested_detach((torch.zeros(()), lazy, torch.zeros(3, 2)))
+    assert isinstance(out[1], tuple) and torch.equal(out[1][0], text) and calls == [3]
