@@ -191,7 +191,8 @@ def test_label_capacity_rules(small):
 
 def test_lazy_prediction_logits_behave_like_the_pair(monkeypatch):
     """prediction_logits of a training step (training.LazyPredictionLogits): nothing is computed until the pair is
-    looked at; indexing, unpacking, len() and HF Trainer's nested_detach all see the reference's (text, entity) pair."""
+    looked at; indexing, unpacking, len() and .detach() all see the reference's (text, entity) pair, and HF Trainer's
+    nested_detach passes the object through (it only rebuilds lists / tuples / mappings / tensors)."""
     from transformers.trainer_pt_utils import nested_detach
     from stonkgs_b200 import training
     calls = []
@@ -207,4 +208,6 @@ def test_lazy_prediction_logits_behave_like_the_pair(monkeypatch):
     assert calls == [3] and text.shape == (3, 256, 7) and ent.shape == (3, 256, 5)
     assert lazy[0] is text and lazy[1] is ent and calls == [3]
     out = nested_detach((torch.zeros(()), lazy, torch.zeros(3, 2)))
-    assert isinstance(out[1], tuple) and torch.equal(out[1][0], text) and calls == [3]
+    assert torch.equal(out[1][0], text) and torch.equal(out[1][1], ent) and calls == [3]
+    det = lazy.detach()
+    assert isinstance(det, tuple) and torch.equal(det[0], text)
