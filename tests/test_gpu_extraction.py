@@ -77,6 +77,7 @@ def test_streamed_embed_arrays(full_model):
     assert st.run(ids.astype(np.int32), mask.astype(np.int32), types.astype(np.int32), out=out) is out
     assert np.array_equal(out, ref)
     assert np.array_equal(st.run(ids[:5], mask[:5], types[:5]), ref[:5])          # the streamer is reusable
+    assert st.run(ids[:0], mask[:0], types[:0]).shape == (0, 768)                 # empty input: empty result, no launch
     assert st.h2d_bytes == (n + 5) * 512 * 8 * 3 and st.d2h_bytes == (n + 5) * 768 * 4
     bad = ids.copy()
     bad[70, 300] = n_kg + 3

@@ -211,3 +211,18 @@ def test_lazy_prediction_logits_behave_like_the_pair(monkeypatch):
     assert torch.equal(out[1][0], text) and torch.equal(out[1][1], ent) and calls == [3]
     det = lazy.detach()
     assert isinstance(det, tuple) and torch.equal(det[0], text)
+
+
+def test_get_stonkgs_embeddings_empty_frame():
+    """An empty frame gives the reference's empty result (``pd.DataFrame(columns=["embedding"])``, stonkgs_for_embeddings.py:164)."""
+    import pandas as pd
+    from stonkgs_b200.embeddings import get_stonkgs_embeddings
+    df = pd.DataFrame({"input_ids": [], "attention_mask": [], "token_type_ids": []})
+    seen = []
+
+    def fake_embed(i, m, t):
+        seen.append(i.shape[0])
+        return np.zeros((0, 768), dtype=np.float32)
+
+    out = get_stonkgs_embeddings(df, _embed_fn=fake_embed)
+    assert list(out.columns) == ["embedding"] and len(out) == 0 and seen == [0]
