@@ -29,7 +29,7 @@ extern "C" {
 #define STK_ERR_CUDA (-2)
 #define STK_ERR_UNSUPPORTED (-3)
 
-#define STK_VERSION 102
+#define STK_VERSION 103
 
 /* library version (STK_VERSION) */
 int stk_version(void);
@@ -221,6 +221,11 @@ int stk_linear_ce_bwd(int device, void* stream, const void* t_bf16, const void* 
  * ---------------------------------------------------------------------------------------------- */
 int stk_attn_fwd(int device, void* stream, const void* qkv_bf16, const float* key_bias, int B, int S,
                  void* out_bf16, float* lse);
+/* Same, for the first q_rows query rows of every sequence only (q_rows a multiple of 128, <= S); the other rows of out /
+ * lse are not written.  The extraction path needs only row 0 of the last layer: pooler_output reads hidden[:, 0]
+ * (HF:456-468 BertPooler; stonkgs_for_embeddings.py:180). */
+int stk_attn_fwd_qrows(int device, void* stream, const void* qkv_bf16, const float* key_bias, int B, int S, int q_rows,
+                       void* out_bf16, float* lse);
 /* dqkv: bf16 [B*S, 2304].  dout/out: bf16 [B*S, 768].
  * workspace: fp32 [B*S*768 + B*12*S] (dQ accumulator over key blocks, then row dot(dO,O)). */
 int stk_attn_bwd(int device, void* stream, const void* qkv_bf16, const float* key_bias, int B, int S,

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # STK_LIB: bring-up override (A/B runs of two builds of the kernel library); the product path is the in-tree build
 LIB_PATH = os.environ.get("STK_LIB") or os.path.join(_HERE, "libstk.so")
 
-STK_VERSION = 102
+STK_VERSION = 103
 
 # epilogue ids (include/stk.h)
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GELU_SAVE, EPI_BIAS_RESID, EPI_BIAS_TANH_F32 = 0, 1, 2, 3, 4
@@ -77,6 +77,7 @@ _SIGNATURES = {
     "stk_gemm": (c_int, [c_int, _P, c_int, c_int, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int64,
                          POINTER(GemmEpilogue), c_int]),
     "stk_attn_fwd": (c_int, [c_int, _P, _P, _P, c_int, c_int, _P, _P]),
+    "stk_attn_fwd_qrows": (c_int, [c_int, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
     "stk_attn_bwd": (c_int, [c_int, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P]),
     "stk_attn_fwd_dropout": (c_int, [c_int, _P, _P, _P, c_int, c_int, _P, _P, c_uint32, c_uint32, c_uint32]),
     "stk_attn_bwd_dropout": (c_int, [c_int, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, c_uint32, c_uint32, c_uint32]),

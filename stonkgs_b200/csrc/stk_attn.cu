@@ -60,7 +60,7 @@ constexpr int ATT_SMEM = 16384 * 6 + 4096 + 2048 + 256 + 8192;
 // keep decisions are regenerated in the backward kernel from (seed, site, row, key) — see stk_rng.cuh.
 template <int DBG, bool DROP>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __restrict__ key_bias, int S, int num_items,
+attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __restrict__ key_bias, int S, int nq, int num_items,
                 __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out, uint32_t drop_seed, uint32_t drop_site,
                 uint32_t drop_thr) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -88,7 +88,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
   uint8_t* sOut = smem + 16384 * 6 + 4096 + 2048 + 256;   // [4 warps][32 rows][64 B]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nblk = S >> 7;          // key blocks per item == q-tiles per (head, batch)
+  const int nblk = S >> 7;          // key blocks per item; nq <= nblk query tiles per (head, batch) are computed
   constexpr uint32_t T_S = 0, T_P = 128, T_O = 192;
 
   if (warp == 4) {
@@ -127,7 +127,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
     int item = blockIdx.x;
     int hh = 0, rb = 0, qq = 0;
     auto set_item = [&](int it) {
-      const int qt = it % nblk, rest = it / nblk;
+      const int qt = it % nq, rest = it / nq;
       hh = rest % kHeads;
       rb = (rest / kHeads) * S;
       qq = qt * 128;
@@ -273,7 +273,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
     if (key_bias) {
       int it = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-        const int b = (item / nblk) / kHeads;
+        const int b = (item / nq) / kHeads;
         if (it >= 2) mbar_wait(bar_bfree + (it & 1), ((it >> 1) - 1) & 1);
         float* bias_it = sBias + (it & 1) * 512;
         const float4* src = reinterpret_cast<const float4*>(key_bias + static_cast<int64_t>(b) * S);
@@ -318,15 +318,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
 
     // Item walk without per-item divisions: (q-tile, head, batch) of blockIdx.x, advanced by the decomposition of
     // gridDim.x with carries.
-    int qt = static_cast<int>(blockIdx.x) % nblk, h, b;
+    int qt = static_cast<int>(blockIdx.x) % nq, h, b;
     {
-      const int rest = static_cast<int>(blockIdx.x) / nblk;
+      const int rest = static_cast<int>(blockIdx.x) / nq;
       h = rest % kHeads;
       b = rest / kHeads;
     }
-    const int d_qt = static_cast<int>(gridDim.x) % nblk;
-    const int d_h = (static_cast<int>(gridDim.x) / nblk) % kHeads;
-    const int d_b = (static_cast<int>(gridDim.x) / nblk) / kHeads;
+    const int d_qt = static_cast<int>(gridDim.x) % nq;
+    const int d_h = (static_cast<int>(gridDim.x) / nq) % kHeads;
+    const int d_b = (static_cast<int>(gridDim.x) / nq) / kHeads;
 
     // The output of an item is written while the FIRST key block of the CTA's next item is in flight: its last P V
     // product completes behind that block's score load / max / exponentials instead of stalling the softmax warps.
@@ -540,7 +540,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
       pending = true;
       // next item of this CTA
       qt += d_qt;
-      if (qt >= nblk) { qt -= nblk; ++h; }
+      if (qt >= nq) { qt -= nq; ++h; }
       h += d_h;
       if (h >= kHeads) { h -= kHeads; ++b; }
       b += d_b;
@@ -565,9 +565,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const float* __rest
 using namespace stk;
 
 static int attn_fwd_impl(int device, void* stream, const void* qkv, const float* key_bias, int B, int S, void* out,
-                         float* lse, bool drop, uint32_t drop_seed, uint32_t drop_site, uint32_t drop_thr) {
+                         float* lse, bool drop, uint32_t drop_seed, uint32_t drop_site, uint32_t drop_thr, int q_rows = 0) {
   STK_REQUIRE(qkv && out && B > 0, "stk_attn_fwd: bad arguments");
   STK_REQUIRE(S == 128 || S == 256 || S == 384 || S == 512, "stk_attn_fwd: S must be 128, 256, 384 or 512 (got %d)", S);
+  if (q_rows == 0) q_rows = S;
+  STK_REQUIRE(q_rows > 0 && q_rows <= S && q_rows % 128 == 0, "stk_attn_fwd: q_rows must be a multiple of 128 in (0, S] (got %d)", q_rows);
+  const int nq = q_rows / 128;
   STK_CHECK_CUDA(cudaSetDevice(device));
   CUtensorMap map;
   int rc = make_tmap_2d(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, 3 * kHidden, static_cast<uint64_t>(B) * S,
@@ -578,12 +581,12 @@ static int attn_fwd_impl(int device, void* stream, const void* qkv, const float*
     const char* e = getenv("STK_ATTN_DEBUG");
     dbg = e ? atoi(e) : 0;
   }
-  const int num_items = (S / 128) * kHeads * B;
+  const int num_items = nq * kHeads * B;
   const int grid = num_items < 2 * persistent_sms(device) ? num_items : 2 * persistent_sms(device);
   auto go = [&](auto kern) -> int {
     STK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     kern<<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(
-        map, key_bias, S, num_items, static_cast<__nv_bfloat16*>(out), lse, drop_seed, drop_site, drop_thr);
+        map, key_bias, S, nq, num_items, static_cast<__nv_bfloat16*>(out), lse, drop_seed, drop_site, drop_thr);
     return STK_OK;
   };
   // 64 = record a clock64 timeline of CTA 0 (tools/attn_dbg.py); every other value runs the production kernel
@@ -604,6 +607,11 @@ extern "C" int stk_attn_fwd_dropout(int device, void* stream, const void* qkv, c
                                     void* out, float* lse, uint32_t seed, uint32_t site, uint32_t thr) {
   STK_REQUIRE(thr < 128, "stk_attn_fwd_dropout: thr must be below 128");
   return attn_fwd_impl(device, stream, qkv, key_bias, B, S, out, lse, thr > 0, seed, site, thr);
+}
+
+extern "C" int stk_attn_fwd_qrows(int device, void* stream, const void* qkv, const float* key_bias, int B, int S,
+                                  int q_rows, void* out, float* lse) {
+  return attn_fwd_impl(device, stream, qkv, key_bias, B, S, out, lse, false, 0, 0, 0, q_rows);
 }
 
 // (backward kernel: see stk_attn_bwd.cu)

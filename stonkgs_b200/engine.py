@@ -116,16 +116,29 @@ class DropCtx:
 # forward
 # --------------------------------------------------------------------------------------------------
 def encoder_layer_fwd(x, lw: LayerWeights, B: int, S: int, key_bias, cache: Optional[list] = None,
-                      drop: Optional[DropCtx] = None, enc: int = 0, li: int = 0, head_scale=None):
+                      drop: Optional[DropCtx] = None, enc: int = 0, li: int = 0, head_scale=None,
+                      first_row_only: bool = False):
     """One BertLayer (post-LN). x: bf16 [B*S, 768].
 
     eval() and train() take the same kernels: in train() the attention kernel drops probabilities (HF:132) and the
     dense outputs are dropped inside the fused bias + residual + LayerNorm GEMM epilogue (HF:296-298, 354-356), masks
     being a pure function of (seed, site, row, column).  ``head_scale`` (fp32 [12], optional) is this layer's row of the
-    reference's ``head_mask``: a per-head factor on the attention probabilities, i.e. on the context columns."""
+    reference's ``head_mask``: a per-head factor on the attention probabilities, i.e. on the context columns.
+
+    ``first_row_only`` (eval, last layer of the extraction path): the caller only reads row 0 of every sequence
+    (BertPooler, HF:456-468), so everything after the K / V projection runs on those B rows — same kernels, same
+    per-row arithmetic: the attention computes the first 128-query tile of every (head, pair), the three GEMMs read
+    row b*S through the operand pitch.  Returns bf16 [B, 768]."""
     M = x.shape[0]
     train = cache is not None
     qkv = ops.linear(x, lw.wqkv, lw.bqkv)
+    if first_row_only:
+        assert not train and drop is None and head_scale is None and FUSED_LN
+        ctx = ops.attention(qkv, key_bias, B, S, q_rows=128)
+        x0 = x.view(B, S, H)[:, 0]
+        x1 = ops.linear_resid_ln(ctx.view(B, S, H)[:, 0], lw.wo, lw.bo, x0, lw.ln1_g, lw.ln1_b)
+        h = ops.linear(x1, lw.w1, lw.b1, ops.EPI_BIAS_GELU)
+        return ops.linear_resid_ln(h, lw.w2, lw.b2, x1, lw.ln2_g, lw.ln2_b)
     d_attn = drop.attention(enc, li) if drop is not None else None
     d_o = drop.attn_out(enc, li) if drop is not None else None
     d_f = drop.ffn_out(enc, li) if drop is not None else None
@@ -183,11 +196,14 @@ def encoder_layer_fwd(x, lw: LayerWeights, B: int, S: int, key_bias, cache: Opti
 
 
 def encoder_fwd(x, ew: EncoderWeights, B: int, S: int, key_bias, cache: Optional[list] = None,
-                drop: Optional[DropCtx] = None, enc: int = 0, head_mask=None):
-    """``head_mask``: fp32 [layers, 12] on the device, or None."""
+                drop: Optional[DropCtx] = None, enc: int = 0, head_mask=None, first_row_only: bool = False):
+    """``head_mask``: fp32 [layers, 12] on the device, or None.  ``first_row_only``: the LAST layer produces row 0 of
+    every sequence only (bf16 [B, 768] instead of [B*S, 768])."""
+    last = len(ew.layers) - 1
     for li, lw in enumerate(ew.layers):
         x = encoder_layer_fwd(x, lw, B, S, key_bias, cache, drop, enc, li,
-                              head_mask[li] if head_mask is not None else None)
+                              head_mask[li] if head_mask is not None else None,
+                              first_row_only=first_row_only and li == last)
     return x
 
 
@@ -219,10 +235,13 @@ def lm_special_rows(ew: EncoderWeights, token_ids) -> torch.Tensor:
 
 def joint_fwd(bert: EncoderWeights, input_ids, token_type_ids, attention_mask, lm_hidden, kg_table, *,
               cache: Optional[dict] = None, want_inputs_embeds=False, err_flag=None, drop: Optional[DropCtx] = None,
-              shape: ops.SeqShape = ops.STONKGS_SHAPE, head_mask=None):
+              shape: ops.SeqShape = ops.STONKGS_SHAPE, head_mask=None, pooled_only: bool = False):
     """KG lookup + concat + joint embeddings + 12 layers + pooler (stonkgs_model.py:182-212).
     Activations hold ``shape.seq_pad`` rows per pair (== the sequence length for STonKGs; the 260-token TransE variant is
-    padded to 384 rows whose tail is masked out as attention keys)."""
+    padded to 384 rows whose tail is masked out as attention keys).
+
+    ``pooled_only`` (eval callers that read ``pooler_output`` alone): the last layer runs on the [CLS] rows only and the
+    returned ``seq`` is None; the pooled output is the same arithmetic per row as the full pass."""
     B = input_ids.shape[0]
     S, SP = shape.seq_len, shape.seq_pad
     train = cache is not None
@@ -240,9 +259,13 @@ def joint_fwd(bert: EncoderWeights, input_ids, token_type_ids, attention_mask, l
         attention_mask = am
     key_bias = ops.mask_to_bias(attention_mask) if attention_mask is not None else None
     layer_cache = [] if train else None
-    seq = encoder_fwd(x, bert, B, SP, key_bias, layer_cache, drop, 1, head_mask)
+    pooled_only = pooled_only and not train and drop is None and head_mask is None and FUSED_LN
+    seq = encoder_fwd(x, bert, B, SP, key_bias, layer_cache, drop, 1, head_mask, first_row_only=pooled_only)
     # BertPooler: tanh(W h[:, 0] + b); rows b*SP are read in place through the A pitch
-    pooled = ops.gemm(seq.view(B, SP, H)[:, 0], bert.wp, M=B, N=H, K=H, epilogue=ops.EPI_BIAS_TANH_F32, bias=bert.bp)
+    cls = seq if pooled_only else seq.view(B, SP, H)[:, 0]
+    pooled = ops.gemm(cls, bert.wp, M=B, N=H, K=H, epilogue=ops.EPI_BIAS_TANH_F32, bias=bert.bp)
+    if pooled_only:
+        seq = None
     if train:
         cache.update(emb_mean=mean, emb_rstd=rstd, key_bias=key_bias, layers=layer_cache, lm_hidden=lm_hidden, drop=drop,
                      shape=shape, head_mask=head_mask)

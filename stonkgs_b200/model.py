@@ -354,8 +354,9 @@ class STonKGsForPreTraining(BertForPreTraining):
                 raise KeyError(int(bad))
 
     def encode(self, input_ids, attention_mask=None, token_type_ids=None, *, cache=None, want_inputs_embeds=False,
-               need_heads=False, err_flag=None, head_mask=None):
-        """LM backbone -> KG lookup -> joint encoder -> pooler.  Returns (seq bf16 [B*seq_pad,768], pooled fp32, emb)."""
+               need_heads=False, err_flag=None, head_mask=None, pooled_only=False):
+        """LM backbone -> KG lookup -> joint encoder -> pooler.  Returns (seq bf16 [B*seq_pad,768], pooled fp32, emb);
+        with ``pooled_only`` (eval) the last layer runs on the [CLS] rows alone and ``seq`` is None."""
         st = self._device_state(need_heads)
         dev = self.kg_table.device
         sh = self.seq_shape
@@ -376,7 +377,8 @@ class STonKGsForPreTraining(BertForPreTraining):
         lm_hidden = engine.lm_backbone_fwd(st["lm"], input_ids[:, :sh.text_len], None, err_flag=err, drop=drop)
         seq, pooled, emb = engine.joint_fwd(st["bert"], input_ids, token_type_ids, attention_mask, lm_hidden,
                                             self.kg_table, cache=cache, want_inputs_embeds=want_inputs_embeds,
-                                            err_flag=err, drop=drop, shape=sh, head_mask=hm)
+                                            err_flag=err, drop=drop, shape=sh, head_mask=hm,
+                                            pooled_only=pooled_only and cache is None)
         if cache is not None:
             cache.update(input_ids=input_ids, token_type_ids=token_type_ids, err=err)
         if err_flag is None:
@@ -463,13 +465,19 @@ class STonKGsForPreTraining(BertForPreTraining):
                            "produced by the reference's pre-processing) or pass the label tensors on the CPU")
 
     @torch.no_grad()
-    def embed(self, input_ids, attention_mask=None, token_type_ids=None, err_flag=None, pooling: str = "pooler") -> torch.Tensor:
+    def embed(self, input_ids, attention_mask=None, token_type_ids=None, err_flag=None, pooling: str = "pooler",
+              cls_rows_only: bool = False) -> torch.Tensor:
         """Extraction path, heads skipped.  ``pooling="pooler"`` (default) is the reference's output: the BERT pooler
         ``tanh(W h[:, 0] + b)`` (stonkgs_for_embeddings.py:180).  ``pooling="mean"`` is an extra: the mean of the last
-        hidden state over the attended tokens (``attention_mask != 0``) of each pair."""
+        hidden state over the attended tokens (``attention_mask != 0``) of each pair.
+
+        ``cls_rows_only`` (with the pooler, eval): the pooler reads ``hidden[:, 0]`` alone, so the last encoder layer is
+        evaluated for the [CLS] rows only (keys / values still come from all 512 rows) — identical output, about 1/12 of
+        the joint encoder's work less.  Off by default: every number quoted for this path runs the full last layer."""
         if pooling not in ("pooler", "mean"):
             raise StkError(f"pooling must be 'pooler' or 'mean', got {pooling!r}")
-        seq, pooled, _ = self.encode(input_ids, attention_mask, token_type_ids, err_flag=err_flag)
+        seq, pooled, _ = self.encode(input_ids, attention_mask, token_type_ids, err_flag=err_flag,
+                                     pooled_only=cls_rows_only and pooling == "pooler" and not self.training)
         if pooling == "pooler":
             return pooled
         am = attention_mask

@@ -309,13 +309,25 @@ def dropout_resid_ln(x, resid, gamma, beta, d: Drop, save_for_backward=False):
 
 
 def attention(qkv: torch.Tensor, key_bias: Optional[torch.Tensor], B: int, S: int, save_lse=False, out=None,
-              drop: Optional["Drop"] = None):
+              drop: Optional["Drop"] = None, q_rows: Optional[int] = None):
+    """``q_rows`` (multiple of 128): only the first q_rows query rows of every sequence are computed; the other rows of
+    the returned context are uninitialised (eval only; see engine.encoder_layer_fwd ``first_row_only``)."""
     _req(qkv, torch.bfloat16, "qkv")
     assert qkv.shape == (B * S, 3 * H) and qkv.is_contiguous()
     dev, stream = _ctx(qkv)
     ctx = torch.empty((B * S, H), dtype=torch.bfloat16, device=qkv.device) if out is None else out
     lse = torch.empty((B, HEADS, S), dtype=torch.float32, device=qkv.device) if save_lse else None
     prof = _PROFILER
+    if q_rows is not None and q_rows < S:
+        assert drop is None and not save_lse
+        if prof is not None:
+            e0, e1 = prof.span("attn_fwd_qrows", 4.0 * B * HEADS * q_rows * S * 64)
+            e0.record()
+        check(_lib.load().stk_attn_fwd_qrows(dev, stream, _ptr(qkv), _ptr(key_bias), B, S, q_rows, _ptr(ctx), None),
+              "stk_attn_fwd_qrows")
+        if prof is not None:
+            e1.record()
+        return ctx
     if prof is not None:
         e0, e1 = prof.span("attn_fwd", 4.0 * B * HEADS * S * S * 64)
         e0.record()

@@ -86,6 +86,30 @@ def test_streamed_embed_arrays(full_model):
     assert np.array_equal(embed_arrays(model, ids, mask, types, batch_size=64), ref)   # the flag does not stick
 
 
+def test_cls_rows_only_last_layer_is_identical(full_model):
+    """``cls_rows_only``: the pooler reads hidden[:, 0] alone (HF BertPooler), so the last encoder layer may be evaluated
+    for the [CLS] rows only — attention for the first query tile of every (head, pair), the three GEMMs over B rows read
+    through the operand pitch.  Same kernels and the same arithmetic per row: the embeddings are bit-identical to the
+    full pass, for one batch, for streamed batches with a ragged tail, and for a single pair; mean pooling (which needs
+    every row) ignores the switch."""
+    from stonkgs_b200 import synthetic
+    from stonkgs_b200.embeddings import embed_arrays
+    model, n_kg = full_model
+    n = 2 * 64 + 23
+    batch = synthetic.make_batch(n, n_kg, seed=11, with_labels=False)
+    ref = model.embed(**batch)
+    got = model.embed(**batch, cls_rows_only=True)
+    assert got.shape == ref.shape and got.dtype == torch.float32
+    assert torch.equal(got, ref), float((got - ref).abs().max())
+    ids, mask, types = (batch[k].numpy() for k in ("input_ids", "attention_mask", "token_type_ids"))
+    streamed = embed_arrays(model, ids, mask, types, batch_size=64, cls_rows_only=True)
+    assert np.array_equal(streamed, ref.cpu().numpy())
+    one = model.embed(batch["input_ids"][:1], batch["attention_mask"][:1], batch["token_type_ids"][:1], cls_rows_only=True)
+    assert torch.equal(one, ref[:1])
+    mean_ref = model.embed(**batch, pooling="mean")
+    assert torch.equal(model.embed(**batch, pooling="mean", cls_rows_only=True), mean_ref)
+
+
 def test_mean_pooled_extraction_vs_oracle():
     """pooling="mean" (an extra beside the reference's pooler_output): masked mean of the last hidden state, against the
     fp32 oracle's sequence_output on a golden case; stated tolerance atol 3e-2 (a mean over >= 288 rows of bf16 states)."""

@@ -246,6 +246,26 @@ def case_gemm_ln():
         res.append(_err_report(mean, zref.mean(1), f"ln_train_mean_{M}x{K}", 2e-3))
         res.append(_err_report(rstd, (zref.var(1, unbiased=False) + 1e-12).rsqrt(), f"ln_train_rstd_{M}x{K}", 2e-3))
         res.append({"case": f"ln_same_{M}x{K}", "ok": bool(torch.equal(y, y2))})
+    # A and the residual read through a row pitch (row b*512 of a [B*512, 768] activation: the [CLS] rows of the
+    # extraction path's last layer), at row counts below and above one tile; same arithmetic per row as the dense call
+    for (Bq, K) in [(1, 768), (7, 768), (130, 768), (256, 3072), (300, 768)]:
+        N, S = 768, 512
+        a_all = _mk(Bq * S, K, "cuda", 0.5)
+        r_all = _mk(Bq * S, N, "cuda")
+        w = _mk(N, K, "cuda", 0.05)
+        bias = torch.randn(N, device="cuda") * 0.5
+        gamma = 1.0 + 0.2 * torch.randn(N, device="cuda")
+        beta = 0.3 * torch.randn(N, device="cuda")
+        a0, r0 = a_all.view(Bq, S, K)[:, 0], r_all.view(Bq, S, N)[:, 0]
+        y = ops.linear_resid_ln(a0, w, bias, r0, gamma, beta)
+        y_all = ops.linear_resid_ln(a_all, w, bias, r_all, gamma, beta)
+        torch.cuda.synchronize()
+        zref = _gemm_ref(a0.contiguous(), w, 0, 0) + bias + r0.float()
+        yref = torch.nn.functional.layer_norm(zref, (N,), gamma, beta, 1e-12)
+        res.append(_err_report(y, yref, f"ln_pitched_rows_{Bq}x{K}", 6e-2))
+        dense0 = y_all.view(Bq, S, N)[:, 0]
+        res.append({"case": f"ln_pitched_rows_same_as_dense_{Bq}x{K}", "ok": bool(torch.equal(y, dense0)),
+                    "max_abs": float((y.float() - dense0.float()).abs().max())})
     # a row with a large common offset: the chunked (mean, M2) merge must not cancel catastrophically
     M, K, N = 256, 768, 768
     a = _mk(M, K, "cuda", 0.5)
@@ -516,6 +536,21 @@ def case_attn():
         # determinism across launches (no race between items)
         out2, lse2 = ops.attention(qkv, bias, B, S, save_lse=True)
         res.append({"case": f"attn_fwd_deterministic_B{B}_S{S}", "ok": bool(torch.equal(out, out2) and torch.equal(lse, lse2))})
+    # first query tile(s) only (stk_attn_fwd_qrows): the computed rows are bit-identical to the full kernel's, the other
+    # rows of the output are not written; several items per CTA at the larger batch
+    for (B, S, q_rows) in [(3, 512, 128), (700, 512, 128), (5, 384, 256), (2, 256, 128)]:
+        qkv = _mk(B * S, 2304, "cuda", 1.0)
+        m = torch.ones(B, S, dtype=torch.long, device="cuda")
+        lens = torch.randint(3, S // 2 + 1, (B,), device="cuda")
+        m[:, : S // 2] = (torch.arange(S // 2, device="cuda")[None, :] < lens[:, None]).long()
+        bias = ops.mask_to_bias(m)
+        full = ops.attention(qkv, bias, B, S)
+        part = torch.full((B * S, 768), 7.0, dtype=torch.bfloat16, device="cuda")
+        ops.attention(qkv, bias, B, S, out=part, q_rows=q_rows)
+        torch.cuda.synchronize()
+        f3, p3 = full.view(B, S, 768), part.view(B, S, 768)
+        res.append({"case": f"attn_qrows_same_B{B}_S{S}_q{q_rows}", "ok": bool(torch.equal(f3[:, :q_rows], p3[:, :q_rows]))})
+        res.append({"case": f"attn_qrows_untouched_B{B}_S{S}_q{q_rows}", "ok": bool((p3[:, q_rows:] == 7.0).all())})
     # large, growing scores: later key blocks dominate -> exercises the lazy O rescale in TMEM
     B, S = 2, 512
     qkv = _mk(B * S, 2304, "cuda", 1.0)
