@@ -87,4 +87,7 @@ def test_workspace_query_and_head_entry_points():
     epi.resid, epi.ldr, epi.ln_gamma, epi.ln_beta = 16, 768, 16, 16
     rc = lib.stk_gemm(0, None, 0, 0, p16, 768, p16, 768, 256, 768, 768, _lib.EPI_BIAS_DROP_RESID_LN, p16, 768, ctypes.byref(epi), 1)
     assert rc == -1 and "drop_thr" in _lib.last_error()
+    for q_rows in (100, 640, -128):                                    # multiples of 128 in (0, S] only
+        rc = lib.stk_attn_fwd_qrows(0, None, p16, None, 2, 512, q_rows, p16, None)
+        assert rc == -1 and "q_rows" in _lib.last_error()
     assert lib.stk_launch_count() == 0
