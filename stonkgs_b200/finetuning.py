@@ -76,9 +76,12 @@ class STonKGsForSequenceClassification(STonKGsForPreTraining):
         return SequenceClassifierOutput(loss=loss, logits=logits, hidden_states=None, attentions=None)
 
     @torch.no_grad()
-    def predict_proba(self, input_ids, attention_mask=None, token_type_ids=None, err_flag=None) -> torch.Tensor:
-        """softmax(logits) for a batch: what ``infer_iter`` of the reference yields row by row."""
-        _, pooled, _ = self.encode(input_ids, attention_mask, token_type_ids, err_flag=err_flag)
+    def predict_proba(self, input_ids, attention_mask=None, token_type_ids=None, err_flag=None,
+                      cls_rows_only: bool = False) -> torch.Tensor:
+        """softmax(logits) for a batch: what ``infer_iter`` of the reference yields row by row.  The classifier reads the
+        pooled [CLS] row only, so ``cls_rows_only`` applies as in :meth:`STonKGsForPreTraining.embed` (same bits)."""
+        _, pooled, _ = self.encode(input_ids, attention_mask, token_type_ids, err_flag=err_flag,
+                                   pooled_only=cls_rows_only and not self.training)
         logits, _ = ops.cls_head(pooled, self.classifier.weight.data, self.classifier.bias.data)
         return torch.softmax(logits, dim=1)
 
@@ -135,11 +138,15 @@ class _FinetuneStep(torch.autograd.Function):
 
 def infer_arrays(model: STonKGsForSequenceClassification, input_ids: np.ndarray,
                  attention_mask: Optional[np.ndarray] = None, token_type_ids: Optional[np.ndarray] = None,
-                 batch_size: int = 256) -> np.ndarray:
+                 batch_size: int = 256, cls_rows_only: bool = False) -> np.ndarray:
     """Class probabilities [n, num_labels] for host id arrays [n, 512] (batched ``infer_iter``), streamed through the
     same reusable pinned staging ring as the embedding extraction (embeddings.EmbeddingStreamer)."""
     from .embeddings import EmbeddingStreamer
-    st = EmbeddingStreamer(model, batch_size, fn=model.predict_proba, out_width=model.num_labels)
+    fn = model.predict_proba
+    if cls_rows_only:
+        def fn(*cols, err_flag=None):
+            return model.predict_proba(*cols, err_flag=err_flag, cls_rows_only=True)
+    st = EmbeddingStreamer(model, batch_size, fn=fn, out_width=model.num_labels)
     return st.run(input_ids, attention_mask, token_type_ids)
 
 

@@ -112,6 +112,8 @@ def test_batched_inference_matches_rowwise():
     all_at_once = infer_arrays(model, ids, mask, types, batch_size=2)
     rowwise = np.concatenate([infer_arrays(model, ids[i:i + 1], mask[i:i + 1], types[i:i + 1]) for i in range(len(ids))])
     assert np.array_equal(all_at_once, rowwise)            # batch composition does not change a row's result
+    # the classifier reads the pooled [CLS] row alone: the last layer over those rows only gives the same bits
+    assert np.array_equal(infer_arrays(model, ids, mask, types, batch_size=2, cls_rows_only=True), all_at_once)
     rows_iter = [dict(input_ids=ids[i].tolist(), attention_mask=mask[i].tolist(), token_type_ids=types[i].tolist())
                  for i in range(len(ids))]
     got = [p for _, p in infer_iter(model, rows_iter, batch_size=2)]
