@@ -53,13 +53,16 @@ class EmbeddingStreamer:
     what crossed the bus."""
 
     def __init__(self, model: STonKGsForPreTraining, batch_size: int = 256, slots: int = 2, columns: int = 3,
-                 pooling: str = "pooler", fn=None, out_width: int = 768, cls_rows_only: bool = False):
+                 pooling: str = "pooler", fn=None, out_width: int = 768, cls_rows_only: bool = False,
+                 skip_padding: bool = False):
         """``fn(input_ids, attention_mask, token_type_ids, err_flag=...)`` -> fp32 [m, out_width] on the device replaces
         ``model.embed`` (the fine-tuning model streams class probabilities through the same staging ring).
-        ``cls_rows_only``: see :meth:`STonKGsForPreTraining.embed`."""
+        ``cls_rows_only`` / ``skip_padding``: see :meth:`STonKGsForPreTraining.embed` (the plan of the padded rows is
+        made from the staged host copy of the mask: no synchronisation)."""
         self.model = model
         self.pooling = pooling
         self.cls_rows_only = bool(cls_rows_only)
+        self.skip_padding = bool(skip_padding) and columns >= 2
         self.fn = fn
         self.out_width = int(out_width)
         self.dev = model.bert.pooler.dense.weight.device
@@ -115,7 +118,9 @@ class EmbeddingStreamer:
             if self.fn is not None:
                 pooled = self.fn(*dcols, err_flag=self.err)
             else:
-                pooled = model.embed(*dcols, err_flag=self.err, pooling=self.pooling, cls_rows_only=self.cls_rows_only)
+                pooled = model.embed(*dcols, err_flag=self.err, pooling=self.pooling, cls_rows_only=self.cls_rows_only,
+                                     skip_padding=self.skip_padding and cols[1] is not None,
+                                     host_mask=slot.h_in_np[1, :m] if self.skip_padding else None)
             ready = torch.cuda.Event()
             ready.record(compute)
             with torch.cuda.stream(self.copy_stream):
@@ -136,12 +141,12 @@ class EmbeddingStreamer:
 def embed_arrays(model: STonKGsForPreTraining, input_ids, attention_mask=None, token_type_ids=None,
                  batch_size: int = 256, out: Optional[np.ndarray] = None,
                  streamer: Optional[EmbeddingStreamer] = None, pooling: str = "pooler",
-                 cls_rows_only: bool = False) -> np.ndarray:
+                 cls_rows_only: bool = False, skip_padding: bool = False) -> np.ndarray:
     """Pooled 768-d embeddings (``pooler_output``, stonkgs_for_embeddings.py:180; ``pooling="mean"``: masked mean of the
     last hidden state) for host id arrays ``[n, 512]``.  Returns float32 ``[n, 768]``; see :class:`EmbeddingStreamer`
-    for the staging scheme and :meth:`STonKGsForPreTraining.embed` for ``cls_rows_only``."""
+    for the staging scheme and :meth:`STonKGsForPreTraining.embed` for ``cls_rows_only`` / ``skip_padding``."""
     st = streamer if streamer is not None else EmbeddingStreamer(model, batch_size, pooling=pooling,
-                                                                 cls_rows_only=cls_rows_only)
+                                                                 cls_rows_only=cls_rows_only, skip_padding=skip_padding)
     return st.run(input_ids, attention_mask, token_type_ids, out=out)
 
 

@@ -12,6 +12,7 @@ import os
 from dataclasses import dataclass, field
 from typing import List, Optional
 
+import numpy as np
 import torch
 
 from . import ops
@@ -233,15 +234,51 @@ def lm_special_rows(ew: EncoderWeights, token_ids) -> torch.Tensor:
     return out.view(n, 128, H)[:, 0].float()
 
 
+def plan_live_rows(mask: np.ndarray, tile: int = 128):
+    """Host-side plan of the ``skip_padding`` extraction pass.  ``mask``: the attention mask [B, S] (0 = padding).
+
+    A padded row is never attended to as a key (additive bias finfo.min: its probability is exactly 0) and, as a query,
+    only feeds its own output row, which the pooler does not read.  Keys may be visited in any order, so every pair's
+    rows are reordered — row 0 ([CLS]) first, then the attended rows in their original order, then the padding — and
+    the pair is cut after the first multiple of ``tile`` rows that holds all of them (a pair that needs all S rows is
+    left in its original order: bit-identical to the full pass).  Pairs are grouped by that length.
+
+    Returns a list of ``(S_b, pair_idx int64 [n_b], row_idx int32 [n_b * S_b])`` in decreasing ``S_b``: ``row_idx`` are the
+    source rows (``pair * S + position``) of the group's packed activations.  A pair without a single attended key keeps
+    all S rows (the reference then attends uniformly over every key)."""
+    mask = np.asarray(mask)
+    B, S = mask.shape
+    key = (mask != 0).astype(np.int8)
+    attended = key.sum(axis=1)
+    key[:, 0] = 2
+    order = np.argsort(-key, axis=1, kind="stable").astype(np.int32)          # [B, S] positions, live first
+    live = (key > 0).sum(axis=1)
+    length = np.minimum(((live + tile - 1) // tile) * tile, S)
+    length[attended == 0] = S
+    if S % tile:
+        length[:] = S
+    order[length == S] = np.arange(S, dtype=np.int32)                          # nothing to cut: keep the pair as it is
+    groups = []
+    base = (np.arange(B, dtype=np.int32) * S)[:, None]
+    for sb in sorted(set(length.tolist()), reverse=True):
+        pairs = np.nonzero(length == sb)[0]
+        rows = (base[pairs] + order[pairs, :sb]).reshape(-1)
+        groups.append((int(sb), pairs.astype(np.int64), np.ascontiguousarray(rows, dtype=np.int32)))
+    return groups
+
+
 def joint_fwd(bert: EncoderWeights, input_ids, token_type_ids, attention_mask, lm_hidden, kg_table, *,
               cache: Optional[dict] = None, want_inputs_embeds=False, err_flag=None, drop: Optional[DropCtx] = None,
-              shape: ops.SeqShape = ops.STONKGS_SHAPE, head_mask=None, pooled_only: bool = False):
+              shape: ops.SeqShape = ops.STONKGS_SHAPE, head_mask=None, pooled_only: bool = False, live_plan=None):
     """KG lookup + concat + joint embeddings + 12 layers + pooler (stonkgs_model.py:182-212).
     Activations hold ``shape.seq_pad`` rows per pair (== the sequence length for STonKGs; the 260-token TransE variant is
     padded to 384 rows whose tail is masked out as attention keys).
 
     ``pooled_only`` (eval callers that read ``pooler_output`` alone): the last layer runs on the [CLS] rows only and the
-    returned ``seq`` is None; the pooled output is the same arithmetic per row as the full pass."""
+    returned ``seq`` is None; the pooled output is the same arithmetic per row as the full pass.
+
+    ``live_plan`` (eval, pooler only; :func:`plan_live_rows` of the host copy of ``attention_mask``): the joint encoder
+    runs on each group's packed rows instead of all ``B * S``; ``seq`` is None."""
     B = input_ids.shape[0]
     S, SP = shape.seq_len, shape.seq_pad
     train = cache is not None
@@ -260,6 +297,22 @@ def joint_fwd(bert: EncoderWeights, input_ids, token_type_ids, attention_mask, l
     key_bias = ops.mask_to_bias(attention_mask) if attention_mask is not None else None
     layer_cache = [] if train else None
     pooled_only = pooled_only and not train and drop is None and head_mask is None and FUSED_LN
+    if live_plan is not None and len(live_plan) == 1 and live_plan[0][0] == SP:
+        live_plan = None                                                           # no pair can be cut: the plain pass
+    if live_plan is not None and not train and drop is None and head_mask is None and key_bias is not None and SP == S:
+        pooled = torch.empty((B, H), dtype=torch.float32, device=x.device)
+        flat_bias = key_bias.view(-1)
+        for sb, pairs, rows in live_plan:
+            nb = int(pairs.shape[0])
+            # pinned staging: a copy from pageable memory would make the host wait for the stream
+            rows_d = torch.from_numpy(rows).pin_memory().to(x.device, non_blocking=True)
+            xb = ops.gather_rows(x, rows_d)                                        # packed activations [nb * sb, 768]
+            kb = torch.index_select(flat_bias, 0, rows_d).view(nb, sb)             # the same rows of the key bias
+            out = encoder_fwd(xb, bert, nb, sb, kb, None, None, 1, None, first_row_only=pooled_only)
+            cls = out if pooled_only else out.view(nb, sb, H)[:, 0]                 # [CLS] is packed row 0 of every pair
+            pb = ops.gemm(cls, bert.wp, M=nb, N=H, K=H, epilogue=ops.EPI_BIAS_TANH_F32, bias=bert.bp)
+            pooled.index_copy_(0, torch.from_numpy(pairs).pin_memory().to(x.device, non_blocking=True), pb)
+        return None, pooled, emb
     seq = encoder_fwd(x, bert, B, SP, key_bias, layer_cache, drop, 1, head_mask, first_row_only=pooled_only)
     # BertPooler: tanh(W h[:, 0] + b); rows b*SP are read in place through the A pitch
     cls = seq if pooled_only else seq.view(B, SP, H)[:, 0]

@@ -354,9 +354,10 @@ class STonKGsForPreTraining(BertForPreTraining):
                 raise KeyError(int(bad))
 
     def encode(self, input_ids, attention_mask=None, token_type_ids=None, *, cache=None, want_inputs_embeds=False,
-               need_heads=False, err_flag=None, head_mask=None, pooled_only=False):
+               need_heads=False, err_flag=None, head_mask=None, pooled_only=False, live_plan=None):
         """LM backbone -> KG lookup -> joint encoder -> pooler.  Returns (seq bf16 [B*seq_pad,768], pooled fp32, emb);
-        with ``pooled_only`` (eval) the last layer runs on the [CLS] rows alone and ``seq`` is None."""
+        with ``pooled_only`` (eval) the last layer runs on the [CLS] rows alone and ``seq`` is None; ``live_plan``:
+        see engine.joint_fwd."""
         st = self._device_state(need_heads)
         dev = self.kg_table.device
         sh = self.seq_shape
@@ -378,7 +379,8 @@ class STonKGsForPreTraining(BertForPreTraining):
         seq, pooled, emb = engine.joint_fwd(st["bert"], input_ids, token_type_ids, attention_mask, lm_hidden,
                                             self.kg_table, cache=cache, want_inputs_embeds=want_inputs_embeds,
                                             err_flag=err, drop=drop, shape=sh, head_mask=hm,
-                                            pooled_only=pooled_only and cache is None)
+                                            pooled_only=pooled_only and cache is None,
+                                            live_plan=live_plan if cache is None else None)
         if cache is not None:
             cache.update(input_ids=input_ids, token_type_ids=token_type_ids, err=err)
         if err_flag is None:
@@ -466,18 +468,35 @@ class STonKGsForPreTraining(BertForPreTraining):
 
     @torch.no_grad()
     def embed(self, input_ids, attention_mask=None, token_type_ids=None, err_flag=None, pooling: str = "pooler",
-              cls_rows_only: bool = False) -> torch.Tensor:
+              cls_rows_only: bool = False, skip_padding: bool = False, host_mask=None) -> torch.Tensor:
         """Extraction path, heads skipped.  ``pooling="pooler"`` (default) is the reference's output: the BERT pooler
         ``tanh(W h[:, 0] + b)`` (stonkgs_for_embeddings.py:180).  ``pooling="mean"`` is an extra: the mean of the last
         hidden state over the attended tokens (``attention_mask != 0``) of each pair.
 
         ``cls_rows_only`` (with the pooler, eval): the pooler reads ``hidden[:, 0]`` alone, so the last encoder layer is
         evaluated for the [CLS] rows only (keys / values still come from all 512 rows) — identical output, about 1/12 of
-        the joint encoder's work less.  Off by default: every number quoted for this path runs the full last layer."""
+        the joint encoder's work less.  Off by default: every number quoted for this path runs the full last layer.
+
+        ``skip_padding`` (with the pooler, eval, STonKGs shape): the joint encoder leaves out the padded rows of every
+        pair — they are masked as keys and, as queries, only produce rows the pooler never reads — by packing each
+        pair's attended rows first and running pairs that fit in 384 (256, 128) rows at that length
+        (engine.plan_live_rows).  Same mathematics; the attention sums run over the keys in a different grouping, so the
+        embeddings agree with the full pass to rounding (not bit for bit), except for pairs that keep all 512 rows.
+        The plan is made on the host from ``host_mask`` (a host copy of ``attention_mask``; without it a device mask
+        is copied back, which synchronises).  Off by default and never part of a quoted number."""
         if pooling not in ("pooler", "mean"):
             raise StkError(f"pooling must be 'pooler' or 'mean', got {pooling!r}")
+        plan = None
+        sh = self.seq_shape
+        if (skip_padding and pooling == "pooler" and not self.training and attention_mask is not None
+                and sh.seq_pad == sh.seq_len):
+            hm = host_mask if host_mask is not None else attention_mask
+            if isinstance(hm, torch.Tensor):
+                hm = hm.cpu().numpy()
+            plan = engine.plan_live_rows(hm)
         seq, pooled, _ = self.encode(input_ids, attention_mask, token_type_ids, err_flag=err_flag,
-                                     pooled_only=cls_rows_only and pooling == "pooler" and not self.training)
+                                     pooled_only=cls_rows_only and pooling == "pooler" and not self.training,
+                                     live_plan=plan)
         if pooling == "pooler":
             return pooled
         am = attention_mask

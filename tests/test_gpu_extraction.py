@@ -110,6 +110,58 @@ def test_cls_rows_only_last_layer_is_identical(full_model):
     assert torch.equal(model.embed(**batch, pooling="mean", cls_rows_only=True), mean_ref)
 
 
+def test_skip_padding_matches_the_full_pass(full_model):
+    """``skip_padding``: the joint encoder runs on packed rows (attended rows first, pairs cut to 128 / 256 / 384 / 512
+    rows).  Same mathematics, different grouping of the attention sums: pairs that keep all 512 rows are bit-identical
+    to the full pass, the others agree to bf16 rounding of a 12-layer encoder with random weights (stated: max |d| <= 4e-2,
+    mean <= 3e-3 on a tanh output — measured 2.4e-2 / 1.6e-3; the full pass itself is held to 5e-2 against the fp32
+    oracle); combined with ``cls_rows_only``, streamed with the host mask, and with a device-side mask."""
+    from stonkgs_b200 import synthetic
+    from stonkgs_b200.embeddings import embed_arrays
+    model, n_kg = full_model
+    n = 64 + 23
+    batch = synthetic.make_batch(n, n_kg, seed=21, with_labels=False)
+    batch["attention_mask"][1, 40:256] = 0          # short text: 40 + 256 rows -> 384
+    batch["attention_mask"][2, 5:256] = 0
+    batch["attention_mask"][2, 300:512] = 0         # 5 + 44 rows -> 128
+    batch["attention_mask"][3] = 0                  # nothing attended: kept whole (uniform attention, like the reference)
+    batch["attention_mask"][4] = 1
+    ref = model.embed(**batch)
+    got = model.embed(**batch, skip_padding=True)
+    assert got.shape == ref.shape and torch.isfinite(got).all()
+    d = (got - ref).abs()
+    assert d.max().item() <= 4e-2 and d.mean().item() <= 3e-3, (d.max().item(), d.mean().item())
+    whole = (batch["attention_mask"].sum(1) > 384) | (batch["attention_mask"].sum(1) == 0)
+    assert whole.sum() >= 10 and torch.equal(got[whole.cuda()], ref[whole.cuda()])
+    assert (~whole).sum() >= 10 and d[(~whole).cuda()].max().item() > 0          # the packed pairs did take the other path
+    both = model.embed(**batch, skip_padding=True, cls_rows_only=True)
+    assert torch.equal(both, got)                                                 # cls_rows_only stays exact on packed rows
+    dev_batch = {k: v.cuda() for k, v in batch.items()}
+    assert torch.equal(model.embed(**dev_batch, skip_padding=True), got)          # device mask: copied back for the plan
+    ids, mask, types = (batch[k].numpy() for k in ("input_ids", "attention_mask", "token_type_ids"))
+    streamed = embed_arrays(model, ids, mask, types, batch_size=32, skip_padding=True)
+    ds = np.abs(streamed - ref.cpu().numpy())
+    assert ds.max() <= 4e-2 and ds.mean() <= 3e-3
+    # no mask: nothing to skip
+    assert torch.equal(model.embed(batch["input_ids"], None, batch["token_type_ids"], skip_padding=True),
+                       model.embed(batch["input_ids"], None, batch["token_type_ids"]))
+
+
+def test_skip_padding_vs_oracle():
+    """The packed pass against the fp32 oracle's pooler_output on a golden case, at the tolerance of the full pass (5e-2)."""
+    from _util import build_model, load_fixture, seeded_weights
+    from oracle import stonkgs_oracle as orc
+    fix, meta, batch = load_fixture("L2_B2_N997")
+    sd, rows = seeded_weights(meta)
+    model = build_model(meta, sd, rows, "cuda")
+    ids, mask, types = batch["input_ids"], batch["attention_mask"].clone(), batch["token_type_ids"]
+    mask[0, 30:256] = 0
+    with torch.no_grad():
+        want = orc.forward(sd, orc.build_kg_table(sd, rows), ids, mask, types)["pooler_output"]
+    got = model.embed(ids, mask, types, skip_padding=True, cls_rows_only=True).cpu()
+    torch.testing.assert_close(got, want, atol=5e-2, rtol=0)
+
+
 def test_mean_pooled_extraction_vs_oracle():
     """pooling="mean" (an extra beside the reference's pooler_output): masked mean of the last hidden state, against the
     fp32 oracle's sequence_output on a golden case; stated tolerance atol 3e-2 (a mean over >= 288 rows of bf16 states)."""

@@ -226,3 +226,45 @@ def test_get_stonkgs_embeddings_empty_frame():
 
     out = get_stonkgs_embeddings(df, _embed_fn=fake_embed)
     assert list(out.columns) == ["embedding"] and len(out) == 0 and seen == [0]
+
+
+def test_plan_live_rows():
+    """engine.plan_live_rows (skip_padding extraction): every pair's attended rows come first ([CLS] in front, original
+    order kept), the pair is cut at the first multiple of 128 rows that holds them, pairs are grouped by that length; a pair
+    without any attended key keeps all rows."""
+    from stonkgs_b200 import engine, synthetic
+    batch = synthetic.make_batch(37, 997, seed=2, with_labels=False)
+    mask = batch["attention_mask"].numpy().copy()
+    mask[3] = 0                     # nothing attended: the reference's uniform attention needs every key
+    mask[4, :] = 1                  # no padding at all
+    mask[5, 0] = 0                  # [CLS] masked as a key: still the first packed row (it is read as a query)
+    mask[6, 10:256] = 0
+    mask[6, 300:400] = 0            # holes in the KG half: 10 + 156 = 166 attended rows -> 256
+    mask[7, 1:256] = 0              # 1 + 256 attended rows: one more than two tiles -> 384
+    S = mask.shape[1]
+    plan = engine.plan_live_rows(mask)
+    lengths = [sb for sb, _, _ in plan]
+    assert lengths == sorted(set(lengths), reverse=True) and set(lengths) <= {128, 256, 384, 512}
+    seen = {}
+    for sb, pairs, rows in plan:
+        assert pairs.dtype == np.int64 and rows.dtype == np.int32 and rows.shape == (len(pairs) * sb,)
+        for b, r in zip(pairs.tolist(), rows.reshape(len(pairs), sb)):
+            pos = r - b * S
+            assert pos[0] == 0 and len(set(pos.tolist())) == sb and pos.min() >= 0 and pos.max() < S
+            attended = set(np.nonzero(mask[b])[0].tolist())
+            if sb == S:
+                assert list(pos) == list(range(S))                             # nothing cut: the pair is left as it is
+            if attended:
+                n_live = len(attended | {0})
+                assert sb == min(S, -(-n_live // 128) * 128)
+                assert attended | {0} <= set(pos.tolist())                   # every attended row is kept ...
+                if sb < S:
+                    assert set(pos[:n_live].tolist()) == attended | {0}      # ... in front ...
+                    assert list(pos[1:n_live]) == sorted(pos[1:n_live])        # ... in its original order
+            else:
+                assert sb == S and list(pos) == list(range(S))
+            seen[b] = sb
+    assert sorted(seen) == list(range(37))
+    assert seen[3] == 512 and seen[4] == 512 and seen[6] == 256 and seen[7] == 384
+    # a sequence length that is not a multiple of the tile keeps every pair whole
+    assert [sb for sb, _, _ in engine.plan_live_rows(np.ones((3, 260), dtype=np.int64))] == [260]
