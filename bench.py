@@ -16,7 +16,8 @@ encoder -> pooler.  N > 1 (torchrun): every rank embeds its own shard of the pai
                 (N > 1) + clip + AdamW — 64 pairs per GPU (global 512 at N = 8): value, e2e, roofline, and at N > 1
                 the exposed all-reduce time and the bytes on the wire
   cls_rows_only (inside the top level; NOT the headline) the extraction step with the last encoder layer evaluated for the
-                [CLS] rows only — bit-identical embeddings, ~1/24 of the work less; `value` always runs the full layer
+                [CLS] rows only — bit-identical embeddings, ~1/24 of the work less; `value` always runs the full layer;
+                its `skip_padding` entry adds the joint encoder on packed rows (padding left out; equal to rounding)
   bulk          configs[4]: >= 1 M pairs per GPU streamed from host arrays through embeddings.embed_arrays
                 (double-buffered pinned staging, copy stream), pairs/s and the gap to `value`
   library_baseline  the same extraction through HF BertModel x 2 in bf16 + SDPA (cuBLAS / flash kernels) on the same
