@@ -15,7 +15,7 @@ import ctypes
 
 import torch
 
-from . import _lib, ops
+from . import _lib
 from ._lib import AdamSeg, StkError, check
 
 CHUNK = 65536

@@ -9,7 +9,7 @@ slices of that buffer while the rest of backward is still running (``dp.py``).
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional
+from typing import Dict, Optional
 
 import torch
 
